@@ -1,0 +1,59 @@
+// Shared declarations of the spb200 engine (B200 / sm_100a SuperPoint inference).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+namespace spb200 {
+
+enum Precision { PREC_FP32 = 0, PREC_FP16 = 1, PREC_BF16 = 2 };
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e != cudaSuccess)
+        throw CudaError(std::string(what) + ": " + cudaGetErrorString(e) + " (" + file + ":" + std::to_string(line) + ")");
+}
+#define SPB_CUDA(x) ::spb200::cuda_check((x), #x, __FILE__, __LINE__)
+#define SPB_CHECK_LAUNCH() ::spb200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
+
+constexpr int kMaxTaps = 9;
+constexpr int kMaxSegs = 3;
+
+// One K segment of an implicit-GEMM convolution: `ntaps` taps over a `cin`-channel NHWC source.
+// Output pixel (oy, ox) reads source pixel (oy*stride + dy[t], ox*stride + dx[t]); pixels outside
+// the source are zero (that is the convolution's zero padding).
+struct SegDev {
+    const void* src;      // NHWC activations, element type given by the kernel
+    int H, W, C;          // source dims; C = stored channels per pixel
+    int cin;              // channels consumed by this segment (<= C, multiple of 16)
+    int ntaps;
+    int stride;
+    int koff;             // first K index of this segment in the packed weights
+    int8_t dy[kMaxTaps], dx[kMaxTaps];
+};
+
+// out[p, co] = act( bias[co] + sum_seg sum_tap sum_ci src_seg[pix(p, tap), ci] * W[k, co] + residual[p, co] )
+struct ConvDev {
+    SegDev seg[kMaxSegs];
+    int nseg;
+    const void* w;        // SIMT: fp32 [K][cout_pad]; tensor-core path: 16-bit [cout_pad][K]
+    const float* bias;    // [cout_pad], BatchNorm folded
+    const void* residual; // NHWC, same pixel grid as the GEMM rows, res_C channels per pixel, or null
+    void* dst;            // NHWC
+    int B, OH, OW;        // GEMM rows = B*OH*OW output pixels
+    int K, cout_pad;
+    int dst_H, dst_W, dst_C;
+    int dst_stride, dst_off_y, dst_off_x;   // dst pixel = (oy*dst_stride + off_y, ox*dst_stride + off_x)
+    int res_C;
+    int relu;
+    int dst_fp32;         // tensor-core path: store fp32 instead of the 16-bit operand type
+};
+
+}  // namespace spb200

@@ -1,0 +1,617 @@
+// spb200::Engine implementation: weight folding/packing, workspace, launch sequence.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace spb200 {
+
+namespace {
+
+constexpr float kBnEps = 1e-5f;   // nn.BatchNorm2d default (reference python/src/resnet_blocks.py:8)
+
+template <typename T>
+T* dev_alloc(size_t n) {
+    void* p = nullptr;
+    SPB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    return static_cast<T*>(p);
+}
+
+template <typename T>
+T* dev_upload(const std::vector<T>& v) {
+    T* p = dev_alloc<T>(v.size());
+    if (!v.empty()) SPB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+uint16_t f32_to_f16_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
+uint16_t f32_to_bf16_bits(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct Engine::HostStage {
+    float* img = nullptr;          // pinned
+    size_t img_bytes = 0;
+    int* count = nullptr;          // pinned [B]
+    int* xy = nullptr;             // pinned packed
+    float* conf = nullptr;
+    float* desc = nullptr;
+    size_t out_cap = 0;            // keypoints the pinned output buffers hold
+    int B = 0;
+    // device
+    float* d_img = nullptr;
+    size_t d_img_bytes = 0;
+    int* d_count = nullptr;
+    int* d_xy = nullptr;
+    float* d_conf = nullptr;
+    float* d_desc = nullptr;
+    int d_B = 0, d_cap = 0;
+    cudaStream_t stream = nullptr;
+    ~HostStage() {
+        if (img) cudaFreeHost(img);
+        if (count) cudaFreeHost(count);
+        if (xy) cudaFreeHost(xy);
+        if (conf) cudaFreeHost(conf);
+        if (desc) cudaFreeHost(desc);
+        cudaFree(d_img); cudaFree(d_count); cudaFree(d_xy); cudaFree(d_conf); cudaFree(d_desc);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+Engine::Engine(int device) : device_(device) {
+    int n = 0;
+    SPB_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) throw std::invalid_argument("invalid CUDA device index");
+    SPB_CUDA(cudaSetDevice(device_));
+    cudaDeviceProp prop{};
+    SPB_CUDA(cudaGetDeviceProperties(&prop, device_));
+    if (prop.major < 10)
+        throw std::runtime_error(std::string("spb200 needs a Blackwell (sm_100a) GPU, found ") + prop.name);
+    buf_.fill(nullptr);
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device_);
+    release_workspace();
+    release_weights();
+    cudaFree(nms_.stamp); cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters);
+}
+
+void Engine::release_workspace() {
+    for (auto& op : ops_) { if (op.plan) { tc_plan_destroy(op.plan); op.plan = nullptr; } }
+    for (auto& p : buf_) { cudaFree(p); p = nullptr; }
+    cudaFree(d_prob_); d_prob_ = nullptr;
+    wsB_ = wsH_ = wsW_ = 0;
+}
+
+void Engine::release_weights() {
+    for (auto& op : ops_) {
+        if (op.plan) tc_plan_destroy(op.plan);
+        cudaFree(op.d_bias); cudaFree(op.d_w32); cudaFree(op.d_w16);
+    }
+    ops_.clear();
+    convs_.clear();
+    cudaFree(d_stem_w_[0]); cudaFree(d_stem_w_[1]); cudaFree(d_stem_b_);
+    d_stem_w_[0] = d_stem_w_[1] = d_stem_b_ = nullptr;
+}
+
+void Engine::load_checkpoint(const std::string& path) {
+    std::string err;
+    StateDict sd;
+    if (!read_checkpoint(path, sd, err)) throw std::runtime_error("failed to load checkpoint " + path + ": " + err);
+    sd_ = std::move(sd);
+    finalized_ = false;
+}
+
+void Engine::load_tensor(const std::string& key, const float* data, const int64_t* shape, int rank) {
+    HostTensor t;
+    t.shape.assign(shape, shape + rank);
+    t.data.assign(data, data + t.numel());
+    sd_[key] = std::move(t);
+    finalized_ = false;
+}
+
+// conv (no bias unless has_bias) followed by eval-mode BatchNorm: w' = w * s, b' = beta - mean * s (+ bias * s),
+// s = gamma / sqrt(var + eps).  A transposed conv's weight is [cin][cout][kh][kw]; it is stored here
+// re-indexed as [cout][cin][kh][kw] without flipping (the taps are enumerated explicitly).
+const HostConv* Engine::fold(const std::string& conv_key, const std::string& bn_key, bool transposed, bool has_bias) {
+    auto need = [&](const std::string& k) -> const HostTensor& {
+        auto it = sd_.find(k);
+        if (it == sd_.end()) throw std::runtime_error("checkpoint is missing key '" + k + "'");
+        return it->second;
+    };
+    const HostTensor& w = need(conv_key + ".weight");
+    if (w.shape.size() != 4) throw std::runtime_error(conv_key + ".weight is not 4-d");
+    auto hc = std::make_unique<HostConv>();
+    hc->cout = (int)(transposed ? w.shape[1] : w.shape[0]);
+    hc->cin = (int)(transposed ? w.shape[0] : w.shape[1]);
+    hc->kh = (int)w.shape[2];
+    hc->kw = (int)w.shape[3];
+    const HostTensor& g = need(bn_key + ".weight");
+    const HostTensor& be = need(bn_key + ".bias");
+    const HostTensor& mu = need(bn_key + ".running_mean");
+    const HostTensor& var = need(bn_key + ".running_var");
+    for (const HostTensor* t : {&g, &be, &mu, &var})
+        if (t->numel() != hc->cout) throw std::runtime_error(bn_key + " has the wrong number of channels");
+    const HostTensor* cb = has_bias ? &need(conv_key + ".bias") : nullptr;
+    hc->w.resize((size_t)hc->cout * hc->cin * hc->kh * hc->kw);
+    hc->b.resize(hc->cout);
+    for (int co = 0; co < hc->cout; ++co) {
+        const float s = g.data[co] / std::sqrt(var.data[co] + kBnEps);
+        hc->b[co] = be.data[co] - mu.data[co] * s + (cb ? cb->data[co] * s : 0.f);
+        for (int ci = 0; ci < hc->cin; ++ci)
+            for (int y = 0; y < hc->kh; ++y)
+                for (int x = 0; x < hc->kw; ++x) {
+                    const size_t src = transposed ? ((((size_t)ci * hc->cout + co) * hc->kh + y) * hc->kw + x)
+                                                  : ((((size_t)co * hc->cin + ci) * hc->kh + y) * hc->kw + x);
+                    hc->w[(((size_t)co * hc->cin + ci) * hc->kh + y) * hc->kw + x] = w.data[src] * s;
+                }
+    }
+    convs_.push_back(std::move(hc));
+    return convs_.back().get();
+}
+
+static std::vector<TapSpec> taps3x3() {
+    std::vector<TapSpec> t;
+    for (int y = 0; y < 3; ++y)
+        for (int x = 0; x < 3; ++x) t.push_back({y - 1, x - 1, y, x});
+    return t;
+}
+
+// One residual block (reference python/src/resnet_blocks.py:14-27) as two implicit GEMMs:
+//   Y   = relu(conv3x3_s(X) + b1)
+//   OUT = relu(conv1x1(Y) [+ conv1x1_s(X) as extra K] + b2 [+ bd] [+ X])
+// `srcs` lists the source buffers that are concatenated along channels (one, or two for layer_out.0,
+// python/src/superpoint.py:59) with the channel count each contributes.
+void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> srcs, int y_buf, int dst_buf,
+                       int stride, int cout, bool dst_fp32) {
+    const bool has_ds = sd_.count(p + ".identity_downsample.0.weight") > 0;
+    const HostConv* c1 = fold(p + ".conv1", p + ".bn1", false, false);
+    const HostConv* c2 = fold(p + ".conv2", p + ".bn2", false, false);
+    const HostConv* cd = has_ds ? fold(p + ".identity_downsample.0", p + ".identity_downsample.1", false, false) : nullptr;
+    int cin_total = 0;
+    for (auto& s : srcs) cin_total += s.second;
+    if (c1->cin != cin_total || c1->cout != cout || c1->kh != 3 || c2->cin != cout || c2->cout != cout || c2->kh != 1)
+        throw std::runtime_error("unexpected convolution shapes in block " + p);
+    if (cd && (cd->cin != cin_total || cd->cout != cout || cd->kh != 1))
+        throw std::runtime_error("unexpected downsample shape in block " + p);
+    const int cout_pad = bufspec_[y_buf].C;
+
+    OpSpec a;
+    a.name = p + ".conv1";
+    int off = 0;
+    for (auto& s : srcs) {
+        a.segs.push_back(SegSpec{s.first, c1, off, s.second, stride, taps3x3()});
+        off += s.second;
+    }
+    a.cout_real = cout; a.cout_pad = cout_pad; a.dst_buf = y_buf; a.relu = true;
+    a.bias.assign(cout_pad, 0.f);
+    std::copy(c1->b.begin(), c1->b.end(), a.bias.begin());
+    ops_.push_back(std::move(a));
+
+    OpSpec b;
+    b.name = p + ".conv2";
+    b.segs.push_back(SegSpec{y_buf, c2, 0, cout, 1, {TapSpec{0, 0, 0, 0}}});
+    b.bias.assign(cout_pad, 0.f);
+    std::copy(c2->b.begin(), c2->b.end(), b.bias.begin());
+    if (cd) {
+        off = 0;
+        for (auto& s : srcs) {
+            b.segs.push_back(SegSpec{s.first, cd, off, s.second, stride, {TapSpec{0, 0, 0, 0}}});
+            off += s.second;
+        }
+        for (int i = 0; i < cout; ++i) b.bias[i] += cd->b[i];
+    } else {
+        if (srcs.size() != 1 || stride != 1) throw std::runtime_error("identity shortcut needs one same-size source: " + p);
+        b.res_buf = srcs[0].first;
+    }
+    b.cout_real = cout; b.cout_pad = cout_pad; b.dst_buf = dst_buf; b.relu = true; b.dst_fp32 = dst_fp32;
+    ops_.push_back(std::move(b));
+}
+
+void Engine::build_ops() {
+    const int dc = det_c_;
+    bufspec_[BUF_POOL] = {4, 64, false};
+    for (int b : {BUF_L1A_Y, BUF_L1A, BUF_L1B_Y, BUF_L1B}) bufspec_[b] = {4, 64, false};
+    for (int b : {BUF_L2A_Y, BUF_L2A, BUF_L2B_Y, BUF_FEAT}) bufspec_[b] = {8, 128, false};
+    for (int b : {BUF_D0_Y, BUF_D0, BUF_D1_Y}) bufspec_[b] = {8, dc, false};
+    bufspec_[BUF_LOGITS] = {8, dc, true};
+    for (int b : {BUF_I0_Y, BUF_I0, BUF_I1_Y, BUF_I1}) bufspec_[b] = {16, 256, false};
+    for (int b : {BUF_UP, BUF_O0_Y, BUF_O0, BUF_O1_Y, BUF_DESC}) bufspec_[b] = {8, 128, false};
+
+    // encoder (reference python/src/superpoint.py:16-17), detector (:32), descriptor (:43-50)
+    add_block("encoder.layer1.0", {{BUF_POOL, 64}}, BUF_L1A_Y, BUF_L1A, 1, 64, false);
+    add_block("encoder.layer1.1", {{BUF_L1A, 64}}, BUF_L1B_Y, BUF_L1B, 1, 64, false);
+    add_block("encoder.layer2.0", {{BUF_L1B, 64}}, BUF_L2A_Y, BUF_L2A, 2, 128, false);
+    add_block("encoder.layer2.1", {{BUF_L2A, 128}}, BUF_L2B_Y, BUF_FEAT, 1, 128, false);
+    add_block("detector.layer.0", {{BUF_FEAT, 128}}, BUF_D0_Y, BUF_D0, 1, 65, false);
+    add_block("detector.layer.1", {{BUF_D0, 65}}, BUF_D1_Y, BUF_LOGITS, 1, 65, true);
+    const size_t first_desc_op = ops_.size();
+    add_block("descriptor.layer_in.0", {{BUF_FEAT, 128}}, BUF_I0_Y, BUF_I0, 2, 256, false);
+    add_block("descriptor.layer_in.1", {{BUF_I0, 256}}, BUF_I1_Y, BUF_I1, 1, 256, false);
+    // ConvTranspose2d(256,128,k3,s2,p1,op1)+bias -> BN -> ReLU (python/src/superpoint.py:45-47,55-57) as four
+    // output phases: out[2m+py, 2n+px]; even outputs use kernel index 1 from input m, odd outputs kernel
+    // index 2 from input m and kernel index 0 from input m+1 (out index o = 2i - 1 + k).
+    const HostConv* up = fold("descriptor.up_sample", "descriptor.bn", true, true);
+    if (up->cin != 256 || up->cout != 128 || up->kh != 3) throw std::runtime_error("unexpected up_sample shape");
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            OpSpec o;
+            o.name = "descriptor.up_sample.phase" + std::to_string(py) + std::to_string(px);
+            std::vector<TapSpec> taps;
+            const int ky[2][2] = {{1, -1}, {2, 0}}, dyv[2] = {0, 1};
+            for (int a = 0; a < 2; ++a) {
+                if (ky[py][a] < 0) continue;
+                for (int c = 0; c < 2; ++c) {
+                    if (ky[px][c] < 0) continue;
+                    taps.push_back({dyv[a], dyv[c], ky[py][a], ky[px][c]});
+                }
+            }
+            o.segs.push_back(SegSpec{BUF_I1, up, 0, 256, 1, taps});
+            o.cout_real = 128; o.cout_pad = 128; o.dst_buf = BUF_UP; o.relu = true;
+            o.dst_stride = 2; o.off_y = py; o.off_x = px;
+            o.bias = up->b;
+            ops_.push_back(std::move(o));
+        }
+    add_block("descriptor.layer_out.0", {{BUF_UP, 128}, {BUF_FEAT, 128}}, BUF_O0_Y, BUF_O0, 1, 128, false);
+    add_block("descriptor.layer_out.1", {{BUF_O0, 128}}, BUF_O1_Y, BUF_DESC, 1, 128, false);
+    (void)first_desc_op;
+
+    // pack and upload
+    for (auto& op : ops_) {
+        int K = 0;
+        for (auto& s : op.segs) K += (int)s.taps.size() * bufspec_[s.src_buf].C;
+        op.K = K;
+        std::vector<float> w32((size_t)K * op.cout_pad, 0.f);
+        int koff = 0;
+        for (auto& s : op.segs) {
+            const int cpad = bufspec_[s.src_buf].C;
+            for (size_t t = 0; t < s.taps.size(); ++t)
+                for (int ci = 0; ci < s.cin_real; ++ci)
+                    for (int co = 0; co < op.cout_real; ++co)
+                        w32[(size_t)(koff + (int)t * cpad + ci) * op.cout_pad + co] =
+                            s.conv->at(co, s.ci_off + ci, s.taps[t].kh, s.taps[t].kw);
+            koff += (int)s.taps.size() * cpad;
+        }
+        op.d_bias = dev_upload(op.bias);
+        if (precision_ == PREC_FP32) {
+            op.d_w32 = dev_upload(w32);
+        } else {
+            std::vector<uint16_t> w16((size_t)op.cout_pad * K);
+            for (int k = 0; k < K; ++k)
+                for (int co = 0; co < op.cout_pad; ++co) {
+                    const float v = w32[(size_t)k * op.cout_pad + co];
+                    w16[(size_t)co * K + k] = precision_ == PREC_FP16 ? f32_to_f16_bits(v) : f32_to_bf16_bits(v);
+                }
+            op.d_w16 = dev_upload(w16);
+        }
+    }
+
+    // stem: conv7x7 s2 p3 (no bias) + BN (python/src/superpoint.py:12-13); the 1-channel variant sums the
+    // three input-channel kernels, exact for a gray image replicated to RGB (python/src/dataset_utils.py:18-20)
+    const HostConv* st = fold("encoder.conv1", "encoder.bn1", false, false);
+    if (st->cin != 3 || st->cout != 64 || st->kh != 7) throw std::runtime_error("unexpected encoder.conv1 shape");
+    std::vector<float> w3((size_t)3 * 49 * 64), w1((size_t)49 * 64, 0.f);
+    for (int c = 0; c < 3; ++c)
+        for (int y = 0; y < 7; ++y)
+            for (int x = 0; x < 7; ++x)
+                for (int co = 0; co < 64; ++co) {
+                    const float v = st->at(co, c, y, x);
+                    w3[((size_t)(c * 49 + y * 7 + x)) * 64 + co] = v;
+                    w1[((size_t)(y * 7 + x)) * 64 + co] += v;
+                }
+    d_stem_w_[0] = dev_upload(w1);
+    d_stem_w_[1] = dev_upload(w3);
+    d_stem_b_ = dev_upload(st->b);
+}
+
+void Engine::finalize(int precision) {
+    if (precision != PREC_FP32 && precision != PREC_FP16 && precision != PREC_BF16)
+        throw std::invalid_argument("precision must be 0 (fp32 CUDA cores), 1 (fp16 tcgen05) or 2 (bf16 tcgen05)");
+    if (sd_.empty()) throw std::runtime_error("no weights loaded");
+    SPB_CUDA(cudaSetDevice(device_));
+    SPB_CUDA(cudaDeviceSynchronize());
+    release_workspace();
+    release_weights();
+    precision_ = precision;
+    det_c_ = precision == PREC_FP32 ? 80 : 128;
+    build_ops();
+    finalized_ = true;
+}
+
+int Engine::max_keypoints(int H, int W, int nms_dist) {
+    const int r = std::max(nms_dist, 0);
+    return ((H + r) / (r + 1)) * ((W + r) / (r + 1));
+}
+
+void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
+    if (!finalized_) throw std::runtime_error("weights are not finalized (call spb200_finalize_weights)");
+    if (B <= 0 || H <= 0 || W <= 0 || H % 16 != 0 || W % 16 != 0)
+        throw std::invalid_argument("image height and width must be positive multiples of 16");
+    if (C != 1 && C != 3) throw std::invalid_argument("images must have 1 or 3 channels");
+    if (B == wsB_ && H == wsH_ && W == wsW_) return;
+    SPB_CUDA(cudaStreamSynchronize(st));
+    SPB_CUDA(cudaDeviceSynchronize());
+    release_workspace();
+    const size_t esz = precision_ == PREC_FP32 ? 4 : 2;
+    for (int i = 0; i < BUF_COUNT; ++i) {
+        const BufSpec& bs = bufspec_[i];
+        const size_t n = (size_t)B * (H / bs.div) * (W / bs.div) * bs.C;
+        const size_t bytes = n * (bs.fp32 ? 4 : esz);
+        SPB_CUDA(cudaMalloc(&buf_[i], bytes));
+        SPB_CUDA(cudaMemset(buf_[i], 0, bytes));     // padded channels stay zero forever
+    }
+    d_prob_ = dev_alloc<float>((size_t)B * H * W);
+    wsB_ = B; wsH_ = H; wsW_ = W;
+    if (precision_ != PREC_FP32)
+        for (auto& op : ops_) op.plan = tc_plan_create(make_conv_dev(op), precision_);
+}
+
+void Engine::ensure_nms(int B, int H, int W) {
+    const int r = params_.nms_dist;
+    if (B <= nmsB_ && H == nmsH_ && W == nmsW_ && r == nmsR_) return;
+    SPB_CUDA(cudaDeviceSynchronize());
+    cudaFree(nms_.stamp); cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters);
+    nms_.kcap = max_keypoints(H, W, r);
+    nms_.stamp = dev_alloc<uint16_t>((size_t)B * H * W);
+    nms_.keys = dev_alloc<unsigned long long>((size_t)B * nms_.kcap);
+    nms_.keys_alt = dev_alloc<unsigned long long>((size_t)B * nms_.kcap);
+    nms_.counters = dev_alloc<int>((size_t)B * 4);
+    nmsB_ = B; nmsH_ = H; nmsW_ = W; nmsR_ = r;
+}
+
+ConvDev Engine::make_conv_dev(const OpSpec& op) const {
+    ConvDev d{};
+    const BufSpec& ds = bufspec_[op.dst_buf];
+    d.nseg = (int)op.segs.size();
+    int koff = 0;
+    for (int i = 0; i < d.nseg; ++i) {
+        const SegSpec& s = op.segs[i];
+        const BufSpec& bs = bufspec_[s.src_buf];
+        SegDev& sd = d.seg[i];
+        sd.src = buf_[s.src_buf];
+        sd.H = wsH_ / bs.div; sd.W = wsW_ / bs.div; sd.C = bs.C;
+        sd.cin = bs.C;
+        sd.ntaps = (int)s.taps.size();
+        sd.stride = s.stride;
+        sd.koff = koff;
+        for (int t = 0; t < sd.ntaps; ++t) { sd.dy[t] = (int8_t)s.taps[t].dy; sd.dx[t] = (int8_t)s.taps[t].dx; }
+        koff += sd.ntaps * bs.C;
+    }
+    d.w = precision_ == PREC_FP32 ? (const void*)op.d_w32 : (const void*)op.d_w16;
+    d.bias = op.d_bias;
+    d.residual = op.res_buf >= 0 ? buf_[op.res_buf] : nullptr;
+    d.res_C = op.res_buf >= 0 ? bufspec_[op.res_buf].C : 0;
+    d.dst = buf_[op.dst_buf];
+    d.B = wsB_;
+    d.dst_H = wsH_ / ds.div; d.dst_W = wsW_ / ds.div; d.dst_C = ds.C;
+    d.dst_stride = op.dst_stride; d.dst_off_y = op.off_y; d.dst_off_x = op.off_x;
+    d.OH = d.dst_H / op.dst_stride; d.OW = d.dst_W / op.dst_stride;
+    d.K = op.K; d.cout_pad = op.cout_pad;
+    d.relu = op.relu ? 1 : 0;
+    d.dst_fp32 = (op.dst_fp32 || precision_ == PREC_FP32) ? 1 : 0;
+    return d;
+}
+
+// ---- per-launch profiling -------------------------------------------------------------------------
+void Engine::profile_begin() {
+    for (auto& e : prof_) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+    prof_.clear();
+    profiling_ = true;
+}
+
+const std::vector<Engine::ProfEntry>& Engine::profile_end() {
+    profiling_ = false;
+    SPB_CUDA(cudaDeviceSynchronize());
+    for (auto& e : prof_) SPB_CUDA(cudaEventElapsedTime(&e.ms, e.start, e.stop));
+    return prof_;
+}
+
+void Engine::prof_open(const std::string& name, double flops, double bytes, cudaStream_t st) {
+    if (!profiling_) return;
+    ProfEntry e{name, nullptr, nullptr, flops, bytes, 0.f};
+    SPB_CUDA(cudaEventCreate(&e.start));
+    SPB_CUDA(cudaEventCreate(&e.stop));
+    SPB_CUDA(cudaEventRecord(e.start, st));
+    prof_.push_back(e);
+}
+
+void Engine::prof_close(cudaStream_t st) {
+    if (!profiling_) return;
+    SPB_CUDA(cudaEventRecord(prof_.back().stop, st));
+}
+
+// algorithmic FLOPs of one launch: 2 x MACs of the reference convolution, real (unpadded) channels
+double Engine::op_flops(const OpSpec& op) const {
+    const BufSpec& ds = bufspec_[op.dst_buf];
+    const double rows = (double)wsB_ * (wsH_ / ds.div / op.dst_stride) * (wsW_ / ds.div / op.dst_stride);
+    double k = 0;
+    for (auto& s : op.segs) k += (double)s.taps.size() * s.cin_real;
+    return 2.0 * rows * k * op.cout_real;
+}
+
+void Engine::run_network(const float* img, int B, int C, int H, int W, cudaStream_t st) {
+    ensure_workspace(B, C, H, W, st);
+    // gray-folded stem: 49 MACs per output (the reference's 3-channel stem does 147 on replicated input)
+    prof_open("stem_pool", 2.0 * B * (H / 2) * (W / 2) * 64.0 * 49.0 * C,
+              (double)B * C * H * W * 4 + (double)B * (H / 4) * (W / 4) * 64 * (precision_ == PREC_FP32 ? 4 : 2), st);
+    launch_stem_pool(img, B, C, H, W, d_stem_w_[C == 1 ? 0 : 1], d_stem_b_, buf_[BUF_POOL], precision_, st);
+    prof_close(st);
+    ++launches_;
+    for (auto& op : ops_) {
+        if (!params_.descriptor_enabled && op.name.compare(0, 11, "descriptor.") == 0) continue;
+        prof_open(op.name, op_flops(op), 0.0, st);
+        if (precision_ == PREC_FP32) launch_conv_simt(make_conv_dev(op), st);
+        else launch_conv_tc(op.plan, st);
+        prof_close(st);
+        ++launches_;
+    }
+}
+
+void Engine::forward(const float* img, int B, int C, int H, int W, float* prob, float* desc_nchw, float* logits_nchw,
+                     cudaStream_t st) {
+    SPB_CUDA(cudaSetDevice(device_));
+    run_network(img, B, C, H, W, st);
+    const int Hc = H / 8, Wc = W / 8;
+    float* heat = prob ? prob : d_prob_;
+    launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc, heat, st);
+    ++launches_;
+    if (logits_nchw) {
+        launch_nhwc_to_nchw(buf_[BUF_LOGITS], PREC_FP32, B, Hc * Wc, det_c_, 65, logits_nchw, st);
+        ++launches_;
+    }
+    if (desc_nchw) {
+        if (params_.descriptor_enabled) {
+            launch_nhwc_to_nchw(buf_[BUF_DESC], precision_, B, Hc * Wc, 128, 128, desc_nchw, st);
+            ++launches_;
+        } else {
+            // MagicPoint: zeros (reference python/src/superpoint.py:105-109)
+            SPB_CUDA(cudaMemsetAsync(desc_nchw, 0, sizeof(float) * (size_t)B * 128 * Hc * Wc, st));
+        }
+    }
+}
+
+void Engine::detect(const float* img, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                    float* desc, float* prob, cudaStream_t st) {
+    SPB_CUDA(cudaSetDevice(device_));
+    if (cap <= 0) throw std::invalid_argument("capacity must be positive");
+    run_network(img, B, C, H, W, st);
+    const int Hc = H / 8, Wc = W / 8;
+    float* heat = prob ? prob : d_prob_;
+    prof_open("heatmap", 0.0, (double)B * (65.0 * Hc * Wc * 4 + (double)H * W * 4), st);
+    launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc, heat, st);
+    prof_close(st);
+    ++launches_;
+    ensure_nms(B, H, W);
+    prof_open("nms+sort", 0.0, (double)B * H * W * 4, st);       // + 12 B per survivor, added by the caller
+    launch_nms(heat, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_,
+               count, xy, conf, st);
+    prof_close(st);
+    launches_ += 2;
+    if (desc) {
+        if (params_.descriptor_enabled) {
+            prof_open("descriptors", 0.0, 0.0, st);              // bytes depend on the keypoint count (caller)
+            launch_sample_descriptors(buf_[BUF_DESC], precision_, (long)Hc * Wc * 128, 1, 128, B, 128, Hc, Wc, H, W, cap,
+                                      count, xy, desc, st);
+            prof_close(st);
+            ++launches_;
+        } else {
+            SPB_CUDA(cudaMemsetAsync(desc, 0, sizeof(float) * (size_t)B * cap * 128, st));
+        }
+    }
+}
+
+void Engine::heatmap_from_logits(const float* logits_nchw, int B, int H, int W, float* prob, cudaStream_t st) {
+    SPB_CUDA(cudaSetDevice(device_));
+    if (H % 8 || W % 8) throw std::invalid_argument("H and W must be multiples of 8");
+    const int Hc = H / 8, Wc = W / 8;
+    launch_heatmap(logits_nchw, (long)65 * Hc * Wc, (long)Hc * Wc, 1, B, Hc, Wc, prob, st);
+    ++launches_;
+}
+
+void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, int* xy, float* conf, cudaStream_t st) {
+    SPB_CUDA(cudaSetDevice(device_));
+    if (cap <= 0) throw std::invalid_argument("capacity must be positive");
+    ensure_nms(B, H, W);
+    launch_nms(prob, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_,
+               count, xy, conf, st);
+    launches_ += 2;
+}
+
+void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int W, int cap, const int* count,
+                                const int* xy, float* out, cudaStream_t st) {
+    SPB_CUDA(cudaSetDevice(device_));
+    const int Hc = H / 8, Wc = W / 8;
+    launch_sample_descriptors(desc_nchw, PREC_FP32, (long)D * Hc * Wc, (long)Hc * Wc, 1, B, D, Hc, Wc, H, W, cap, count,
+                              xy, out, st);
+    ++launches_;
+}
+
+void Engine::buffer_dims(int id, int* C, int* H, int* W) const {
+    if (id < 0 || id >= BUF_COUNT) throw std::invalid_argument("bad buffer id");
+    *C = bufspec_[id].C; *H = wsH_ / bufspec_[id].div; *W = wsW_ / bufspec_[id].div;
+}
+
+void Engine::export_buffer(int id, float* dst_nchw, int channels, cudaStream_t st) {
+    if (id < 0 || id >= BUF_COUNT || !buf_[id]) throw std::invalid_argument("bad buffer id or no workspace");
+    const BufSpec& bs = bufspec_[id];
+    launch_nhwc_to_nchw(buf_[id], bs.fp32 ? PREC_FP32 : precision_, wsB_, (wsH_ / bs.div) * (wsW_ / bs.div), bs.C,
+                        channels, dst_nchw, st);
+}
+
+// Host-buffer entry point: what ProcessFrame / InferenceWrapper.run do around the network (H2D of the
+// frame, D2H of keypoints and descriptors), with pinned staging and one packed download.
+void Engine::detect_host(const float* img, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                         float* desc) {
+    SPB_CUDA(cudaSetDevice(device_));
+    if (!stage_) {
+        stage_ = std::make_unique<HostStage>();
+        SPB_CUDA(cudaStreamCreateWithFlags(&stage_->stream, cudaStreamNonBlocking));
+    }
+    HostStage& s = *stage_;
+    const size_t img_bytes = sizeof(float) * (size_t)B * C * H * W;
+    if (img_bytes > s.img_bytes) {
+        if (s.img) cudaFreeHost(s.img);
+        SPB_CUDA(cudaHostAlloc((void**)&s.img, img_bytes, cudaHostAllocDefault));
+        s.img_bytes = img_bytes;
+    }
+    if (img_bytes > s.d_img_bytes) {
+        cudaFree(s.d_img);
+        SPB_CUDA(cudaMalloc((void**)&s.d_img, img_bytes));
+        s.d_img_bytes = img_bytes;
+    }
+    if (B > s.d_B || cap > s.d_cap) {
+        cudaFree(s.d_count); cudaFree(s.d_xy); cudaFree(s.d_conf); cudaFree(s.d_desc);
+        if (s.count) cudaFreeHost(s.count);
+        s.d_count = dev_alloc<int>(B);
+        s.d_xy = dev_alloc<int>((size_t)B * cap * 2);
+        s.d_conf = dev_alloc<float>((size_t)B * cap);
+        s.d_desc = dev_alloc<float>((size_t)B * cap * 128);
+        SPB_CUDA(cudaHostAlloc((void**)&s.count, sizeof(int) * B, cudaHostAllocDefault));
+        s.d_B = B; s.d_cap = cap;
+    }
+    cudaStream_t st = s.stream;
+    std::memcpy(s.img, img, img_bytes);
+    SPB_CUDA(cudaMemcpyAsync(s.d_img, s.img, img_bytes, cudaMemcpyHostToDevice, st));
+    detect(s.d_img, B, C, H, W, s.d_cap, s.d_count, s.d_xy, s.d_conf, desc ? s.d_desc : nullptr, nullptr, st);
+    SPB_CUDA(cudaMemcpyAsync(s.count, s.d_count, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
+    SPB_CUDA(cudaStreamSynchronize(st));
+    size_t total = 0;
+    for (int b = 0; b < B; ++b) total += (size_t)std::min(s.count[b], cap);
+    if (total > s.out_cap) {
+        if (s.xy) cudaFreeHost(s.xy);
+        if (s.conf) cudaFreeHost(s.conf);
+        if (s.desc) cudaFreeHost(s.desc);
+        const size_t n = total + total / 2 + 1024;
+        SPB_CUDA(cudaHostAlloc((void**)&s.xy, sizeof(int) * 2 * n, cudaHostAllocDefault));
+        SPB_CUDA(cudaHostAlloc((void**)&s.conf, sizeof(float) * n, cudaHostAllocDefault));
+        SPB_CUDA(cudaHostAlloc((void**)&s.desc, sizeof(float) * 128 * n, cudaHostAllocDefault));
+        s.out_cap = n;
+    }
+    size_t off = 0;
+    for (int b = 0; b < B; ++b) {
+        const size_t n = (size_t)std::min(s.count[b], cap);
+        if (n) {
+            SPB_CUDA(cudaMemcpyAsync(s.xy + off * 2, s.d_xy + (size_t)b * s.d_cap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, st));
+            SPB_CUDA(cudaMemcpyAsync(s.conf + off, s.d_conf + (size_t)b * s.d_cap, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+            if (desc)
+                SPB_CUDA(cudaMemcpyAsync(s.desc + off * 128, s.d_desc + (size_t)b * s.d_cap * 128, sizeof(float) * 128 * n, cudaMemcpyDeviceToHost, st));
+        }
+        off += n;
+    }
+    SPB_CUDA(cudaStreamSynchronize(st));
+    off = 0;
+    for (int b = 0; b < B; ++b) {
+        const size_t n = (size_t)std::min(s.count[b], cap);
+        count[b] = (int)n;
+        std::memcpy(xy + (size_t)b * cap * 2, s.xy + off * 2, sizeof(int) * 2 * n);
+        std::memcpy(conf + (size_t)b * cap, s.conf + off, sizeof(float) * n);
+        if (desc) std::memcpy(desc + (size_t)b * cap * 128, s.desc + off * 128, sizeof(float) * 128 * n);
+        off += n;
+    }
+}
+
+}  // namespace spb200

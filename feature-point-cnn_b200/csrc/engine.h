@@ -1,0 +1,156 @@
+// spb200::Engine - the SuperPoint/MagicPoint inference engine behind the C ABI (include/spb200.h).
+//
+// Owns the folded/packed weights and the per-shape workspace on one CUDA device; runs the reference's
+// hot path (python/src/superpoint.py:91-115 -> python/src/netutils.py:78-121) as a fixed sequence of
+// kernel launches on the caller's stream.  Not thread-safe per instance; instances are independent.
+#pragma once
+#include <array>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ckpt_reader.h"
+#include "kernels.h"
+
+namespace spb200 {
+
+struct Params {
+    float conf_thresh = 0.015f;   // python/src/settings.py:5
+    int nms_dist = 4;             // python/src/settings.py:4
+    int border_remove = 4;        // python/src/settings.py:8
+    int top_k = 0;                // 0 = every survivor (the reference has no top-k)
+    int descriptor_enabled = 1;   // SuperPoint.is_descriptor_enabled, python/src/superpoint.py:67
+};
+
+struct HostConv {                 // BatchNorm-folded convolution, [cout][cin][kh][kw]
+    int cout = 0, cin = 0, kh = 0, kw = 0;
+    std::vector<float> w, b;
+    float at(int co, int ci, int y, int x) const { return w[(((size_t)co * cin + ci) * kh + y) * kw + x]; }
+};
+
+struct TapSpec { int dy, dx, kh, kw; };
+
+struct SegSpec {
+    int src_buf;
+    const HostConv* conv;
+    int ci_off, cin_real;
+    int stride;
+    std::vector<TapSpec> taps;
+};
+
+struct OpSpec {
+    std::string name;
+    std::vector<SegSpec> segs;
+    int cout_real = 0, cout_pad = 0;
+    int dst_buf = -1, res_buf = -1;
+    bool relu = true, dst_fp32 = false;
+    int dst_stride = 1, off_y = 0, off_x = 0;
+    int K = 0;
+    std::vector<float> bias;      // [cout_pad]
+    // device
+    float* d_bias = nullptr;
+    float* d_w32 = nullptr;       // [K][cout_pad]
+    void* d_w16 = nullptr;        // [cout_pad][K]
+    TcConvPlan* plan = nullptr;   // per workspace shape
+};
+
+enum BufId {
+    BUF_POOL, BUF_L1A_Y, BUF_L1A, BUF_L1B_Y, BUF_L1B, BUF_L2A_Y, BUF_L2A, BUF_L2B_Y, BUF_FEAT,
+    BUF_D0_Y, BUF_D0, BUF_D1_Y, BUF_LOGITS,
+    BUF_I0_Y, BUF_I0, BUF_I1_Y, BUF_I1, BUF_UP, BUF_O0_Y, BUF_O0, BUF_O1_Y, BUF_DESC,
+    BUF_COUNT
+};
+
+struct BufSpec { int div; int C; bool fp32; };
+
+class Engine {
+public:
+    explicit Engine(int device);
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    void load_checkpoint(const std::string& path);
+    void load_tensor(const std::string& key, const float* data, const int64_t* shape, int rank);
+    void finalize(int precision);
+    void set_params(const Params& p) { params_ = p; }
+    const Params& params() const { return params_; }
+    int precision() const { return precision_; }
+    int descriptor_dim() const { return 128; }
+    bool finalized() const { return finalized_; }
+
+    // reference SuperPoint.forward (python/src/superpoint.py:91-115); all pointers are device memory,
+    // desc_nchw / logits_nchw may be null
+    void forward(const float* img, int B, int C, int H, int W, float* prob, float* desc_nchw, float* logits_nchw,
+                 cudaStream_t st);
+    // reference InferenceWrapper.run per image of the batch (python/src/inferencewrapper.py:29-46)
+    void detect(const float* img, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf, float* desc,
+                float* prob, cudaStream_t st);
+    void detect_host(const float* img, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                     float* desc);
+    // stage-level entry points (reference restore_prob_map / get_points / get_descriptors)
+    void heatmap_from_logits(const float* logits_nchw, int B, int H, int W, float* prob, cudaStream_t st);
+    void nms(const float* prob, int B, int H, int W, int cap, int* count, int* xy, float* conf, cudaStream_t st);
+    void sample_descriptors(const float* desc_nchw, int B, int D, int H, int W, int cap, const int* count,
+                            const int* xy, float* out, cudaStream_t st);
+
+    // intermediate activation (debug / parity tests): copies buffer `id` as NCHW fp32 to dst (device)
+    void export_buffer(int id, float* dst_nchw, int channels, cudaStream_t st);
+    void buffer_dims(int id, int* C, int* H, int* W) const;
+
+    // per-launch CUDA-event timing (bench.py roofline): begin, run any inference calls, end
+    struct ProfEntry { std::string name; cudaEvent_t start, stop; double flops, bytes; float ms; };
+    void profile_begin();
+    const std::vector<ProfEntry>& profile_end();
+
+    long launches() const { return launches_; }
+    void reset_launches() { launches_ = 0; }
+    static int max_keypoints(int H, int W, int nms_dist);
+
+    std::string last_error;
+
+private:
+    void build_ops();
+    void ensure_workspace(int B, int C, int H, int W, cudaStream_t st);
+    void ensure_nms(int B, int H, int W);
+    void release_workspace();
+    void release_weights();
+    void run_network(const float* img, int B, int C, int H, int W, cudaStream_t st);
+    ConvDev make_conv_dev(const OpSpec& op) const;
+    const HostConv* fold(const std::string& conv_key, const std::string& bn_key, bool transposed, bool has_bias);
+    void add_block(const std::string& prefix, std::vector<std::pair<int, int>> srcs, int y_buf, int dst_buf, int stride,
+                   int cout, bool dst_fp32);
+
+    int device_;
+    int precision_ = PREC_FP32;
+    bool finalized_ = false;
+    Params params_;
+    StateDict sd_;
+    std::vector<std::unique_ptr<HostConv>> convs_;
+    std::vector<OpSpec> ops_;
+    std::array<BufSpec, BUF_COUNT> bufspec_{};
+    int det_c_ = 80;
+    float* d_stem_w_[2] = {nullptr, nullptr};      // [0]: 1-channel (gray-folded), [1]: 3-channel
+    float* d_stem_b_ = nullptr;
+
+    // workspace
+    int wsB_ = 0, wsH_ = 0, wsW_ = 0;
+    std::array<void*, BUF_COUNT> buf_{};
+    float* d_prob_ = nullptr;
+    // nms workspace
+    int nmsB_ = 0, nmsH_ = 0, nmsW_ = 0, nmsR_ = -1;
+    NmsWorkspace nms_{};
+    // detect_host staging
+    struct HostStage;
+    std::unique_ptr<HostStage> stage_;
+
+    long launches_ = 0;
+    bool profiling_ = false;
+    std::vector<ProfEntry> prof_;
+    cudaEvent_t prof_mark(cudaStream_t st);
+    void prof_open(const std::string& name, double flops, double bytes, cudaStream_t st);
+    void prof_close(cudaStream_t st);
+    double op_flops(const OpSpec& op) const;
+};
+
+}  // namespace spb200

@@ -1,0 +1,47 @@
+// Kernel launchers of the spb200 engine (one translation unit per kernel family).
+#pragma once
+#include "common.cuh"
+
+namespace spb200 {
+
+// ---- conv_simt.cu --------------------------------------------------------------------------------
+// img NCHW fp32 [B,C,H,W] (C = 1 or 3), w fp32 [C*49][64] with BatchNorm folded, dst NHWC [B,H/4,W/4,64].
+void launch_stem_pool(const float* img, int B, int C, int H, int W, const float* w, const float* bias, void* dst,
+                      int dst_type, cudaStream_t st);
+void launch_conv_simt(const ConvDev& p, cudaStream_t st);
+void launch_nhwc_to_nchw(const void* src, int src_type, int B, int HW, int Cs, int C, float* dst, cudaStream_t st);
+
+// ---- conv_tc.cu ----------------------------------------------------------------------------------
+struct TcConvPlan;   // tensor maps + launch geometry of one tcgen05 convolution (conv_tc.cu)
+TcConvPlan* tc_plan_create(const ConvDev& p, int operand_type);
+void tc_plan_destroy(TcConvPlan* plan);
+void launch_conv_tc(const TcConvPlan* plan, cudaStream_t st);
+
+// ---- postproc.cu ---------------------------------------------------------------------------------
+// Softmax-with-epsilon over 65 channels, drop the dustbin, depth-to-space (reference
+// python/src/superpoint.py:111-114, python/src/netutils.py:64-75).  logits element (b, c, i, j) is at
+// logits[b*batch_stride + c*chan_stride + (i*Wc + j)*cell_stride].
+void launch_heatmap(const float* logits, long batch_stride, long chan_stride, long cell_stride, int B, int Hc, int Wc,
+                    float* heat, cudaStream_t st);
+
+struct NmsWorkspace {
+    uint16_t* stamp;        // [B][H][W] decision stamps
+    unsigned long long* keys;      // [B][kcap] survivors as sortable keys (conf bits << 32 | ~pixel index)
+    unsigned long long* keys_alt;  // [B][kcap] ping-pong buffer of the radix sort
+    int* counters;          // [B][4]: survivors, undecided totals of rounds k%3
+    int kcap;               // capacity of keys per image: ceil(H/(r+1))*ceil(W/(r+1)), the survivor bound
+};
+// Greedy-equivalent grid NMS + border removal + descending sort + top-k truncation (reference
+// python/src/netutils.py:78-100, python/src/nms.py:4-53).  Outputs per image: count (clamped to cap and
+// top_k), xy int32 [cap][2] as (x, y), conf fp32 [cap].
+void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, int top_k, int cap,
+                const NmsWorkspace& ws, int* count, int* xy, float* conf, cudaStream_t st);
+
+// Bilinear sampling (align_corners=True) of the descriptor map at the keypoints + L2 normalisation
+// (reference python/src/netutils.py:103-121).  map element (b, c, i, j) is at
+// map[b*batch_stride + c*chan_stride + (i*Wc + j)*cell_stride]; map_type is a Precision value.
+void launch_sample_descriptors(const void* map, int map_type, long batch_stride, long chan_stride, long cell_stride,
+                               int B, int D, int Hc, int Wc, int H, int W, int cap, const int* count, const int* xy,
+                               float* out, cudaStream_t st);
+
+}  // namespace spb200

@@ -1,0 +1,462 @@
+// Memory-bound post-processing kernels of the spb200 engine (sm_100a).
+//
+//  K3 heatmap_kernel      softmax-with-epsilon over 65 channels, drop dustbin, depth-to-space
+//                         (reference python/src/superpoint.py:111-114, python/src/netutils.py:64-75)
+//  K4 nms_cluster_kernel  exact parallel form of the reference's greedy grid NMS
+//                         (python/src/nms.py:4-53, threshold of python/src/netutils.py:59), one
+//                         thread-block cluster per image, smem-tiled separable window maxima
+//  K5 sort_emit_kernel    block-wide LSD radix sort of the survivors by descending confidence
+//                         (python/src/netutils.py:92-93) + top-k truncation
+//  K6 sample_desc_kernel  bilinear sampling (align_corners=True) + L2 normalisation
+//                         (python/src/netutils.py:103-121), one warp per keypoint, 128-bit loads
+#include <cooperative_groups.h>
+
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace spb200 {
+
+// ================================================================================================
+// K3: logits -> full-resolution heatmap
+// ================================================================================================
+constexpr int kHeatCells = 32;     // cells of one cell-row per block
+constexpr int kHeatPitch = 72;     // smem pitch (floats): 72 % 32 == 8 -> conflict-free depth-to-space reads
+
+__global__ void __launch_bounds__(256)
+heatmap_kernel(const float* __restrict__ logits, long batch_stride, long chan_stride, long cell_stride, int Hc, int Wc,
+               float* __restrict__ heat) {
+    __shared__ float s_e[kHeatCells][kHeatPitch];
+    __shared__ float s_den[kHeatCells];
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const int b = blockIdx.z, i = blockIdx.y, j0 = blockIdx.x * kHeatCells;
+    const int ncell = min(kHeatCells, Wc - j0);
+    const float* base = logits + (size_t)b * batch_stride + (size_t)(i * Wc + j0) * cell_stride;
+
+    if (chan_stride == 1) {            // channels-last: walk channels fastest
+        for (int idx = tid; idx < ncell * 65; idx += 256) {
+            const int cell = idx / 65, c = idx % 65;
+            s_e[cell][c] = expf(base[(size_t)cell * cell_stride + c]);
+        }
+    } else {                           // planar: walk cells fastest
+        for (int idx = tid; idx < kHeatCells * 65; idx += 256) {
+            const int c = idx / kHeatCells, cell = idx % kHeatCells;
+            if (cell < ncell) s_e[cell][c] = expf(base[(size_t)c * chan_stride + (size_t)cell * cell_stride]);
+        }
+    }
+    __syncthreads();
+    for (int cell = warp; cell < ncell; cell += 8) {
+        float s = s_e[cell][lane] + s_e[cell][lane + 32] + (lane == 0 ? s_e[cell][64] : 0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) s_den[cell] = s + 0.00001f;
+    }
+    __syncthreads();
+    const int H = Hc * 8, W = Wc * 8;
+    const int j = tid / 8, dx = tid % 8;
+    if (j < ncell) {
+        const float den = s_den[j];
+        float* orow = heat + ((size_t)b * H + (size_t)i * 8) * W + (size_t)(j0 + j) * 8 + dx;
+#pragma unroll
+        for (int dy = 0; dy < 8; ++dy) orow[(size_t)dy * W] = s_e[j][dy * 8 + dx] / den;
+    }
+}
+
+void launch_heatmap(const float* logits, long batch_stride, long chan_stride, long cell_stride, int B, int Hc, int Wc,
+                    float* heat, cudaStream_t st) {
+    dim3 grid((Wc + kHeatCells - 1) / kHeatCells, Hc, B);
+    heatmap_kernel<<<grid, 256, 0, st>>>(logits, batch_stride, chan_stride, cell_stride, Hc, Wc, heat);
+    SPB_CHECK_LAUNCH();
+}
+
+// ================================================================================================
+// K4: NMS.  The reference visits candidates by descending confidence; a live candidate is kept and
+// kills its (2r+1)^2 window.  Equivalent rounds: every undecided candidate that is the maximum of the
+// undecided candidates in its window is kept; every undecided candidate inside the window of a new
+// keeper is suppressed; repeat until none is undecided.  (Induction on the visiting order: a window
+// maximum has only decided superiors, all suppressed, or it would have been suppressed with them.)
+// Ties are ordered by ascending pixel index through the composite key, like the oracle.
+//
+// stamp (uint16 per pixel): 1 = undecided candidate, 2k+2 = kept in round k, 2k+3 = suppressed in
+// round k.  Tiles of one round are processed concurrently and update stamps in place; a reader in
+// round k treats "decided in round >= k" as still undecided, which is the state at the round's start.
+// ================================================================================================
+constexpr int kNmsTW = 32, kNmsTH = 16;          // interior tile
+constexpr int kNmsThreads = kNmsTW * kNmsTH;     // 512, one thread per interior pixel
+constexpr int kNmsMaxR = 8;
+constexpr int kNmsCluster = 8;
+
+__device__ __forceinline__ unsigned sortable_bits(float v) {
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_sortable_bits(unsigned s) {
+    return __uint_as_float((s & 0x80000000u) ? (s & 0x7fffffffu) : ~s);
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_cluster_kernel(const float* __restrict__ heat, int H, int W, float thresh, int r, int border, int kcap,
+                   uint16_t* __restrict__ stamp, unsigned long long* __restrict__ keys, int* __restrict__ counters,
+                   int tiles_per_cta) {
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    const int LW = kNmsTW + 4 * r, LH = kNmsTH + 4 * r;      // loaded region
+    const int EW = kNmsTW + 2 * r, EH = kNmsTH + 2 * r;      // region where keepers are evaluated
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(nms_smem);   // [LH][LW]
+    unsigned long long* s_row = s_key + LH * LW;                                   // [LH][EW]
+    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_row + LH * EW);     // [EH][EW]
+    unsigned char* s_ro = s_keep + EH * EW;                                        // [EH][kNmsTW]
+    unsigned char* s_alive = s_ro + EH * kNmsTW;                                   // [tiles_per_cta]
+    __shared__ int s_left;
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x / kNmsCluster;
+    const int rank = (int)cluster.block_rank();
+    const int tiles_x = (W + kNmsTW - 1) / kNmsTW, tiles_y = (H + kNmsTH - 1) / kNmsTH;
+    const int ntiles = tiles_x * tiles_y;
+    const float* hmap = heat + (size_t)b * H * W;
+    uint16_t* smap = stamp + (size_t)b * H * W;
+    unsigned long long* kout = keys + (size_t)b * kcap;
+    int* cnt = counters + b * 4;            // [0] survivors, [1..3] undecided totals (round % 3)
+
+    for (int i = tid; i < tiles_per_cta; i += kNmsThreads) s_alive[i] = 1;
+    __syncthreads();
+
+    for (int k = 0;; ++k) {
+        if (k >= 32000) break;              // stamp range guard (never reached in practice)
+        int left_local = 0;
+        for (int slot = 0; slot < tiles_per_cta; ++slot) {
+            const int t = rank + slot * kNmsCluster;
+            if (t >= ntiles || !s_alive[slot]) continue;       // block-uniform
+            const int ty0 = (t / tiles_x) * kNmsTH, tx0 = (t % tiles_x) * kNmsTW;
+            // 1. composite keys of the undecided candidates in the loaded region
+            for (int i = tid; i < LH * LW; i += kNmsThreads) {
+                const int gy = ty0 - 2 * r + i / LW, gx = tx0 - 2 * r + i % LW;
+                unsigned long long key = 0ull;
+                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                    const int pix = gy * W + gx;
+                    const float h = __ldg(hmap + pix);
+                    if (h >= thresh) {
+                        bool undecided = true;
+                        if (k > 0) {
+                            const int s = (int)__ldcg(smap + pix);
+                            undecided = (s == 1) || (s >= 2 && ((s - 2) >> 1) >= k);
+                        }
+                        if (undecided) key = ((unsigned long long)sortable_bits(h) << 32) | (unsigned)(~(unsigned)pix);
+                    }
+                }
+                s_key[i] = key;
+            }
+            __syncthreads();
+            // 2. horizontal window maxima
+            for (int i = tid; i < LH * EW; i += kNmsThreads) {
+                const int ly = i / EW, ex = i % EW;
+                const unsigned long long* p = s_key + ly * LW + ex;     // columns ex .. ex+2r of L
+                unsigned long long m = p[0];
+                for (int d = 1; d <= 2 * r; ++d) m = max(m, p[d]);
+                s_row[i] = m;
+            }
+            __syncthreads();
+            // 3. vertical maxima -> new keepers on the evaluation region
+            for (int i = tid; i < EH * EW; i += kNmsThreads) {
+                const int ey = i / EW, ex = i % EW;
+                const unsigned long long* p = s_row + ey * EW + ex;     // rows ey .. ey+2r of L
+                unsigned long long m = p[0];
+                for (int d = 1; d <= 2 * r; ++d) m = max(m, p[d * EW]);
+                const unsigned long long me = s_key[(ey + r) * LW + ex + r];
+                s_keep[i] = (me != 0ull && me == m) ? 1 : 0;
+            }
+            __syncthreads();
+            // 4. horizontal OR of the keeper flags
+            for (int i = tid; i < EH * kNmsTW; i += kNmsThreads) {
+                const int ey = i / kNmsTW, ix = i % kNmsTW;
+                const unsigned char* p = s_keep + ey * EW + ix;         // columns ix .. ix+2r of E
+                unsigned char o = 0;
+                for (int d = 0; d <= 2 * r; ++d) o |= p[d];
+                s_ro[i] = o;
+            }
+            __syncthreads();
+            // 5. decide the interior pixel of this thread
+            const int iy = tid / kNmsTW, ix = tid % kNmsTW;
+            const int gy = ty0 + iy, gx = tx0 + ix;
+            const unsigned long long me = s_key[(iy + 2 * r) * LW + ix + 2 * r];
+            bool still = false, emit = false;
+            if (me != 0ull) {       // undecided candidate inside the image
+                const int pix = gy * W + gx;
+                if (s_keep[(iy + r) * EW + ix + r]) {
+                    smap[pix] = (uint16_t)(2 * k + 2);
+                    emit = !(gx < border || gx >= W - border || gy < border || gy >= H - border);
+                } else {
+                    unsigned char sup = 0;
+                    for (int d = 0; d <= 2 * r; ++d) sup |= s_ro[(iy + d) * kNmsTW + ix];
+                    if (sup) smap[pix] = (uint16_t)(2 * k + 3);
+                    else { still = true; if (k == 0) smap[pix] = 1; }
+                }
+            }
+            // survivors: warp-aggregated append
+            const unsigned em = __ballot_sync(0xffffffffu, emit);
+            if (em) {
+                const int lane = tid % 32;
+                int basepos = 0;
+                if (lane == __ffs(em) - 1) basepos = atomicAdd(cnt, __popc(em));
+                basepos = __shfl_sync(0xffffffffu, basepos, __ffs(em) - 1);
+                if (emit) {
+                    const int pos = basepos + __popc(em & ((1u << lane) - 1u));
+                    if (pos < kcap) kout[pos] = me;
+                }
+            }
+            const int left = __syncthreads_count(still);     // also fences smem reuse by the next tile
+            if (tid == 0) s_alive[slot] = left > 0;
+            left_local += left;
+        }
+        // cluster-wide total of the still-undecided candidates of this round
+        if (tid == 0) {
+            if (left_local) atomicAdd(cnt + 1 + k % 3, left_local);
+            if (rank == 0) cnt[1 + (k + 1) % 3] = 0;
+            __threadfence();
+        }
+        cluster.sync();
+        if (tid == 0) s_left = __ldcg(cnt + 1 + k % 3);
+        __syncthreads();
+        if (s_left == 0) break;
+    }
+}
+
+// ================================================================================================
+// K5: one block per image: LSD radix sort (8-bit digits) of the survivor keys by descending key,
+// then emit (x, y), confidence and the count.  Digit positions on which all keys agree are skipped.
+// ================================================================================================
+constexpr int kSortThreads = 1024;
+
+__global__ void __launch_bounds__(kSortThreads)
+sort_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ keys_alt,
+                 int* __restrict__ counters, int kcap, int W, int cap_out, int top_k, int* __restrict__ count,
+                 int* __restrict__ xy, float* __restrict__ conf) {
+    __shared__ unsigned s_hist[8][256];
+    __shared__ unsigned s_base[256];
+    __shared__ unsigned s_wcnt[32][256];
+    __shared__ unsigned s_warp_tot[8];
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const int b = blockIdx.x;
+    const int n = min(counters[b * 4], kcap);
+    unsigned long long* src = keys + (size_t)b * kcap;
+    unsigned long long* dst = keys_alt + (size_t)b * kcap;
+
+    for (int i = tid; i < 8 * 256; i += kSortThreads) (&s_hist[0][0])[i] = 0;
+    for (int i = tid; i < 32 * 256; i += kSortThreads) (&s_wcnt[0][0])[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kSortThreads) {
+        const unsigned long long v = ~src[i];          // ascending on ~key == descending on key
+#pragma unroll
+        for (int d = 0; d < 8; ++d) atomicAdd(&s_hist[d][(unsigned)(v >> (8 * d)) & 255u], 1u);
+    }
+    __syncthreads();
+
+    for (int pass = 0; pass < 8 && n > 1; ++pass) {
+        // skip a digit position on which every key agrees (block-uniform decision)
+        const int hit = (tid < 256 && s_hist[pass][tid] == (unsigned)n) ? 1 : 0;
+        if (__syncthreads_or(hit)) continue;
+        // exclusive scan of the 256-bin histogram
+        if (tid < 256) {
+            const unsigned v = s_hist[pass][tid];
+            unsigned inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_warp_tot[warp] = inc;
+            s_base[tid] = inc - v;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned add = 0;
+            for (int w = 0; w < warp; ++w) add += s_warp_tot[w];
+            s_base[tid] += add;
+        }
+        __syncthreads();
+        const int shift = 8 * pass;
+        for (int r0 = 0; r0 < n; r0 += kSortThreads) {
+            const int i = r0 + tid;
+            const bool valid = i < n;
+            const unsigned long long key = valid ? src[i] : 0ull;
+            const int dig = valid ? (int)((unsigned)((~key) >> shift) & 255u) : 256 + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, dig);
+            const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank_in_warp == 0) s_wcnt[warp][dig] = __popc(peers);
+            __syncthreads();
+            if (tid < 256) {
+                unsigned off = s_base[tid];
+                for (int w = 0; w < 32; ++w) {
+                    const unsigned c = s_wcnt[w][tid];
+                    s_wcnt[w][tid] = off;
+                    off += c;
+                }
+                s_base[tid] = off;
+            }
+            __syncthreads();
+            if (valid) dst[s_wcnt[warp][dig] + rank_in_warp] = key;
+            __syncwarp();
+            if (valid && rank_in_warp == 0) s_wcnt[warp][dig] = 0;
+            __syncthreads();
+        }
+        unsigned long long* t = src; src = dst; dst = t;
+        __syncthreads();
+    }
+
+    int nout = min(n, cap_out);
+    if (top_k > 0) nout = min(nout, top_k);
+    for (int i = tid; i < nout; i += kSortThreads) {
+        const unsigned long long key = src[i];
+        const unsigned pix = ~(unsigned)(key & 0xffffffffull);
+        xy[((size_t)b * cap_out + i) * 2 + 0] = (int)(pix % (unsigned)W);
+        xy[((size_t)b * cap_out + i) * 2 + 1] = (int)(pix / (unsigned)W);
+        conf[(size_t)b * cap_out + i] = from_sortable_bits((unsigned)(key >> 32));
+    }
+    if (tid == 0) count[b] = nout;
+}
+
+void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, int top_k, int cap,
+                const NmsWorkspace& ws, int* count, int* xy, float* conf, cudaStream_t st) {
+    if (radius < 0 || radius > kNmsMaxR) throw std::invalid_argument("nms_dist must be in [0, 8]");
+    if ((long)H * W >= (1l << 31)) throw std::invalid_argument("image too large");
+    const int r = radius;
+    const int LW = kNmsTW + 4 * r, LH = kNmsTH + 4 * r, EW = kNmsTW + 2 * r, EH = kNmsTH + 2 * r;
+    const int ntiles = ((W + kNmsTW - 1) / kNmsTW) * ((H + kNmsTH - 1) / kNmsTH);
+    const int tiles_per_cta = (ntiles + kNmsCluster - 1) / kNmsCluster;
+    const size_t smem = (size_t)LH * LW * 8 + (size_t)LH * EW * 8 + (size_t)EH * EW + (size_t)EH * kNmsTW + tiles_per_cta + 16;
+    SPB_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * 4 * B, st));
+    SPB_CUDA(cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * kNmsCluster);
+    cfg.blockDim = dim3(kNmsThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kNmsCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SPB_CUDA(cudaLaunchKernelEx(&cfg, nms_cluster_kernel, heat, H, W, thresh, r, border, ws.kcap, ws.stamp, ws.keys,
+                                ws.counters, tiles_per_cta));
+    sort_emit_kernel<<<B, kSortThreads, 0, st>>>(ws.keys, ws.keys_alt, ws.counters, ws.kcap, W, cap, top_k, count, xy, conf);
+    SPB_CHECK_LAUNCH();
+}
+
+// ================================================================================================
+// K6: descriptors.  One warp per keypoint; each lane owns 4 consecutive channels per 128-channel
+// slab.  grid_sample(align_corners=True): ix = ((gx + 1)/2)*(Wc-1) with gx = x/(W/2) - 1 evaluated in
+// double and rounded to float, exactly as the reference builds its sampling grid
+// (python/src/netutils.py:110-115).  The L2 norm has no epsilon (netutils.py:120): an all-zero sample
+// yields NaN there and here.
+// ================================================================================================
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, long chan_stride, float (&v)[4]);
+
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, long cs, float (&v)[4]) {
+    if (cs == 1) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __ldg(p + i * cs);
+    }
+}
+template <>
+__device__ __forceinline__ void load4<__half>(const __half* p, long cs, float (&v)[4]) {
+    if (cs == 1) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        const __half2 a = *reinterpret_cast<const __half2*>(&t.x), b = *reinterpret_cast<const __half2*>(&t.y);
+        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __half2float(p[i * cs]);
+    }
+}
+template <>
+__device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, long cs, float (&v)[4]) {
+    if (cs == 1) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+        v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __bfloat162float(p[i * cs]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_stride, long cell_stride, int D, int Hc,
+                   int Wc, int H, int W, int cap, const int* __restrict__ count, const int* __restrict__ xy,
+                   float* __restrict__ out) {
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= min(count[b], cap)) return;
+    const int x = xy[((size_t)b * cap + i) * 2 + 0], y = xy[((size_t)b * cap + i) * 2 + 1];
+    const float gx = (float)((double)x / ((double)W / 2.) - 1.);
+    const float gy = (float)((double)y / ((double)H / 2.) - 1.);
+    const float ix = ((gx + 1.f) / 2.f) * (float)(Wc - 1);
+    const float iy = ((gy + 1.f) / 2.f) * (float)(Hc - 1);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    const float wgt[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+    const int cx[4] = {x0, x0 + 1, x0, x0 + 1}, cy[4] = {y0, y0, y0 + 1, y0 + 1};
+    const T* mb = map + (size_t)b * batch_stride;
+    float* o = out + ((size_t)b * cap + i) * D;
+
+    float ss = 0.f;
+    constexpr int kMaxSlabs = 4;                      // D <= 512
+    float acc[kMaxSlabs][4];
+    const int nslab = (D + 127) / 128;
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s) {
+        if (s >= nslab) break;
+        const int c = s * 128 + lane * 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[s][q] = 0.f;
+        if (c < D) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (cx[k] < 0 || cx[k] >= Wc || cy[k] < 0 || cy[k] >= Hc) continue;     // zeros padding
+                float v[4];
+                load4<T>(mb + (size_t)(cy[k] * Wc + cx[k]) * cell_stride + (size_t)c * chan_stride, chan_stride, v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[s][q] = fmaf(wgt[k], v[q], acc[s][q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ss = fmaf(acc[s][q], acc[s][q], ss);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    const float nrm = sqrtf(ss);
+#pragma unroll
+    for (int s = 0; s < kMaxSlabs; ++s) {
+        if (s >= nslab) break;
+        const int c = s * 128 + lane * 4;
+        if (c < D) *reinterpret_cast<float4*>(o + c) = make_float4(acc[s][0] / nrm, acc[s][1] / nrm, acc[s][2] / nrm, acc[s][3] / nrm);
+    }
+}
+
+void launch_sample_descriptors(const void* map, int map_type, long batch_stride, long chan_stride, long cell_stride,
+                               int B, int D, int Hc, int Wc, int H, int W, int cap, const int* count, const int* xy,
+                               float* out, cudaStream_t st) {
+    if (D % 4 != 0 || D > 512) throw std::invalid_argument("descriptor dimension must be a multiple of 4, at most 512");
+    if (cap <= 0 || B <= 0) return;
+    dim3 grid((cap + 7) / 8, B);
+    if (map_type == PREC_FP32)
+        sample_desc_kernel<float><<<grid, 256, 0, st>>>((const float*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, H, W, cap, count, xy, out);
+    else if (map_type == PREC_FP16)
+        sample_desc_kernel<__half><<<grid, 256, 0, st>>>((const __half*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, H, W, cap, count, xy, out);
+    else
+        sample_desc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, H, W, cap, count, xy, out);
+    SPB_CHECK_LAUNCH();
+}
+
+}  // namespace spb200

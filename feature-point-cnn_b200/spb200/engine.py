@@ -1,0 +1,190 @@
+"""Thin Python owner of a spb200 engine handle; all compute happens in libspb200.so."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PRECISIONS = {'fp32': 0, 'fp16': 1, 'bf16': 2}
+
+# activation buffer ids (csrc/engine.h BufId) for spb200_export_activation
+BUFFERS = ['pool', 'l1a_y', 'l1a', 'l1b_y', 'l1b', 'l2a_y', 'l2a', 'l2b_y', 'feat', 'd0_y', 'd0', 'd1_y', 'logits',
+           'i0_y', 'i0', 'i1_y', 'i1', 'up', 'o0_y', 'o0', 'o1_y', 'desc']
+
+
+class Spb200Error(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self.device = int(device)
+        rc = self._lib.spb200_create(self.device, ctypes.byref(self._h))
+        if rc != 0:
+            msg = self._lib.spb200_last_error(None)
+            self._h = None
+            raise Spb200Error('spb200_create failed: %s' % (msg.decode() if msg else rc))
+        self.precision = None
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.spb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.spb200_last_error(self._h)
+            err = Spb200Error('%s failed: %s' % (what, msg.decode() if msg else rc))
+            if rc == 1:
+                raise ValueError(str(err))
+            raise err
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- weights -------------------------------------------------------------------------------
+    def load_checkpoint(self, path):
+        self._check(self._lib.spb200_load_checkpoint(self._h, str(path).encode()), 'spb200_load_checkpoint')
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            a = np.ascontiguousarray(v.detach().cpu().to(torch.float32).numpy())
+            shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
+            self._check(self._lib.spb200_load_tensor(self._h, k.encode(), ctypes.c_void_p(a.ctypes.data), shape, a.ndim),
+                        'spb200_load_tensor(%s)' % k)
+
+    def finalize(self, precision='fp16'):
+        self._check(self._lib.spb200_finalize_weights(self._h, PRECISIONS[precision]), 'spb200_finalize_weights')
+        self.precision = precision
+
+    def set_params(self, conf_thresh=0.015, nms_dist=4, border_remove=4, top_k=0, descriptor_enabled=True):
+        self._check(self._lib.spb200_set_params(self._h, float(conf_thresh), int(nms_dist), int(border_remove),
+                                                int(top_k), int(bool(descriptor_enabled))), 'spb200_set_params')
+
+    # ---- inference -----------------------------------------------------------------------------
+    def _img(self, img):
+        if img.dim() != 4 or img.dtype != torch.float32 or not img.is_cuda:
+            raise ValueError('img must be a float32 CUDA tensor B*C*H*W')
+        return img.contiguous()
+
+    def forward(self, img, want_desc=True, want_logits=True):
+        img = self._img(img)
+        b, c, h, w = img.shape
+        dev = img.device
+        prob = torch.empty((b, h, w), dtype=torch.float32, device=dev)
+        desc = torch.empty((b, 128, h // 8, w // 8), dtype=torch.float32, device=dev) if want_desc else None
+        logits = torch.empty((b, 65, h // 8, w // 8), dtype=torch.float32, device=dev) if want_logits else None
+        self._check(self._lib.spb200_forward(self._h, _ptr(img), b, c, h, w, _ptr(prob), _ptr(desc), _ptr(logits),
+                                             self._stream()), 'spb200_forward')
+        return prob, desc, logits
+
+    def max_keypoints(self, h, w, nms_dist=4):
+        return self._lib.spb200_max_keypoints(h, w, nms_dist)
+
+    def detect(self, img, capacity, want_desc=True, want_prob=False, out=None):
+        """Returns (count[B] i32, xy[B,cap,2] i32, conf[B,cap] f32, desc[B,cap,128] f32 or None, prob or None)."""
+        img = self._img(img)
+        b, c, h, w = img.shape
+        dev = img.device
+        if out is None:
+            out = self.alloc_outputs(b, capacity, dev, want_desc, (h, w) if want_prob else None)
+        count, xy, conf, desc, prob = out
+        self._check(self._lib.spb200_detect(self._h, _ptr(img), b, c, h, w, capacity, _ptr(count), _ptr(xy), _ptr(conf),
+                                            _ptr(desc), _ptr(prob), self._stream()), 'spb200_detect')
+        return out
+
+    @staticmethod
+    def alloc_outputs(b, capacity, dev, want_desc=True, prob_hw=None):
+        count = torch.zeros((b,), dtype=torch.int32, device=dev)
+        xy = torch.zeros((b, capacity, 2), dtype=torch.int32, device=dev)
+        conf = torch.zeros((b, capacity), dtype=torch.float32, device=dev)
+        desc = torch.zeros((b, capacity, 128), dtype=torch.float32, device=dev) if want_desc else None
+        prob = torch.empty((b,) + tuple(prob_hw), dtype=torch.float32, device=dev) if prob_hw else None
+        return count, xy, conf, desc, prob
+
+    def detect_host(self, img, capacity, want_desc=True, out=None):
+        """img: float32 numpy B*C*H*W (host).  Returns numpy (count, xy, conf, desc)."""
+        img = np.ascontiguousarray(img, dtype=np.float32)
+        b, c, h, w = img.shape
+        if out is None:
+            out = (np.zeros((b,), np.int32), np.zeros((b, capacity, 2), np.int32), np.zeros((b, capacity), np.float32),
+                   np.zeros((b, capacity, 128), np.float32) if want_desc else None)
+        count, xy, conf, desc = out
+        self._check(self._lib.spb200_detect_host(self._h, ctypes.c_void_p(img.ctypes.data), b, c, h, w, capacity,
+                                                 ctypes.c_void_p(count.ctypes.data), ctypes.c_void_p(xy.ctypes.data),
+                                                 ctypes.c_void_p(conf.ctypes.data),
+                                                 ctypes.c_void_p(desc.ctypes.data if desc is not None else 0)),
+                    'spb200_detect_host')
+        return out
+
+    # ---- stage-level ---------------------------------------------------------------------------
+    def heatmap_from_logits(self, logits, h, w):
+        logits = logits.contiguous()
+        b = logits.shape[0]
+        prob = torch.empty((b, h, w), dtype=torch.float32, device=logits.device)
+        self._check(self._lib.spb200_heatmap_from_logits(self._h, _ptr(logits), b, h, w, _ptr(prob), self._stream()),
+                    'spb200_heatmap_from_logits')
+        return prob
+
+    def nms(self, prob, capacity):
+        prob = prob.contiguous()
+        b, h, w = prob.shape
+        count, xy, conf, _, _ = self.alloc_outputs(b, capacity, prob.device, False)
+        self._check(self._lib.spb200_nms(self._h, _ptr(prob), b, h, w, capacity, _ptr(count), _ptr(xy), _ptr(conf),
+                                         self._stream()), 'spb200_nms')
+        return count, xy, conf
+
+    def sample_descriptors(self, desc_map, h, w, count, xy):
+        desc_map = desc_map.contiguous()
+        b, d = desc_map.shape[:2]
+        cap = xy.shape[1]
+        out = torch.zeros((b, cap, d), dtype=torch.float32, device=desc_map.device)
+        self._check(self._lib.spb200_sample_descriptors(self._h, _ptr(desc_map), b, d, h, w, cap, _ptr(count), _ptr(xy),
+                                                        _ptr(out), self._stream()), 'spb200_sample_descriptors')
+        return out
+
+    def export_activation(self, name, batch):
+        bid = BUFFERS.index(name)
+        c, h, w = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.spb200_activation_dims(self._h, bid, ctypes.byref(c), ctypes.byref(h), ctypes.byref(w)),
+                    'spb200_activation_dims')
+        out = torch.empty((batch, c.value, h.value, w.value), dtype=torch.float32, device='cuda:%d' % self.device)
+        self._check(self._lib.spb200_export_activation(self._h, bid, _ptr(out), c.value, self._stream()),
+                    'spb200_export_activation')
+        return out
+
+    def profile_begin(self):
+        self._check(self._lib.spb200_profile_begin(self._h), 'spb200_profile_begin')
+
+    def profile_end(self, max_entries=4096):
+        """-> list of (name, ms, flops, bytes) per kernel launch since profile_begin()."""
+        names = ctypes.create_string_buffer(64 * max_entries)
+        ms = (ctypes.c_float * max_entries)()
+        fl = (ctypes.c_double * max_entries)()
+        by = (ctypes.c_double * max_entries)()
+        n = ctypes.c_int()
+        self._check(self._lib.spb200_profile_end(self._h, max_entries, names, ms, fl, by, ctypes.byref(n)),
+                    'spb200_profile_end')
+        raw = names.raw
+        return [(raw[i * 64:(i + 1) * 64].split(b'\0')[0].decode(), float(ms[i]), float(fl[i]), float(by[i]))
+                for i in range(n.value)]
+
+    @property
+    def kernel_launches(self):
+        return self._lib.spb200_kernel_launches(self._h)
+
+    def reset_kernel_launches(self):
+        self._lib.spb200_reset_kernel_launches(self._h)

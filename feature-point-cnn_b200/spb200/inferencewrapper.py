@@ -1,0 +1,73 @@
+"""Drop-in for the reference's ``InferenceWrapper`` (python/src/inferencewrapper.py:12-91).
+
+``InferenceWrapper(weights_path, settings).run(img)`` -> ``(points (3,N) float64, descriptors (128,N)
+float32)`` exactly as the reference documents, computed by one fused device pipeline
+(spb200_detect): only the keypoints and their descriptors leave the GPU.
+"""
+import numpy as np
+import torch
+
+from .engine import Engine
+
+
+class InferenceWrapper(object):
+    def __init__(self, weights_path, settings):
+        self.name = 'SuperPoint'
+        self.settings = settings
+        self.engine = Engine(getattr(settings, 'device', 0))
+        try:
+            # load_checkpoint_for_inference (python/src/saveutils.py:6-18), strict
+            self.engine.load_checkpoint(weights_path)
+            self.engine.finalize(getattr(settings, 'precision', 'fp16'))
+        except Exception as e:   # the reference prints and exit(1)s (inferencewrapper.py:19-20)
+            print('Failed to load checkpoint: %s (%s)' % (weights_path, e))
+            raise SystemExit(1)
+        self.descriptor_enabled = True
+
+    def _params(self):
+        s = self.settings
+        self.engine.set_params(s.confidence_thresh, s.nms_dist, s.border_remove, getattr(s, 'top_k', 0),
+                               self.descriptor_enabled)
+
+    def prepare_input(self, img):
+        """python/src/inferencewrapper.py:70-81: HWC float32 RGB ndarray -> 1*3*H*W tensor; tensors pass through."""
+        if not torch.is_tensor(img):
+            assert img.ndim == 3
+            assert img.dtype == np.float32, 'Image must be float32.'
+            assert img.shape[2] == 3, 'Image must be rgb.'
+            return torch.from_numpy(np.ascontiguousarray(img.transpose((2, 0, 1)))).unsqueeze(0)
+        return img
+
+    def run(self, img):
+        """One image -> (points (3,N) float64 [x;y;conf] by descending confidence, descriptors (128,N) float32)."""
+        pts, dsc = self.run_batch(self.prepare_input(img))
+        assert len(pts) == 1, 'run() takes one image (the reference merges batch items, netutils.py:59-61)'
+        return pts[0], dsc[0]
+
+    @torch.no_grad()
+    def run_batch(self, images):
+        """B*C*H*W tensor -> per-image lists of points / descriptors (the reference applied per image)."""
+        self._params()
+        dev = 'cuda:%d' % self.engine.device
+        x = images.to(dev, torch.float32)
+        b, _, h, w = x.shape
+        k = getattr(self.settings, 'top_k', 0)
+        cap = max(self.engine.max_keypoints(h, w, self.settings.nms_dist), 1)
+        if k:
+            cap = min(cap, k)
+        count, xy, conf, desc, _ = self.engine.detect(x, cap)
+        count = count.cpu().numpy()
+        pts, dsc = [], []
+        for i in range(b):
+            n = int(count[i])
+            p = np.zeros((3, n))
+            p[:2] = xy[i, :n].t().cpu().numpy()
+            p[2] = conf[i, :n].cpu().numpy()
+            pts.append(p)
+            dsc.append(desc[i, :n].t().contiguous().cpu().numpy())
+        return pts, dsc
+
+    def forward(self, images):
+        """The network triple (SuperPoint.forward, python/src/superpoint.py:91-115) for a B*C*H*W tensor."""
+        self._params()
+        return self.engine.forward(images.to('cuda:%d' % self.engine.device, torch.float32))

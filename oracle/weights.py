@@ -142,43 +142,20 @@ def load_state_dict(path):
     return ck['model_state_dict'] if 'model_state_dict' in ck else ck
 
 
+def _synth():
+    """Synthetic input images live with the product (spb200/synth.py) so that bench.py does not need the
+    oracle for its inputs; the oracle re-exports them."""
+    import importlib
+    import sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'feature-point-cnn_b200')
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    return importlib.import_module('spb200.synth')
+
+
 def rand_image(i, h, w):
-    """'rand' family: uniform noise, adversarial for precision."""
-    gen = torch.Generator().manual_seed(1000 + i)
-    return torch.rand((h, w), generator=gen)
+    return _synth().rand_image(i, h, w)
 
 
 def shapes_image(i, h, w):
-    """A 'shapes'-like grayscale image: blurred random polygons, lines and a checkerboard patch on
-    a smooth background, in [0,1].  Own generator (cv2 only); the reference's synthetic_shapes
-    images used for the golden vectors are stored as uint8 fixtures instead."""
-    import cv2
-    rs = np.random.RandomState(2000 + i)
-    img = np.full((h, w), rs.randint(40, 200), np.uint8)
-    bg = cv2.resize(rs.randint(0, 255, (max(h // 60, 2), max(w // 60, 2))).astype(np.uint8), (w, h),
-                    interpolation=cv2.INTER_CUBIC)
-    img = cv2.addWeighted(img, 0.6, bg, 0.4, 0)
-    kind = i % 4
-    if kind in (0, 3):
-        s = max(min(h, w) // 8, 8)
-        ox, oy = rs.randint(0, w // 3), rs.randint(0, h // 3)
-        a, b = int(rs.randint(0, 100)), int(rs.randint(150, 255))
-        for r in range(5):
-            for c in range(6):
-                cv2.rectangle(img, (ox + c * s, oy + r * s), (ox + (c + 1) * s, oy + (r + 1) * s),
-                              a if (r + c) % 2 else b, -1)
-    if kind in (1, 3):
-        for _ in range(6):
-            k = rs.randint(3, 7)
-            ctr = np.array([rs.randint(0, w), rs.randint(0, h)])
-            rad = rs.randint(min(h, w) // 10, min(h, w) // 3)
-            ang = np.sort(rs.uniform(0, 2 * np.pi, k))
-            pts = (ctr + rad * np.stack([np.cos(ang), np.sin(ang)], 1)).astype(np.int32)
-            cv2.fillPoly(img, [pts], int(rs.randint(0, 255)))
-    if kind in (2, 3):
-        for _ in range(12):
-            p0 = (int(rs.randint(0, w)), int(rs.randint(0, h)))
-            p1 = (int(rs.randint(0, w)), int(rs.randint(0, h)))
-            cv2.line(img, p0, p1, int(rs.randint(0, 255)), int(rs.randint(1, 4)))
-    img = cv2.GaussianBlur(img, (5, 5), 0)
-    return torch.from_numpy(img.astype(np.float32) / 255.0)
+    return _synth().shapes_image(i, h, w)

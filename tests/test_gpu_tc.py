@@ -1,0 +1,180 @@
+"""GPU tests of the tcgen05 / TMA tensor-core path (run on the B200 box with ``pytest -m gpu``).
+
+1. the implicit-GEMM convolution kernel alone (spb200_test_conv_tc) against an fp32 torch convolution
+   of the same 16-bit-rounded operands (this is the one place a torch reference is kept: a
+   floating-point kernel);
+2. the whole path with fp16 operands against the oracle at the north-star bars
+   (heatmap <= 1e-2, keypoints >= 99 %, descriptor cosine >= 0.999);
+3. bf16 operands: measured and reported, sanity-bounded (8 mantissa bits miss the bars);
+4. the host-buffer entry point and a second (harsh / MagicPoint) checkpoint.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model, postproc, weights
+from _gpu_common import (GOLDEN, CKPT, GOLDEN_CASES, LazyEngines, load_spb, golden_image, pset, points_from,
+                         compare_path)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def engines():
+    e = LazyEngines()
+    yield e
+    e.close()
+
+
+def run_conv_tc(x, w, bias, taps, stride, relu, out_fp32, prec):
+    """x: B,H,W,Cin 16-bit cuda; w: Cout, taps*Cin 16-bit cuda (K order tap-major, channel-minor)."""
+    from spb200 import _lib
+    lib = _lib.load()
+    b, h, wd, cin = x.shape
+    cout = w.shape[0]
+    y = torch.full((b, h // stride, wd // stride, cout), float('nan'),
+                   dtype=torch.float32 if out_fp32 else x.dtype, device='cuda')
+    rc = lib.spb200_test_conv_tc(1 if prec == 'fp16' else 2, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()),
+                                 ctypes.c_void_p(bias.data_ptr()), ctypes.c_void_p(y.data_ptr()), b, h, wd, cin, cout,
+                                 taps, stride, int(relu), int(out_fp32), ctypes.c_void_p(0))
+    assert rc == 0, lib.spb200_last_error(None)
+    torch.cuda.synchronize()
+    return y
+
+
+CONV_CASES = [
+    # b, h, w, cin, cout, taps, stride
+    (1, 8, 16, 64, 64, 1, 1),        # exactly one tile, one K step
+    (1, 8, 16, 64, 64, 9, 1),
+    (2, 30, 40, 64, 64, 9, 1),       # ragged tiles
+    (2, 30, 40, 128, 128, 9, 1),
+    (1, 60, 80, 64, 128, 9, 2),      # stride 2 through the parity view
+    (2, 30, 40, 128, 256, 9, 2),
+    (1, 16, 24, 256, 256, 9, 1),
+    (3, 30, 40, 128, 128, 1, 1),
+    (1, 60, 80, 64, 128, 1, 2),
+    (1, 120, 160, 64, 64, 9, 1),
+]
+
+
+@pytest.mark.parametrize('prec', ['fp16', 'bf16'])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_tcgen05_conv_kernel(case, prec):
+    b, h, w, cin, cout, taps, stride = case
+    dt = torch.float16 if prec == 'fp16' else torch.bfloat16
+    g = torch.Generator(device='cuda').manual_seed(sum(case))
+    x = (torch.rand((b, h, w, cin), generator=g, device='cuda') * 2 - 0.5).to(dt)
+    k = 3 if taps == 9 else 1
+    wt = ((torch.rand((cout, cin, k, k), generator=g, device='cuda') - 0.5) * (2.0 / (cin * taps) ** 0.5)).to(dt)
+    bias = torch.rand((cout,), generator=g, device='cuda') - 0.5
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, taps * cin).contiguous()        # [cout][tap][cin]
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride, k // 2)
+    ref = torch.relu(ref).permute(0, 2, 3, 1)
+    for out_fp32 in (True, False):
+        y = run_conv_tc(x, wp, bias, taps, stride, True, out_fp32, prec)
+        err = (y.float() - ref).abs()
+        tol = 2e-3 if out_fp32 else (2e-2 if prec == 'fp16' else 6e-2)
+        bad = int((~(err <= tol)).sum())
+        if bad:
+            idx = torch.nonzero(~(err <= tol))[:8].tolist()
+            print('[conv_tc %s %s out_fp32=%s] max err %.4g, %d bad of %d, first bad (b,y,x,c): %s' %
+                  (case, prec, out_fp32, float(err.nan_to_num(1e9).max()), bad, err.numel(), idx))
+        assert bad == 0
+
+
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_path_fp16_tensor_cores_meets_bars(name, engines, golden_sd):
+    compare_path(engines['fp16'], golden_image(name), golden_sd, 1e-2, 0.99, 0.999, 'fp16 ' + name)
+
+
+def test_block_outputs_fp16_vs_fp32(engines):
+    """Per-stage comparison of the tensor-core path with the fp32 CUDA-core path on the device."""
+    img = golden_image('shapes240_0')[None, None].cuda()
+    e32, e16 = engines['fp32'], engines['fp16']
+    e32.forward(img)
+    e16.forward(img)
+    for name in ['pool', 'l1a_y', 'l1a', 'l1b', 'l2a', 'feat', 'd0', 'logits', 'i0', 'i1', 'up', 'o0', 'desc']:
+        a, b = e32.export_activation(name, 1), e16.export_activation(name, 1)
+        c = min(a.shape[1], b.shape[1])
+        scale = float(a.abs().max()) + 1e-6
+        err = float((a[:, :c] - b[:, :c]).abs().max())
+        print('[stage %-6s] max|fp32| %.3f  max abs diff %.4f  (rel %.2e)' % (name, scale, err, err / scale))
+        assert err / scale < 2e-2, name
+
+
+@pytest.mark.parametrize('name', ['shapes240_0', 'rand240_0'])
+def test_path_bf16_tensor_cores_reported(name, engines, golden_sd):
+    """bf16 operands: 8 mantissa bits do not meet the 1e-2 heatmap bar on every image;
+    the numbers are printed and only sanity-bounded here, fp16 is the default operand type."""
+    compare_path(engines['bf16'], golden_image(name), golden_sd, 0.3, 0.85, 0.99, 'bf16 ' + name)
+
+
+def test_batch_equals_single_images_fp16(engines):
+    e = engines['fp16']
+    imgs = torch.stack([golden_image('shapes240_%d' % i) for i in range(3)] + [golden_image('rand240_0')])[:, None]
+    cap = e.max_keypoints(240, 320)
+    count, xy, conf, dsc, prob = [t.clone() for t in e.detect(imgs.cuda(), cap, want_prob=True)]
+    for i in range(imgs.shape[0]):
+        c1, xy1, conf1, d1, p1 = e.detect(imgs[i:i + 1].cuda(), cap, want_prob=True)
+        assert torch.equal(prob[i], p1[0])
+        n = int(c1[0])
+        assert int(count[i]) == n and torch.equal(xy[i, :n], xy1[0, :n]) and torch.equal(dsc[i, :n], d1[0, :n])
+
+
+def test_full_size_batch_runs_and_is_consistent(engines):
+    """BASELINE config 3 size (64 x 480 x 640): image i of the batch == the same image run alone."""
+    e = engines['fp16']
+    base = torch.stack([weights.shapes_image(i, 480, 640) for i in range(4)])
+    imgs = base.repeat(16, 1, 1)[:, None].contiguous().cuda()
+    cap = 2048
+    e.set_params(top_k=2048)
+    count, xy, conf, dsc, _ = [t.clone() if t is not None else None for t in e.detect(imgs, cap)]
+    for i in (0, 5, 63):
+        c1, xy1, conf1, d1, _ = e.detect(imgs[i:i + 1], cap)
+        n = int(c1[0])
+        assert int(count[i]) == n and n > 100
+        assert torch.equal(xy[i, :n], xy1[0, :n]) and torch.equal(dsc[i, :n], d1[0, :n])
+    assert torch.equal(count[:4], count[4:8])
+    e.set_params()
+
+
+def test_detect_host_matches_device(engines):
+    e = engines['fp16']
+    imgs = torch.stack([golden_image('shapes240_0'), golden_image('rand240_1')])[:, None].contiguous()
+    cap = e.max_keypoints(240, 320)
+    count, xy, conf, dsc, _ = e.detect(imgs.cuda(), cap)
+    hc, hxy, hconf, hdsc = e.detect_host(imgs.numpy(), cap)
+    np.testing.assert_array_equal(hc, count.cpu().numpy())
+    for i in range(2):
+        n = int(hc[i])
+        np.testing.assert_array_equal(hxy[i, :n], xy[i, :n].cpu().numpy())
+        np.testing.assert_array_equal(hconf[i, :n], conf[i, :n].cpu().numpy())
+        np.testing.assert_array_equal(hdsc[i, :n], dsc[i, :n].cpu().numpy())
+
+
+def test_other_checkpoints_harsh_and_magicpoint(tmp_path):
+    """Synthetic 'harsh' preset + a magic_point.pt written in the reference's checkpoint format."""
+    spb = load_spb()
+    sd = weights.make_state_dict(seed=3, preset='harsh')
+    path = weights.save_checkpoint(sd, str(tmp_path / 'magic_point.pt'))
+    e = spb.Engine(0)
+    e.load_checkpoint(path)
+    e.finalize('fp16')
+    e.set_params(descriptor_enabled=False)
+    imgs = torch.stack([weights.shapes_image(i, 240, 320) for i in range(4)])[:, None]
+    cap = e.max_keypoints(240, 320)
+    count, xy, conf, _, prob = e.detect(imgs.cuda(), cap, want_desc=False, want_prob=True)
+    tot, hit = 0, 0
+    for i in range(4):
+        po, _, _ = model.forward(imgs[i:i + 1], sd, descriptor_enabled=False)
+        want = pset(postproc.get_points(po.numpy()))
+        got = pset(points_from(count, xy, conf, i))
+        tot += len(want)
+        hit += len(want & got)
+        print('[harsh fp16] image %d heat max-abs %.3e' % (i, float((prob[i].cpu() - po[0]).abs().max())))
+    print('[harsh fp16] keypoints %d/%d' % (hit, tot))
+    assert hit >= 0.97 * tot
+    e.close()
