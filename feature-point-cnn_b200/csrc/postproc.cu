@@ -289,8 +289,10 @@ sort_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __re
                 unsigned off = s_base[tid];
                 for (int w = 0; w < 32; ++w) {
                     const unsigned c = s_wcnt[w][tid];
-                    s_wcnt[w][tid] = off;
-                    off += c;
+                    if (c) {                   // untouched entries must stay 0: only a group's leader resets its entry
+                        s_wcnt[w][tid] = off;
+                        off += c;
+                    }
                 }
                 s_base[tid] = off;
             }
