@@ -486,9 +486,11 @@ void Engine::detect(const float* img, int B, int C, int H, int W, int cap, int* 
     prof_close(st);
     ++launches_;
     ensure_nms(B, H, W);
-    prof_open("nms+sort", 0.0, (double)B * H * W * 4, st);       // + 12 B per survivor, added by the caller
-    launch_nms(heat, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_,
-               count, xy, conf, st);
+    prof_open("nms", 0.0, (double)B * H * W * 4, st);            // + 8 B per survivor, added by the caller
+    launch_nms(heat, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
+    prof_close(st);
+    prof_open("sort_topk", 0.0, 0.0, st);                        // 8 B in + 12 B out per survivor (caller)
+    launch_sort_emit(B, W, params_.top_k, cap, nms_, count, xy, conf, st);
     prof_close(st);
     launches_ += 2;
     if (desc) {
@@ -516,8 +518,8 @@ void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, in
     SPB_CUDA(cudaSetDevice(device_));
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
     ensure_nms(B, H, W);
-    launch_nms(prob, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_,
-               count, xy, conf, st);
+    launch_nms(prob, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
+    launch_sort_emit(B, W, params_.top_k, cap, nms_, count, xy, conf, st);
     launches_ += 2;
 }
 

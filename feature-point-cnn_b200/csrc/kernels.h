@@ -31,11 +31,14 @@ struct NmsWorkspace {
     int* counters;          // [B][4]: survivors, undecided totals of rounds k%3
     int kcap;               // capacity of keys per image: ceil(H/(r+1))*ceil(W/(r+1)), the survivor bound
 };
-// Greedy-equivalent grid NMS + border removal + descending sort + top-k truncation (reference
-// python/src/netutils.py:78-100, python/src/nms.py:4-53).  Outputs per image: count (clamped to cap and
-// top_k), xy int32 [cap][2] as (x, y), conf fp32 [cap].
-void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, int top_k, int cap,
-                const NmsWorkspace& ws, int* count, int* xy, float* conf, cudaStream_t st);
+// Greedy-equivalent grid NMS + border removal (reference python/src/nms.py:4-53, python/src/netutils.py:59,95-99):
+// leaves the survivors of every image as unsorted keys in ws.keys / ws.counters.
+void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, const NmsWorkspace& ws,
+                cudaStream_t st);
+// Descending sort of the survivors (python/src/netutils.py:92-93) + top-k truncation.  Outputs per image: count
+// (clamped to cap and top_k), xy int32 [cap][2] as (x, y), conf fp32 [cap].
+void launch_sort_emit(int B, int W, int top_k, int cap, const NmsWorkspace& ws, int* count, int* xy, float* conf,
+                      cudaStream_t st);
 
 // Bilinear sampling (align_corners=True) of the descriptor map at the keypoints + L2 normalisation
 // (reference python/src/netutils.py:103-121).  map element (b, c, i, j) is at

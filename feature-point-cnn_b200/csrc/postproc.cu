@@ -318,8 +318,8 @@ sort_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __re
     if (tid == 0) count[b] = nout;
 }
 
-void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, int top_k, int cap,
-                const NmsWorkspace& ws, int* count, int* xy, float* conf, cudaStream_t st) {
+void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, const NmsWorkspace& ws,
+                cudaStream_t st) {
     if (radius < 0 || radius > kNmsMaxR) throw std::invalid_argument("nms_dist must be in [0, 8]");
     if ((long)H * W >= (1l << 31)) throw std::invalid_argument("image too large");
     const int r = radius;
@@ -343,6 +343,10 @@ void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius
     cfg.numAttrs = 1;
     SPB_CUDA(cudaLaunchKernelEx(&cfg, nms_cluster_kernel, heat, H, W, thresh, r, border, ws.kcap, ws.stamp, ws.keys,
                                 ws.counters, tiles_per_cta));
+}
+
+void launch_sort_emit(int B, int W, int top_k, int cap, const NmsWorkspace& ws, int* count, int* xy, float* conf,
+                      cudaStream_t st) {
     sort_emit_kernel<<<B, kSortThreads, 0, st>>>(ws.keys, ws.keys_alt, ws.counters, ws.kcap, W, cap, top_k, count, xy, conf);
     SPB_CHECK_LAUNCH();
 }

@@ -80,6 +80,6 @@ def compare_path(e, gray, sd, heat_tol, kp_frac, cos_min, tag):
     if int(count[0]):
         nrm = dsc[0, :int(count[0])].norm(dim=1)
         assert float((nrm - 1).abs().max()) < 1e-4
-    return dh, frac, cos
+    return dh, frac, cos, inter, len(pset(pts_o))
 
 
