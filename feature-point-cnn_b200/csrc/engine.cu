@@ -77,7 +77,7 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     release_workspace();
     release_weights();
-    cudaFree(nms_.stamp); cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters);
+    cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und);
 }
 
 void Engine::release_workspace() {
@@ -96,6 +96,12 @@ void Engine::release_weights() {
     convs_.clear();
     cudaFree(d_stem_w_[0]); cudaFree(d_stem_w_[1]); cudaFree(d_stem_b_);
     d_stem_w_[0] = d_stem_w_[1] = d_stem_b_ = nullptr;
+    for (int i = 0; i < 2; ++i) {
+        if (stem_plan_[i]) stem_tc_plan_destroy(stem_plan_[i]);
+        stem_plan_[i] = nullptr;
+        cudaFree(d_stem_w16_[i]);
+        d_stem_w16_[i] = nullptr;
+    }
 }
 
 void Engine::load_checkpoint(const std::string& path) {
@@ -306,6 +312,28 @@ void Engine::build_ops() {
     d_stem_w_[0] = dev_upload(w1);
     d_stem_w_[1] = dev_upload(w3);
     d_stem_b_ = dev_upload(st->b);
+    if (precision_ != PREC_FP32) {
+        // tensor-core stem: [cout][k] with k = c*49 + ky*7 + kx, K zero-padded to a multiple of 64; the
+        // 1-channel variant also carries the lo parts (w - float(w16)) for the split-precision MMAs
+        for (int v = 0; v < 2; ++v) {
+            const int cin = v == 0 ? 1 : 3, kpad = (49 * cin + 63) / 64 * 64, nparts = v == 0 ? 2 : 1;
+            const std::vector<float>& src = v == 0 ? w1 : w3;
+            std::vector<uint16_t> w16((size_t)64 * kpad * nparts, 0);
+            auto to16 = [&](float f) { return precision_ == PREC_FP16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); };
+            auto from16 = [&](uint16_t h) {
+                return precision_ == PREC_FP16 ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
+            };
+            for (int k = 0; k < 49 * cin; ++k)
+                for (int co = 0; co < 64; ++co) {
+                    const float f = src[(size_t)k * 64 + co];
+                    const uint16_t hi = to16(f);
+                    w16[(size_t)co * kpad * nparts + k] = hi;
+                    if (nparts == 2) w16[(size_t)co * kpad * nparts + kpad + k] = to16(f - from16(hi));
+                }
+            d_stem_w16_[v] = dev_upload(w16);
+            stem_plan_[v] = stem_tc_plan_create(d_stem_w16_[v], d_stem_b_, cin, precision_);
+        }
+    }
 }
 
 void Engine::finalize(int precision) {
@@ -354,12 +382,14 @@ void Engine::ensure_nms(int B, int H, int W) {
     const int r = params_.nms_dist;
     if (B <= nmsB_ && H == nmsH_ && W == nmsW_ && r == nmsR_) return;
     SPB_CUDA(cudaDeviceSynchronize());
-    cudaFree(nms_.stamp); cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters);
+    cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und);
     nms_.kcap = max_keypoints(H, W, r);
-    nms_.stamp = dev_alloc<uint16_t>((size_t)B * H * W);
+    nms_.mask_w = (W + 31) / 32;
     nms_.keys = dev_alloc<unsigned long long>((size_t)B * nms_.kcap);
     nms_.keys_alt = dev_alloc<unsigned long long>((size_t)B * nms_.kcap);
-    nms_.counters = dev_alloc<int>((size_t)B * 4);
+    nms_.counters = dev_alloc<int>((size_t)B * 8);
+    nms_.mask = dev_alloc<unsigned>((size_t)B * H * nms_.mask_w);
+    nms_.und = dev_alloc<unsigned>((size_t)B * H * W);
     nmsB_ = B; nmsH_ = H; nmsW_ = W; nmsR_ = r;
 }
 
@@ -438,7 +468,10 @@ void Engine::run_network(const float* img, int B, int C, int H, int W, cudaStrea
     // gray-folded stem: 49 MACs per output (the reference's 3-channel stem does 147 on replicated input)
     prof_open("stem_pool", 2.0 * B * (H / 2) * (W / 2) * 64.0 * 49.0 * C,
               (double)B * C * H * W * 4 + (double)B * (H / 4) * (W / 4) * 64 * (precision_ == PREC_FP32 ? 4 : 2), st);
-    launch_stem_pool(img, B, C, H, W, d_stem_w_[C == 1 ? 0 : 1], d_stem_b_, buf_[BUF_POOL], precision_, st);
+    if (precision_ == PREC_FP32)
+        launch_stem_pool(img, B, C, H, W, d_stem_w_[C == 1 ? 0 : 1], d_stem_b_, buf_[BUF_POOL], precision_, st);
+    else
+        launch_stem_tc(stem_plan_[C == 1 ? 0 : 1], img, buf_[BUF_POOL], B, H, W, st);
     prof_close(st);
     ++launches_;
     for (auto& op : ops_) {
@@ -492,7 +525,7 @@ void Engine::detect(const float* img, int B, int C, int H, int W, int cap, int* 
     prof_open("sort_topk", 0.0, 0.0, st);                        // 8 B in + 12 B out per survivor (caller)
     launch_sort_emit(B, W, params_.top_k, cap, nms_, count, xy, conf, st);
     prof_close(st);
-    launches_ += 2;
+    launches_ += 3;
     if (desc) {
         if (params_.descriptor_enabled) {
             prof_open("descriptors", 0.0, 0.0, st);              // bytes depend on the keypoint count (caller)
@@ -520,7 +553,7 @@ void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, in
     ensure_nms(B, H, W);
     launch_nms(prob, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
     launch_sort_emit(B, W, params_.top_k, cap, nms_, count, xy, conf, st);
-    launches_ += 2;
+    launches_ += 3;
 }
 
 void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int W, int cap, const int* count,

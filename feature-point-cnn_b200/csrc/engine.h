@@ -132,6 +132,8 @@ private:
     int det_c_ = 80;
     float* d_stem_w_[2] = {nullptr, nullptr};      // [0]: 1-channel (gray-folded), [1]: 3-channel
     float* d_stem_b_ = nullptr;
+    void* d_stem_w16_[2] = {nullptr, nullptr};     // tensor-core stem: [64][nchunk*64] 16-bit, K-major
+    StemTcPlan* stem_plan_[2] = {nullptr, nullptr};
 
     // workspace
     int wsB_ = 0, wsH_ = 0, wsW_ = 0;

@@ -17,6 +17,12 @@ TcConvPlan* tc_plan_create(const ConvDev& p, int operand_type);
 void tc_plan_destroy(TcConvPlan* plan);
 void launch_conv_tc(const TcConvPlan* plan, cudaStream_t st);
 
+// ---- stem_tc.cu ----------------------------------------------------------------------------------
+struct StemTcPlan;
+StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type);
+void stem_tc_plan_destroy(StemTcPlan* plan);
+void launch_stem_tc(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st);
+
 // ---- postproc.cu ---------------------------------------------------------------------------------
 // Softmax-with-epsilon over 65 channels, drop the dustbin, depth-to-space (reference
 // python/src/superpoint.py:111-114, python/src/netutils.py:64-75).  logits element (b, c, i, j) is at
@@ -25,14 +31,16 @@ void launch_heatmap(const float* logits, long batch_stride, long chan_stride, lo
                     float* heat, cudaStream_t st);
 
 struct NmsWorkspace {
-    uint16_t* stamp;        // [B][H][W] decision stamps
     unsigned long long* keys;      // [B][kcap] survivors as sortable keys (conf bits << 32 | ~pixel index)
     unsigned long long* keys_alt;  // [B][kcap] ping-pong buffer of the radix sort
-    int* counters;          // [B][4]: survivors, undecided totals of rounds k%3
-    int kcap;               // capacity of keys per image: ceil(H/(r+1))*ceil(W/(r+1)), the survivor bound
+    int* counters;                 // [B][8]: survivors, undecided after round 0, round totals (sortkey.cuh)
+    int kcap;                      // capacity of keys per image: ceil(H/(r+1))*ceil(W/(r+1)), the survivor bound
+    unsigned* mask;                // [B][H][mask_w] bit per pixel: undecided candidate
+    int mask_w;                    // 32-bit words per image row
+    unsigned* und;                 // [B][H*W] pixel indices of the candidates still undecided after round 0
 };
 // Greedy-equivalent grid NMS + border removal (reference python/src/nms.py:4-53, python/src/netutils.py:59,95-99):
-// leaves the survivors of every image as unsorted keys in ws.keys / ws.counters.
+// leaves the survivors of every image as unsorted keys in ws.keys / ws.counters.  Two launches.
 void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, const NmsWorkspace& ws,
                 cudaStream_t st);
 // Descending sort of the survivors (python/src/netutils.py:92-93) + top-k truncation.  Outputs per image: count

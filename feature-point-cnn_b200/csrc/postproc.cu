@@ -2,18 +2,13 @@
 //
 //  K3 heatmap_kernel      softmax-with-epsilon over 65 channels, drop dustbin, depth-to-space
 //                         (reference python/src/superpoint.py:111-114, python/src/netutils.py:64-75)
-//  K4 nms_cluster_kernel  exact parallel form of the reference's greedy grid NMS
-//                         (python/src/nms.py:4-53, threshold of python/src/netutils.py:59), one
-//                         thread-block cluster per image, smem-tiled separable window maxima
+//  K4 (nms.cu)            exact parallel form of the reference's greedy grid NMS
 //  K5 sort_emit_kernel    block-wide LSD radix sort of the survivors by descending confidence
 //                         (python/src/netutils.py:92-93) + top-k truncation
 //  K6 sample_desc_kernel  bilinear sampling (align_corners=True) + L2 normalisation
 //                         (python/src/netutils.py:103-121), one warp per keypoint, 128-bit loads
-#include <cooperative_groups.h>
-
 #include "kernels.h"
-
-namespace cg = cooperative_groups;
+#include "sortkey.cuh"
 
 namespace spb200 {
 
@@ -70,159 +65,6 @@ void launch_heatmap(const float* logits, long batch_stride, long chan_stride, lo
 }
 
 // ================================================================================================
-// K4: NMS.  The reference visits candidates by descending confidence; a live candidate is kept and
-// kills its (2r+1)^2 window.  Equivalent rounds: every undecided candidate that is the maximum of the
-// undecided candidates in its window is kept; every undecided candidate inside the window of a new
-// keeper is suppressed; repeat until none is undecided.  (Induction on the visiting order: a window
-// maximum has only decided superiors, all suppressed, or it would have been suppressed with them.)
-// Ties are ordered by ascending pixel index through the composite key, like the oracle.
-//
-// stamp (uint16 per pixel): 1 = undecided candidate, 2k+2 = kept in round k, 2k+3 = suppressed in
-// round k.  Tiles of one round are processed concurrently and update stamps in place; a reader in
-// round k treats "decided in round >= k" as still undecided, which is the state at the round's start.
-// ================================================================================================
-constexpr int kNmsTW = 32, kNmsTH = 16;          // interior tile
-constexpr int kNmsThreads = kNmsTW * kNmsTH;     // 512, one thread per interior pixel
-constexpr int kNmsMaxR = 8;
-constexpr int kNmsCluster = 8;
-
-__device__ __forceinline__ unsigned sortable_bits(float v) {
-    const unsigned u = __float_as_uint(v);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float from_sortable_bits(unsigned s) {
-    return __uint_as_float((s & 0x80000000u) ? (s & 0x7fffffffu) : ~s);
-}
-
-__global__ void __launch_bounds__(kNmsThreads)
-nms_cluster_kernel(const float* __restrict__ heat, int H, int W, float thresh, int r, int border, int kcap,
-                   uint16_t* __restrict__ stamp, unsigned long long* __restrict__ keys, int* __restrict__ counters,
-                   int tiles_per_cta) {
-    cg::cluster_group cluster = cg::this_cluster();
-    extern __shared__ __align__(16) unsigned char nms_smem[];
-    const int LW = kNmsTW + 4 * r, LH = kNmsTH + 4 * r;      // loaded region
-    const int EW = kNmsTW + 2 * r, EH = kNmsTH + 2 * r;      // region where keepers are evaluated
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(nms_smem);   // [LH][LW]
-    unsigned long long* s_row = s_key + LH * LW;                                   // [LH][EW]
-    unsigned char* s_keep = reinterpret_cast<unsigned char*>(s_row + LH * EW);     // [EH][EW]
-    unsigned char* s_ro = s_keep + EH * EW;                                        // [EH][kNmsTW]
-    unsigned char* s_alive = s_ro + EH * kNmsTW;                                   // [tiles_per_cta]
-    __shared__ int s_left;
-
-    const int tid = threadIdx.x;
-    const int b = blockIdx.x / kNmsCluster;
-    const int rank = (int)cluster.block_rank();
-    const int tiles_x = (W + kNmsTW - 1) / kNmsTW, tiles_y = (H + kNmsTH - 1) / kNmsTH;
-    const int ntiles = tiles_x * tiles_y;
-    const float* hmap = heat + (size_t)b * H * W;
-    uint16_t* smap = stamp + (size_t)b * H * W;
-    unsigned long long* kout = keys + (size_t)b * kcap;
-    int* cnt = counters + b * 4;            // [0] survivors, [1..3] undecided totals (round % 3)
-
-    for (int i = tid; i < tiles_per_cta; i += kNmsThreads) s_alive[i] = 1;
-    __syncthreads();
-
-    for (int k = 0;; ++k) {
-        if (k >= 32000) break;              // stamp range guard (never reached in practice)
-        int left_local = 0;
-        for (int slot = 0; slot < tiles_per_cta; ++slot) {
-            const int t = rank + slot * kNmsCluster;
-            if (t >= ntiles || !s_alive[slot]) continue;       // block-uniform
-            const int ty0 = (t / tiles_x) * kNmsTH, tx0 = (t % tiles_x) * kNmsTW;
-            // 1. composite keys of the undecided candidates in the loaded region
-            for (int i = tid; i < LH * LW; i += kNmsThreads) {
-                const int gy = ty0 - 2 * r + i / LW, gx = tx0 - 2 * r + i % LW;
-                unsigned long long key = 0ull;
-                if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                    const int pix = gy * W + gx;
-                    const float h = __ldg(hmap + pix);
-                    if (h >= thresh) {
-                        bool undecided = true;
-                        if (k > 0) {
-                            const int s = (int)__ldcg(smap + pix);
-                            undecided = (s == 1) || (s >= 2 && ((s - 2) >> 1) >= k);
-                        }
-                        if (undecided) key = ((unsigned long long)sortable_bits(h) << 32) | (unsigned)(~(unsigned)pix);
-                    }
-                }
-                s_key[i] = key;
-            }
-            __syncthreads();
-            // 2. horizontal window maxima
-            for (int i = tid; i < LH * EW; i += kNmsThreads) {
-                const int ly = i / EW, ex = i % EW;
-                const unsigned long long* p = s_key + ly * LW + ex;     // columns ex .. ex+2r of L
-                unsigned long long m = p[0];
-                for (int d = 1; d <= 2 * r; ++d) m = max(m, p[d]);
-                s_row[i] = m;
-            }
-            __syncthreads();
-            // 3. vertical maxima -> new keepers on the evaluation region
-            for (int i = tid; i < EH * EW; i += kNmsThreads) {
-                const int ey = i / EW, ex = i % EW;
-                const unsigned long long* p = s_row + ey * EW + ex;     // rows ey .. ey+2r of L
-                unsigned long long m = p[0];
-                for (int d = 1; d <= 2 * r; ++d) m = max(m, p[d * EW]);
-                const unsigned long long me = s_key[(ey + r) * LW + ex + r];
-                s_keep[i] = (me != 0ull && me == m) ? 1 : 0;
-            }
-            __syncthreads();
-            // 4. horizontal OR of the keeper flags
-            for (int i = tid; i < EH * kNmsTW; i += kNmsThreads) {
-                const int ey = i / kNmsTW, ix = i % kNmsTW;
-                const unsigned char* p = s_keep + ey * EW + ix;         // columns ix .. ix+2r of E
-                unsigned char o = 0;
-                for (int d = 0; d <= 2 * r; ++d) o |= p[d];
-                s_ro[i] = o;
-            }
-            __syncthreads();
-            // 5. decide the interior pixel of this thread
-            const int iy = tid / kNmsTW, ix = tid % kNmsTW;
-            const int gy = ty0 + iy, gx = tx0 + ix;
-            const unsigned long long me = s_key[(iy + 2 * r) * LW + ix + 2 * r];
-            bool still = false, emit = false;
-            if (me != 0ull) {       // undecided candidate inside the image
-                const int pix = gy * W + gx;
-                if (s_keep[(iy + r) * EW + ix + r]) {
-                    smap[pix] = (uint16_t)(2 * k + 2);
-                    emit = !(gx < border || gx >= W - border || gy < border || gy >= H - border);
-                } else {
-                    unsigned char sup = 0;
-                    for (int d = 0; d <= 2 * r; ++d) sup |= s_ro[(iy + d) * kNmsTW + ix];
-                    if (sup) smap[pix] = (uint16_t)(2 * k + 3);
-                    else { still = true; if (k == 0) smap[pix] = 1; }
-                }
-            }
-            // survivors: warp-aggregated append
-            const unsigned em = __ballot_sync(0xffffffffu, emit);
-            if (em) {
-                const int lane = tid % 32;
-                int basepos = 0;
-                if (lane == __ffs(em) - 1) basepos = atomicAdd(cnt, __popc(em));
-                basepos = __shfl_sync(0xffffffffu, basepos, __ffs(em) - 1);
-                if (emit) {
-                    const int pos = basepos + __popc(em & ((1u << lane) - 1u));
-                    if (pos < kcap) kout[pos] = me;
-                }
-            }
-            const int left = __syncthreads_count(still);     // also fences smem reuse by the next tile
-            if (tid == 0) s_alive[slot] = left > 0;
-            left_local += left;
-        }
-        // cluster-wide total of the still-undecided candidates of this round
-        if (tid == 0) {
-            if (left_local) atomicAdd(cnt + 1 + k % 3, left_local);
-            if (rank == 0) cnt[1 + (k + 1) % 3] = 0;
-            __threadfence();
-        }
-        cluster.sync();
-        if (tid == 0) s_left = __ldcg(cnt + 1 + k % 3);
-        __syncthreads();
-        if (s_left == 0) break;
-    }
-}
-
-// ================================================================================================
 // K5: one block per image: LSD radix sort (8-bit digits) of the survivor keys by descending key,
 // then emit (x, y), confidence and the count.  Digit positions on which all keys agree are skipped.
 // ================================================================================================
@@ -238,7 +80,7 @@ sort_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __re
     __shared__ unsigned s_warp_tot[8];
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     const int b = blockIdx.x;
-    const int n = min(counters[b * 4], kcap);
+    const int n = min(counters[b * kNmsCounters], kcap);
     unsigned long long* src = keys + (size_t)b * kcap;
     unsigned long long* dst = keys_alt + (size_t)b * kcap;
 
@@ -316,33 +158,6 @@ sort_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __re
         conf[(size_t)b * cap_out + i] = from_sortable_bits((unsigned)(key >> 32));
     }
     if (tid == 0) count[b] = nout;
-}
-
-void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, const NmsWorkspace& ws,
-                cudaStream_t st) {
-    if (radius < 0 || radius > kNmsMaxR) throw std::invalid_argument("nms_dist must be in [0, 8]");
-    if ((long)H * W >= (1l << 31)) throw std::invalid_argument("image too large");
-    const int r = radius;
-    const int LW = kNmsTW + 4 * r, LH = kNmsTH + 4 * r, EW = kNmsTW + 2 * r, EH = kNmsTH + 2 * r;
-    const int ntiles = ((W + kNmsTW - 1) / kNmsTW) * ((H + kNmsTH - 1) / kNmsTH);
-    const int tiles_per_cta = (ntiles + kNmsCluster - 1) / kNmsCluster;
-    const size_t smem = (size_t)LH * LW * 8 + (size_t)LH * EW * 8 + (size_t)EH * EW + (size_t)EH * kNmsTW + tiles_per_cta + 16;
-    SPB_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * 4 * B, st));
-    SPB_CUDA(cudaFuncSetAttribute(nms_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(B * kNmsCluster);
-    cfg.blockDim = dim3(kNmsThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kNmsCluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SPB_CUDA(cudaLaunchKernelEx(&cfg, nms_cluster_kernel, heat, H, W, thresh, r, border, ws.kcap, ws.stamp, ws.keys,
-                                ws.counters, tiles_per_cta));
 }
 
 void launch_sort_emit(int B, int W, int top_k, int cap, const NmsWorkspace& ws, int* count, int* xy, float* conf,
