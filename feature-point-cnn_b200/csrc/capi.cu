@@ -214,7 +214,7 @@ int spb200_test_conv_tc(int precision, const void* x, const void* w, const float
         spb200::ConvDev d{};
         d.nseg = 1;
         spb200::SegDev& s = d.seg[0];
-        s.src = x; s.H = H; s.W = W; s.C = cin; s.cin = cin; s.ntaps = taps; s.stride = stride; s.koff = 0;
+        s.src = x; s.H = H; s.W = W; s.C = cin; s.cin = cin; s.cin_real = cin; s.ntaps = taps; s.stride = stride; s.koff = 0;
         for (int t = 0; t < taps; ++t) {
             s.dy[t] = (int8_t)(taps == 9 ? t / 3 - 1 : 0);
             s.dx[t] = (int8_t)(taps == 9 ? t % 3 - 1 : 0);

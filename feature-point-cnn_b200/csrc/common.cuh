@@ -33,6 +33,7 @@ struct SegDev {
     const void* src;      // NHWC activations, element type given by the kernel
     int H, W, C;          // source dims; C = stored channels per pixel
     int cin;              // channels consumed by this segment (<= C, multiple of 16)
+    int cin_real;         // of which real (the rest is zero padding)
     int ntaps;
     int stride;
     int koff;             // first K index of this segment in the packed weights

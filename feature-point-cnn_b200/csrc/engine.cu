@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace spb200 {
@@ -70,6 +71,9 @@ Engine::Engine(int device) : device_(device) {
     SPB_CUDA(cudaGetDeviceProperties(&prop, device_));
     if (prop.major < 10)
         throw std::runtime_error(std::string("spb200 needs a Blackwell (sm_100a) GPU, found ") + prop.name);
+    num_sms_ = prop.multiProcessorCount;
+    const char* nf = std::getenv("SPB200_NO_FUSE");
+    fuse_blocks_ = !(nf && nf[0] == '1');
     buf_.fill(nullptr);
 }
 
@@ -81,7 +85,10 @@ Engine::~Engine() {
 }
 
 void Engine::release_workspace() {
-    for (auto& op : ops_) { if (op.plan) { tc_plan_destroy(op.plan); op.plan = nullptr; } }
+    for (auto& op : ops_) {
+        if (op.plan) { tc_plan_destroy(op.plan); op.plan = nullptr; }
+        if (op.fused) { tc_block_plan_destroy(op.fused); op.fused = nullptr; }
+    }
     for (auto& p : buf_) { cudaFree(p); p = nullptr; }
     cudaFree(d_prob_); d_prob_ = nullptr;
     wsB_ = wsH_ = wsW_ = 0;
@@ -90,6 +97,7 @@ void Engine::release_workspace() {
 void Engine::release_weights() {
     for (auto& op : ops_) {
         if (op.plan) tc_plan_destroy(op.plan);
+        if (op.fused) tc_block_plan_destroy(op.fused);
         cudaFree(op.d_bias); cudaFree(op.d_w32); cudaFree(op.d_w16);
     }
     ops_.clear();
@@ -374,8 +382,22 @@ void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
     }
     d_prob_ = dev_alloc<float>((size_t)B * H * W);
     wsB_ = B; wsH_ = H; wsW_ = W;
-    if (precision_ != PREC_FP32)
-        for (auto& op : ops_) op.plan = tc_plan_create(make_conv_dev(op), precision_);
+    if (precision_ != PREC_FP32) {
+        for (size_t i = 0; i < ops_.size(); ++i) {
+            OpSpec& op = ops_[i];
+            op.fused_skip = false;
+            if (!fuse_blocks_) { op.plan = tc_plan_create(make_conv_dev(op), precision_); continue; }
+            const bool is_conv1 = op.name.size() > 6 && op.name.compare(op.name.size() - 6, 6, ".conv1") == 0;
+            if (is_conv1 && i + 1 < ops_.size()) {
+                const ConvDev c1 = make_conv_dev(op), c2 = make_conv_dev(ops_[i + 1]);
+                op.fused = tc_block_plan_create(c1, &c2, precision_, op.cout_real, num_sms_);
+                ops_[i + 1].fused_skip = true;
+                ++i;
+            } else {
+                op.fused = tc_block_plan_create(make_conv_dev(op), nullptr, precision_, op.cout_real, num_sms_);
+            }
+        }
+    }
 }
 
 void Engine::ensure_nms(int B, int H, int W) {
@@ -405,6 +427,7 @@ ConvDev Engine::make_conv_dev(const OpSpec& op) const {
         sd.src = buf_[s.src_buf];
         sd.H = wsH_ / bs.div; sd.W = wsW_ / bs.div; sd.C = bs.C;
         sd.cin = bs.C;
+        sd.cin_real = s.cin_real;
         sd.ntaps = (int)s.taps.size();
         sd.stride = s.stride;
         sd.koff = koff;
@@ -474,11 +497,22 @@ void Engine::run_network(const float* img, int B, int C, int H, int W, cudaStrea
         launch_stem_tc(stem_plan_[C == 1 ? 0 : 1], img, buf_[BUF_POOL], B, H, W, st);
     prof_close(st);
     ++launches_;
-    for (auto& op : ops_) {
+    for (size_t i = 0; i < ops_.size(); ++i) {
+        OpSpec& op = ops_[i];
         if (!params_.descriptor_enabled && op.name.compare(0, 11, "descriptor.") == 0) continue;
-        prof_open(op.name, op_flops(op), 0.0, st);
-        if (precision_ == PREC_FP32) launch_conv_simt(make_conv_dev(op), st);
-        else launch_conv_tc(op.plan, st);
+        if (op.fused_skip) continue;
+        if (precision_ == PREC_FP32) {
+            prof_open(op.name, op_flops(op), 0.0, st);
+            launch_conv_simt(make_conv_dev(op), st);
+        } else if (op.fused) {
+            const bool block = i + 1 < ops_.size() && ops_[i + 1].fused_skip;
+            prof_open(block ? op.name.substr(0, op.name.size() - 6) : op.name,
+                      op_flops(op) + (block ? op_flops(ops_[i + 1]) : 0.0), 0.0, st);
+            launch_block_tc(op.fused, st);
+        } else {
+            prof_open(op.name, op_flops(op), 0.0, st);
+            launch_conv_tc(op.plan, st);
+        }
         prof_close(st);
         ++launches_;
     }

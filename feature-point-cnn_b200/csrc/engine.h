@@ -51,7 +51,9 @@ struct OpSpec {
     float* d_bias = nullptr;
     float* d_w32 = nullptr;       // [K][cout_pad]
     void* d_w16 = nullptr;        // [cout_pad][K]
-    TcConvPlan* plan = nullptr;   // per workspace shape
+    TcConvPlan* plan = nullptr;   // per workspace shape (unfused tensor-core path, kept for A/B runs)
+    TcBlockPlan* fused = nullptr; // per workspace shape: this op fused with the next one (block) or alone
+    bool fused_skip = false;      // executed as the second half of the previous op's fused plan
 };
 
 enum BufId {
@@ -130,6 +132,8 @@ private:
     std::vector<OpSpec> ops_;
     std::array<BufSpec, BUF_COUNT> bufspec_{};
     int det_c_ = 80;
+    int num_sms_ = 148;
+    bool fuse_blocks_ = true;     // SPB200_NO_FUSE=1 in the environment runs one kernel per convolution
     float* d_stem_w_[2] = {nullptr, nullptr};      // [0]: 1-channel (gray-folded), [1]: 3-channel
     float* d_stem_b_ = nullptr;
     void* d_stem_w16_[2] = {nullptr, nullptr};     // tensor-core stem: [64][nchunk*64] 16-bit, K-major

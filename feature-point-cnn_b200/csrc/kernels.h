@@ -17,6 +17,12 @@ TcConvPlan* tc_plan_create(const ConvDev& p, int operand_type);
 void tc_plan_destroy(TcConvPlan* plan);
 void launch_conv_tc(const TcConvPlan* plan, cudaStream_t st);
 
+// ---- block_tc.cu ---------------------------------------------------------------------------------
+struct TcBlockPlan;  // fused residual block (3x3 conv -> 1x1 conv + shortcut) or a single convolution, persistent
+TcBlockPlan* tc_block_plan_create(const ConvDev& c1, const ConvDev* c2, int operand_type, int real_cout, int num_sms);
+void tc_block_plan_destroy(TcBlockPlan* plan);
+void launch_block_tc(const TcBlockPlan* plan, cudaStream_t st);
+
 // ---- stem_tc.cu ----------------------------------------------------------------------------------
 struct StemTcPlan;
 StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type);

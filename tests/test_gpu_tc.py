@@ -109,7 +109,7 @@ def test_block_outputs_fp16_vs_fp32(engines):
     e32, e16 = engines['fp32'], engines['fp16']
     e32.forward(img)
     e16.forward(img)
-    for name in ['pool', 'l1a_y', 'l1a', 'l1b', 'l2a', 'feat', 'd0', 'logits', 'i0', 'i1', 'up', 'o0', 'desc']:
+    for name in ['pool', 'l1a', 'l1b', 'l2a', 'feat', 'd0', 'logits', 'i0', 'i1', 'up', 'o0', 'desc']:   # the fused blocks never materialise *_y
         a, b = e32.export_activation(name, 1), e16.export_activation(name, 1)
         c = min(a.shape[1], b.shape[1])
         scale = float(a.abs().max()) + 1e-6
