@@ -339,7 +339,7 @@ void Engine::build_ops() {
                     if (nparts == 2) w16[(size_t)co * kpad * nparts + kpad + k] = to16(f - from16(hi));
                 }
             d_stem_w16_[v] = dev_upload(w16);
-            stem_plan_[v] = stem_tc_plan_create(d_stem_w16_[v], d_stem_b_, cin, precision_);
+            stem_plan_[v] = stem_tc_plan_create(d_stem_w16_[v], d_stem_b_, cin, precision_, num_sms_);
         }
     }
 }

@@ -25,7 +25,7 @@ void launch_block_tc(const TcBlockPlan* plan, cudaStream_t st);
 
 // ---- stem_tc.cu ----------------------------------------------------------------------------------
 struct StemTcPlan;
-StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type);
+StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type, int num_sms);
 void stem_tc_plan_destroy(StemTcPlan* plan);
 void launch_stem_tc(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st);
 

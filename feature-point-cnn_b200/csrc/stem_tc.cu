@@ -16,6 +16,7 @@
 // HBM traffic is the algorithmic minimum: the fp32 image in, the pooled tensor out.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "kernels.h"
@@ -35,6 +36,7 @@ struct StemParams {
     const float* bias;        // [64]
     void* dst;                // NHWC [B][H/4][W/4][64] 16-bit
     int H, W;
+    int tiles_x, tiles_per_img, total_tiles;
 };
 
 template <int CIN, bool SPLIT, typename T>
@@ -56,11 +58,7 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
     uint8_t* s_conv = s_a;                                            // aliases A after the MMAs: [256 rows][128 B]
 
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-    const int b = blockIdx.z;
     const int H = p.H, W = p.W, CH = H / 2, CW = W / 2, PH = H / 4, PW = W / 4;
-    const int py0 = blockIdx.y * kStPH, px0 = blockIdx.x * kStPW;
-    const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;                   // conv coords of region origin
-    const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;                   // input coords of patch origin
 
     if (tid == 0) {
         mbar_init(&bar_w, 1);
@@ -80,125 +78,141 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
         mbar_expect_tx(&bar_w, NPART * NCHUNK * 64 * 128);
         for (int c = 0; c < NPART * NCHUNK; ++c) tma_load_2d(s_w + c * 64 * 128, &p.tmW, &bar_w, c * 64, 0);
     }
-    for (int i = tid; i < CIN * kStIH * kStIW; i += kStThreads) {
-        const int c = i / (kStIH * kStIW), r = i % (kStIH * kStIW);
-        const int y = iy0 + r / kStIW, x = ix0 + r % kStIW;
-        float v = 0.f;
-        if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(p.img + ((size_t)(b * CIN + c) * H + y) * W + x);
-        s_in[i] = v;
-    }
+    // persistent: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the input patch of the next
+    // tile is fetched while the tensor core works on the current one
+    auto load_patch = [&](int tile) {
+        const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
+        const int iy0 = 4 * ((tt / p.tiles_x) * kStPH) - 5, ix0 = 4 * ((tt % p.tiles_x) * kStPW) - 5;
+        for (int i = tid; i < CIN * kStIH * kStIW; i += kStThreads) {
+            const int c = i / (kStIH * kStIW), r = i % (kStIH * kStIW);
+            const int y = iy0 + r / kStIW, x = ix0 + r % kStIW;
+            float v = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(p.img + ((size_t)(b * CIN + c) * H + y) * W + x);
+            s_in[i] = v;
+        }
+    };
+    if ((int)blockIdx.x < p.total_tiles) load_patch(blockIdx.x);
     __syncthreads();
-
-    // ---- im2col row of this thread, written in the SWIZZLE_128B K-major layout -------------------
-    {
-        const int row = tid;                                   // 0..255, rows >= 231 are zero rows
-        const int mt = row >> 7, rr = row & 127;
-        const bool live = row < kStRows;
-        const int cyl = row / kStCW, cxl = row % kStCW;
-        const float* pin = s_in + (2 * cyl) * kStIW + 2 * cxl;
-#pragma unroll
-        for (int ck = 0; ck < NCHUNK; ++ck) {
-            uint8_t* arow = s_a + ((mt * NCHUNK + ck) * NPART) * kATile + rr * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {                      // 16-byte chunk j holds k = ck*64 + 8j .. +7
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int k = ck * 64 + j * 8 + e;
-                    float x = 0.f;
-                    if (live && k < 49 * CIN) {
-                        const int c = k / 49, t = k % 49;
-                        x = pin[c * kStIH * kStIW + (t / 7) * kStIW + (t % 7)];
+    uint32_t mma_phase = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, mma_phase ^= 1u, first = false) {
+        const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
+        const int py0 = (tt / p.tiles_x) * kStPH, px0 = (tt % p.tiles_x) * kStPW;
+        const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;               // conv coords of the region origin
+        // ---- im2col row of this thread, written in the SWIZZLE_128B K-major layout -------------------
+        {
+            const int row = tid;                                   // 0..255, rows >= 231 are zero rows
+            const int mt = row >> 7, rr = row & 127;
+            const bool live = row < kStRows;
+            const int cyl = row / kStCW, cxl = row % kStCW;
+            const float* pin = s_in + (2 * cyl) * kStIW + 2 * cxl;
+    #pragma unroll
+            for (int ck = 0; ck < NCHUNK; ++ck) {
+                uint8_t* arow = s_a + ((mt * NCHUNK + ck) * NPART) * kATile + rr * 128;
+    #pragma unroll
+                for (int j = 0; j < 8; ++j) {                      // 16-byte chunk j holds k = ck*64 + 8j .. +7
+                    float v[8];
+    #pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int k = ck * 64 + j * 8 + e;
+                        float x = 0.f;
+                        if (live && k < 49 * CIN) {
+                            const int c = k / 49, t = k % 49;
+                            x = pin[c * kStIH * kStIW + (t / 7) * kStIW + (t % 7)];
+                        }
+                        v[e] = x;
                     }
-                    v[e] = x;
-                }
-                const uint4 u = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
-                *reinterpret_cast<uint4*>(arow + ((j ^ (rr & 7)) << 4)) = u;
-                if (SPLIT) {                                   // lo part: what the 16-bit rounding dropped
-                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-                    uint32_t l[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 h = unpack2<T>(w[e]);
-                        l[e] = pack2<T>(v[2 * e] - h.x, v[2 * e + 1] - h.y);
+                    const uint4 u = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
+                    *reinterpret_cast<uint4*>(arow + ((j ^ (rr & 7)) << 4)) = u;
+                    if (SPLIT) {                                   // lo part: what the 16-bit rounding dropped
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                        uint32_t l[4];
+    #pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 h = unpack2<T>(w[e]);
+                            l[e] = pack2<T>(v[2 * e] - h.x, v[2 * e + 1] - h.y);
+                        }
+                        *reinterpret_cast<uint4*>(arow + kATile + ((j ^ (rr & 7)) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
                     }
-                    *reinterpret_cast<uint4*>(arow + kATile + ((j ^ (rr & 7)) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
                 }
             }
         }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> tensor-core reads
-    __syncthreads();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> tensor-core reads
+        __syncthreads();
 
-    if (tid == 0) {
-        mbar_wait(&bar_w, 0);
+        if (tid == 0) {
+            if (first) mbar_wait(&bar_w, 0);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(s_a), w_addr = smem_u32(s_w);
+    #pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+    #pragma unroll
+                for (int ck = 0; ck < NCHUNK; ++ck)
+    #pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint32_t a_hi = a_addr + ((mt * NCHUNK + ck) * NPART) * kATile + kk * 32;
+                        const uint32_t w_hi = w_addr + ck * 64 * 128 + kk * 32;
+                        umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi), kIdesc, (ck > 0 || kk > 0) ? 1u : 0u);
+                        if (SPLIT) {
+                            umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi + kATile), umma_smem_desc(w_hi), kIdesc, 1u);
+                            umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi + NCHUNK * 64 * 128), kIdesc, 1u);
+                        }
+                    }
+            umma_commit(&bar_mma);
+        }
+        __syncwarp();
+
+        if (tile + (int)gridDim.x < p.total_tiles) load_patch(tile + gridDim.x);      // s_in is free after the build
+        mbar_wait(&bar_mma, mma_phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(s_a), w_addr = smem_u32(s_w);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int ck = 0; ck < NCHUNK; ++ck)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint32_t a_hi = a_addr + ((mt * NCHUNK + ck) * NPART) * kATile + kk * 32;
-                    const uint32_t w_hi = w_addr + ck * 64 * 128 + kk * 32;
-                    umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi), kIdesc, (ck > 0 || kk > 0) ? 1u : 0u);
-                    if (SPLIT) {
-                        umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi + kATile), umma_smem_desc(w_hi), kIdesc, 1u);
-                        umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi + NCHUNK * 64 * 128), kIdesc, 1u);
-                    }
-                }
-        umma_commit(&bar_mma);
-    }
-    __syncwarp();
-    mbar_wait(&bar_mma, 0);
-    tc_fence_after();
 
-    // ---- epilogue: warps 0-3 own M-tile 0 (TMEM columns 0-63), warps 4-7 own M-tile 1 (64-127) ----
-    {
-        const int mt = warp >> 2, q = warp & 3;
-        const int row = mt * 128 + q * 32 + lane;
-        const int cy = cy0 + row / kStCW, cx = cx0 + row % kStCW;
-        const bool real = row < kStRows && cy >= 0 && cy < CH && cx >= 0 && cx < CW;
-        uint8_t* crow = s_conv + row * 128;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + half * 32), r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    v[e] = real ? fmaxf(__uint_as_float(r[j * 8 + e]) + s_bias[half * 32 + j * 8 + e], 0.f) : 0.f;
-                const uint4 u = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
-                *reinterpret_cast<uint4*>(crow + (((half * 4 + j) ^ (row & 7)) << 4)) = u;     // same XOR swizzle: conflict-free
+        // ---- epilogue: warps 0-3 own M-tile 0 (TMEM columns 0-63), warps 4-7 own M-tile 1 (64-127) ----
+        {
+            const int mt = warp >> 2, q = warp & 3;
+            const int row = mt * 128 + q * 32 + lane;
+            const int cy = cy0 + row / kStCW, cx = cx0 + row % kStCW;
+            const bool real = row < kStRows && cy >= 0 && cy < CH && cx >= 0 && cx < CW;
+            uint8_t* crow = s_conv + row * 128;
+    #pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + half * 32), r);
+                tmem_ld_wait();
+    #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v[8];
+    #pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        v[e] = real ? fmaxf(__uint_as_float(r[j * 8 + e]) + s_bias[half * 32 + j * 8 + e], 0.f) : 0.f;
+                    const uint4 u = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
+                    *reinterpret_cast<uint4*>(crow + (((half * 4 + j) ^ (row & 7)) << 4)) = u;     // same XOR swizzle: conflict-free
+                }
             }
         }
-    }
-    tc_fence_before();
-    __syncthreads();
+        tc_fence_before();
+        __syncthreads();
 
-    // ---- 3x3 / stride-2 max-pool over the staged conv tile, two channels per thread --------------
-    T* out = static_cast<T*>(p.dst);
-    for (int o = tid; o < kStPH * kStPW * 32; o += kStThreads) {
-        const int c2 = o % 32, pp = o / 32;
-        const int ppy = pp / kStPW, ppx = pp % kStPW;
-        const int py = py0 + ppy, px = px0 + ppx;
-        if (py >= PH || px >= PW) continue;
-        float m0 = 0.f, m1 = 0.f;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int row = (2 * ppy + dy) * kStCW + 2 * ppx + dx;
-                const uint32_t u = *reinterpret_cast<const uint32_t*>(s_conv + row * 128 + (((c2 >> 2) ^ (row & 7)) << 4) + (c2 & 3) * 4);
-                const float2 f = unpack2<T>(u);
-                m0 = fmaxf(m0, f.x);
-                m1 = fmaxf(m1, f.y);
-            }
-        *reinterpret_cast<uint32_t*>(out + ((size_t)(b * PH + py) * PW + px) * 64 + c2 * 2) = pack2<T>(m0, m1);
+        // ---- 3x3 / stride-2 max-pool over the staged conv tile, two channels per thread --------------
+        T* out = static_cast<T*>(p.dst);
+        for (int o = tid; o < kStPH * kStPW * 32; o += kStThreads) {
+            const int c2 = o % 32, pp = o / 32;
+            const int ppy = pp / kStPW, ppx = pp % kStPW;
+            const int py = py0 + ppy, px = px0 + ppx;
+            if (py >= PH || px >= PW) continue;
+            float m0 = 0.f, m1 = 0.f;
+    #pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+    #pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int row = (2 * ppy + dy) * kStCW + 2 * ppx + dx;
+                    const uint32_t u = *reinterpret_cast<const uint32_t*>(s_conv + row * 128 + (((c2 >> 2) ^ (row & 7)) << 4) + (c2 & 3) * 4);
+                    const float2 f = unpack2<T>(u);
+                    m0 = fmaxf(m0, f.x);
+                    m1 = fmaxf(m1, f.y);
+                }
+            *reinterpret_cast<uint32_t*>(out + ((size_t)(b * PH + py) * PW + px) * 64 + c2 * 2) = pack2<T>(m0, m1);
+        }
+        __syncthreads();           // pooling reads s_conv (aliases the A tiles) and s_in is rewritten: next build may start
     }
     __syncthreads();
     if (warp == 0) {
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
 
 struct StemTcPlan {
     StemParams params;
-    int cin, operand_type;
+    int cin, operand_type, num_sms;
 };
 
 template <int CIN, bool SPLIT, typename T>
@@ -221,7 +235,11 @@ static void launch_stem_tc_t(const StemTcPlan* plan, const float* img, void* dst
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StemParams p = plan->params;
     p.img = img; p.dst = dst; p.H = H; p.W = W;
-    dim3 grid((W / 4 + kStPW - 1) / kStPW, (H / 4 + kStPH - 1) / kStPH, B);
+    p.tiles_x = (W / 4 + kStPW - 1) / kStPW;
+    p.tiles_per_img = p.tiles_x * ((H / 4 + kStPH - 1) / kStPH);
+    p.total_tiles = p.tiles_per_img * B;
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int grid = std::min(p.total_tiles, plan->num_sms * per_sm);
     kern<<<grid, kStThreads, smem, st>>>(p);
     SPB_CHECK_LAUNCH();
 }
@@ -238,12 +256,13 @@ void launch_stem_tc(const StemTcPlan* plan, const float* img, void* dst, int B, 
 
 // w16: device [64][nparts*nchunk*64] 16-bit K-major (k = c*49 + ky*7 + kx, zero padded to nchunk*64; the hi
 // parts first, then - for the 1-channel path - the lo parts), bias: device [64] fp32
-StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type) {
+StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type, int num_sms) {
     if (cin != 1 && cin != 3) throw std::invalid_argument("stem: input must have 1 or 3 channels");
     auto* plan = new StemTcPlan();
     std::memset(&plan->params, 0, sizeof(plan->params));
     plan->cin = cin;
     plan->operand_type = operand_type;
+    plan->num_sms = num_sms;
     const int nchunk = (49 * cin + 63) / 64;
     const CUtensorMapDataType dt = operand_type == PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const int nparts = cin == 1 ? 2 : 1;
