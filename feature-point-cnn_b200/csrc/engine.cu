@@ -321,10 +321,10 @@ void Engine::build_ops() {
     d_stem_w_[1] = dev_upload(w3);
     d_stem_b_ = dev_upload(st->b);
     if (precision_ != PREC_FP32) {
-        // tensor-core stem: [cout][k] with k = c*49 + ky*7 + kx, K zero-padded to a multiple of 64; the
-        // 1-channel variant also carries the lo parts (w - float(w16)) for the split-precision MMAs
+        // tensor-core stem: [cout][k] with k = c*49 + ky*7 + kx, K zero-padded to a multiple of 64, followed by
+        // the lo parts (w - float(w16)) for the split-precision MMAs
         for (int v = 0; v < 2; ++v) {
-            const int cin = v == 0 ? 1 : 3, kpad = (49 * cin + 63) / 64 * 64, nparts = v == 0 ? 2 : 1;
+            const int cin = v == 0 ? 1 : 3, kpad = (49 * cin + 63) / 64 * 64, nparts = 2;
             const std::vector<float>& src = v == 0 ? w1 : w3;
             std::vector<uint16_t> w16((size_t)64 * kpad * nparts, 0);
             auto to16 = [&](float f) { return precision_ == PREC_FP16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); };

@@ -6,10 +6,11 @@
 //   1. the 27x47 input patch is loaded once (fp32, zero padded),
 //   2. every thread builds one im2col row (49*C taps, K padded to 64 per chunk) straight into the
 //      128B-swizzled K-major smem layout the UMMA descriptor expects (no im2col in HBM),
-//   3. one thread issues the tcgen05.mma chain (weights arrive by TMA), accumulators in TMEM; for the
-//      1-channel (grayscale) path both operands are split into 16-bit hi + lo parts and three MMAs
-//      (hi*hi + lo*hi + hi*lo) are accumulated, which makes the stem as accurate as fp32 at no
-//      measurable cost (the tensor work of the stem is tiny),
+//   3. one thread issues the tcgen05.mma chain (weights arrive by TMA), accumulators in TMEM.  Precision:
+//      the image is multiplied by 255 before the 16-bit rounding, so 8-bit images (value = k/255, what
+//      cameras and the reference's loaders produce) are represented exactly; the weights are split into
+//      16-bit hi + lo parts and two MMAs (a*w_hi + a*w_lo) are accumulated; 1/255 is applied to the fp32
+//      accumulator.  The stem is then as accurate as fp32 for 8-bit inputs at negligible tensor cost,
 //   4. the epilogue adds bias, applies ReLU, zeroes rows outside the conv output (neutral for the max,
 //      all real values are >= 0) and stages the 231x64 tile in smem,
 //   5. the 3x3/s2 max-pool reads that tile and writes NHWC 16-bit.
@@ -42,7 +43,7 @@ struct StemParams {
 template <int CIN, bool SPLIT, typename T>
 __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_constant__ StemParams p) {
     constexpr int NCHUNK = (49 * CIN + 63) / 64;
-    constexpr int NPART = SPLIT ? 2 : 1;                              // hi (+ lo) operand parts
+    constexpr int NPART = SPLIT ? 2 : 1;                              // weight parts: hi (+ lo)
     constexpr int kATile = 128 * 128;                                 // bytes of one M-tile of one K chunk of one part
     constexpr uint32_t kIdesc = (1u << 4) | (OperandFmt<T>::value << 7) | (OperandFmt<T>::value << 10) |
                                 ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -52,8 +53,8 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
     __shared__ float s_bias[64];
 
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023);
-    uint8_t* s_a = base;                                              // [2 M-tiles][NCHUNK][NPART][128 rows][128 B]
-    uint8_t* s_w = s_a + 2 * NCHUNK * NPART * kATile;                 // [NPART][NCHUNK][64 rows][128 B]
+    uint8_t* s_a = base;                                              // [2 M-tiles][NCHUNK][128 rows][128 B]
+    uint8_t* s_w = s_a + 2 * NCHUNK * kATile;                 // [NPART][NCHUNK][64 rows][128 B]
     float* s_in = reinterpret_cast<float*>(s_w + NPART * NCHUNK * 64 * 128);  // [CIN][27][47]
     uint8_t* s_conv = s_a;                                            // aliases A after the MMAs: [256 rows][128 B]
 
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
             const float* pin = s_in + (2 * cyl) * kStIW + 2 * cxl;
     #pragma unroll
             for (int ck = 0; ck < NCHUNK; ++ck) {
-                uint8_t* arow = s_a + ((mt * NCHUNK + ck) * NPART) * kATile + rr * 128;
+                uint8_t* arow = s_a + (mt * NCHUNK + ck) * kATile + rr * 128;
     #pragma unroll
                 for (int j = 0; j < 8; ++j) {                      // 16-byte chunk j holds k = ck*64 + 8j .. +7
                     float v[8];
@@ -118,22 +119,12 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
                         float x = 0.f;
                         if (live && k < 49 * CIN) {
                             const int c = k / 49, t = k % 49;
-                            x = pin[c * kStIH * kStIW + (t / 7) * kStIW + (t % 7)];
+                            x = pin[c * kStIH * kStIW + (t / 7) * kStIW + (t % 7)] * 255.f;
                         }
                         v[e] = x;
                     }
                     const uint4 u = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
                     *reinterpret_cast<uint4*>(arow + ((j ^ (rr & 7)) << 4)) = u;
-                    if (SPLIT) {                                   // lo part: what the 16-bit rounding dropped
-                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-                        uint32_t l[4];
-    #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 h = unpack2<T>(w[e]);
-                            l[e] = pack2<T>(v[2 * e] - h.x, v[2 * e + 1] - h.y);
-                        }
-                        *reinterpret_cast<uint4*>(arow + kATile + ((j ^ (rr & 7)) << 4)) = make_uint4(l[0], l[1], l[2], l[3]);
-                    }
                 }
             }
         }
@@ -150,13 +141,10 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
                 for (int ck = 0; ck < NCHUNK; ++ck)
     #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t a_hi = a_addr + ((mt * NCHUNK + ck) * NPART) * kATile + kk * 32;
+                        const uint32_t a_hi = a_addr + (mt * NCHUNK + ck) * kATile + kk * 32;
                         const uint32_t w_hi = w_addr + ck * 64 * 128 + kk * 32;
                         umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi), kIdesc, (ck > 0 || kk > 0) ? 1u : 0u);
-                        if (SPLIT) {
-                            umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi + kATile), umma_smem_desc(w_hi), kIdesc, 1u);
-                            umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi + NCHUNK * 64 * 128), kIdesc, 1u);
-                        }
+                        if (SPLIT) umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi + NCHUNK * 64 * 128), kIdesc, 1u);
                     }
             umma_commit(&bar_mma);
         }
@@ -183,7 +171,7 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
                     float v[8];
     #pragma unroll
                     for (int e = 0; e < 8; ++e)
-                        v[e] = real ? fmaxf(__uint_as_float(r[j * 8 + e]) + s_bias[half * 32 + j * 8 + e], 0.f) : 0.f;
+                        v[e] = real ? fmaxf(fmaf(__uint_as_float(r[j * 8 + e]), 1.f / 255.f, s_bias[half * 32 + j * 8 + e]), 0.f) : 0.f;
                     const uint4 u = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
                     *reinterpret_cast<uint4*>(crow + (((half * 4 + j) ^ (row & 7)) << 4)) = u;     // same XOR swizzle: conflict-free
                 }
@@ -231,14 +219,14 @@ static void launch_stem_tc_t(const StemTcPlan* plan, const float* img, void* dst
     constexpr int NCHUNK = (49 * CIN + 63) / 64;
     constexpr int NPART = SPLIT ? 2 : 1;
     auto kern = stem_tc_kernel<CIN, SPLIT, T>;
-    const size_t smem = (size_t)2 * NCHUNK * NPART * 128 * 128 + (size_t)NPART * NCHUNK * 64 * 128 + (size_t)CIN * kStIH * kStIW * 4 + 1024;
+    const size_t smem = (size_t)2 * NCHUNK * 128 * 128 + (size_t)NPART * NCHUNK * 64 * 128 + (size_t)CIN * kStIH * kStIW * 4 + 1024;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StemParams p = plan->params;
     p.img = img; p.dst = dst; p.H = H; p.W = W;
     p.tiles_x = (W / 4 + kStPW - 1) / kStPW;
     p.tiles_per_img = p.tiles_x * ((H / 4 + kStPH - 1) / kStPH);
     p.total_tiles = p.tiles_per_img * B;
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
     const int grid = std::min(p.total_tiles, plan->num_sms * per_sm);
     kern<<<grid, kStThreads, smem, st>>>(p);
     SPB_CHECK_LAUNCH();
@@ -247,15 +235,15 @@ static void launch_stem_tc_t(const StemTcPlan* plan, const float* img, void* dst
 void launch_stem_tc(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st) {
     if (plan->operand_type == PREC_FP16) {
         if (plan->cin == 1) launch_stem_tc_t<1, true, __half>(plan, img, dst, B, H, W, st);
-        else launch_stem_tc_t<3, false, __half>(plan, img, dst, B, H, W, st);
+        else launch_stem_tc_t<3, true, __half>(plan, img, dst, B, H, W, st);
     } else {
         if (plan->cin == 1) launch_stem_tc_t<1, true, __nv_bfloat16>(plan, img, dst, B, H, W, st);
-        else launch_stem_tc_t<3, false, __nv_bfloat16>(plan, img, dst, B, H, W, st);
+        else launch_stem_tc_t<3, true, __nv_bfloat16>(plan, img, dst, B, H, W, st);
     }
 }
 
 // w16: device [64][nparts*nchunk*64] 16-bit K-major (k = c*49 + ky*7 + kx, zero padded to nchunk*64; the hi
-// parts first, then - for the 1-channel path - the lo parts), bias: device [64] fp32
+// parts first, then the lo parts w - float(w_hi)), bias: device [64] fp32
 StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type, int num_sms) {
     if (cin != 1 && cin != 3) throw std::invalid_argument("stem: input must have 1 or 3 channels");
     auto* plan = new StemTcPlan();
@@ -265,7 +253,7 @@ StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int
     plan->num_sms = num_sms;
     const int nchunk = (49 * cin + 63) / 64;
     const CUtensorMapDataType dt = operand_type == PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    const int nparts = cin == 1 ? 2 : 1;
+    const int nparts = 2;
     cuuint64_t dims[2] = {(cuuint64_t)nparts * nchunk * 64, 64};
     cuuint64_t str[1] = {(cuuint64_t)nparts * nchunk * 64 * 2};
     cuuint32_t box[2] = {64, 64};
