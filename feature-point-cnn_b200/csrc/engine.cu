@@ -82,6 +82,7 @@ Engine::~Engine() {
     release_workspace();
     release_weights();
     cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und);
+    cudaFree(d_gtab_);
 }
 
 void Engine::release_workspace() {
@@ -415,6 +416,27 @@ void Engine::ensure_nms(int B, int H, int W) {
     nmsB_ = B; nmsH_ = H; nmsW_ = W; nmsR_ = r;
 }
 
+// ix = ((gx + 1) / 2) * (Wc - 1) with gx = float(x / (W / 2.) - 1.): the arithmetic of the reference's
+// get_descriptors (python/src/netutils.py:110-115) followed by grid_sample's align_corners=True un-normalisation.
+const float* Engine::grid_table(int H, int W) {
+    if (d_gtab_ && H == gtabH_ && W == gtabW_) return d_gtab_;
+    SPB_CUDA(cudaDeviceSynchronize());
+    cudaFree(d_gtab_);
+    std::vector<float> t((size_t)W + H);
+    const int Hc = H / 8, Wc = W / 8;
+    for (int x = 0; x < W; ++x) {
+        const float gx = (float)((double)x / ((double)W / 2.) - 1.);
+        t[x] = ((gx + 1.f) / 2.f) * (float)(Wc - 1);
+    }
+    for (int y = 0; y < H; ++y) {
+        const float gy = (float)((double)y / ((double)H / 2.) - 1.);
+        t[(size_t)W + y] = ((gy + 1.f) / 2.f) * (float)(Hc - 1);
+    }
+    d_gtab_ = dev_upload(t);
+    gtabH_ = H; gtabW_ = W;
+    return d_gtab_;
+}
+
 ConvDev Engine::make_conv_dev(const OpSpec& op) const {
     ConvDev d{};
     const BufSpec& ds = bufspec_[op.dst_buf];
@@ -563,8 +585,8 @@ void Engine::detect(const float* img, int B, int C, int H, int W, int cap, int* 
     if (desc) {
         if (params_.descriptor_enabled) {
             prof_open("descriptors", 0.0, 0.0, st);              // bytes depend on the keypoint count (caller)
-            launch_sample_descriptors(buf_[BUF_DESC], precision_, (long)Hc * Wc * 128, 1, 128, B, 128, Hc, Wc, H, W, cap,
-                                      count, xy, desc, st);
+            launch_sample_descriptors(buf_[BUF_DESC], precision_, (long)Hc * Wc * 128, 1, 128, B, 128, Hc, Wc, W,
+                                      grid_table(H, W), cap, count, xy, desc, st);
             prof_close(st);
             ++launches_;
         } else {
@@ -594,8 +616,8 @@ void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int
                                 const int* xy, float* out, cudaStream_t st) {
     SPB_CUDA(cudaSetDevice(device_));
     const int Hc = H / 8, Wc = W / 8;
-    launch_sample_descriptors(desc_nchw, PREC_FP32, (long)D * Hc * Wc, (long)Hc * Wc, 1, B, D, Hc, Wc, H, W, cap, count,
-                              xy, out, st);
+    launch_sample_descriptors(desc_nchw, PREC_FP32, (long)D * Hc * Wc, (long)Hc * Wc, 1, B, D, Hc, Wc, W, grid_table(H, W), cap,
+                              count, xy, out, st);
     ++launches_;
 }
 

@@ -146,6 +146,10 @@ private:
     // nms workspace
     int nmsB_ = 0, nmsH_ = 0, nmsW_ = 0, nmsR_ = -1;
     NmsWorkspace nms_{};
+    // descriptor sampling positions per pixel column / row (see launch_sample_descriptors)
+    float* d_gtab_ = nullptr;
+    int gtabH_ = 0, gtabW_ = 0;
+    const float* grid_table(int H, int W);
     // detect_host staging
     struct HostStage;
     std::unique_ptr<HostStage> stage_;

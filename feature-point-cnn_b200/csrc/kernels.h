@@ -56,9 +56,10 @@ void launch_sort_emit(int B, int W, int top_k, int cap, const NmsWorkspace& ws, 
 
 // Bilinear sampling (align_corners=True) of the descriptor map at the keypoints + L2 normalisation
 // (reference python/src/netutils.py:103-121).  map element (b, c, i, j) is at
-// map[b*batch_stride + c*chan_stride + (i*Wc + j)*cell_stride]; map_type is a Precision value.
+// map[b*batch_stride + c*chan_stride + (i*Wc + j)*cell_stride]; map_type is a Precision value; gtab[x] / gtab[W+y]
+// are the sampling positions ix / iy of pixel column x / row y (host-built, device memory).
 void launch_sample_descriptors(const void* map, int map_type, long batch_stride, long chan_stride, long cell_stride,
-                               int B, int D, int Hc, int Wc, int H, int W, int cap, const int* count, const int* xy,
-                               float* out, cudaStream_t st);
+                               int B, int D, int Hc, int Wc, int W, const float* gtab, int cap, const int* count,
+                               const int* xy, float* out, cudaStream_t st);
 
 }  // namespace spb200

@@ -170,7 +170,7 @@ void launch_sort_emit(int B, int W, int top_k, int cap, const NmsWorkspace& ws, 
 // K6: descriptors.  One warp per keypoint; each lane owns 4 consecutive channels per 128-channel
 // slab.  grid_sample(align_corners=True): ix = ((gx + 1)/2)*(Wc-1) with gx = x/(W/2) - 1 evaluated in
 // double and rounded to float, exactly as the reference builds its sampling grid
-// (python/src/netutils.py:110-115).  The L2 norm has no epsilon (netutils.py:120): an all-zero sample
+// (python/src/netutils.py:110-115); those per-coordinate values come from a small host-built table.  The L2 norm has no epsilon (netutils.py:120): an all-zero sample
 // yields NaN there and here.
 // ================================================================================================
 template <typename T>
@@ -209,20 +209,19 @@ __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, lon
     }
 }
 
+// gtab: per-coordinate sampling positions precomputed on the host exactly as the reference does
+// (double division, then float): gtab[x] = ix for x < W, gtab[W + y] = iy for y < H.
 template <typename T>
 __global__ void __launch_bounds__(256)
 sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_stride, long cell_stride, int D, int Hc,
-                   int Wc, int H, int W, int cap, const int* __restrict__ count, const int* __restrict__ xy,
-                   float* __restrict__ out) {
+                   int Wc, int W, const float* __restrict__ gtab, int cap, const int* __restrict__ count,
+                   const int* __restrict__ xy, float* __restrict__ out) {
     const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
     const int b = blockIdx.y;
     const int i = blockIdx.x * 8 + warp;
-    if (i >= min(count[b], cap)) return;
-    const int x = xy[((size_t)b * cap + i) * 2 + 0], y = xy[((size_t)b * cap + i) * 2 + 1];
-    const float gx = (float)((double)x / ((double)W / 2.) - 1.);
-    const float gy = (float)((double)y / ((double)H / 2.) - 1.);
-    const float ix = ((gx + 1.f) / 2.f) * (float)(Wc - 1);
-    const float iy = ((gy + 1.f) / 2.f) * (float)(Hc - 1);
+    if (i >= min(__ldg(count + b), cap)) return;
+    const int2 pt = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)b * cap + i);
+    const float ix = __ldg(gtab + pt.x), iy = __ldg(gtab + W + pt.y);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
     const int x0 = (int)fx0, y0 = (int)fy0;
@@ -242,13 +241,18 @@ sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_strid
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[s][q] = 0.f;
         if (c < D) {
+            float v[4][4];
+            bool ok[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {             // all four corner loads in flight before any use
+                ok[k] = !(cx[k] < 0 || cx[k] >= Wc || cy[k] < 0 || cy[k] >= Hc);     // zeros padding
+                if (ok[k]) load4<T>(mb + (size_t)(cy[k] * Wc + cx[k]) * cell_stride + (size_t)c * chan_stride, chan_stride, v[k]);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (cx[k] < 0 || cx[k] >= Wc || cy[k] < 0 || cy[k] >= Hc) continue;     // zeros padding
-                float v[4];
-                load4<T>(mb + (size_t)(cy[k] * Wc + cx[k]) * cell_stride + (size_t)c * chan_stride, chan_stride, v);
+                if (!ok[k]) continue;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) acc[s][q] = fmaf(wgt[k], v[q], acc[s][q]);
+                for (int q = 0; q < 4; ++q) acc[s][q] = fmaf(wgt[k], v[k][q], acc[s][q]);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) ss = fmaf(acc[s][q], acc[s][q], ss);
@@ -256,27 +260,27 @@ sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_strid
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    const float nrm = sqrtf(ss);
+    const float inv = 1.f / sqrtf(ss);                // 0-vector -> inf * 0 = NaN, like the reference's 0/0
 #pragma unroll
     for (int s = 0; s < kMaxSlabs; ++s) {
         if (s >= nslab) break;
         const int c = s * 128 + lane * 4;
-        if (c < D) *reinterpret_cast<float4*>(o + c) = make_float4(acc[s][0] / nrm, acc[s][1] / nrm, acc[s][2] / nrm, acc[s][3] / nrm);
+        if (c < D) __stcs(reinterpret_cast<float4*>(o + c), make_float4(acc[s][0] * inv, acc[s][1] * inv, acc[s][2] * inv, acc[s][3] * inv));
     }
 }
 
 void launch_sample_descriptors(const void* map, int map_type, long batch_stride, long chan_stride, long cell_stride,
-                               int B, int D, int Hc, int Wc, int H, int W, int cap, const int* count, const int* xy,
-                               float* out, cudaStream_t st) {
+                               int B, int D, int Hc, int Wc, int W, const float* gtab, int cap, const int* count,
+                               const int* xy, float* out, cudaStream_t st) {
     if (D % 4 != 0 || D > 512) throw std::invalid_argument("descriptor dimension must be a multiple of 4, at most 512");
     if (cap <= 0 || B <= 0) return;
     dim3 grid((cap + 7) / 8, B);
     if (map_type == PREC_FP32)
-        sample_desc_kernel<float><<<grid, 256, 0, st>>>((const float*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, H, W, cap, count, xy, out);
+        sample_desc_kernel<float><<<grid, 256, 0, st>>>((const float*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, W, gtab, cap, count, xy, out);
     else if (map_type == PREC_FP16)
-        sample_desc_kernel<__half><<<grid, 256, 0, st>>>((const __half*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, H, W, cap, count, xy, out);
+        sample_desc_kernel<__half><<<grid, 256, 0, st>>>((const __half*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, W, gtab, cap, count, xy, out);
     else
-        sample_desc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, H, W, cap, count, xy, out);
+        sample_desc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, W, gtab, cap, count, xy, out);
     SPB_CHECK_LAUNCH();
 }
 
