@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libspb200.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
-SOURCES = ['ckpt_reader.cpp', 'conv_simt.cu', 'conv_tc.cu', 'block_tc.cu', 'stem_tc.cu', 'nms.cu', 'postproc.cu', 'engine.cu', 'capi.cu']
+SOURCES = ['ckpt_reader.cpp', 'conv_simt.cu', 'conv_tc.cu', 'block_tc.cu', 'halo_tc.cu', 'stem_tc.cu', 'nms.cu', 'postproc.cu', 'engine.cu', 'capi.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
          '-Xcompiler', '-fvisibility=hidden', '-I', INCLUDE, '-I', CSRC]
@@ -47,7 +47,19 @@ def build(force=False, verbose=False):
         objs = list(ex.map(lambda s: _compile(s, force, verbose), SOURCES))
     if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         subprocess.check_call([NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    build_cpp_demo(force)
     return LIB
+
+
+def build_cpp_demo(force=False):
+    """The C++ facade (cpp/superpoint.h, header-only over the C ABI) compiled into its headless demo."""
+    cpp = os.path.join(HERE, 'cpp')
+    exe, src, hdr = os.path.join(cpp, 'demo'), os.path.join(cpp, 'demo.cc'), os.path.join(cpp, 'superpoint.h')
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(LIB)):
+        return exe
+    subprocess.check_call(['g++', '-std=c++17', '-O2', '-Wall', '-Wextra', '-Werror', '-I', INCLUDE, '-I', cpp, src, '-L', HERE,
+                           '-lspb200', '-Wl,-rpath,$ORIGIN/..', '-o', exe])
+    return exe
 
 
 if __name__ == '__main__':

@@ -205,8 +205,8 @@ int spb200_checkpoint_tensor(const char* path, const char* key, float* dst, long
     return SPB200_OK;
 }
 
-int spb200_test_conv_tc(int precision, const void* x, const void* w, const float* bias, void* y, int B, int H, int W,
-                        int cin, int cout, int taps, int stride, int relu, int out_fp32, void* stream) {
+static int test_conv_impl(int kernel, int precision, const void* x, const void* w, const float* bias, void* y, int B, int H, int W,
+                          int cin, int cout, int taps, int stride, int relu, int out_fp32, void* stream) {
     try {
         if (precision != SPB200_PREC_FP16 && precision != SPB200_PREC_BF16) return SPB200_E_INVALID;
         if ((taps != 1 && taps != 9) || (stride != 1 && stride != 2) || cin % 64 || cout % 16 || H % stride || W % stride)
@@ -223,16 +223,42 @@ int spb200_test_conv_tc(int precision, const void* x, const void* w, const float
         d.B = B; d.OH = H / stride; d.OW = W / stride; d.K = taps * cin; d.cout_pad = cout;
         d.dst_H = d.OH; d.dst_W = d.OW; d.dst_C = cout; d.dst_stride = 1; d.dst_off_y = 0; d.dst_off_x = 0;
         d.res_C = 0; d.relu = relu; d.dst_fp32 = out_fp32;
-        spb200::TcConvPlan* plan = spb200::tc_plan_create(d, precision);
-        spb200::launch_conv_tc(plan, (cudaStream_t)stream);
-        cudaError_t err = cudaStreamSynchronize((cudaStream_t)stream);
-        spb200::tc_plan_destroy(plan);
+        cudaError_t err = cudaSuccess;
+        if (kernel == 0) {
+            spb200::TcConvPlan* plan = spb200::tc_plan_create(d, precision);
+            spb200::launch_conv_tc(plan, (cudaStream_t)stream);
+            err = cudaStreamSynchronize((cudaStream_t)stream);
+            spb200::tc_plan_destroy(plan);
+        } else if (kernel == 1) {
+            spb200::TcBlockPlan* plan = spb200::tc_block_plan_create(d, nullptr, precision, cout, 148);
+            spb200::launch_block_tc(plan, (cudaStream_t)stream);
+            err = cudaStreamSynchronize((cudaStream_t)stream);
+            spb200::tc_block_plan_destroy(plan);
+        } else if (kernel == 2) {
+            spb200::TcHaloPlan* plan = spb200::tc_halo_plan_create(d, nullptr, precision, cout, 148);
+            if (!plan) { g_create_error = "the haloed-tile kernel does not take this convolution"; return SPB200_E_INVALID; }
+            spb200::launch_halo_tc(plan, (cudaStream_t)stream);
+            err = cudaStreamSynchronize((cudaStream_t)stream);
+            spb200::tc_halo_plan_destroy(plan);
+        } else {
+            return SPB200_E_INVALID;
+        }
         if (err != cudaSuccess) { g_create_error = cudaGetErrorString(err); return SPB200_E_RUNTIME; }
         return SPB200_OK;
     } catch (const std::exception& ex) {
         g_create_error = ex.what();
         return SPB200_E_RUNTIME;
     }
+}
+
+int spb200_test_conv_tc(int precision, const void* x, const void* w, const float* bias, void* y, int B, int H, int W,
+                        int cin, int cout, int taps, int stride, int relu, int out_fp32, void* stream) {
+    return test_conv_impl(0, precision, x, w, bias, y, B, H, W, cin, cout, taps, stride, relu, out_fp32, stream);
+}
+
+int spb200_test_conv_kernel(int kernel, int precision, const void* x, const void* w, const float* bias, void* y, int B, int H,
+                            int W, int cin, int cout, int taps, int stride, int relu, int out_fp32, void* stream) {
+    return test_conv_impl(kernel, precision, x, w, bias, y, B, H, W, cin, cout, taps, stride, relu, out_fp32, stream);
 }
 
 }  // extern "C"

@@ -74,6 +74,8 @@ Engine::Engine(int device) : device_(device) {
     num_sms_ = prop.multiProcessorCount;
     const char* nf = std::getenv("SPB200_NO_FUSE");
     fuse_blocks_ = !(nf && nf[0] == '1');
+    const char* nh = std::getenv("SPB200_NO_HALO");
+    use_halo_ = !(nh && nh[0] == '1');
     buf_.fill(nullptr);
 }
 
@@ -89,6 +91,7 @@ void Engine::release_workspace() {
     for (auto& op : ops_) {
         if (op.plan) { tc_plan_destroy(op.plan); op.plan = nullptr; }
         if (op.fused) { tc_block_plan_destroy(op.fused); op.fused = nullptr; }
+        if (op.halo) { tc_halo_plan_destroy(op.halo); op.halo = nullptr; }
     }
     for (auto& p : buf_) { cudaFree(p); p = nullptr; }
     cudaFree(d_prob_); d_prob_ = nullptr;
@@ -99,6 +102,7 @@ void Engine::release_weights() {
     for (auto& op : ops_) {
         if (op.plan) tc_plan_destroy(op.plan);
         if (op.fused) tc_block_plan_destroy(op.fused);
+        if (op.halo) tc_halo_plan_destroy(op.halo);
         cudaFree(op.d_bias); cudaFree(op.d_w32); cudaFree(op.d_w16);
     }
     ops_.clear();
@@ -391,11 +395,14 @@ void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
             const bool is_conv1 = op.name.size() > 6 && op.name.compare(op.name.size() - 6, 6, ".conv1") == 0;
             if (is_conv1 && i + 1 < ops_.size()) {
                 const ConvDev c1 = make_conv_dev(op), c2 = make_conv_dev(ops_[i + 1]);
-                op.fused = tc_block_plan_create(c1, &c2, precision_, op.cout_real, num_sms_);
+                if (use_halo_) op.halo = tc_halo_plan_create(c1, &c2, precision_, op.cout_real, num_sms_);
+                if (!op.halo) op.fused = tc_block_plan_create(c1, &c2, precision_, op.cout_real, num_sms_);
                 ops_[i + 1].fused_skip = true;
                 ++i;
             } else {
-                op.fused = tc_block_plan_create(make_conv_dev(op), nullptr, precision_, op.cout_real, num_sms_);
+                const ConvDev c1 = make_conv_dev(op);
+                if (use_halo_) op.halo = tc_halo_plan_create(c1, nullptr, precision_, op.cout_real, num_sms_);
+                if (!op.halo) op.fused = tc_block_plan_create(c1, nullptr, precision_, op.cout_real, num_sms_);
             }
         }
     }
@@ -526,11 +533,12 @@ void Engine::run_network(const float* img, int B, int C, int H, int W, cudaStrea
         if (precision_ == PREC_FP32) {
             prof_open(op.name, op_flops(op), 0.0, st);
             launch_conv_simt(make_conv_dev(op), st);
-        } else if (op.fused) {
+        } else if (op.fused || op.halo) {
             const bool block = i + 1 < ops_.size() && ops_[i + 1].fused_skip;
             prof_open(block ? op.name.substr(0, op.name.size() - 6) : op.name,
                       op_flops(op) + (block ? op_flops(ops_[i + 1]) : 0.0), 0.0, st);
-            launch_block_tc(op.fused, st);
+            if (op.halo) launch_halo_tc(op.halo, st);
+            else launch_block_tc(op.fused, st);
         } else {
             prof_open(op.name, op_flops(op), 0.0, st);
             launch_conv_tc(op.plan, st);

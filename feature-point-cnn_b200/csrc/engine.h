@@ -53,6 +53,7 @@ struct OpSpec {
     void* d_w16 = nullptr;        // [cout_pad][K]
     TcConvPlan* plan = nullptr;   // per workspace shape (unfused tensor-core path, kept for A/B runs)
     TcBlockPlan* fused = nullptr; // per workspace shape: this op fused with the next one (block) or alone
+    TcHaloPlan* halo = nullptr;   // per workspace shape: haloed-tile kernel (preferred over `fused` when it applies)
     bool fused_skip = false;      // executed as the second half of the previous op's fused plan
 };
 
@@ -133,6 +134,7 @@ private:
     std::array<BufSpec, BUF_COUNT> bufspec_{};
     int det_c_ = 80;
     int num_sms_ = 148;
+    bool use_halo_ = true;        // SPB200_NO_HALO=1 keeps every block on the per-tap kernel
     bool fuse_blocks_ = true;     // SPB200_NO_FUSE=1 in the environment runs one kernel per convolution
     float* d_stem_w_[2] = {nullptr, nullptr};      // [0]: 1-channel (gray-folded), [1]: 3-channel
     float* d_stem_b_ = nullptr;

@@ -23,6 +23,13 @@ TcBlockPlan* tc_block_plan_create(const ConvDev& c1, const ConvDev* c2, int oper
 void tc_block_plan_destroy(TcBlockPlan* plan);
 void launch_block_tc(const TcBlockPlan* plan, cudaStream_t st);
 
+// ---- halo_tc.cu ----------------------------------------------------------------------------------
+struct TcHaloPlan;   // stride-1 blocks with 64/128 output channels: haloed activation tiles, shared weight slabs
+// nullptr when the block does not fit (the caller falls back to tc_block_plan_create)
+TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operand_type, int real_cout, int num_sms);
+void tc_halo_plan_destroy(TcHaloPlan* plan);
+void launch_halo_tc(const TcHaloPlan* plan, cudaStream_t st);
+
 // ---- stem_tc.cu ----------------------------------------------------------------------------------
 struct StemTcPlan;
 StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type, int num_sms);

@@ -38,6 +38,8 @@ SYMBOLS = {
     'spb200_checkpoint_tensor': (_c.c_int, [_c.c_char_p, _c.c_char_p, _P, _c.c_long, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int)]),
     'spb200_test_conv_tc': (_c.c_int, [_c.c_int, _P, _P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P]),
+    'spb200_test_conv_kernel': (_c.c_int, [_c.c_int, _c.c_int, _P, _P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                           _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P]),
 }
 
 _lib = None

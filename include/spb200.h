@@ -142,6 +142,12 @@ SPB200_API int spb200_checkpoint_tensor(const char* path, const char* key, float
 SPB200_API int spb200_test_conv_tc(int precision, const void* x, const void* w, const float* bias, void* y, int B, int H, int W,
                         int cin, int cout, int taps, int stride, int relu, int out_fp32, void* stream);
 
+/* Same hook with the kernel chosen explicitly: 0 = one-convolution kernel (conv_tc.cu), 1 = persistent per-tap
+ * block kernel run as a single convolution (block_tc.cu), 2 = haloed-tile kernel (halo_tc.cu; stride 1,
+ * cout = 128 only; SPB200_E_INVALID when the convolution does not fit it). */
+SPB200_API int spb200_test_conv_kernel(int kernel, int precision, const void* x, const void* w, const float* bias, void* y, int B,
+                            int H, int W, int cin, int cout, int taps, int stride, int relu, int out_fp32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,17 +29,19 @@ def engines():
     e.close()
 
 
-def run_conv_tc(x, w, bias, taps, stride, relu, out_fp32, prec):
-    """x: B,H,W,Cin 16-bit cuda; w: Cout, taps*Cin 16-bit cuda (K order tap-major, channel-minor)."""
+def run_conv_tc(x, w, bias, taps, stride, relu, out_fp32, prec, kernel=0):
+    """x: B,H,W,Cin 16-bit cuda; w: Cout, taps*Cin 16-bit cuda (K order tap-major, channel-minor).
+    kernel: 0 = conv_tc.cu, 1 = block_tc.cu as a single convolution, 2 = halo_tc.cu."""
     from spb200 import _lib
     lib = _lib.load()
     b, h, wd, cin = x.shape
     cout = w.shape[0]
     y = torch.full((b, h // stride, wd // stride, cout), float('nan'),
                    dtype=torch.float32 if out_fp32 else x.dtype, device='cuda')
-    rc = lib.spb200_test_conv_tc(1 if prec == 'fp16' else 2, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()),
-                                 ctypes.c_void_p(bias.data_ptr()), ctypes.c_void_p(y.data_ptr()), b, h, wd, cin, cout,
-                                 taps, stride, int(relu), int(out_fp32), ctypes.c_void_p(0))
+    rc = lib.spb200_test_conv_kernel(kernel, 1 if prec == 'fp16' else 2, ctypes.c_void_p(x.data_ptr()),
+                                     ctypes.c_void_p(w.data_ptr()), ctypes.c_void_p(bias.data_ptr()),
+                                     ctypes.c_void_p(y.data_ptr()), b, h, wd, cin, cout, taps, stride, int(relu),
+                                     int(out_fp32), ctypes.c_void_p(0))
     assert rc == 0, lib.spb200_last_error(None)
     torch.cuda.synchronize()
     return y
@@ -60,9 +62,31 @@ CONV_CASES = [
 ]
 
 
+HALO_CASES = [
+    # stride 1, cout 128: the haloed-tile kernel as a single convolution (two tiles share every weight slab)
+    (1, 16, 8, 64, 128, 9, 1),       # one tile, one chunk
+    (1, 16, 16, 64, 128, 9, 1),      # one super-tile of two tiles
+    (2, 30, 40, 128, 128, 9, 1),     # ragged tiles, two chunks, odd tile count per image
+    (1, 60, 80, 256, 128, 9, 1),     # four chunks
+    (3, 30, 40, 128, 128, 1, 1),     # 1x1
+    (1, 120, 160, 64, 128, 9, 1),    # many tiles per CTA (ring wrap-around)
+]
+
+
+@pytest.mark.parametrize('kernel', [1, 2])
+@pytest.mark.parametrize('prec', ['fp16', 'bf16'])
+@pytest.mark.parametrize('case', HALO_CASES)
+def test_tcgen05_persistent_conv_kernels(case, prec, kernel):
+    check_conv_case(case, prec, kernel)
+
+
 @pytest.mark.parametrize('prec', ['fp16', 'bf16'])
 @pytest.mark.parametrize('case', CONV_CASES)
 def test_tcgen05_conv_kernel(case, prec):
+    check_conv_case(case, prec, 0)
+
+
+def check_conv_case(case, prec, kernel):
     b, h, w, cin, cout, taps, stride = case
     dt = torch.float16 if prec == 'fp16' else torch.bfloat16
     g = torch.Generator(device='cuda').manual_seed(sum(case))
@@ -74,14 +98,14 @@ def test_tcgen05_conv_kernel(case, prec):
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride, k // 2)
     ref = torch.relu(ref).permute(0, 2, 3, 1)
     for out_fp32 in (True, False):
-        y = run_conv_tc(x, wp, bias, taps, stride, True, out_fp32, prec)
+        y = run_conv_tc(x, wp, bias, taps, stride, True, out_fp32, prec, kernel)
         err = (y.float() - ref).abs()
         tol = 2e-3 if out_fp32 else (2e-2 if prec == 'fp16' else 6e-2)
         bad = int((~(err <= tol)).sum())
         if bad:
             idx = torch.nonzero(~(err <= tol))[:8].tolist()
-            print('[conv_tc %s %s out_fp32=%s] max err %.4g, %d bad of %d, first bad (b,y,x,c): %s' %
-                  (case, prec, out_fp32, float(err.nan_to_num(1e9).max()), bad, err.numel(), idx))
+            print('[conv kernel %d %s %s out_fp32=%s] max err %.4g, %d bad of %d, first bad (b,y,x,c): %s' %
+                  (kernel, case, prec, out_fp32, float(err.nan_to_num(1e9).max()), bad, err.numel(), idx))
         assert bad == 0
 
 
