@@ -18,11 +18,10 @@
 // convolution is issued while its chunk of X is resident (centre-tap view) straight into the GEMM 2
 // accumulator; an identity shortcut is added in the second epilogue.
 //
-// Warp roles (352 threads, one persistent CTA per SM): warp 0 = activation TMA producer, warp 1 = weight
-// TMA producer, warp 2 = TMEM allocator + MMA issuer, warps 3-10 = epilogue (two warps per TMEM lane
-// quarter: one per tile when T = 2, one per column half when T = 1).  With NBUF = 2 (64-channel blocks,
-// transposed-conv phases) the accumulators and Y are double buffered, so GEMM 1 of the next tile runs
-// under the epilogues of the current one.
+// Warp roles (384 threads, one persistent CTA per SM): warp 0 = activation TMA producer, warp 1 = weight
+// TMA producer, warps 2-3 = MMA issuers (one per tile of the pair; warp 2 also owns the TMEM allocation),
+// warps 4-11 = epilogue (two warps per TMEM lane quarter, one per tile).  With NBUF = 2 (transposed-conv
+// phases) the accumulator is double buffered, so the next tile pair runs under the epilogue of this one.
 #include <cuda.h>
 
 #include <algorithm>
@@ -44,22 +43,29 @@ constexpr int kHaloBufBytes = 23552;                        // rounded up to a m
 constexpr int kHaloSbo = kHaloG * 128;                      // 8-pixel groups are one haloed row apart
 constexpr int kMaxSteps = 48;
 constexpr int kMaxChunks = 8;
-constexpr int kHaloThreads = 352;
+__host__ __device__ constexpr int halo_threads(int T) { return (2 + T + 8) * 32; }   // 2 producers, T MMA issuers, 8 epilogue warps
 
-// One weight slab [N x 64 K] and the MMAs that consume it.
-struct HaloStep {
-    uint16_t kcoord;     // K coordinate / 64 in the weight tensor (W1 for gemm 0, W2 otherwise)
-    uint16_t a_off16;    // gemm 0/1: byte offset / 16 of the tap view inside the haloed box; gemm 2: of the Y chunk
-    uint8_t gemm;        // 0: 3x3 taps -> D1;  1: 1x1 shortcut (centre view) -> D2;  2: 1x1 over Y -> D2
-    uint8_t nkk;         // K = 16 MMA steps in this slab (1..4)
-    uint8_t flags;       // bit 0: first slab of an activation chunk; bit 1: last slab using it
-    uint8_t pad;
-};
+// One weight slab [N x 64 K] and the MMAs that consume it, packed into 64 bits so that the issuing warps fetch a
+// step with one constant load and a few bit-field extracts (their instruction count is the bottleneck):
+//   bits  0-15  a_lo    descriptor-low offset (bytes / 16) of the A view: tap view in the haloed box, or Y chunk
+//   bits 16-31  w_lo    descriptor-low offset of the slab in the weight ring (slot * N * 128 / 16)
+//   bits 32-35  slot    weight ring slot (static: step index modulo the ring size)
+//   bits 36-37  gemm    0: 3x3 taps -> D1;  1: 1x1 shortcut (centre view) -> D2;  2: 1x1 over Y -> D2
+//   bits 38-40  nkk     K = 16 MMA steps in this slab (1..4)
+//   bit  41     first slab of an activation chunk (wait for it);  bit 42  last slab using it (release it)
+//   bit  43     acc0    accumulate flag of the first MMA of the slab
+//   bits 48-59  kcoord  K coordinate / 64 in the weight tensor (W1 for gemm 0, W2 otherwise)
+using HaloStep = unsigned long long;
+__host__ __device__ constexpr HaloStep halo_step(unsigned a_lo, unsigned w_lo, unsigned slot, unsigned gemm, unsigned nkk,
+                                                 unsigned first, unsigned last, unsigned acc0, unsigned kcoord) {
+    return (HaloStep)a_lo | ((HaloStep)w_lo << 16) | ((HaloStep)slot << 32) | ((HaloStep)gemm << 36) | ((HaloStep)nkk << 38) |
+           ((HaloStep)first << 41) | ((HaloStep)last << 42) | ((HaloStep)acc0 << 43) | ((HaloStep)kcoord << 48);
+}
 
 struct HaloParams {
     CUtensorMap tmA[kMaxSegs];
     CUtensorMap tmW1, tmW2;
-    HaloStep steps[kMaxSteps];
+    HaloStep steps[kMaxSteps + 1];   // one spare entry: the issuing loop prefetches step e + 1
     int nsteps, n1steps;           // all slabs; slabs of GEMM 1 + shortcut (they come first)
     int chunk_seg[kMaxChunks], chunk_c0[kMaxChunks], nchunks;
     int lo_s, lo_g;                // origin of the haloed box relative to the tile origin
@@ -73,48 +79,37 @@ struct HaloParams {
     void* dst;
     int res_C, dst_H, dst_W, dst_C, dst_stride, dst_off_y, dst_off_x;
     int relu, dst_fp32, n_mma;
-    unsigned long long* stats;     // debug (SPB200_HALO_STATS=1): [grid][16] cycles spent waiting per role, else null
 };
 
-// mbarrier wait that adds the cycles it spent to a debug counter when stats are collected
-__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long* acc) {
-    if (acc) {
-        const long long t0 = clock64();
-        mbar_wait(bar, parity);
-        *acc += (unsigned long long)(clock64() - t0);
-    } else {
-        mbar_wait(bar, parity);
-    }
-}
-
 template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, typename Tp>
-__global__ void __launch_bounds__(kHaloThreads, 1) halo_tc_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __grid_constant__ HaloParams p) {
     constexpr int kWBytes = N * 128;
-    constexpr int kYTile = (N / 64) * 16384;
     constexpr uint32_t kAccCols = NBUF * T * N;
     constexpr uint32_t kTmemCols = (FUSED ? 2 : 1) * kAccCols;
     static_assert(kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
     static_assert(!(FUSED && NBUF == 2) || WRES, "pipelined GEMM 2 needs resident weights (slab order)");
+    static_assert(T == 2 || !FUSED, "the in-place Y write-back assumes one epilogue warp per lane quarter and tile");
 
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full[SW], w_empty[SW];
-    __shared__ __align__(8) uint64_t d1_full[NBUF], d1_empty[NBUF], y_full[NBUF], y_empty[NBUF], d2_full[NBUF], d2_empty[NBUF];
+    __shared__ __align__(8) uint64_t d1_full[NBUF], d1_empty[NBUF], y_full[NBUF], d2_full[NBUF], d2_empty[NBUF];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias1[N], s_bias2[N];
 
     uint8_t* a_ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023);
     uint8_t* w_ring = a_ring + SA * T * kHaloBufBytes;
-    uint8_t* y_buf = w_ring + SW * kWBytes;                 // [NBUF][T][N/64][128 rows][128 B]
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so the role loops below run on the
+    // uniform datapath (loop counters, ring state, descriptors in uniform registers) instead of R2UR round trips
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
     const uint32_t idesc = (1u << 4) | (OperandFmt<Tp>::value << 7) | (OperandFmt<Tp>::value << 10) |
                            ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int n_local = (p.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], T); }
+        for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], T); }
         for (int b = 0; b < NBUF; ++b) {
-            mbar_init(&d1_full[b], 1); mbar_init(&y_empty[b], 1); mbar_init(&d2_full[b], 1);
+            mbar_init(&d1_full[b], T); mbar_init(&d2_full[b], T);
             mbar_init(&d1_empty[b], 8); mbar_init(&y_full[b], 8); mbar_init(&d2_empty[b], 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -126,7 +121,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) halo_tc_kernel(const __grid_c
         if (FUSED) prefetch_tmap(&p.tmW2);
     }
     if (warp == 2) tmem_alloc(&tmem_slot, kTmemCols);
-    for (int i = threadIdx.x; i < N; i += kHaloThreads) {
+    for (int i = threadIdx.x; i < N; i += halo_threads(T)) {
         s_bias1[i] = p.bias1[i];
         s_bias2[i] = FUSED ? p.bias2[i] : 0.f;
     }
@@ -134,10 +129,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) halo_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
-    unsigned long long st_acc[6] = {0, 0, 0, 0, 0, 0};
-    const bool stats = p.stats != nullptr;
-#define ST(i) (stats ? &st_acc[i] : nullptr)
-    const long long t_begin = stats ? clock64() : 0;
 
     // The three issuing roles run as WHOLE warps: loop counters, ring indices and phases are warp-uniform
     // (they live in uniform registers), every lane polls the mbarriers, and only the instructions that must come
@@ -159,7 +150,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) halo_tc_kernel(const __grid_c
                 cg[t] = (tt % p.tiles_g) * 8 + p.lo_g;
             }
             for (int ci = 0; ci < p.nchunks; ++ci) {
-                mbar_wait_t(&a_empty[sa], pha ^ 1u, ST(0));
+                mbar_wait(&a_empty[sa], pha ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(&a_full[sa], (uint32_t)(T * kHaloLoadBytes));
                     const CUtensorMap* tm = &p.tmA[p.chunk_seg[ci]];
@@ -167,34 +158,41 @@ __global__ void __launch_bounds__(kHaloThreads, 1) halo_tc_kernel(const __grid_c
                     for (int t = 0; t < T; ++t)
                         tma_load_4d(a_ring + (sa * T + t) * kHaloBufBytes, tm, &a_full[sa], p.chunk_c0[ci], cg[t], cs[t], cimg[t]);
                 }
-                __syncwarp();
                 if (++sa == SA) { sa = 0; pha ^= 1u; }
             }
         }
-        if (stats && lane == 0) { p.stats[blockIdx.x * 16 + 6] = st_acc[0]; }
     } else if (warp == 1) {
         // ============================ weight producer ============================
-        int sw = 0;
-        uint32_t phw = 0;
+        uint32_t eph = 0;                                      // per-slot parity of the next w_empty wait
+        const uint32_t bar_full = smem_u32(&w_full[0]), bar_empty = smem_u32(&w_empty[0]), ring = smem_u32(w_ring);
         const int passes = WRES ? min(n_local, 1) : n_local;
         for (int j = 0; j < passes; ++j) {
             for (int e = 0; e < p.nsteps; ++e) {
                 const HaloStep s = p.steps[e];
-                if (!WRES) mbar_wait_t(&w_empty[sw], phw ^ 1u, ST(0));
+                const uint32_t hi = (uint32_t)(s >> 32), slot = hi & 15u;
+                if (!WRES) { mbar_wait_a(bar_empty + slot * 8, ((eph >> slot) & 1u) ^ 1u); eph ^= 1u << slot; }
                 if (elect_one()) {
-                    mbar_expect_tx(&w_full[sw], (uint32_t)kWBytes);
-                    tma_load_2d(w_ring + sw * kWBytes, s.gemm == 0 ? &p.tmW1 : &p.tmW2, &w_full[sw], (int)s.kcoord * 64, 0);
+                    mbar_expect_tx_a(bar_full + slot * 8, (uint32_t)kWBytes);
+                    tma_load_2d_a(ring + slot * kWBytes, ((hi >> 4) & 3u) == 0 ? &p.tmW1 : &p.tmW2, bar_full + slot * 8,
+                                  (int)((hi >> 16) & 0xfffu) * 64, 0);
                 }
-                __syncwarp();
-                if (++sw == SW) { sw = 0; phw ^= 1u; }
             }
         }
-        if (stats && lane == 0) { p.stats[blockIdx.x * 16 + 7] = st_acc[0]; }
-    } else if (warp == 2) {
-        // ============================ MMA issuer ============================
-        int sa = 0, sw = 0;
-        uint32_t pha = 0, phw = 0;
-        const uint32_t a_base = smem_u32(a_ring), w_base = smem_u32(w_ring), y_base = smem_u32(y_buf);
+    } else if (warp < 2 + T) {
+        // ============================ MMA issuers: one warp per tile ============================
+        // Non-MMA instructions of an issuing warp are not hidden behind the tensor pipe (measured: every branch, wait
+        // or commit between two tcgen05.mma adds its latency), so (a) each tile of the pair has its own issuing warp -
+        // while one polls a barrier or commits, the other feeds the pipe with independent MMAs - and (b) a step costs
+        // one 64-bit constant load (prefetched), bit-field extracts, one wait, four MMAs whose descriptors differ by
+        // immediates, and one commit; ring slots are static per step, their phases are a bit mask.
+        const int mt = warp - 2;
+        int sa = 0;
+        uint32_t pha = 0, wph = 0;
+        const uint32_t a_lo_base = umma_desc_lo(smem_u32(a_ring) + mt * kHaloBufBytes);
+        const uint32_t w_lo_base = umma_desc_lo(smem_u32(w_ring));
+        const uint32_t d_base = tmem_base + (uint32_t)(mt * N);
+        const uint32_t bar_wfull = smem_u32(&w_full[0]), bar_wempty = smem_u32(&w_empty[0]);
+        const uint32_t bar_afull = smem_u32(&a_full[0]), bar_aempty = smem_u32(&a_empty[0]);
         constexpr uint32_t kHiA = ((uint32_t)kHaloSbo >> 4) | (1u << 14) | (2u << 29);   // SBO = haloed row pitch
         constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);                // SBO = 1024 (dense tile)
         constexpr int LAG = (FUSED && NBUF == 2) ? 1 : 0;
@@ -202,87 +200,70 @@ __global__ void __launch_bounds__(kHaloThreads, 1) halo_tc_kernel(const __grid_c
             if (j < n_local) {
                 const int b = j % NBUF;
                 const uint32_t ph = (uint32_t)(j / NBUF) & 1u;
-                mbar_wait_t(&d1_empty[b], ph ^ 1u, ST(0));          // epilogue has drained D1[b]
-                if (FUSED && p.has_ds) mbar_wait_t(&d2_empty[b], ph ^ 1u, ST(0));
+                // fused: D1[b] holds Y until GEMM 2 of its previous use has read it, and that GEMM 2 was issued by this
+                // warp before this point (MMAs of one thread execute in order): no barrier needed
+                if (!FUSED) mbar_wait(&d1_empty[b], ph ^ 1u);          // epilogue has drained D1[b]
+                if (FUSED && p.has_ds) mbar_wait(&d2_empty[b], ph ^ 1u);
                 tc_fence_after();
-                uint32_t acc1 = 0, accd = 0;
+                HaloStep rec = p.steps[0];
                 for (int e = 0; e < p.n1steps; ++e) {
-                    const HaloStep s = p.steps[e];
-                    if (s.flags & 1) mbar_wait_t(&a_full[sa], pha, ST(1));
-                    const int slot = WRES ? e : sw;
-                    mbar_wait_t(&w_full[slot], WRES ? 0u : phw, ST(2));
+                    const HaloStep s = rec;
+                    rec = p.steps[e + 1];
+                    const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+                    const uint32_t slot = hi & 15u, nkk = (hi >> 6) & 7u, acc0 = (hi >> 11) & 1u;
+                    if (hi & (1u << 9)) mbar_wait_a(bar_afull + sa * 8, pha);
+                    if (!WRES || j == 0) mbar_wait_a(bar_wfull + slot * 8, (wph >> slot) & 1u);
                     tc_fence_after();
-                    const uint32_t blo = umma_desc_lo(w_base + slot * kWBytes);
-                    const uint32_t alo = umma_desc_lo(a_base + sa * T * kHaloBufBytes + (uint32_t)s.a_off16 * 16u);
-                    const uint32_t acc = s.gemm == 0 ? acc1 : accd;
-                    const uint32_t d0 = tmem_base + (s.gemm == 0 ? 0u : kAccCols) + (uint32_t)(b * T * N);
+                    const uint32_t alo = a_lo_base + (uint32_t)(sa * T * (kHaloBufBytes >> 4)) + (lo & 0xffffu);
+                    const uint32_t blo = w_lo_base + (lo >> 16);
+                    const uint32_t d = d_base + (((hi >> 4) & 3u) == 0 ? 0u : kAccCols) + (uint32_t)(b * T * N);
                     if (elect_one()) {
-#pragma unroll
-                        for (int t = 0; t < T; ++t) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                if (kk < s.nkk)
-                                    umma_f16_w(d0 + t * N, alo + t * (kHaloBufBytes >> 4) + kk * 2, kHiA, blo + kk * 2, kHiB, idesc,
-                                               acc | (uint32_t)kk);
-                        }
-                        if (!WRES) umma_commit(&w_empty[sw]);
-                        if (s.flags & 2) umma_commit(&a_empty[sa]);
+                        umma_f16_w(d, alo, kHiA, blo, kHiB, idesc, acc0);
+                        if (nkk > 1) umma_f16_w(d, alo + 2, kHiA, blo + 2, kHiB, idesc, 1u);
+                        if (nkk > 2) umma_f16_w(d, alo + 4, kHiA, blo + 4, kHiB, idesc, 1u);
+                        if (nkk > 3) umma_f16_w(d, alo + 6, kHiA, blo + 6, kHiB, idesc, 1u);
+                        if (!WRES) umma_commit_a(bar_wempty + slot * 8);
+                        if (hi & (1u << 10)) umma_commit_a(bar_aempty + sa * 8);
                     }
-                    __syncwarp();
-                    if (s.gemm == 0) acc1 = 1u; else accd = 1u;
-                    if (!WRES) { if (++sw == SW) { sw = 0; phw ^= 1u; } }
-                    if (s.flags & 2) { if (++sa == SA) { sa = 0; pha ^= 1u; } }
+                    if (!WRES) wph ^= 1u << slot;
+                    if (hi & (1u << 10)) { if (++sa == SA) { sa = 0; pha ^= 1u; } }
                 }
                 if (elect_one()) umma_commit(&d1_full[b]);
-                __syncwarp();
             }
             if (FUSED && j >= LAG) {
                 const int jj = j - LAG;
                 const int b = jj % NBUF;
                 const uint32_t ph = (uint32_t)(jj / NBUF) & 1u;
-                mbar_wait_t(&y_full[b], ph, ST(3));                 // Y written by the epilogue warps
-                if (!p.has_ds) mbar_wait_t(&d2_empty[b], ph ^ 1u, ST(3));
+                mbar_wait(&y_full[b], ph);                 // Y written by the epilogue warps
+                if (!p.has_ds) mbar_wait(&d2_empty[b], ph ^ 1u);
                 tc_fence_after();
-                uint32_t acc = p.has_ds ? 1u : 0u;
                 for (int e = p.n1steps; e < p.nsteps; ++e) {
                     const HaloStep s = p.steps[e];
-                    const int slot = WRES ? e : sw;
-                    mbar_wait_t(&w_full[slot], WRES ? 0u : phw, ST(4));
+                    const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+                    const uint32_t slot = hi & 15u, nkk = (hi >> 6) & 7u, acc0 = (hi >> 11) & 1u;
+                    if (!WRES || jj == 0) mbar_wait_a(bar_wfull + slot * 8, (wph >> slot) & 1u);
                     tc_fence_after();
-                    const uint32_t blo = umma_desc_lo(w_base + slot * kWBytes);
-                    const uint32_t alo = umma_desc_lo(y_base + b * T * kYTile + (uint32_t)s.a_off16 * 16u);
-                    const uint32_t d0 = tmem_base + kAccCols + (uint32_t)(b * T * N);
+                    // A = Y, 16-bit, packed in place over the first N/2 columns of D1[b] by the epilogue warps
+                    const uint32_t ya = d_base + (uint32_t)(b * T * N) + (lo & 0xffffu);
+                    const uint32_t blo = w_lo_base + (lo >> 16);
+                    const uint32_t d = d_base + kAccCols + (uint32_t)(b * T * N);
                     if (elect_one()) {
-#pragma unroll
-                        for (int t = 0; t < T; ++t) {
-#pragma unroll
-                            for (int kk = 0; kk < 4; ++kk)
-                                if (kk < s.nkk)
-                                    umma_f16_w(d0 + t * N, alo + t * (kYTile >> 4) + kk * 2, kHiB, blo + kk * 2, kHiB, idesc,
-                                               acc | (uint32_t)kk);
-                        }
-                        if (!WRES) umma_commit(&w_empty[sw]);
+                        umma_f16_ts(d, ya, blo, kHiB, idesc, acc0);
+                        if (nkk > 1) umma_f16_ts(d, ya + 8, blo + 2, kHiB, idesc, 1u);
+                        if (nkk > 2) umma_f16_ts(d, ya + 16, blo + 4, kHiB, idesc, 1u);
+                        if (nkk > 3) umma_f16_ts(d, ya + 24, blo + 6, kHiB, idesc, 1u);
+                        if (!WRES) umma_commit_a(bar_wempty + slot * 8);
                     }
-                    __syncwarp();
-                    acc = 1u;
-                    if (!WRES) { if (++sw == SW) { sw = 0; phw ^= 1u; } }
+                    if (!WRES) wph ^= 1u << slot;
                 }
-                if (elect_one()) {
-                    umma_commit(&d2_full[b]);
-                    umma_commit(&y_empty[b]);
-                }
-                __syncwarp();
+                if (elect_one()) umma_commit(&d2_full[b]);
             }
         }
-        if (stats && lane == 0) {
-            unsigned long long* o = p.stats + blockIdx.x * 16;
-            o[0] = (unsigned long long)(clock64() - t_begin);
-            for (int i = 0; i < 5; ++i) o[1 + i] = st_acc[i];
-        }
+        __syncwarp();
     } else {
         // ============================ epilogue ============================
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
-        const int eh = (warp - 3) >> 2;                        // 0/1: tile (T = 2) or column half (T = 1)
+        const int eh = (warp - (2 + T)) >> 2;                        // 0/1: tile (T = 2) or column half (T = 1)
         const int row = q * 32 + lane;                         // GEMM row = TMEM lane
         const int ti = row >> 3, tr = row & 7;                 // slow row, pixel within the group
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -306,33 +287,29 @@ __global__ void __launch_bounds__(kHaloThreads, 1) halo_tc_kernel(const __grid_c
                                 (ox * p.dst_stride + p.dst_off_x);
             const uint32_t tmem_d1 = tmem_base + (uint32_t)((b * T + t) * N) + lane_off;
             const uint32_t tmem_d2 = tmem_d1 + kAccCols;
-            mbar_wait_t(&d1_full[b], ph, ST(0));
+            mbar_wait(&d1_full[b], ph);
             tc_fence_after();
             if (FUSED) {
-                mbar_wait_t(&y_empty[b], ph ^ 1u, ST(1));               // GEMM 2 of the previous use has finished reading Y[b]
-                uint8_t* yrow = y_buf + (b * T + t) * kYTile + row * 128;
+                // Y = relu(D1 + b1) rounded to 16 bits, written back IN PLACE: block k (fp32 columns 32k..32k+31, all
+                // in registers by then) becomes packed columns 16k..16k+15 of the same lanes, which blocks < k no longer need
 #pragma unroll 1
                 for (int blk = blk_lo; blk < blk_hi; ++blk) {
                     const int c0 = blk * 32;
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_d1 + (uint32_t)c0, r);
                     tmem_ld_wait();
-                    uint8_t* ychunk = yrow + (c0 >> 6) * 16384;
+                    uint32_t y[16];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        float v[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = fmaxf(__uint_as_float(r[jj * 8 + e]) + s_bias1[c0 + jj * 8 + e], 0.f);
-                        const int cj = ((c0 & 63) >> 3) + jj;
-                        *reinterpret_cast<uint4*>(ychunk + ((cj ^ (row & 7)) << 4)) =
-                            make_uint4(pack2<Tp>(v[0], v[1]), pack2<Tp>(v[2], v[3]), pack2<Tp>(v[4], v[5]), pack2<Tp>(v[6], v[7]));
-                    }
+                    for (int e = 0; e < 16; ++e)
+                        y[e] = pack2<Tp>(fmaxf(__uint_as_float(r[2 * e]) + s_bias1[c0 + 2 * e], 0.f),
+                                         fmaxf(__uint_as_float(r[2 * e + 1]) + s_bias1[c0 + 2 * e + 1], 0.f));
+                    tmem_st_32x16(tmem_d1 + (uint32_t)(c0 >> 1), y);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&d1_empty[b]); mbar_arrive(&y_full[b]); }
-                mbar_wait_t(&d2_full[b], ph, ST(2));
+                if (lane == 0) mbar_arrive(&y_full[b]);
+                mbar_wait(&d2_full[b], ph);
                 tc_fence_after();
             }
             const uint32_t tmem_out = FUSED ? tmem_d2 : tmem_d1;
@@ -382,13 +359,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) halo_tc_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(FUSED ? &d2_empty[b] : &d1_empty[b]);
         }
-        if (stats && warp == 3 && lane == 0) {
-            unsigned long long* o = p.stats + blockIdx.x * 16;
-            o[8] = st_acc[0]; o[9] = st_acc[1]; o[10] = st_acc[2];
-            o[11] = (unsigned long long)(clock64() - t_begin);
-        }
     }
-#undef ST
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
@@ -408,41 +379,26 @@ struct TcHaloPlan {
 template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, typename Tp>
 static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
     auto kern = halo_tc_kernel<N, T, NBUF, SA, SW, FUSED, WRES, Tp>;
-    const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + (FUSED ? (size_t)NBUF * T * (N / 64) * 16384 : 0) + 1024;
+    const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + 1024;
     static bool configured = false;       // per instantiation
     if (!configured) {
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    kern<<<plan->grid, kHaloThreads, smem, st>>>(plan->params);
+    kern<<<plan->grid, halo_threads(T), smem, st>>>(plan->params);
     SPB_CHECK_LAUNCH();
-    if (plan->params.stats) {
-        SPB_CUDA(cudaStreamSynchronize(st));
-        std::vector<unsigned long long> h((size_t)plan->grid * 16);
-        SPB_CUDA(cudaMemcpy(h.data(), plan->params.stats, h.size() * 8, cudaMemcpyDeviceToHost));
-        double a[16] = {0};
-        for (int c = 0; c < plan->grid; ++c)
-            for (int i = 0; i < 16; ++i) a[i] += (double)h[(size_t)c * 16 + i] / plan->grid;
-        const HaloParams& q = plan->params;
-        const double nloc = (double)q.n_super / plan->grid;
-        std::fprintf(stderr,
-                     "[halo stats] N=%d T=%d steps=%d supertiles/CTA=%.1f | per super-tile (cycles): mma total %.0f = wait acc-free %.0f + a_full %.0f + "
-                     "w_full(g1) %.0f + y_full %.0f + w_full(g2) %.0f + issue %.0f | producers wait: a_empty %.0f w_empty %.0f | epilogue: "
-                     "total %.0f wait d1_full %.0f y_empty %.0f d2_full %.0f\n",
-                     N, T, q.nsteps, nloc, a[0] / nloc, a[1] / nloc, a[2] / nloc, a[3] / nloc, a[4] / nloc, a[5] / nloc,
-                     (a[0] - a[1] - a[2] - a[3] - a[4] - a[5]) / nloc, a[6] / nloc, a[7] / nloc, a[11] / nloc, a[8] / nloc, a[9] / nloc,
-                     a[10] / nloc);
-    }
 }
 
-constexpr int kHaloResidentSlabs = 11;
+constexpr int kHaloResidentSlabs = 11;   // variant 0: every slab of a 64-channel block stays in shared memory
+constexpr int kHaloRing1 = 8;            // variant 1: weight ring slots (16 KB each)
+constexpr int kHaloRing2 = 6;            // variant 2
 
 template <typename Tp>
 static void launch_halo_v(const TcHaloPlan* plan, cudaStream_t st) {
     switch (plan->variant) {
-        case 0: launch_halo_t<64, 1, 2, 3, kHaloResidentSlabs, true, true, Tp>(plan, st); break;
-        case 1: launch_halo_t<128, 2, 1, 2, 4, true, false, Tp>(plan, st); break;
-        case 2: launch_halo_t<128, 2, 2, 2, 6, false, false, Tp>(plan, st); break;
+        case 0: launch_halo_t<64, 2, 2, 2, kHaloResidentSlabs, true, true, Tp>(plan, st); break;
+        case 1: launch_halo_t<128, 2, 1, 2, kHaloRing1, true, false, Tp>(plan, st); break;
+        case 2: launch_halo_t<128, 2, 2, 2, kHaloRing2, false, false, Tp>(plan, st); break;
         default: throw std::invalid_argument("tcgen05 halo block: bad variant");
     }
 }
@@ -453,10 +409,7 @@ void launch_halo_tc(const TcHaloPlan* plan, cudaStream_t st) {
     else launch_halo_v<__nv_bfloat16>(plan, st);
 }
 
-void tc_halo_plan_destroy(TcHaloPlan* plan) {
-    if (plan && plan->params.stats) cudaFree(plan->params.stats);
-    delete plan;
-}
+void tc_halo_plan_destroy(TcHaloPlan* plan) { delete plan; }
 
 // Returns nullptr when the block does not fit this kernel (stride 2, 256 channels, ...): the caller then
 // uses the per-tap kernel of block_tc.cu.  Arguments as tc_block_plan_create.
@@ -487,7 +440,7 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     const CUtensorMapDataType dt = operand_type == PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     plan->operand_type = operand_type;
     plan->variant = N == 64 ? 0 : (c2 ? 1 : 2);
-    const int T = N == 64 ? 1 : 2;
+    const int T = 2;
 
     // tile orientation: 16 x 8 (group axis = x) or 8 x 16 (group axis = y), whichever needs fewer tiles
     const long n0 = (long)((c1.OH + 15) / 16) * ((c1.OW + 7) / 8), n1 = (long)((c1.OH + 7) / 8) * ((c1.OW + 15) / 16);
@@ -518,6 +471,12 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     }
 
     int nsteps = 0, nchunks = 0;
+    const int ring = plan->variant == 0 ? kHaloResidentSlabs : (plan->variant == 1 ? kHaloRing1 : kHaloRing2);
+    bool first_g1 = true, first_ds = true;
+    auto add_step = [&](unsigned a_lo, unsigned gemm, unsigned nkk, bool first, bool last, bool acc0, int kcoord) {
+        const unsigned slot = (unsigned)(nsteps % ring);
+        p.steps[nsteps++] = halo_step(a_lo, slot * (unsigned)(N * 128 / 16), slot, gemm, nkk, first, last, acc0, (unsigned)kcoord);
+    };
     for (int s = 0; s < c1.nseg; ++s) {
         const SegDev& sg = c1.seg[s];
         const int nch = sg.cin / 64;
@@ -538,18 +497,13 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
             const int nkk = c == nch - 1 ? kk_last : 4;
             for (int t = 0; t < sg.ntaps; ++t) {
                 if (nsteps >= kMaxSteps) return nullptr;
-                HaloStep& e = p.steps[nsteps++];
-                e.kcoord = (uint16_t)(sg.koff / 64 + t * nch + c);
-                e.a_off16 = view16(sg.dy[t], sg.dx[t]);
-                e.gemm = 0; e.nkk = (uint8_t)nkk;
-                e.flags = (uint8_t)((t == 0 ? 1 : 0) | ((t == sg.ntaps - 1 && !ds) ? 2 : 0));
+                add_step(view16(sg.dy[t], sg.dx[t]), 0, nkk, t == 0, t == sg.ntaps - 1 && !ds, !first_g1, sg.koff / 64 + t * nch + c);
+                first_g1 = false;
             }
             if (ds) {
                 if (nsteps >= kMaxSteps) return nullptr;
-                HaloStep& e = p.steps[nsteps++];
-                e.kcoord = (uint16_t)(ds->koff / 64 + c);
-                e.a_off16 = view16(0, 0);
-                e.gemm = 1; e.nkk = (uint8_t)nkk; e.flags = 2;
+                add_step(view16(0, 0), 1, nkk, 0, 1, !first_ds, ds->koff / 64 + c);
+                first_ds = false;
             }
         }
         // activations: dims {C, group axis, slow axis, image}
@@ -581,10 +535,7 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         if (c2->seg[0].koff != 0) return nullptr;
         for (int c = 0; c < ych; ++c) {
             if (nsteps >= kMaxSteps) return nullptr;
-            HaloStep& e = p.steps[nsteps++];
-            e.kcoord = (uint16_t)c;
-            e.a_off16 = (uint16_t)(c * 16384 / 16);
-            e.gemm = 2; e.nkk = (uint8_t)(c == ych - 1 ? y_kk_last : 4); e.flags = 0;
+            add_step((unsigned)(c * 32), 2, c == ych - 1 ? y_kk_last : 4, 0, 0, p.has_ds || c > 0, c);
         }
         cuuint64_t dims[2] = {(cuuint64_t)c2->K, (cuuint64_t)N};
         cuuint64_t str[1] = {(cuuint64_t)c2->K * 2};
@@ -601,11 +552,6 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     p.res_C = last.res_C; p.dst_H = last.dst_H; p.dst_W = last.dst_W; p.dst_C = last.dst_C;
     p.dst_stride = last.dst_stride; p.dst_off_y = last.dst_off_y; p.dst_off_x = last.dst_off_x;
     p.relu = last.relu; p.dst_fp32 = last.dst_fp32;
-    const char* se = std::getenv("SPB200_HALO_STATS");
-    if (se && se[0] == '1') {
-        SPB_CUDA(cudaMalloc((void**)&p.stats, (size_t)plan->grid * 16 * sizeof(unsigned long long)));
-        SPB_CUDA(cudaMemset(p.stats, 0, (size_t)plan->grid * 16 * sizeof(unsigned long long)));
-    }
     return plan.release();
 }
 
