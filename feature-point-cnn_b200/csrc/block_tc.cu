@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
 
     uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_y = ring + STAGES * kStageBytes;            // [kYChunks][128 rows][128 B]
-    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    // shuffle: makes the warp index warp-uniform for the compiler (role loops then run on the uniform datapath)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
     const uint32_t idesc = (1u << 4) | (OperandFmt<T>::value << 7) | (OperandFmt<T>::value << 10) |
                            ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const bool fused = p.ksteps2 > 0;
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
 
     if (warp == 0) {
         // ============================ TMA producer ============================
-        if (lane == 0) {
+        // whole warp runs the loops; only the TMA issue sits under elect.sync (see halo_tc.cu)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -113,9 +115,11 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                         for (int c = 0; c < sg.nchunks; ++c, ++k1) {
                             mbar_wait(&empty_bar[stage], phase ^ 1u);
                             uint8_t* a_dst = ring + stage * kStageBytes;
-                            mbar_expect_tx(&full_bar[stage], (uint32_t)kStageBytes);
-                            tma_load_5d(a_dst, &p.tmA[s], &full_bar[stage], cc + c * 64, cx, cp, cy, img);
-                            tma_load_2d(a_dst + kBlkABytes, &p.tmW1, &full_bar[stage], k1 * 64, 0);
+                            if (elect_one()) {
+                                mbar_expect_tx(&full_bar[stage], (uint32_t)kStageBytes);
+                                tma_load_5d(a_dst, &p.tmA[s], &full_bar[stage], cc + c * 64, cx, cp, cy, img);
+                                tma_load_2d(a_dst + kBlkABytes, &p.tmW1, &full_bar[stage], k1 * 64, 0);
+                            }
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
                     }
@@ -125,8 +129,10 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                     for (int c = 0; c < p.y_chunks; ++c, ++k2) {           // A = Y (already in smem): weights only
                         mbar_wait(&empty_bar[stage], phase ^ 1u);
                         uint8_t* a_dst = ring + stage * kStageBytes;
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)kBBytes);
-                        tma_load_2d(a_dst + kBlkABytes, &p.tmW2, &full_bar[stage], k2 * 64, 0);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[stage], (uint32_t)kBBytes);
+                            tma_load_2d(a_dst + kBlkABytes, &p.tmW2, &full_bar[stage], k2 * 64, 0);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                     for (int s = 0; s < p.nds; ++s) {                      // 1x1 shortcut: centre pixels of X
@@ -134,9 +140,11 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                         for (int c = 0; c < sg.nchunks; ++c, ++k2) {
                             mbar_wait(&empty_bar[stage], phase ^ 1u);
                             uint8_t* a_dst = ring + stage * kStageBytes;
-                            mbar_expect_tx(&full_bar[stage], (uint32_t)kStageBytes);
-                            tma_load_5d(a_dst, &p.tmA[s], &full_bar[stage], c * 64, x0, 0, y0, img);
-                            tma_load_2d(a_dst + kBlkABytes, &p.tmW2, &full_bar[stage], k2 * 64, 0);
+                            if (elect_one()) {
+                                mbar_expect_tx(&full_bar[stage], (uint32_t)kStageBytes);
+                                tma_load_5d(a_dst, &p.tmA[s], &full_bar[stage], c * 64, x0, 0, y0, img);
+                                tma_load_2d(a_dst + kBlkABytes, &p.tmW2, &full_bar[stage], k2 * 64, 0);
+                            }
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
                     }
@@ -146,10 +154,11 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
         __syncwarp();
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        if (lane == 0) {
+        {
             int stage = 0;
             uint32_t phase = 0, tph = 0;
             const uint32_t y_addr = smem_u32(s_y);
+            constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);     // descriptor high word: SBO 1024, SWIZZLE_128B
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, tph ^= 1u) {
                 mbar_wait(&d1_empty, tph ^ 1u);            // epilogue 1 of the previous tile has drained D1
                 tc_fence_after();
@@ -161,16 +170,20 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                             mbar_wait(&full_bar[stage], phase);
                             tc_fence_after();
                             const uint32_t a_addr = smem_u32(ring + stage * kStageBytes), b_addr = a_addr + kBlkABytes;
+                            const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
                             const int nkk = (c == sg.nchunks - 1) ? sg.kk_last : 4;
-                            for (int kk = 0; kk < nkk; ++kk) {
-                                umma_f16(tmem_d1, umma_smem_desc(a_addr + kk * 32), umma_smem_desc(b_addr + kk * 32), idesc, acc);
-                                acc = 1u;
+                            if (elect_one()) {
+                                umma_f16_w(tmem_d1, alo, kHi, blo, kHi, idesc, acc);
+                                if (nkk > 1) umma_f16_w(tmem_d1, alo + 2, kHi, blo + 2, kHi, idesc, 1u);
+                                if (nkk > 2) umma_f16_w(tmem_d1, alo + 4, kHi, blo + 4, kHi, idesc, 1u);
+                                if (nkk > 3) umma_f16_w(tmem_d1, alo + 6, kHi, blo + 6, kHi, idesc, 1u);
+                                umma_commit(&empty_bar[stage]);
                             }
-                            umma_commit(&empty_bar[stage]);
+                            acc = 1u;
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
                 }
-                umma_commit(&d1_full);
+                if (elect_one()) umma_commit(&d1_full);
                 if (fused) {
                     mbar_wait(&y_full, tph);               // Y tile written by the epilogue warps
                     mbar_wait(&d2_empty, tph ^ 1u);        // epilogue 2 of the previous tile has drained D2
@@ -181,12 +194,16 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                         tc_fence_after();
                         const uint32_t b_addr = smem_u32(ring + stage * kStageBytes) + kBlkABytes;
                         const uint32_t a_addr = y_addr + c * kBlkABytes;
+                        const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
                         const int nkk = (c == p.y_chunks - 1) ? p.y_kk_last : 4;
-                        for (int kk = 0; kk < nkk; ++kk) {
-                            umma_f16(tmem_d2, umma_smem_desc(a_addr + kk * 32), umma_smem_desc(b_addr + kk * 32), idesc, acc);
-                            acc = 1u;
+                        if (elect_one()) {
+                            umma_f16_w(tmem_d2, alo, kHi, blo, kHi, idesc, acc);
+                            if (nkk > 1) umma_f16_w(tmem_d2, alo + 2, kHi, blo + 2, kHi, idesc, 1u);
+                            if (nkk > 2) umma_f16_w(tmem_d2, alo + 4, kHi, blo + 4, kHi, idesc, 1u);
+                            if (nkk > 3) umma_f16_w(tmem_d2, alo + 6, kHi, blo + 6, kHi, idesc, 1u);
+                            umma_commit(&empty_bar[stage]);
                         }
-                        umma_commit(&empty_bar[stage]);
+                        acc = 1u;
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                     for (int s = 0; s < p.nds; ++s) {
@@ -195,15 +212,22 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                             mbar_wait(&full_bar[stage], phase);
                             tc_fence_after();
                             const uint32_t a_addr = smem_u32(ring + stage * kStageBytes), b_addr = a_addr + kBlkABytes;
+                            const uint32_t alo = umma_desc_lo(a_addr), blo = umma_desc_lo(b_addr);
                             const int nkk = (c == sg.nchunks - 1) ? sg.kk_last : 4;
-                            for (int kk = 0; kk < nkk; ++kk)
-                                umma_f16(tmem_d2, umma_smem_desc(a_addr + kk * 32), umma_smem_desc(b_addr + kk * 32), idesc, 1u);
-                            umma_commit(&empty_bar[stage]);
+                            if (elect_one()) {
+                                umma_f16_w(tmem_d2, alo, kHi, blo, kHi, idesc, 1u);
+                                if (nkk > 1) umma_f16_w(tmem_d2, alo + 2, kHi, blo + 2, kHi, idesc, 1u);
+                                if (nkk > 2) umma_f16_w(tmem_d2, alo + 4, kHi, blo + 4, kHi, idesc, 1u);
+                                if (nkk > 3) umma_f16_w(tmem_d2, alo + 6, kHi, blo + 6, kHi, idesc, 1u);
+                                umma_commit(&empty_bar[stage]);
+                            }
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
                     }
-                    umma_commit(&d2_full);
-                    umma_commit(&y_empty);
+                    if (elect_one()) {
+                        umma_commit(&d2_full);
+                        umma_commit(&y_empty);
+                    }
                 }
             }
         }

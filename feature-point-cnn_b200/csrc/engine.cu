@@ -326,23 +326,27 @@ void Engine::build_ops() {
     d_stem_w_[1] = dev_upload(w3);
     d_stem_b_ = dev_upload(st->b);
     if (precision_ != PREC_FP32) {
-        // tensor-core stem: [cout][k] with k = c*49 + ky*7 + kx, K zero-padded to a multiple of 64, followed by
-        // the lo parts (w - float(w16)) for the split-precision MMAs
+        // tensor-core stem: [cout][k] with k = c*64 + ky*8 + kx (kx and ky padded 7 -> 8 with zeros: the eight taps
+        // of one filter row are one 16-byte piece of the im2col row, stem_tc.cu), followed by the lo parts
+        // (w - float(w16)) for the split-precision MMAs
         for (int v = 0; v < 2; ++v) {
-            const int cin = v == 0 ? 1 : 3, kpad = (49 * cin + 63) / 64 * 64, nparts = 2;
+            const int cin = v == 0 ? 1 : 3, kpad = 64 * cin, nparts = 2;
             const std::vector<float>& src = v == 0 ? w1 : w3;
             std::vector<uint16_t> w16((size_t)64 * kpad * nparts, 0);
             auto to16 = [&](float f) { return precision_ == PREC_FP16 ? f32_to_f16_bits(f) : f32_to_bf16_bits(f); };
             auto from16 = [&](uint16_t h) {
                 return precision_ == PREC_FP16 ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
             };
-            for (int k = 0; k < 49 * cin; ++k)
-                for (int co = 0; co < 64; ++co) {
-                    const float f = src[(size_t)k * 64 + co];
-                    const uint16_t hi = to16(f);
-                    w16[(size_t)co * kpad * nparts + k] = hi;
-                    if (nparts == 2) w16[(size_t)co * kpad * nparts + kpad + k] = to16(f - from16(hi));
-                }
+            for (int c = 0; c < cin; ++c)
+                for (int ky = 0; ky < 7; ++ky)
+                    for (int kx = 0; kx < 7; ++kx)
+                        for (int co = 0; co < 64; ++co) {
+                            const float f = src[(size_t)(c * 49 + ky * 7 + kx) * 64 + co];
+                            const int k = c * 64 + ky * 8 + kx;
+                            const uint16_t hi = to16(f);
+                            w16[(size_t)co * kpad * nparts + k] = hi;
+                            w16[(size_t)co * kpad * nparts + kpad + k] = to16(f - from16(hi));
+                        }
             d_stem_w16_[v] = dev_upload(w16);
             stem_plan_[v] = stem_tc_plan_create(d_stem_w16_[v], d_stem_b_, cin, precision_, num_sms_);
         }

@@ -3,9 +3,12 @@
 //
 // A CTA produces a 5x10 tile of pooled pixels x 64 channels.  That needs the 11x21 convolution
 // outputs around it (pool windows overlap), i.e. 231 GEMM rows = two M=128 tcgen05 tiles:
-//   1. the 27x47 input patch is loaded once (fp32, zero padded),
-//   2. every thread builds one im2col row (49*C taps, K padded to 64 per chunk) straight into the
-//      128B-swizzled K-major smem layout the UMMA descriptor expects (no im2col in HBM),
+//   1. the 27x47 input patch is loaded once, multiplied by 255 and rounded to the 16-bit operand type
+//      (double buffered: the next tile's patch is fetched while the tensor core works),
+//   2. every thread builds one im2col row straight into the 128B-swizzled K-major smem layout the UMMA
+//      descriptor expects (no im2col in HBM).  K is ordered (channel, ky, kx) with kx padded 7 -> 8, so
+//      the eight taps of one filter row are eight CONSECUTIVE patch pixels = one 16-byte chunk of the
+//      row: a row costs 7 x (4 LDS.32 + 1 STS.128) per channel instead of 49 scalar loads + converts,
 //   3. one thread issues the tcgen05.mma chain (weights arrive by TMA), accumulators in TMEM.  Precision:
 //      the image is multiplied by 255 before the 16-bit rounding, so 8-bit images (value = k/255, what
 //      cameras and the reference's loaders produce) are represented exactly; the weights are split into
@@ -29,6 +32,7 @@ constexpr int kStPH = 5, kStPW = 10;                  // pooled tile
 constexpr int kStCH = 2 * kStPH + 1, kStCW = 2 * kStPW + 1;   // conv region 11 x 21
 constexpr int kStRows = kStCH * kStCW;                // 231 GEMM rows (<= 256)
 constexpr int kStIH = 2 * kStCH + 5, kStIW = 2 * kStCW + 5;   // input patch 27 x 47
+constexpr int kStIWp = 48;                            // patch row pitch in smem (elements): 8 taps from column 2*20 stay inside
 constexpr int kStThreads = 256;
 
 struct StemParams {
@@ -41,8 +45,8 @@ struct StemParams {
 };
 
 template <int CIN, bool SPLIT, typename T>
-__global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_constant__ StemParams p) {
-    constexpr int NCHUNK = (49 * CIN + 63) / 64;
+__global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(const __grid_constant__ StemParams p) {
+    constexpr int NCHUNK = CIN;                                       // one 64-wide K chunk per channel: k = ky * 8 + kx
     constexpr int NPART = SPLIT ? 2 : 1;                              // weight parts: hi (+ lo)
     constexpr int kATile = 128 * 128;                                 // bytes of one M-tile of one K chunk of one part
     constexpr uint32_t kIdesc = (1u << 4) | (OperandFmt<T>::value << 7) | (OperandFmt<T>::value << 10) |
@@ -55,10 +59,11 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023);
     uint8_t* s_a = base;                                              // [2 M-tiles][NCHUNK][128 rows][128 B]
     uint8_t* s_w = s_a + 2 * NCHUNK * kATile;                 // [NPART][NCHUNK][64 rows][128 B]
-    float* s_in = reinterpret_cast<float*>(s_w + NPART * NCHUNK * 64 * 128);  // [CIN][27][47]
+    T* s_in = reinterpret_cast<T*>(s_w + NPART * NCHUNK * 64 * 128);  // [2 buffers][CIN][27][48], image * 255 in the operand type
+    constexpr int kPatch = CIN * kStIH * kStIWp;
     uint8_t* s_conv = s_a;                                            // aliases A after the MMAs: [256 rows][128 B]
 
-    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
     const int H = p.H, W = p.W, CH = H / 2, CW = W / 2, PH = H / 4, PW = W / 4;
 
     if (tid == 0) {
@@ -81,22 +86,28 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
     }
     // persistent: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the input patch of the next
     // tile is fetched while the tensor core works on the current one
-    auto load_patch = [&](int tile) {
+    auto load_patch = [&](int tile, int buf) {
         const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
         const int iy0 = 4 * ((tt / p.tiles_x) * kStPH) - 5, ix0 = 4 * ((tt % p.tiles_x) * kStPW) - 5;
-        for (int i = tid; i < CIN * kStIH * kStIW; i += kStThreads) {
-            const int c = i / (kStIH * kStIW), r = i % (kStIH * kStIW);
-            const int y = iy0 + r / kStIW, x = ix0 + r % kStIW;
-            float v = 0.f;
-            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(p.img + ((size_t)(b * CIN + c) * H + y) * W + x);
-            s_in[i] = v;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s_in + buf * kPatch);
+        for (int i = tid; i < CIN * kStIH * (kStIWp / 2); i += kStThreads) {      // two pixels per iteration
+            const int c = i / (kStIH * (kStIWp / 2)), r = i % (kStIH * (kStIWp / 2));
+            const int y = iy0 + r / (kStIWp / 2), x = ix0 + 2 * (r % (kStIWp / 2));
+            float v0 = 0.f, v1 = 0.f;
+            if (y >= 0 && y < H) {
+                const float* row = p.img + ((size_t)(b * CIN + c) * H + y) * W;
+                if (x >= 0 && x < W) v0 = __ldg(row + x);
+                if (x + 1 >= 0 && x + 1 < W) v1 = __ldg(row + x + 1);
+            }
+            dst[i] = pack2<T>(v0 * 255.f, v1 * 255.f);
         }
     };
-    if ((int)blockIdx.x < p.total_tiles) load_patch(blockIdx.x);
+    if ((int)blockIdx.x < p.total_tiles) load_patch(blockIdx.x, 0);
     __syncthreads();
+    int buf = 0;
     uint32_t mma_phase = 0;
     bool first = true;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, mma_phase ^= 1u, first = false) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, mma_phase ^= 1u, first = false, buf ^= 1) {
         const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
         const int py0 = (tt / p.tiles_x) * kStPH, px0 = (tt % p.tiles_x) * kStPW;
         const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;               // conv coords of the region origin
@@ -106,24 +117,17 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
             const int mt = row >> 7, rr = row & 127;
             const bool live = row < kStRows;
             const int cyl = row / kStCW, cxl = row % kStCW;
-            const float* pin = s_in + (2 * cyl) * kStIW + 2 * cxl;
+            const T* pin = s_in + buf * kPatch + (2 * cyl) * kStIWp + 2 * cxl;    // 4-byte aligned
     #pragma unroll
-            for (int ck = 0; ck < NCHUNK; ++ck) {
+            for (int ck = 0; ck < NCHUNK; ++ck) {                  // chunk = input channel
                 uint8_t* arow = s_a + (mt * NCHUNK + ck) * kATile + rr * 128;
     #pragma unroll
-                for (int j = 0; j < 8; ++j) {                      // 16-byte chunk j holds k = ck*64 + 8j .. +7
-                    float v[8];
-    #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int k = ck * 64 + j * 8 + e;
-                        float x = 0.f;
-                        if (live && k < 49 * CIN) {
-                            const int c = k / 49, t = k % 49;
-                            x = pin[c * kStIH * kStIW + (t / 7) * kStIW + (t % 7)] * 255.f;
-                        }
-                        v[e] = x;
+                for (int j = 0; j < 8; ++j) {                      // 16-byte piece j = filter row ky = j: patch pixels 2*cxl .. 2*cxl+7
+                    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                    if (live && j < 7) {
+                        const uint32_t* q = reinterpret_cast<const uint32_t*>(pin + ck * kStIH * kStIWp + j * kStIWp);
+                        u = make_uint4(q[0], q[1], q[2], q[3]);
                     }
-                    const uint4 u = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
                     *reinterpret_cast<uint4*>(arow + ((j ^ (rr & 7)) << 4)) = u;
                 }
             }
@@ -131,26 +135,29 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy smem writes -> tensor-core reads
         __syncthreads();
 
-        if (tid == 0) {
+        if (warp == 0) {
             if (first) mbar_wait(&bar_w, 0);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(s_a), w_addr = smem_u32(s_w);
+            const uint32_t a_lo = umma_desc_lo(smem_u32(s_a)), w_lo = umma_desc_lo(smem_u32(s_w));
+            constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            if (elect_one()) {
     #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+                for (int mt = 0; mt < 2; ++mt)
     #pragma unroll
-                for (int ck = 0; ck < NCHUNK; ++ck)
+                    for (int ck = 0; ck < NCHUNK; ++ck)
     #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint32_t a_hi = a_addr + (mt * NCHUNK + ck) * kATile + kk * 32;
-                        const uint32_t w_hi = w_addr + ck * 64 * 128 + kk * 32;
-                        umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi), kIdesc, (ck > 0 || kk > 0) ? 1u : 0u);
-                        if (SPLIT) umma_f16(tmem_acc + mt * 64, umma_smem_desc(a_hi), umma_smem_desc(w_hi + NCHUNK * 64 * 128), kIdesc, 1u);
-                    }
-            umma_commit(&bar_mma);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t a = a_lo + (uint32_t)(((mt * NCHUNK + ck) * kATile + kk * 32) >> 4);
+                            const uint32_t w = w_lo + (uint32_t)((ck * 64 * 128 + kk * 32) >> 4);
+                            umma_f16_w(tmem_acc + mt * 64, a, kHi, w, kHi, kIdesc, (ck > 0 || kk > 0) ? 1u : 0u);
+                            if (SPLIT) umma_f16_w(tmem_acc + mt * 64, a, kHi, w + (uint32_t)((NCHUNK * 64 * 128) >> 4), kHi, kIdesc, 1u);
+                        }
+                umma_commit(&bar_mma);
+            }
         }
         __syncwarp();
 
-        if (tile + (int)gridDim.x < p.total_tiles) load_patch(tile + gridDim.x);      // s_in is free after the build
+        if (tile + (int)gridDim.x < p.total_tiles) load_patch(tile + gridDim.x, buf ^ 1);   // the other patch buffer
         mbar_wait(&bar_mma, mma_phase);
         tc_fence_after();
 
@@ -182,23 +189,22 @@ __global__ void __launch_bounds__(kStThreads) stem_tc_kernel(const __grid_consta
 
         // ---- 3x3 / stride-2 max-pool over the staged conv tile, two channels per thread --------------
         T* out = static_cast<T*>(p.dst);
-        for (int o = tid; o < kStPH * kStPW * 32; o += kStThreads) {
-            const int c2 = o % 32, pp = o / 32;
+        for (int o = tid; o < kStPH * kStPW * 16; o += kStThreads) {
+            const int c4 = o % 16, pp = o / 16;                    // four channels per thread
             const int ppy = pp / kStPW, ppx = pp % kStPW;
             const int py = py0 + ppy, px = px0 + ppx;
             if (py >= PH || px >= PW) continue;
-            float m0 = 0.f, m1 = 0.f;
+            uint2 m = make_uint2(0u, 0u);                          // all staged values are >= 0
     #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
     #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
                     const int row = (2 * ppy + dy) * kStCW + 2 * ppx + dx;
-                    const uint32_t u = *reinterpret_cast<const uint32_t*>(s_conv + row * 128 + (((c2 >> 2) ^ (row & 7)) << 4) + (c2 & 3) * 4);
-                    const float2 f = unpack2<T>(u);
-                    m0 = fmaxf(m0, f.x);
-                    m1 = fmaxf(m1, f.y);
+                    const uint2 u = *reinterpret_cast<const uint2*>(s_conv + row * 128 + (((c4 >> 1) ^ (row & 7)) << 4) + (c4 & 1) * 8);
+                    m.x = max2<T>(m.x, u.x);
+                    m.y = max2<T>(m.y, u.y);
                 }
-            *reinterpret_cast<uint32_t*>(out + ((size_t)(b * PH + py) * PW + px) * 64 + c2 * 2) = pack2<T>(m0, m1);
+            *reinterpret_cast<uint2*>(out + ((size_t)(b * PH + py) * PW + px) * 64 + c4 * 4) = m;
         }
         __syncthreads();           // pooling reads s_conv (aliases the A tiles) and s_in is rewritten: next build may start
     }
@@ -216,10 +222,10 @@ struct StemTcPlan {
 
 template <int CIN, bool SPLIT, typename T>
 static void launch_stem_tc_t(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st) {
-    constexpr int NCHUNK = (49 * CIN + 63) / 64;
+    constexpr int NCHUNK = CIN;
     constexpr int NPART = SPLIT ? 2 : 1;
     auto kern = stem_tc_kernel<CIN, SPLIT, T>;
-    const size_t smem = (size_t)2 * NCHUNK * 128 * 128 + (size_t)NPART * NCHUNK * 64 * 128 + (size_t)CIN * kStIH * kStIW * 4 + 1024;
+    const size_t smem = (size_t)2 * NCHUNK * 128 * 128 + (size_t)NPART * NCHUNK * 64 * 128 + (size_t)2 * CIN * kStIH * kStIWp * 2 + 1024;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StemParams p = plan->params;
     p.img = img; p.dst = dst; p.H = H; p.W = W;
@@ -242,7 +248,7 @@ void launch_stem_tc(const StemTcPlan* plan, const float* img, void* dst, int B, 
     }
 }
 
-// w16: device [64][nparts*nchunk*64] 16-bit K-major (k = c*49 + ky*7 + kx, zero padded to nchunk*64; the hi
+// w16: device [64][nparts*nchunk*64] 16-bit K-major (k = c*64 + ky*8 + kx, zero where ky or kx is 7; the hi
 // parts first, then the lo parts w - float(w_hi)), bias: device [64] fp32
 StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type, int num_sms) {
     if (cin != 1 && cin != 3) throw std::invalid_argument("stem: input must have 1 or 3 channels");
@@ -251,7 +257,7 @@ StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int
     plan->cin = cin;
     plan->operand_type = operand_type;
     plan->num_sms = num_sms;
-    const int nchunk = (49 * cin + 63) / 64;
+    const int nchunk = cin;
     const CUtensorMapDataType dt = operand_type == PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const int nparts = 2;
     cuuint64_t dims[2] = {(cuuint64_t)nparts * nchunk * 64, 64};

@@ -247,6 +247,20 @@ __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
     return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
 
+// element-wise max of two packed 16-bit pairs
+template <typename T>
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b);
+template <>
+__device__ __forceinline__ uint32_t max2<__half>(uint32_t a, uint32_t b) {
+    const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <>
+__device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link dependency on libcuda);
 // 128B swizzle, zero fill out of bounds.
 void tc_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
