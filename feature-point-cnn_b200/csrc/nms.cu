@@ -9,10 +9,11 @@
 // and, had one been kept, the maximum would have been suppressed with it.)  Equal confidences are
 // ordered by ascending pixel index, the oracle's tie rule.
 //
-// Round 0 is a dense streaming pass (nms_round0_kernel): 64x32-pixel tiles with a 2r halo in shared
-// memory, separable window maxima with register sliding windows, keeper flags as row bitmasks, dilation
-// by shifts; it emits the keepers, a bit-per-pixel mask of the still-undecided candidates and their
-// compact list.  After it only a few percent of the candidates are left, so the remaining rounds
+// Round 0 (nms_round0_kernel) works on 64x64-pixel tiles with a 2r halo in shared memory: one dense pass
+// thresholds the tile into sortable keys and compacts the candidates, then the window scans run per
+// candidate (early exit), keeper flags are row bitmasks and suppression is a shifted-word test; it emits
+// the keepers, a bit-per-pixel mask of the still-undecided candidates and their compact list.  After it
+// only a few percent of the candidates are left, so the remaining rounds
 // (nms_rounds_kernel, one 8-CTA cluster per image) work on the compact list: a warp per candidate
 // scans its window through the bitmask (heat is read only where a bit is set), keepers clear their
 // window bits with atomics, the list is compacted, two cluster barriers per round.
@@ -25,7 +26,7 @@ namespace cg = cooperative_groups;
 
 namespace spb200 {
 
-constexpr int kN0TW = 64, kN0TH = 32;        // interior tile of round 0 (two mask words per row)
+constexpr int kN0TW = 64, kN0TH = 64;        // interior tile of round 0 (two mask words per row)
 constexpr int kN0Threads = 256;
 constexpr int kNmsMaxR = 8;
 constexpr int kNmsCluster = 8;
@@ -34,6 +35,10 @@ constexpr int kRoundsThreads = 256;
 // ------------------------------------------------------------------------------------------------
 // Round 0
 // ------------------------------------------------------------------------------------------------
+// Candidate-centric: only a few percent of the pixels pass the threshold, so after one dense pass that turns the
+// tile (+ 2R halo) into sortable keys and compacts the candidates of the evaluation region (interior + R), the
+// window scans run per CANDIDATE with early exit on the first stronger neighbour, keepers become bits, and a
+// candidate is suppressed when a keeper bit lies in its window (nine shifted word tests).
 template <int R>
 __global__ void __launch_bounds__(kN0Threads)
 nms_round0_kernel(const float* __restrict__ heat, int H, int W, float thresh, int border, int kcap,
@@ -41,139 +46,158 @@ nms_round0_kernel(const float* __restrict__ heat, int H, int W, float thresh, in
                   int mask_w, unsigned* __restrict__ und) {
     constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R;      // loaded region (halo 2R)
     constexpr int EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;      // region where keepers are evaluated (halo R)
-    constexpr int EWQ = (EW + 3) / 4;                          // 4-wide strips per row
-    constexpr int EHQ = (EH + 3) / 4;
-    static_assert(EW <= 96, "keeper rows are three 32-bit words");
+    constexpr int KW = (EW + 31) / 32 + 1;                     // keeper bit words per E row (+1 so a 64-bit window read stays inside)
+    constexpr int kMaxKeep = ((kN0TW + R) / (R + 1) + 1) * ((kN0TH + R) / (R + 1) + 1);   // keepers are > R apart
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned* s_key = reinterpret_cast<unsigned*>(smem_raw);   // [LH][LW]   sortable key, 0 = not a candidate
-    unsigned* s_rm = s_key + LH * LW;                          // [LH][EW]   horizontal window maxima
-    unsigned* s_kb = s_rm + LH * EW;                           // [EH][3]    keeper bits, bit ex of row ey
-    unsigned* s_dil = s_kb + EH * 3;                           // [EH][2]    keepers dilated horizontally (interior cols)
-    unsigned* s_sup = s_dil + EH * 2;                          // [TH][2]    ... and vertically: suppressed bits
+    unsigned* s_kb = s_key + LH * LW;                          // [EH][KW]   keeper bits, bit ex of row ey
+    unsigned* s_ub = s_kb + EH * KW;                           // [TH][2]    undecided bits of the interior
+    unsigned* s_und = s_ub + kN0TH * 2;                        // [TH*TW]    undecided pixel indices
+    unsigned long long* s_keep = reinterpret_cast<unsigned long long*>(
+        (reinterpret_cast<uintptr_t>(s_und + kN0TH * kN0TW) + 7) & ~(uintptr_t)7);                 // [kMaxKeep] survivor keys
+    unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_keep + kMaxKeep);               // [EH*EW] ey << 8 | ex
+    __shared__ int s_ncand, s_nund, s_nkeep, s_base_und, s_base_keep;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z;
     const int ty0 = blockIdx.y * kN0TH, tx0 = blockIdx.x * kN0TW;
     const float* hmap = heat + (size_t)b * H * W;
-
-    // 1. keys of the loaded region
-    for (int i = tid; i < LH * LW; i += kN0Threads) {
-        const int gy = ty0 - 2 * R + i / LW, gx = tx0 - 2 * R + i % LW;
-        unsigned key = 0u;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            const float h = __ldg(hmap + (size_t)gy * W + gx);
-            if (h >= thresh) key = sortable_bits(h);
-        }
-        s_key[i] = key;
-    }
-    for (int i = tid; i < EH * 3; i += kN0Threads) s_kb[i] = 0u;
+    if (tid == 0) { s_ncand = 0; s_nund = 0; s_nkeep = 0; }
+    for (int i = tid; i < EH * KW; i += kN0Threads) s_kb[i] = 0u;
+    for (int i = tid; i < kN0TH * 2; i += kN0Threads) s_ub[i] = 0u;
     __syncthreads();
 
-    // 2. horizontal maxima, four adjacent outputs per work item from a (4 + 2R)-wide register window
-    for (int it = tid; it < LH * EWQ; it += kN0Threads) {
-        const int ly = it / EWQ, ex = (it % EWQ) * 4;
-        unsigned v[4 + 2 * R];
+    // 1. keys of the loaded region, four pixels (one 16-byte load) per thread and step; candidates of the evaluation
+    //    region are appended to the list through a warp prefix sum (one shared atomic per warp and step)
+    constexpr int LQ = (LW + 3) / 4;                           // float4 groups per loaded row
+    // groups are then 16-byte aligned and never straddle the image edge
+    const bool vec_ok = ((2 * R) % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(hmap) & 15) == 0);
+    for (int i0 = 0; i0 < LH * LQ; i0 += kN0Threads) {
+        const int i = i0 + tid;
+        unsigned key[4] = {0u, 0u, 0u, 0u};
+        int ly = 0, lx = 0;
+        if (i < LH * LQ) {
+            ly = i / LQ; lx = (i % LQ) * 4;
+            const int gy = ty0 - 2 * R + ly, gx = tx0 - 2 * R + lx;
+            if (gy >= 0 && gy < H) {
+                const float* src = hmap + (size_t)gy * W + gx;
+                float h[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // outside the image: never a candidate
+                if (vec_ok) {
+                    if (gx >= 0 && gx < W) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                        h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
+                    }
+                } else {
 #pragma unroll
-        for (int j = 0; j < 4 + 2 * R; ++j) v[j] = (ex + j < LW) ? s_key[ly * LW + ex + j] : 0u;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            unsigned m = v[o];
-#pragma unroll
-            for (int d = 1; d <= 2 * R; ++d) m = max(m, v[o + d]);
-            if (ex + o < EW) s_rm[ly * EW + ex + o] = m;
-        }
-    }
-    __syncthreads();
-
-    // 3. vertical maxima -> keeper test.  Work items are (strip of 4 rows, column) with the column padded
-    //    to 96 so that a warp owns one 32-bit word of each of its four rows (ballot -> bit row).
-    for (int it = tid; it < EHQ * 96; it += kN0Threads) {
-        const int eq = it / 96, ex = it % 96;
-        const int ey0 = eq * 4;
-        unsigned v[4 + 2 * R];
-#pragma unroll
-        for (int j = 0; j < 4 + 2 * R; ++j) v[j] = (ex < EW && ey0 + j < LH) ? s_rm[(ey0 + j) * EW + ex] : 0u;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const int ey = ey0 + o;
-            bool keep = false;
-            if (ex < EW && ey < EH) {
-                unsigned m = v[o];
-#pragma unroll
-                for (int d = 1; d <= 2 * R; ++d) m = max(m, v[o + d]);
-                const unsigned me = s_key[(ey + R) * LW + ex + R];
-                if (me != 0u && me == m) {
-                    // ties: an equal key earlier in raster order wins
-                    keep = true;
-                    for (int dy = -R; dy <= R && keep; ++dy)
-                        for (int dx = -R; dx <= R; ++dx) {
-                            if (dy > 0 || (dy == 0 && dx >= 0)) break;
-                            if (s_key[(ey + R + dy) * LW + ex + R + dx] == me) { keep = false; break; }
-                        }
+                    for (int e = 0; e < 4; ++e)
+                        if (gx + e >= 0 && gx + e < W) h[e] = __ldg(src + e);
                 }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (h[e] >= thresh) key[e] = sortable_bits(h[e]);
             }
-            const unsigned bits = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0 && ey < EH) s_kb[ey * 3 + (ex >> 5)] = bits;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (lx + e < LW) s_key[ly * LW + lx + e] = key[e];
+        }
+        unsigned flags = 0u;
+        if (ly >= R && ly < R + EH) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (key[e] != 0u && lx + e >= R && lx + e < R + EW) flags |= 1u << e;
+        }
+        const int mine = __popc(flags);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&s_ncand, total);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (flags & (1u << e)) s_cand[base++] = (unsigned short)(((ly - R) << 8) | (lx + e - R));
         }
     }
     __syncthreads();
+    const int ncand = s_ncand;
 
-    // 4. dilate the keeper bits horizontally: interior column ix sees E columns ix .. ix+2R
-    for (int it = tid; it < EH * 2; it += kN0Threads) {
-        const int ey = it >> 1, ws = it & 1;
-        const unsigned w0 = s_kb[ey * 3 + ws], w1 = s_kb[ey * 3 + ws + 1];
-        unsigned acc = w0;
+    // 2. keeper test per candidate: no stronger key in the window, no equal key earlier in raster order
+    for (int c = tid; c < ncand; c += kN0Threads) {
+        const int ey = s_cand[c] >> 8, ex = s_cand[c] & 255;
+        const unsigned* centre = s_key + (ey + R) * LW + ex + R;
+        const unsigned me = *centre;
+        bool keep = true;
+        for (int dy = -R; dy <= R && keep; ++dy) {
+            const unsigned* row = centre + dy * LW;
 #pragma unroll
-        for (int d = 1; d <= 2 * R; ++d) acc |= (w0 >> d) | (w1 << (32 - d));
-        s_dil[it] = acc;
+            for (int dx = -R; dx <= R; ++dx) {
+                const unsigned v = row[dx];
+                if (v > me || (v == me && (dy < 0 || (dy == 0 && dx < 0)))) keep = false;
+            }
+        }
+        if (keep) atomicOr(&s_kb[ey * KW + (ex >> 5)], 1u << (ex & 31));
     }
     __syncthreads();
-    //    ... and vertically: interior row iy sees E rows iy .. iy+2R
-    for (int it = tid; it < kN0TH * 2; it += kN0Threads) {
-        const int iy = it >> 1, ws = it & 1;
-        unsigned acc = 0u;
-#pragma unroll
-        for (int d = 0; d <= 2 * R; ++d) acc |= s_dil[(iy + d) * 2 + ws];
-        s_sup[it] = acc;
-    }
-    __syncthreads();
 
-    // 5. decide the interior: a warp owns one mask word (32 pixels of one row) at a time
+    // 3. interior candidates: kept / suppressed by a keeper in the window / still undecided
     int* cnt = counters + b * kNmsCounters;
-    unsigned long long* kout = keys + (size_t)b * kcap;
-    unsigned* uout = und + (size_t)b * H * W;
-    unsigned* mrow = mask + (size_t)b * H * mask_w;
-    for (int unit = warp; unit < kN0TH * 2; unit += kN0Threads / 32) {
-        const int iy = unit >> 1, ws = unit & 1;
-        const int ix = ws * 32 + lane;
+    for (int c = tid; c < ncand; c += kN0Threads) {
+        const int ey = s_cand[c] >> 8, ex = s_cand[c] & 255;
+        const int iy = ey - R, ix = ex - R;
+        if (iy < 0 || iy >= kN0TH || ix < 0 || ix >= kN0TW) continue;
         const int gy = ty0 + iy, gx = tx0 + ix;
-        const unsigned key = s_key[(iy + 2 * R) * LW + ix + 2 * R];          // 0 outside the image
-        const int ex = ix + R;
-        const bool keep = (s_kb[(iy + R) * 3 + (ex >> 5)] >> (ex & 31)) & 1u;
-        const bool sup = (s_sup[unit] >> lane) & 1u;
-        const bool cand = key != 0u;
-        const bool undecided = cand && !keep && !sup;
-        const bool emit = cand && keep && !(gx < border || gx >= W - border || gy < border || gy >= H - border);
+        const bool keep = (s_kb[ey * KW + (ex >> 5)] >> (ex & 31)) & 1u;
         const unsigned pix = (unsigned)(gy * W + gx);
-        const unsigned ub = __ballot_sync(0xffffffffu, undecided);
-        const unsigned eb = __ballot_sync(0xffffffffu, emit);
-        if (lane == 0 && gy < H && (tx0 >> 5) + ws < mask_w) mrow[(size_t)gy * mask_w + (tx0 >> 5) + ws] = ub;
-        if (eb) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(cnt, __popc(eb));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (emit) {
-                const int pos = base + __popc(eb & ((1u << lane) - 1u));
-                if (pos < kcap) kout[pos] = survivor_key(key, pix);
+        if (keep) {
+            if (!(gx < border || gx >= W - border || gy < border || gy >= H - border)) {
+                const int pos = atomicAdd(&s_nkeep, 1);
+                if (pos < kMaxKeep) s_keep[pos] = survivor_key(s_key[(ey + R) * LW + ex + R], pix);
             }
+            continue;
         }
-        if (ub) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(cnt + 1, __popc(ub));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (undecided) uout[base + __popc(ub & ((1u << lane) - 1u))] = pix;
+        // window columns ex-R .. ex+R of rows ey-R .. ey+R (E coordinates; rows/cols outside E hold no keeper
+        // that could matter: a keeper more than R outside the interior cannot cover an interior pixel... but one
+        // within R can, which is why keepers are evaluated on the whole E region)
+        unsigned any = 0u;
+        const int x0 = ex - R;                                  // may be negative by at most R for ix < R? no: ex >= R here
+#pragma unroll
+        for (int dy = -R; dy <= R; ++dy) {
+            const int yy = ey + dy;
+            if (yy < 0 || yy >= EH) continue;
+            const unsigned* kr = s_kb + yy * KW;
+            const int w0 = x0 >> 5, sh = x0 & 31;
+            const unsigned long long two = (unsigned long long)kr[w0] | ((unsigned long long)kr[w0 + 1] << 32);
+            any |= (unsigned)(two >> sh) & ((1u << (2 * R + 1)) - 1u);
+        }
+        if (!any) {
+            atomicOr(&s_ub[iy * 2 + (ix >> 5)], 1u << (ix & 31));
+            s_und[atomicAdd(&s_nund, 1)] = pix;
         }
     }
+    __syncthreads();
+
+    // 4. write out: undecided mask words of every interior row, the two compact lists behind one atomicAdd each
+    unsigned* mrow = mask + (size_t)b * H * mask_w;
+    for (int i = tid; i < kN0TH * 2; i += kN0Threads) {
+        const int gy = ty0 + (i >> 1), wcol = (tx0 >> 5) + (i & 1);
+        if (gy < H && wcol < mask_w) mrow[(size_t)gy * mask_w + wcol] = s_ub[i];
+    }
+    const int nund = s_nund, nkeep = min(s_nkeep, kMaxKeep);
+    if (tid == 0) {
+        s_base_und = nund ? atomicAdd(cnt + 1, nund) : 0;
+        s_base_keep = nkeep ? atomicAdd(cnt, nkeep) : 0;
+    }
+    __syncthreads();
+    unsigned* uout = und + (size_t)b * H * W + s_base_und;
+    for (int i = tid; i < nund; i += kN0Threads) uout[i] = s_und[i];
+    unsigned long long* kout = keys + (size_t)b * kcap;
+    for (int i = tid; i < nkeep; i += kN0Threads)
+        if (s_base_keep + i < kcap) kout[s_base_keep + i] = s_keep[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -289,7 +313,10 @@ template <int R>
 static void launch_round0_t(const float* heat, int B, int H, int W, float thresh, int border, const NmsWorkspace& ws,
                             cudaStream_t st) {
     constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R, EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;
-    const size_t smem = sizeof(unsigned) * ((size_t)LH * LW + (size_t)LH * EW + EH * 3 + EH * 2 + kN0TH * 2);
+    constexpr int KW = (EW + 31) / 32 + 1;
+    constexpr int kMaxKeep = ((kN0TW + R) / (R + 1) + 1) * ((kN0TH + R) / (R + 1) + 1);
+    const size_t smem = sizeof(unsigned) * ((size_t)LH * LW + EH * KW + kN0TH * 2 + kN0TH * kN0TW) + sizeof(unsigned long long) * kMaxKeep +
+                        sizeof(unsigned short) * ((size_t)EH * EW) + 16;
     auto kern = nms_round0_kernel<R>;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((W + kN0TW - 1) / kN0TW, (H + kN0TH - 1) / kN0TH, B);

@@ -7,6 +7,8 @@
 //                         (python/src/netutils.py:92-93) + top-k truncation
 //  K6 sample_desc_kernel  bilinear sampling (align_corners=True) + L2 normalisation
 //                         (python/src/netutils.py:103-121), one warp per keypoint, 128-bit loads
+#include <type_traits>
+
 #include "kernels.h"
 #include "sortkey.cuh"
 
@@ -269,11 +271,99 @@ sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_strid
     }
 }
 
+// Fast path of K6 for the engine's own descriptor map (NHWC, 16-bit, 128 channels): a HALF-warp per keypoint
+// (16 lanes x 8 channels = one 16-byte load per corner per lane), two keypoints per half-warp in flight, and a
+// grid of (blocks per image, images) whose blocks stride over the image's keypoints - no empty blocks however
+// large `cap` is.  Same arithmetic and summation order as sample_desc_kernel.
+constexpr int kDescBlocksPerImage = 24;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sample_desc128_kernel(const T* __restrict__ map, long batch_stride, int Hc, int Wc, int W, const float* __restrict__ gtab,
+                      int cap, const int* __restrict__ count, const int* __restrict__ xy, float* __restrict__ out) {
+    const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+    const int b = blockIdx.y;
+    const int n = min(__ldg(count + b), cap);
+    const T* mb = map + (size_t)b * batch_stride + hl * 8;
+    const int2* pts = reinterpret_cast<const int2*>(xy) + (size_t)b * cap;
+    const int stride = gridDim.x * 16;
+    // the loop bound is taken on the warp's first keypoint so that both half-warps leave together (full-mask shuffles)
+    for (int base = blockIdx.x * 16 + (hw & ~1); base < n; base += 2 * stride) {
+        const int i0 = base + (hw & 1);
+        uint4 v[2][4];
+        float wgt[2][4];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * stride;
+            live[u] = i < n;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v[u][k] = make_uint4(0u, 0u, 0u, 0u); wgt[u][k] = 0.f; }
+            if (live[u]) {
+                const int2 pt = __ldg(pts + i);
+                const float ix = __ldg(gtab + pt.x), iy = __ldg(gtab + W + pt.y);
+                const float fx0 = floorf(ix), fy0 = floorf(iy);
+                const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
+                const int x0 = (int)fx0, y0 = (int)fy0;
+                wgt[u][0] = wx0 * wy0; wgt[u][1] = wx1 * wy0; wgt[u][2] = wx0 * wy1; wgt[u][3] = wx1 * wy1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int cx = x0 + (k & 1), cy = y0 + (k >> 1);
+                    if (cx < 0 || cx >= Wc || cy < 0 || cy >= Hc) wgt[u][k] = 0.f;     // zeros padding: the corner is skipped
+                    else v[u][k] = __ldg(reinterpret_cast<const uint4*>(mb + (size_t)(cy * Wc + cx) * 128));
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w4[4] = {v[u][k].x, v[u][k].y, v[u][k].z, v[u][k].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float2 f;
+                    if (sizeof(T) == 2 && std::is_same<T, __half>::value) f = __half22float2(*reinterpret_cast<const __half2*>(&w4[e]));
+                    else f = make_float2(__uint_as_float(w4[e] << 16), __uint_as_float(w4[e] & 0xffff0000u));
+                    // a corner outside the map contributes nothing (its weight was zeroed and its value is 0)
+                    acc[2 * e] = fmaf(wgt[u][k], f.x, acc[2 * e]);
+                    acc[2 * e + 1] = fmaf(wgt[u][k], f.y, acc[2 * e + 1]);
+                }
+            }
+            float ss = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; q += 4) {          // same partial-sum grouping as the generic kernel: four channels at a time
+                ss = fmaf(acc[q], acc[q], ss); ss = fmaf(acc[q + 1], acc[q + 1], ss);
+                ss = fmaf(acc[q + 2], acc[q + 2], ss); ss = fmaf(acc[q + 3], acc[q + 3], ss);
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+            if (live[u]) {
+                const float inv = 1.f / sqrtf(ss);    // 0-vector -> NaN, like the reference's 0/0
+                float* o = out + ((size_t)b * cap + (i0 + u * stride)) * 128 + hl * 8;
+                __stcs(reinterpret_cast<float4*>(o), make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv));
+                __stcs(reinterpret_cast<float4*>(o) + 1, make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv));
+            }
+        }
+    }
+}
+
 void launch_sample_descriptors(const void* map, int map_type, long batch_stride, long chan_stride, long cell_stride,
                                int B, int D, int Hc, int Wc, int W, const float* gtab, int cap, const int* count,
                                const int* xy, float* out, cudaStream_t st) {
     if (D % 4 != 0 || D > 512) throw std::invalid_argument("descriptor dimension must be a multiple of 4, at most 512");
     if (cap <= 0 || B <= 0) return;
+    if (map_type != PREC_FP32 && D == 128 && chan_stride == 1 && cell_stride == 128) {
+        dim3 g(kDescBlocksPerImage, B);
+        if (map_type == PREC_FP16)
+            sample_desc128_kernel<__half><<<g, 256, 0, st>>>((const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+        else
+            sample_desc128_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+        SPB_CHECK_LAUNCH();
+        return;
+    }
     dim3 grid((cap + 7) / 8, B);
     if (map_type == PREC_FP32)
         sample_desc_kernel<float><<<grid, 256, 0, st>>>((const float*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, W, gtab, cap, count, xy, out);
