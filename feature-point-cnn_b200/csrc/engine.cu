@@ -33,32 +33,51 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
+// Host-buffer pipeline state of detect_host: three streams (upload, compute, download), two slots of device
+// input / output buffers, pinned count mirrors, and pinned staging used only when the caller's buffers are pageable.
 struct Engine::HostStage {
-    float* img = nullptr;          // pinned
-    size_t img_bytes = 0;
-    int* count = nullptr;          // pinned [B]
-    int* xy = nullptr;             // pinned packed
-    float* conf = nullptr;
-    float* desc = nullptr;
-    size_t out_cap = 0;            // keypoints the pinned output buffers hold
-    int B = 0;
-    // device
-    float* d_img = nullptr;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    float* d_img[2] = {nullptr, nullptr};
     size_t d_img_bytes = 0;
-    int* d_count = nullptr;
-    int* d_xy = nullptr;
-    float* d_conf = nullptr;
-    float* d_desc = nullptr;
+    int* d_count[2] = {nullptr, nullptr};
+    int* d_xy[2] = {nullptr, nullptr};
+    float* d_conf[2] = {nullptr, nullptr};
+    float* d_desc[2] = {nullptr, nullptr};
+    int* h_count[2] = {nullptr, nullptr};      // pinned
     int d_B = 0, d_cap = 0;
-    cudaStream_t stream = nullptr;
+    // pageable callers
+    float* h_img[2] = {nullptr, nullptr};      // pinned
+    size_t h_img_bytes = 0;
+    int* h_xy[2] = {nullptr, nullptr};
+    float* h_conf[2] = {nullptr, nullptr};
+    float* h_desc[2] = {nullptr, nullptr};
+    size_t h_out_cap[2] = {0, 0};              // keypoints the pinned output staging of a slot holds
+    void init() {
+        SPB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        SPB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        SPB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SPB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            SPB_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+            SPB_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+        }
+    }
     ~HostStage() {
-        if (img) cudaFreeHost(img);
-        if (count) cudaFreeHost(count);
-        if (xy) cudaFreeHost(xy);
-        if (conf) cudaFreeHost(conf);
-        if (desc) cudaFreeHost(desc);
-        cudaFree(d_img); cudaFree(d_count); cudaFree(d_xy); cudaFree(d_conf); cudaFree(d_desc);
-        if (stream) cudaStreamDestroy(stream);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(d_img[i]); cudaFree(d_count[i]); cudaFree(d_xy[i]); cudaFree(d_conf[i]); cudaFree(d_desc[i]);
+            if (h_count[i]) cudaFreeHost(h_count[i]);
+            if (h_img[i]) cudaFreeHost(h_img[i]);
+            if (h_xy[i]) cudaFreeHost(h_xy[i]);
+            if (h_conf[i]) cudaFreeHost(h_conf[i]);
+            if (h_desc[i]) cudaFreeHost(h_desc[i]);
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_comp) cudaStreamDestroy(s_comp);
+        if (s_out) cudaStreamDestroy(s_out);
     }
 };
 
@@ -645,76 +664,142 @@ void Engine::export_buffer(int id, float* dst_nchw, int channels, cudaStream_t s
                         channels, dst_nchw, st);
 }
 
-// Host-buffer entry point: what ProcessFrame / InferenceWrapper.run do around the network (H2D of the
-// frame, D2H of keypoints and descriptors), with pinned staging and one packed download.
+// Host-buffer entry point: what ProcessFrame / InferenceWrapper.run do around the network (H2D of the frames, D2H
+// of keypoints and descriptors), pipelined: the batch is cut into chunks; the upload of chunk k+1 and the
+// download of chunk k-1 run on their own streams under the compute of chunk k.  Only count[b] keypoints of every
+// image cross the bus.  Buffers the caller allocated as pinned (cudaHostAlloc / cudaHostRegister / torch
+// pin_memory) are used by the DMA engines directly; pageable buffers go through pinned staging.
+static bool is_pinned_host(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 void Engine::detect_host(const float* img, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                          float* desc) {
     SPB_CUDA(cudaSetDevice(device_));
+    if (B <= 0) throw std::invalid_argument("batch must be positive");
+    if (cap <= 0) throw std::invalid_argument("capacity must be positive");
     if (!stage_) {
         stage_ = std::make_unique<HostStage>();
-        SPB_CUDA(cudaStreamCreateWithFlags(&stage_->stream, cudaStreamNonBlocking));
+        stage_->init();
     }
     HostStage& s = *stage_;
-    const size_t img_bytes = sizeof(float) * (size_t)B * C * H * W;
-    if (img_bytes > s.img_bytes) {
-        if (s.img) cudaFreeHost(s.img);
-        SPB_CUDA(cudaHostAlloc((void**)&s.img, img_bytes, cudaHostAllocDefault));
-        s.img_bytes = img_bytes;
+    int Bc = B;
+    {
+        int want = 16;
+        if (const char* e = std::getenv("SPB200_HOST_CHUNK")) want = std::max(1, std::atoi(e));
+        if (B > want && B % want == 0) Bc = want;
     }
-    if (img_bytes > s.d_img_bytes) {
-        cudaFree(s.d_img);
-        SPB_CUDA(cudaMalloc((void**)&s.d_img, img_bytes));
-        s.d_img_bytes = img_bytes;
-    }
-    if (B > s.d_B || cap > s.d_cap) {
-        cudaFree(s.d_count); cudaFree(s.d_xy); cudaFree(s.d_conf); cudaFree(s.d_desc);
-        if (s.count) cudaFreeHost(s.count);
-        s.d_count = dev_alloc<int>(B);
-        s.d_xy = dev_alloc<int>((size_t)B * cap * 2);
-        s.d_conf = dev_alloc<float>((size_t)B * cap);
-        s.d_desc = dev_alloc<float>((size_t)B * cap * 128);
-        SPB_CUDA(cudaHostAlloc((void**)&s.count, sizeof(int) * B, cudaHostAllocDefault));
-        s.d_B = B; s.d_cap = cap;
-    }
-    cudaStream_t st = s.stream;
-    std::memcpy(s.img, img, img_bytes);
-    SPB_CUDA(cudaMemcpyAsync(s.d_img, s.img, img_bytes, cudaMemcpyHostToDevice, st));
-    detect(s.d_img, B, C, H, W, s.d_cap, s.d_count, s.d_xy, s.d_conf, desc ? s.d_desc : nullptr, nullptr, st);
-    SPB_CUDA(cudaMemcpyAsync(s.count, s.d_count, sizeof(int) * B, cudaMemcpyDeviceToHost, st));
-    SPB_CUDA(cudaStreamSynchronize(st));
-    size_t total = 0;
-    for (int b = 0; b < B; ++b) total += (size_t)std::min(s.count[b], cap);
-    if (total > s.out_cap) {
-        if (s.xy) cudaFreeHost(s.xy);
-        if (s.conf) cudaFreeHost(s.conf);
-        if (s.desc) cudaFreeHost(s.desc);
-        const size_t n = total + total / 2 + 1024;
-        SPB_CUDA(cudaHostAlloc((void**)&s.xy, sizeof(int) * 2 * n, cudaHostAllocDefault));
-        SPB_CUDA(cudaHostAlloc((void**)&s.conf, sizeof(float) * n, cudaHostAllocDefault));
-        SPB_CUDA(cudaHostAlloc((void**)&s.desc, sizeof(float) * 128 * n, cudaHostAllocDefault));
-        s.out_cap = n;
-    }
-    size_t off = 0;
-    for (int b = 0; b < B; ++b) {
-        const size_t n = (size_t)std::min(s.count[b], cap);
-        if (n) {
-            SPB_CUDA(cudaMemcpyAsync(s.xy + off * 2, s.d_xy + (size_t)b * s.d_cap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, st));
-            SPB_CUDA(cudaMemcpyAsync(s.conf + off, s.d_conf + (size_t)b * s.d_cap, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-            if (desc)
-                SPB_CUDA(cudaMemcpyAsync(s.desc + off * 128, s.d_desc + (size_t)b * s.d_cap * 128, sizeof(float) * 128 * n, cudaMemcpyDeviceToHost, st));
+    const int nc = B / Bc;
+    const bool pin_in = is_pinned_host(img);
+    const bool pin_out = is_pinned_host(xy) && is_pinned_host(conf) && is_pinned_host(desc);
+    const size_t img_elems = (size_t)Bc * C * H * W, img_bytes = sizeof(float) * img_elems;
+
+    if (img_bytes > s.d_img_bytes || Bc > s.d_B || cap > s.d_cap) {
+        SPB_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(s.d_img[i]); cudaFree(s.d_count[i]); cudaFree(s.d_xy[i]); cudaFree(s.d_conf[i]); cudaFree(s.d_desc[i]);
+            if (s.h_count[i]) cudaFreeHost(s.h_count[i]);
+            SPB_CUDA(cudaMalloc((void**)&s.d_img[i], img_bytes));
+            s.d_count[i] = dev_alloc<int>(Bc);
+            s.d_xy[i] = dev_alloc<int>((size_t)Bc * cap * 2);
+            s.d_conf[i] = dev_alloc<float>((size_t)Bc * cap);
+            s.d_desc[i] = dev_alloc<float>((size_t)Bc * cap * 128);
+            SPB_CUDA(cudaHostAlloc((void**)&s.h_count[i], sizeof(int) * Bc, cudaHostAllocDefault));
         }
-        off += n;
+        s.d_img_bytes = img_bytes; s.d_B = Bc; s.d_cap = cap;
     }
-    SPB_CUDA(cudaStreamSynchronize(st));
-    off = 0;
-    for (int b = 0; b < B; ++b) {
-        const size_t n = (size_t)std::min(s.count[b], cap);
-        count[b] = (int)n;
-        std::memcpy(xy + (size_t)b * cap * 2, s.xy + off * 2, sizeof(int) * 2 * n);
-        std::memcpy(conf + (size_t)b * cap, s.conf + off, sizeof(float) * n);
-        if (desc) std::memcpy(desc + (size_t)b * cap * 128, s.desc + off * 128, sizeof(float) * 128 * n);
-        off += n;
+    if (!pin_in && img_bytes > s.h_img_bytes) {
+        SPB_CUDA(cudaDeviceSynchronize());
+        for (int i = 0; i < 2; ++i) {
+            if (s.h_img[i]) cudaFreeHost(s.h_img[i]);
+            SPB_CUDA(cudaHostAlloc((void**)&s.h_img[i], img_bytes, cudaHostAllocDefault));
+        }
+        s.h_img_bytes = img_bytes;
     }
+    const int dcap = s.d_cap;
+
+    auto enqueue_chunk = [&](int k) {
+        const int slot = k & 1;
+        const float* src = img + (size_t)k * img_elems;
+        if (k >= 2) SPB_CUDA(cudaStreamWaitEvent(s.s_in, s.ev_comp[slot], 0));     // compute(k-2) has read d_img[slot]
+        if (!pin_in) {
+            if (k >= 2) SPB_CUDA(cudaEventSynchronize(s.ev_in[slot]));             // upload(k-2) has left the staging
+            std::memcpy(s.h_img[slot], src, img_bytes);
+            src = s.h_img[slot];
+        }
+        SPB_CUDA(cudaMemcpyAsync(s.d_img[slot], src, img_bytes, cudaMemcpyHostToDevice, s.s_in));
+        SPB_CUDA(cudaEventRecord(s.ev_in[slot], s.s_in));
+        SPB_CUDA(cudaStreamWaitEvent(s.s_comp, s.ev_in[slot], 0));
+        if (k >= 2) SPB_CUDA(cudaStreamWaitEvent(s.s_comp, s.ev_out[slot], 0));    // download(k-2) has read the output slot
+        detect(s.d_img[slot], Bc, C, H, W, dcap, s.d_count[slot], s.d_xy[slot], s.d_conf[slot], desc ? s.d_desc[slot] : nullptr,
+               nullptr, s.s_comp);
+        SPB_CUDA(cudaMemcpyAsync(s.h_count[slot], s.d_count[slot], sizeof(int) * Bc, cudaMemcpyDeviceToHost, s.s_comp));
+        SPB_CUDA(cudaEventRecord(s.ev_comp[slot], s.s_comp));
+    };
+    // pageable outputs: copy a finished slot's staging to the caller's arrays
+    auto drain_staging = [&](int k) {
+        const int slot = k & 1;
+        SPB_CUDA(cudaEventSynchronize(s.ev_out[slot]));
+        size_t off = 0;
+        for (int b = 0; b < Bc; ++b) {
+            const size_t g = (size_t)k * Bc + b, n = (size_t)count[g];
+            std::memcpy(xy + g * cap * 2, s.h_xy[slot] + off * 2, sizeof(int) * 2 * n);
+            std::memcpy(conf + g * cap, s.h_conf[slot] + off, sizeof(float) * n);
+            if (desc) std::memcpy(desc + g * cap * 128, s.h_desc[slot] + off * 128, sizeof(float) * 128 * n);
+            off += n;
+        }
+    };
+
+    enqueue_chunk(0);
+    for (int k = 0; k < nc; ++k) {
+        const int slot = k & 1;
+        if (k + 1 < nc) enqueue_chunk(k + 1);
+        SPB_CUDA(cudaEventSynchronize(s.ev_comp[slot]));                            // counts of chunk k are on the host
+        size_t total = 0;
+        for (int b = 0; b < Bc; ++b) {
+            const int n = std::min(std::max(s.h_count[slot][b], 0), cap);
+            count[(size_t)k * Bc + b] = n;
+            total += (size_t)n;
+        }
+        if (!pin_out) {
+            if (k >= 2) drain_staging(k - 2);
+            if (total > s.h_out_cap[slot]) {
+                if (s.h_xy[slot]) cudaFreeHost(s.h_xy[slot]);
+                if (s.h_conf[slot]) cudaFreeHost(s.h_conf[slot]);
+                if (s.h_desc[slot]) cudaFreeHost(s.h_desc[slot]);
+                const size_t n = total + total / 2 + 1024;
+                SPB_CUDA(cudaHostAlloc((void**)&s.h_xy[slot], sizeof(int) * 2 * n, cudaHostAllocDefault));
+                SPB_CUDA(cudaHostAlloc((void**)&s.h_conf[slot], sizeof(float) * n, cudaHostAllocDefault));
+                SPB_CUDA(cudaHostAlloc((void**)&s.h_desc[slot], sizeof(float) * 128 * n, cudaHostAllocDefault));
+                s.h_out_cap[slot] = n;
+            }
+        }
+        size_t off = 0;
+        for (int b = 0; b < Bc; ++b) {
+            const size_t g = (size_t)k * Bc + b, n = (size_t)count[g];
+            if (n) {
+                int* dxy = pin_out ? xy + g * cap * 2 : s.h_xy[slot] + off * 2;
+                float* dcf = pin_out ? conf + g * cap : s.h_conf[slot] + off;
+                SPB_CUDA(cudaMemcpyAsync(dxy, s.d_xy[slot] + (size_t)b * dcap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s.s_out));
+                SPB_CUDA(cudaMemcpyAsync(dcf, s.d_conf[slot] + (size_t)b * dcap, sizeof(float) * n, cudaMemcpyDeviceToHost, s.s_out));
+                if (desc) {
+                    float* dds = pin_out ? desc + g * cap * 128 : s.h_desc[slot] + off * 128;
+                    SPB_CUDA(cudaMemcpyAsync(dds, s.d_desc[slot] + (size_t)b * dcap * 128, sizeof(float) * 128 * n, cudaMemcpyDeviceToHost, s.s_out));
+                }
+            }
+            off += n;
+        }
+        SPB_CUDA(cudaEventRecord(s.ev_out[slot], s.s_out));
+    }
+    if (!pin_out) {
+        if (nc >= 2) drain_staging(nc - 2);
+        drain_staging(nc - 1);
+    }
+    SPB_CUDA(cudaStreamSynchronize(s.s_out));
+    SPB_CUDA(cudaStreamSynchronize(s.s_comp));
 }
 
 }  // namespace spb200

@@ -192,6 +192,33 @@ def test_detect_host_matches_device(engines):
         np.testing.assert_array_equal(hdsc[i, :n], dsc[i, :n].cpu().numpy())
 
 
+@pytest.mark.parametrize('pinned', [False, True])
+def test_detect_host_chunked_pipeline(engines, pinned, monkeypatch):
+    """The host entry point cuts the batch into chunks (upload / compute / download overlap): six images in chunks
+    of two, pageable and pinned caller buffers, against the device path image by image."""
+    monkeypatch.setenv('SPB200_HOST_CHUNK', '2')
+    e = engines['fp16']
+    names = ['shapes240_0', 'rand240_1', 'shapes240_1', 'shapes240_2', 'rand240_0', 'shapes240_0']
+    imgs = torch.stack([golden_image(n) for n in names])[:, None].contiguous()
+    cap = e.max_keypoints(240, 320)
+    count, xy, conf, dsc, _ = [t.clone() if t is not None else None for t in e.detect(imgs.cuda(), cap)]
+    if pinned:
+        host_in = imgs.pin_memory().numpy()
+        out = (np.zeros((6,), np.int32), torch.zeros((6, cap, 2), dtype=torch.int32).pin_memory().numpy(),
+               torch.zeros((6, cap), dtype=torch.float32).pin_memory().numpy(),
+               torch.zeros((6, cap, 128), dtype=torch.float32).pin_memory().numpy())
+    else:
+        host_in, out = imgs.numpy(), None
+    for _ in range(2):                                     # second call reuses the pipeline state
+        hc, hxy, hconf, hdsc = e.detect_host(host_in, cap, out=out)
+        np.testing.assert_array_equal(hc, count.cpu().numpy())
+        for i in range(6):
+            n = int(hc[i])
+            np.testing.assert_array_equal(hxy[i, :n], xy[i, :n].cpu().numpy())
+            np.testing.assert_array_equal(hconf[i, :n], conf[i, :n].cpu().numpy())
+            np.testing.assert_array_equal(hdsc[i, :n], dsc[i, :n].cpu().numpy())
+
+
 def test_other_checkpoints_harsh_and_magicpoint(tmp_path):
     """Synthetic 'harsh' preset + a magic_point.pt written in the reference's checkpoint format."""
     spb = load_spb()
