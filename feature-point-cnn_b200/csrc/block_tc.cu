@@ -63,7 +63,9 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias1[BLOCK_N], s_bias2[BLOCK_N];
 
-    uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023);
+    // aligned up to 1024 B by pointer ARITHMETIC on dyn_smem: the compiler keeps the shared address space (LDS/STS,
+    // 32-bit addresses) instead of falling back to generic loads
+    uint8_t* ring = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
     uint8_t* s_y = ring + STAGES * kStageBytes;            // [kYChunks][128 rows][128 B]
     // shuffle: makes the warp index warp-uniform for the compiler (role loops then run on the uniform datapath)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0), lane = threadIdx.x % 32;

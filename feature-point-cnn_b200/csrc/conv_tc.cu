@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias[BLOCK_N];
 
-    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023);
+    // aligned up to 1024 B by pointer ARITHMETIC on dyn_smem: the compiler keeps the shared address space (LDS/STS,
+    // 32-bit addresses) instead of falling back to generic loads
+    uint8_t* tiles = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int img = blockIdx.y;
     const int y0 = (blockIdx.x / p.tiles_x) * p.th, x0 = (blockIdx.x % p.tiles_x) * p.tw;

@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias1[N], s_bias2[N];
 
-    uint8_t* a_ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023);
+    // aligned up to 1024 B by pointer ARITHMETIC on dyn_smem: the compiler keeps the shared address space (LDS/STS,
+    // 32-bit addresses) instead of falling back to generic loads
+    uint8_t* a_ring = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
     uint8_t* w_ring = a_ring + SA * T * kHaloBufBytes;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the role loops below run on the
     // uniform datapath (loop counters, ring state, descriptors in uniform registers) instead of R2UR round trips

@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias[64];
 
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023);
+    // aligned up to 1024 B by pointer ARITHMETIC on dyn_smem: the compiler keeps the shared address space (LDS/STS,
+    // 32-bit addresses) instead of falling back to generic loads
+    uint8_t* base = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
     uint8_t* s_a = base;                                              // [2 M-tiles][NCHUNK][128 rows][128 B]
     uint8_t* s_w = s_a + 2 * NCHUNK * kATile;                 // [NPART][NCHUNK][64 rows][128 B]
     T* s_in = reinterpret_cast<T*>(s_w + NPART * NCHUNK * 64 * 128);  // [2 buffers][CIN][27][48], image * 255 in the operand type
@@ -86,20 +88,37 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
     }
     // persistent: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the input patch of the next
     // tile is fetched while the tensor core works on the current one
+    // patch loader: the (channel, row, pixel pair) a thread fetches in each of its iterations does not depend on the
+    // tile, so the decomposition is done once; per tile only the origin changes
+    constexpr int kPairs = CIN * kStIH * (kStIWp / 2);
+    constexpr int kPatchIters = (kPairs + kStThreads - 1) / kStThreads;
+    int pl_dy[kPatchIters], pl_dx[kPatchIters], pl_c[kPatchIters];
+#pragma unroll
+    for (int it = 0; it < kPatchIters; ++it) {
+        const int i = tid + it * kStThreads;
+        const int r = i % (kStIH * (kStIWp / 2));
+        pl_c[it] = i / (kStIH * (kStIWp / 2));
+        pl_dy[it] = r / (kStIWp / 2);
+        pl_dx[it] = 2 * (r % (kStIWp / 2));
+    }
     auto load_patch = [&](int tile, int buf) {
         const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
         const int iy0 = 4 * ((tt / p.tiles_x) * kStPH) - 5, ix0 = 4 * ((tt % p.tiles_x) * kStPW) - 5;
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_in + buf * kPatch);
-        for (int i = tid; i < CIN * kStIH * (kStIWp / 2); i += kStThreads) {      // two pixels per iteration
-            const int c = i / (kStIH * (kStIWp / 2)), r = i % (kStIH * (kStIWp / 2));
-            const int y = iy0 + r / (kStIWp / 2), x = ix0 + 2 * (r % (kStIWp / 2));
-            float v0 = 0.f, v1 = 0.f;
-            if (y >= 0 && y < H) {
-                const float* row = p.img + ((size_t)(b * CIN + c) * H + y) * W;
-                if (x >= 0 && x < W) v0 = __ldg(row + x);
-                if (x + 1 >= 0 && x + 1 < W) v1 = __ldg(row + x + 1);
+        const float* img_b = p.img + (size_t)b * CIN * H * W;
+#pragma unroll
+        for (int it = 0; it < kPatchIters; ++it) {
+            const int i = tid + it * kStThreads;
+            if (i < kPairs) {
+                const int y = iy0 + pl_dy[it], x = ix0 + pl_dx[it];
+                float v0 = 0.f, v1 = 0.f;
+                if (y >= 0 && y < H) {
+                    const float* row = img_b + ((size_t)pl_c[it] * H + y) * W;
+                    if (x >= 0 && x < W) v0 = __ldg(row + x);
+                    if (x + 1 >= 0 && x + 1 < W) v1 = __ldg(row + x + 1);
+                }
+                dst[i] = pack2<T>(v0 * 255.f, v1 * 255.f);
             }
-            dst[i] = pack2<T>(v0 * 255.f, v1 * 255.f);
         }
     };
     if ((int)blockIdx.x < p.total_tiles) load_patch(blockIdx.x, 0);
@@ -175,11 +194,17 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
                 tmem_ld_wait();
     #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float v[8];
+                    uint4 u = make_uint4(0u, 0u, 0u, 0u);              // rows outside the conv output: neutral for the max
+                    if (real) {
+                        uint32_t w[4];
     #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        v[e] = real ? fmaxf(fmaf(__uint_as_float(r[j * 8 + e]), 1.f / 255.f, s_bias[half * 32 + j * 8 + e]), 0.f) : 0.f;
-                    const uint4 u = make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
+                        for (int e = 0; e < 4; ++e) {
+                            const int c = half * 32 + j * 8 + 2 * e;
+                            w[e] = max2<T>(pack2<T>(fmaf(__uint_as_float(r[j * 8 + 2 * e]), 1.f / 255.f, s_bias[c]),
+                                                    fmaf(__uint_as_float(r[j * 8 + 2 * e + 1]), 1.f / 255.f, s_bias[c + 1])), 0u);
+                        }
+                        u = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
                     *reinterpret_cast<uint4*>(crow + (((half * 4 + j) ^ (row & 7)) << 4)) = u;     // same XOR swizzle: conflict-free
                 }
             }
@@ -232,7 +257,7 @@ static void launch_stem_tc_t(const StemTcPlan* plan, const float* img, void* dst
     p.tiles_x = (W / 4 + kStPW - 1) / kStPW;
     p.tiles_per_img = p.tiles_x * ((H / 4 + kStPH - 1) / kStPH);
     p.total_tiles = p.tiles_per_img * B;
-    const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
+    const int per_sm = std::max(1, std::min(4, (int)((227 * 1024) / (smem + 1536))));
     const int grid = std::min(p.total_tiles, plan->num_sms * per_sm);
     kern<<<grid, kStThreads, smem, st>>>(p);
     SPB_CHECK_LAUNCH();
