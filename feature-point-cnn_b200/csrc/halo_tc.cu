@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full[SW], w_empty[SW];
     __shared__ __align__(8) uint64_t d1_full[NBUF], d1_empty[NBUF], y_full[NBUF], d2_full[NBUF], d2_empty[NBUF];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_bias1[N], s_bias2[N];
+    __shared__ __align__(16) float s_bias1[N], s_bias2[N];
 
     // aligned up to 1024 B by pointer ARITHMETIC on dyn_smem: the compiler keeps the shared address space (LDS/STS,
     // 32-bit addresses) instead of falling back to generic loads
@@ -207,8 +207,30 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 if (!FUSED) mbar_wait(&d1_empty[b], ph ^ 1u);          // epilogue has drained D1[b]
                 if (FUSED && p.has_ds) mbar_wait(&d2_empty[b], ph ^ 1u);
                 tc_fence_after();
+                if (WRES && j > 0) {
+                    // resident weights, nothing left to wait for but the activation chunk (a 64-channel block has one
+                    // chunk): the whole tile is issued from one elect region with no barrier traffic between MMAs
+                    mbar_wait_a(bar_afull + sa * 8, pha);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a0 = a_lo_base + (uint32_t)(sa * T * (kHaloBufBytes >> 4));
+                        for (int e = 0; e < p.n1steps; ++e) {
+                            const HaloStep s = p.steps[e];
+                            const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+                            const uint32_t alo = a0 + (lo & 0xffffu), blo = w_lo_base + (lo >> 16);
+                            const uint32_t d = d_base + (((hi >> 4) & 3u) == 0 ? 0u : kAccCols) + (uint32_t)(b * T * N);
+                            umma_f16_w(d, alo, kHiA, blo, kHiB, idesc, (hi >> 11) & 1u);
+                            umma_f16_w(d, alo + 2, kHiA, blo + 2, kHiB, idesc, 1u);
+                            umma_f16_w(d, alo + 4, kHiA, blo + 4, kHiB, idesc, 1u);
+                            umma_f16_w(d, alo + 6, kHiA, blo + 6, kHiB, idesc, 1u);
+                        }
+                        umma_commit_a(bar_aempty + sa * 8);
+                        umma_commit(&d1_full[b]);
+                    }
+                    if (++sa == SA) { sa = 0; pha ^= 1u; }
+                }
                 HaloStep rec = p.steps[0];
-                for (int e = 0; e < p.n1steps; ++e) {
+                for (int e = 0; e < ((WRES && j > 0) ? 0 : p.n1steps); ++e) {
                     const HaloStep s = rec;
                     rec = p.steps[e + 1];
                     const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
@@ -230,7 +252,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     if (!WRES) wph ^= 1u << slot;
                     if (hi & (1u << 10)) { if (++sa == SA) { sa = 0; pha ^= 1u; } }
                 }
-                if (elect_one()) umma_commit(&d1_full[b]);
+                if (!(WRES && j > 0) && elect_one()) umma_commit(&d1_full[b]);
             }
             if (FUSED && j >= LAG) {
                 const int jj = j - LAG;
@@ -273,65 +295,95 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         const int nblk = p.n_mma / 32;
         const int blk_lo = T == 2 ? 0 : (eh == 0 ? 0 : (nblk + 1) / 2);
         const int blk_hi = T == 2 ? nblk : (eh == 0 ? (nblk + 1) / 2 : nblk);
-        for (int j = 0; j < n_local; ++j) {
-            const int st = blockIdx.x + j * gridDim.x;
-            const int b = j % NBUF;
-            const uint32_t ph = (uint32_t)(j / NBUF) & 1u;
+        constexpr int kResBlk = N / 32;
+        // per-tile coordinates of this thread's output pixel
+        struct Pix { bool valid; size_t gpix, dpix; };
+        auto pixel_of = [&](int jt) {
+            const int st = blockIdx.x + jt * gridDim.x;
             const int tile_raw = st * T + t;
             const int tile = min(tile_raw, p.total_tiles - 1);
             const int img = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
             const int s0 = (tt / p.tiles_g) * 16, g0 = (tt % p.tiles_g) * 8;
             const int oy = p.orient == 0 ? s0 + ti : g0 + tr;
             const int ox = p.orient == 0 ? g0 + tr : s0 + ti;
-            const bool valid = tile_raw < p.total_tiles && oy < p.OH && ox < p.OW;
-            const size_t gpix = ((size_t)img * p.OH + oy) * p.OW + ox;
-            const size_t dpix = ((size_t)img * p.dst_H + (oy * p.dst_stride + p.dst_off_y)) * p.dst_W +
-                                (ox * p.dst_stride + p.dst_off_x);
+            Pix px;
+            px.valid = tile_raw < p.total_tiles && oy < p.OH && ox < p.OW;
+            px.gpix = ((size_t)img * p.OH + oy) * p.OW + ox;
+            px.dpix = ((size_t)img * p.dst_H + (oy * p.dst_stride + p.dst_off_y)) * p.dst_W + (ox * p.dst_stride + p.dst_off_x);
+            return px;
+        };
+        // epilogue 1: Y = relu(D1 + b1) rounded to 16 bits, written back IN PLACE: block k (fp32 columns 32k..32k+31, all
+        // in registers by then) becomes packed columns 16k..16k+15 of the same lanes, which blocks < k no longer need
+        auto epi1 = [&](int jt) {
+            const int b = jt % NBUF;
+            const uint32_t ph = (uint32_t)(jt / NBUF) & 1u;
             const uint32_t tmem_d1 = tmem_base + (uint32_t)((b * T + t) * N) + lane_off;
-            const uint32_t tmem_d2 = tmem_d1 + kAccCols;
             mbar_wait(&d1_full[b], ph);
             tc_fence_after();
-            if (FUSED) {
-                // Y = relu(D1 + b1) rounded to 16 bits, written back IN PLACE: block k (fp32 columns 32k..32k+31, all
-                // in registers by then) becomes packed columns 16k..16k+15 of the same lanes, which blocks < k no longer need
-#pragma unroll 1
-                for (int blk = blk_lo; blk < blk_hi; ++blk) {
-                    const int c0 = blk * 32;
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_d1 + (uint32_t)c0, r);
-                    tmem_ld_wait();
-                    uint32_t y[16];
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        y[e] = pack2<Tp>(fmaxf(__uint_as_float(r[2 * e]) + s_bias1[c0 + 2 * e], 0.f),
-                                         fmaxf(__uint_as_float(r[2 * e + 1]) + s_bias1[c0 + 2 * e + 1], 0.f));
-                    tmem_st_32x16(tmem_d1 + (uint32_t)(c0 >> 1), y);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&y_full[b]);
-                mbar_wait(&d2_full[b], ph);
-                tc_fence_after();
-            }
-            const uint32_t tmem_out = FUSED ? tmem_d2 : tmem_d1;
-            const float* sb = FUSED ? s_bias2 : s_bias1;
 #pragma unroll 1
             for (int blk = blk_lo; blk < blk_hi; ++blk) {
                 const int c0 = blk * 32;
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_out + (uint32_t)c0, r);
-                tmem_ld_wait();
-                if (valid) {
-                    float v[32];
+                tmem_ld_32x32(tmem_d1 + (uint32_t)c0, r);
+                float bb[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + sb[c0 + i];
-                    if (p.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const Tp*>(p.residual) + gpix * p.res_C + c0);
+                for (int e = 0; e < 8; ++e) {
+                    const float4 f = *reinterpret_cast<const float4*>(s_bias1 + c0 + 4 * e);
+                    bb[4 * e] = f.x; bb[4 * e + 1] = f.y; bb[4 * e + 2] = f.z; bb[4 * e + 3] = f.w;
+                }
+                tmem_ld_wait();
+                uint32_t y[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    y[e] = pack2<Tp>(fmaxf(__uint_as_float(r[2 * e]) + bb[2 * e], 0.f), fmaxf(__uint_as_float(r[2 * e + 1]) + bb[2 * e + 1], 0.f));
+                tmem_st_32x16(tmem_d1 + (uint32_t)(c0 >> 1), y);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&y_full[b]);
+        };
+        // epilogue 2 (or the only epilogue of a plain convolution): OUT = act(D + b (+ residual)) -> global.  The
+        // residual is fetched BEFORE the wait on the accumulator so that its latency hides behind the MMAs.
+        auto epi_out = [&](int jt) {
+            const int b = jt % NBUF;
+            const uint32_t ph = (uint32_t)(jt / NBUF) & 1u;
+            const Pix px = pixel_of(jt);
+            uint4 res[kResBlk][4];
+            const bool has_res = p.residual != nullptr && px.valid;
+            if (has_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const Tp*>(p.residual) + px.gpix * p.res_C);
+#pragma unroll
+                for (int k = 0; k < kResBlk; ++k)
+                    if (k >= blk_lo && k < blk_hi) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) res[k][jj] = __ldg(rp + k * 4 + jj);
+                    }
+            }
+            const uint32_t tmem_out = tmem_base + (uint32_t)((b * T + t) * N) + lane_off + (FUSED ? kAccCols : 0u);
+            const float* sb = FUSED ? s_bias2 : s_bias1;
+            mbar_wait(FUSED ? &d2_full[b] : &d1_full[b], ph);
+            tc_fence_after();
+#pragma unroll
+            for (int blk = 0; blk < kResBlk; ++blk) {
+                if (blk < blk_lo || blk >= blk_hi) continue;
+                const int c0 = blk * 32;
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_out + (uint32_t)c0, r);
+                float v[32];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float4 f = *reinterpret_cast<const float4*>(sb + c0 + 4 * e);
+                    v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
+                }
+                tmem_ld_wait();
+                if (px.valid) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+                    if (has_res) {
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
-                            const uint4 u = __ldg(rp + jj);
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                            const uint32_t w[4] = {res[blk][jj].x, res[blk][jj].y, res[blk][jj].z, res[blk][jj].w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 f = unpack2<Tp>(w[e]);
@@ -345,11 +397,11 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
                     if (p.dst_fp32) {
-                        float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.dst) + dpix * p.dst_C + c0);
+                        float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.dst) + px.dpix * p.dst_C + c0);
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) dp[jj] = make_float4(v[jj * 4], v[jj * 4 + 1], v[jj * 4 + 2], v[jj * 4 + 3]);
                     } else {
-                        uint4* dp = reinterpret_cast<uint4*>(static_cast<Tp*>(p.dst) + dpix * p.dst_C + c0);
+                        uint4* dp = reinterpret_cast<uint4*>(static_cast<Tp*>(p.dst) + px.dpix * p.dst_C + c0);
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj)
                             dp[jj] = make_uint4(pack2<Tp>(v[jj * 8], v[jj * 8 + 1]), pack2<Tp>(v[jj * 8 + 2], v[jj * 8 + 3]),
@@ -360,6 +412,22 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(FUSED ? &d2_empty[b] : &d1_empty[b]);
+        };
+        if (!FUSED) {
+            for (int j = 0; j < n_local; ++j) epi_out(j);
+        } else if (NBUF == 2) {
+            // the accumulators are double buffered: the first epilogue of tile j+1 runs before the second epilogue of
+            // tile j, which hides the y_full -> GEMM 2 -> d2_full round trip
+            for (int j = 0; j < n_local; ++j) {
+                epi1(j);
+                if (j > 0) epi_out(j - 1);
+            }
+            if (n_local > 0) epi_out(n_local - 1);
+        } else {
+            for (int j = 0; j < n_local; ++j) {
+                epi1(j);
+                epi_out(j);
+            }
         }
     }
     __syncthreads();
@@ -549,6 +617,11 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     }
     p.nsteps = nsteps;
     if (plan->variant == 0 && nsteps > kHaloResidentSlabs) return nullptr;
+    if (plan->variant == 0) {      // the resident-weight fast path issues four K steps per slab from one activation chunk
+        if (nchunks != 1) return nullptr;
+        for (int e = 0; e < p.n1steps; ++e)
+            if (((p.steps[e] >> 38) & 7u) != 4u) return nullptr;
+    }
     p.OH = c1.OH; p.OW = c1.OW;
     p.residual = last.residual; p.dst = last.dst;
     p.res_C = last.res_C; p.dst_H = last.dst_H; p.dst_W = last.dst_W; p.dst_C = last.dst_C;
