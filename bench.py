@@ -28,6 +28,23 @@ METRIC = 'SuperPoint images/sec @480x640 (kpts+desc)'
 UNIT = 'images/s'
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the newest committed ncu
+    full-set summary under profiles/ (MB columns of scripts/ncu_summary.py); None when there is none."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(REPO, 'profiles', '*ncu_full_summary*.txt'))):
+        for line in open(f):
+            if kernel_substr in line:
+                parts = line[44:].split()
+                try:
+                    best = (float(parts[1]) + float(parts[2])) * 1e6
+                except Exception:
+                    pass
+                break
+    return best
+
+
 def load_peaks():
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -215,11 +232,9 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max * 1e-3)
+    from spb200 import shard
+    ms_max = shard.max_over_ranks(ms, dev)                  # device time, MAX over ranks
+    value = shard.whole_job_rate(B * args.steps, ms * 1e-3, dev)
     kp_mean = float(outs[0].float().mean().item())
 
     # ---- end to end through the host-buffer C ABI (spb200_detect_host) ------------------------------
@@ -241,10 +256,7 @@ def main():
         d2h += int(host_out[0].sum()) * (8 + 4 + 512) + 4 * B
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
+    e2e_value = shard.whole_job_rate(B * e2e_steps, dt, dev)
 
     # ---- per-kernel CUDA-event profile (separate pass; roofline) -----------------------------------
     prof_steps = 3
@@ -283,12 +295,23 @@ def main():
     conv_rows = [r for r in table if 'tflops' in r]
     conv_ms = sum(r['ms'] for r in conv_rows)
     conv_flops = sum(a['flops'] for n_, a in agg.items() if a['flops'])
-    if 'tflops' in top:
+    # the bound of the dominant kernel: tensor pipe unless its algorithmic intensity is below the ridge of the
+    # measured peaks (the fused stem: 131 FLOP/B vs a ridge of ~212), then HBM
+    ridge = peaks['tc_sustained'] * 1e12 / (peaks['hbm_gbs'] * 1e9)
+    top_ai = (agg[top['kernel']]['flops'] / agg[top['kernel']]['bytes']) if agg[top['kernel']]['flops'] and agg[top['kernel']]['bytes'] else None
+    if 'tflops' in top and not (top_ai is not None and top_ai < ridge):
         roofline = {'bound': 'tensor', 'kernel': top['kernel'], 'achieved': top['tflops'], 'peak': peaks['tc_sustained'],
                     'unit': 'TFLOP/s', 'frac': top['tflops'] / peaks['tc_sustained'], 'traffic': None}
     else:
         roofline = {'bound': 'hbm', 'kernel': top['kernel'], 'achieved': top.get('gbs'), 'peak': peaks['hbm_gbs'],
                     'unit': 'GB/s', 'frac': top.get('frac_hbm'), 'traffic': None}
+        if top_ai is not None:
+            roofline['algorithmic_intensity_flop_per_byte'] = top_ai
+            roofline['ridge_flop_per_byte'] = ridge
+    ncu_name = {'stem_pool': 'stem_tc_kernel', 'nms': 'nms_round0_kernel', 'descriptors': 'sample_desc', 'heatmap': 'heatmap_kernel',
+                'sort_topk': 'sort_emit_kernel'}.get(top['kernel'])
+    roofline['traffic'] = ncu_traffic(ncu_name) if ncu_name and B == 64 and H == 480 and W == 640 else None
+    roofline['traffic_source'] = 'ncu --set full capture of the same workload committed under profiles/ (dram bytes read + written per launch)'
     roofline['peak_source'] = peaks['source'] + (', sustained bf16 GEMM figure' if roofline['bound'] == 'tensor' else '')
     roofline['share_of_step'] = top['share']
     roofline['all_convs'] = {'tflops': conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
