@@ -14,9 +14,10 @@
 //      cameras and the reference's loaders produce) are represented exactly; the weights are split into
 //      16-bit hi + lo parts and two MMAs (a*w_hi + a*w_lo) are accumulated; 1/255 is applied to the fp32
 //      accumulator.  The stem is then as accurate as fp32 for 8-bit inputs at negligible tensor cost,
-//   4. the epilogue adds bias, applies ReLU, zeroes rows outside the conv output (neutral for the max,
-//      all real values are >= 0) and stages the 231x64 tile in smem,
-//   5. the 3x3/s2 max-pool reads that tile and writes NHWC 16-bit.
+//   4. the epilogue scales, adds the bias and stages the 231x64 tile in smem transposed (channel quad major),
+//      rows outside the conv output as 0,
+//   5. the 3x3/s2 max-pool runs per (pooled pixel, channel quad) with packed 16-bit maxima; its running maximum
+//      starts at 0, which is the ReLU (max and ReLU commute); NHWC 16-bit out.
 // HBM traffic is the algorithmic minimum: the fp32 image in, the pooled tensor out.
 #include <cuda.h>
 
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
     uint8_t* s_w = s_a + 2 * NCHUNK * kATile;                 // [NPART][NCHUNK][64 rows][128 B]
     T* s_in = reinterpret_cast<T*>(s_w + NPART * NCHUNK * 64 * 128);  // [2 buffers][CIN][27][48], image * 255 in the operand type
     constexpr int kPatch = CIN * kStIH * kStIWp;
-    uint8_t* s_conv = s_a;                                            // aliases A after the MMAs: [256 rows][128 B]
+    uint8_t* s_conv = s_a;                                            // aliases A after the MMAs: [16 channel quads][231 rows][8 B]
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
     const int H = p.H, W = p.W, CH = H / 2, CW = W / 2, PH = H / 4, PW = W / 4;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
     // tile, so the decomposition is done once; per tile only the origin changes
     constexpr int kPairs = CIN * kStIH * (kStIWp / 2);
     constexpr int kPatchIters = (kPairs + kStThreads - 1) / kStThreads;
-    int pl_dy[kPatchIters], pl_dx[kPatchIters], pl_c[kPatchIters];
+    int pl_dy[kPatchIters], pl_dx[kPatchIters], pl_c[kPatchIters], pl_off[kPatchIters];
 #pragma unroll
     for (int it = 0; it < kPatchIters; ++it) {
         const int i = tid + it * kStThreads;
@@ -100,24 +101,37 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
         pl_c[it] = i / (kStIH * (kStIWp / 2));
         pl_dy[it] = r / (kStIWp / 2);
         pl_dx[it] = 2 * (r % (kStIWp / 2));
+        pl_off[it] = (pl_c[it] * p.H + pl_dy[it]) * p.W + pl_dx[it];          // offset from the patch origin (interior tiles)
     }
     auto load_patch = [&](int tile, int buf) {
         const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
         const int iy0 = 4 * ((tt / p.tiles_x) * kStPH) - 5, ix0 = 4 * ((tt % p.tiles_x) * kStPW) - 5;
         uint32_t* dst = reinterpret_cast<uint32_t*>(s_in + buf * kPatch);
         const float* img_b = p.img + (size_t)b * CIN * H * W;
+        if (iy0 >= 0 && iy0 + kStIH <= H && ix0 >= 0 && ix0 + kStIWp <= W) {       // patch entirely inside the image
+            const float* org = img_b + (size_t)iy0 * W + ix0;
 #pragma unroll
-        for (int it = 0; it < kPatchIters; ++it) {
-            const int i = tid + it * kStThreads;
-            if (i < kPairs) {
-                const int y = iy0 + pl_dy[it], x = ix0 + pl_dx[it];
-                float v0 = 0.f, v1 = 0.f;
-                if (y >= 0 && y < H) {
-                    const float* row = img_b + ((size_t)pl_c[it] * H + y) * W;
-                    if (x >= 0 && x < W) v0 = __ldg(row + x);
-                    if (x + 1 >= 0 && x + 1 < W) v1 = __ldg(row + x + 1);
+            for (int it = 0; it < kPatchIters; ++it) {
+                const int i = tid + it * kStThreads;
+                if (i < kPairs) {
+                    const float* q = org + pl_off[it];
+                    dst[i] = pack2<T>(__ldg(q) * 255.f, __ldg(q + 1) * 255.f);
                 }
-                dst[i] = pack2<T>(v0 * 255.f, v1 * 255.f);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < kPatchIters; ++it) {
+                const int i = tid + it * kStThreads;
+                if (i < kPairs) {
+                    const int y = iy0 + pl_dy[it], x = ix0 + pl_dx[it];
+                    float v0 = 0.f, v1 = 0.f;
+                    if (y >= 0 && y < H) {
+                        const float* row = img_b + ((size_t)pl_c[it] * H + y) * W;
+                        if (x >= 0 && x < W) v0 = __ldg(row + x);
+                        if (x + 1 >= 0 && x + 1 < W) v1 = __ldg(row + x + 1);
+                    }
+                    dst[i] = pack2<T>(v0 * 255.f, v1 * 255.f);
+                }
             }
         }
     };
@@ -137,17 +151,19 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
             const bool live = row < kStRows;
             const int cyl = row / kStCW, cxl = row % kStCW;
             const T* pin = s_in + buf * kPatch + (2 * cyl) * kStIWp + 2 * cxl;    // 4-byte aligned
+            const int sw = (rr & 7) << 4;                          // the row's swizzle phase
     #pragma unroll
             for (int ck = 0; ck < NCHUNK; ++ck) {                  // chunk = input channel
                 uint8_t* arow = s_a + (mt * NCHUNK + ck) * kATile + rr * 128;
+                const T* pc = pin + ck * kStIH * kStIWp;
     #pragma unroll
                 for (int j = 0; j < 8; ++j) {                      // 16-byte piece j = filter row ky = j: patch pixels 2*cxl .. 2*cxl+7
-                    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                    uint4 u = make_uint4(0u, 0u, 0u, 0u);          // (a warp writes piece j of 32 rows: the XOR spreads them over all banks)
                     if (live && j < 7) {
-                        const uint32_t* q = reinterpret_cast<const uint32_t*>(pin + ck * kStIH * kStIWp + j * kStIWp);
+                        const uint32_t* q = reinterpret_cast<const uint32_t*>(pc + j * kStIWp);
                         u = make_uint4(q[0], q[1], q[2], q[3]);
                     }
-                    *reinterpret_cast<uint4*>(arow + ((j ^ (rr & 7)) << 4)) = u;
+                    *reinterpret_cast<uint4*>(arow + ((j << 4) ^ sw)) = u;
                 }
             }
         }
@@ -186,26 +202,33 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
             const int row = mt * 128 + q * 32 + lane;
             const int cy = cy0 + row / kStCW, cx = cx0 + row % kStCW;
             const bool real = row < kStRows && cy >= 0 && cy < CH && cx >= 0 && cx < CW;
-            uint8_t* crow = s_conv + row * 128;
+            // staged transposed: [channel quad 0..15][conv row 0..230] 8-byte entries, so that the pool addresses a
+            // fixed quad with immediate row offsets and neither side has bank conflicts.  No ReLU here: the pool's
+            // running maximum starts at 0, which is the ReLU; rows outside the conv output store 0 (neutral).
+            uint8_t* cq = s_conv + row * 8;
     #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + half * 32), r);
+                float bb[32];
+    #pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float4 f = *reinterpret_cast<const float4*>(s_bias + half * 32 + 4 * e);
+                    bb[4 * e] = f.x; bb[4 * e + 1] = f.y; bb[4 * e + 2] = f.z; bb[4 * e + 3] = f.w;
+                }
                 tmem_ld_wait();
+                if (row < kStRows) {
     #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 u = make_uint4(0u, 0u, 0u, 0u);              // rows outside the conv output: neutral for the max
-                    if (real) {
-                        uint32_t w[4];
-    #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = half * 32 + j * 8 + 2 * e;
-                            w[e] = max2<T>(pack2<T>(fmaf(__uint_as_float(r[j * 8 + 2 * e]), 1.f / 255.f, s_bias[c]),
-                                                    fmaf(__uint_as_float(r[j * 8 + 2 * e + 1]), 1.f / 255.f, s_bias[c + 1])), 0u);
+                    for (int j = 0; j < 8; ++j) {                  // channel quad half * 8 + j
+                        uint2 u = make_uint2(0u, 0u);
+                        if (real) {
+                            u.x = pack2<T>(fmaf(__uint_as_float(r[4 * j]), 1.f / 255.f, bb[4 * j]),
+                                           fmaf(__uint_as_float(r[4 * j + 1]), 1.f / 255.f, bb[4 * j + 1]));
+                            u.y = pack2<T>(fmaf(__uint_as_float(r[4 * j + 2]), 1.f / 255.f, bb[4 * j + 2]),
+                                           fmaf(__uint_as_float(r[4 * j + 3]), 1.f / 255.f, bb[4 * j + 3]));
                         }
-                        u = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint2*>(cq + (half * 8 + j) * (kStRows * 8)) = u;
                     }
-                    *reinterpret_cast<uint4*>(crow + (((half * 4 + j) ^ (row & 7)) << 4)) = u;     // same XOR swizzle: conflict-free
                 }
             }
         }
@@ -215,17 +238,18 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
         // ---- 3x3 / stride-2 max-pool over the staged conv tile, two channels per thread --------------
         T* out = static_cast<T*>(p.dst);
         for (int o = tid; o < kStPH * kStPW * 16; o += kStThreads) {
-            const int c4 = o % 16, pp = o / 16;                    // four channels per thread
-            const int ppy = pp / kStPW, ppx = pp % kStPW;
+            // one work item = one pooled pixel x four channels; the nine taps sit at immediate offsets from one base
+            const int c4 = o & 15, pp = o >> 4;
+            const int ppy = pp / kStPW, ppx = pp - ppy * kStPW;
             const int py = py0 + ppy, px = px0 + ppx;
             if (py >= PH || px >= PW) continue;
-            uint2 m = make_uint2(0u, 0u);                          // all staged values are >= 0
+            const uint8_t* src = s_conv + c4 * (kStRows * 8) + ((2 * ppy) * kStCW + 2 * ppx) * 8;
+            uint2 m = make_uint2(0u, 0u);                          // max with 0 = the ReLU
     #pragma unroll
             for (int dy = 0; dy < 3; ++dy)
     #pragma unroll
                 for (int dx = 0; dx < 3; ++dx) {
-                    const int row = (2 * ppy + dy) * kStCW + 2 * ppx + dx;
-                    const uint2 u = *reinterpret_cast<const uint2*>(s_conv + row * 128 + (((c4 >> 1) ^ (row & 7)) << 4) + (c4 & 1) * 8);
+                    const uint2 u = *reinterpret_cast<const uint2*>(src + (dy * kStCW + dx) * 8);
                     m.x = max2<T>(m.x, u.x);
                     m.y = max2<T>(m.y, u.y);
                 }
