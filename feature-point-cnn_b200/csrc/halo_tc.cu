@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 uint32_t y[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e)
-                    y[e] = pack2<Tp>(fmaxf(__uint_as_float(r[2 * e]) + bb[2 * e], 0.f), fmaxf(__uint_as_float(r[2 * e + 1]) + bb[2 * e + 1], 0.f));
+                    y[e] = pack2_relu<Tp>(__uint_as_float(r[2 * e]) + bb[2 * e], __uint_as_float(r[2 * e + 1]) + bb[2 * e + 1]);
                 tmem_st_32x16(tmem_d1 + (uint32_t)(c0 >> 1), y);
             }
             tmem_st_wait();
@@ -343,23 +343,28 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&y_full[b]);
         };
+        // the identity-shortcut operand of a tile, fetched long before it is needed (the call sites put a whole first
+        // epilogue or the accumulator wait between this and its use)
+        uint4 res[kResBlk][4];
+        auto prefetch_res = [&](int jt) {
+            if (p.residual == nullptr) return;
+            const Pix px = pixel_of(jt);
+            if (!px.valid) return;
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const Tp*>(p.residual) + px.gpix * p.res_C);
+#pragma unroll
+            for (int k = 0; k < kResBlk; ++k)
+                if (k >= blk_lo && k < blk_hi) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) res[k][jj] = __ldg(rp + k * 4 + jj);
+                }
+        };
         // epilogue 2 (or the only epilogue of a plain convolution): OUT = act(D + b (+ residual)) -> global.  The
         // residual is fetched BEFORE the wait on the accumulator so that its latency hides behind the MMAs.
         auto epi_out = [&](int jt) {
             const int b = jt % NBUF;
             const uint32_t ph = (uint32_t)(jt / NBUF) & 1u;
             const Pix px = pixel_of(jt);
-            uint4 res[kResBlk][4];
             const bool has_res = p.residual != nullptr && px.valid;
-            if (has_res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const Tp*>(p.residual) + px.gpix * p.res_C);
-#pragma unroll
-                for (int k = 0; k < kResBlk; ++k)
-                    if (k >= blk_lo && k < blk_hi) {
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) res[k][jj] = __ldg(rp + k * 4 + jj);
-                    }
-            }
             const uint32_t tmem_out = tmem_base + (uint32_t)((b * T + t) * N) + lane_off + (FUSED ? kAccCols : 0u);
             const float* sb = FUSED ? s_bias2 : s_bias1;
             mbar_wait(FUSED ? &d2_full[b] : &d1_full[b], ph);
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                             }
                         }
                     }
-                    if (p.relu) {
+                    if (p.relu && p.dst_fp32) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
@@ -403,9 +408,15 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     } else {
                         uint4* dp = reinterpret_cast<uint4*>(static_cast<Tp*>(p.dst) + px.dpix * p.dst_C + c0);
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            dp[jj] = make_uint4(pack2<Tp>(v[jj * 8], v[jj * 8 + 1]), pack2<Tp>(v[jj * 8 + 2], v[jj * 8 + 3]),
-                                                pack2<Tp>(v[jj * 8 + 4], v[jj * 8 + 5]), pack2<Tp>(v[jj * 8 + 6], v[jj * 8 + 7]));
+                        if (p.relu) {
+                            for (int jj = 0; jj < 4; ++jj)
+                                dp[jj] = make_uint4(pack2_relu<Tp>(v[jj * 8], v[jj * 8 + 1]), pack2_relu<Tp>(v[jj * 8 + 2], v[jj * 8 + 3]),
+                                                    pack2_relu<Tp>(v[jj * 8 + 4], v[jj * 8 + 5]), pack2_relu<Tp>(v[jj * 8 + 6], v[jj * 8 + 7]));
+                        } else {
+                            for (int jj = 0; jj < 4; ++jj)
+                                dp[jj] = make_uint4(pack2<Tp>(v[jj * 8], v[jj * 8 + 1]), pack2<Tp>(v[jj * 8 + 2], v[jj * 8 + 3]),
+                                                    pack2<Tp>(v[jj * 8 + 4], v[jj * 8 + 5]), pack2<Tp>(v[jj * 8 + 6], v[jj * 8 + 7]));
+                        }
                     }
                 }
             }
@@ -414,17 +425,19 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             if (lane == 0) mbar_arrive(FUSED ? &d2_empty[b] : &d1_empty[b]);
         };
         if (!FUSED) {
-            for (int j = 0; j < n_local; ++j) epi_out(j);
+            for (int j = 0; j < n_local; ++j) { prefetch_res(j); epi_out(j); }
         } else if (NBUF == 2) {
             // the accumulators are double buffered: the first epilogue of tile j+1 runs before the second epilogue of
-            // tile j, which hides the y_full -> GEMM 2 -> d2_full round trip
+            // tile j, which hides the y_full -> GEMM 2 -> d2_full round trip (and the shortcut fetch of tile j)
             for (int j = 0; j < n_local; ++j) {
+                if (j > 0) prefetch_res(j - 1);
                 epi1(j);
                 if (j > 0) epi_out(j - 1);
             }
-            if (n_local > 0) epi_out(n_local - 1);
+            if (n_local > 0) { prefetch_res(n_local - 1); epi_out(n_local - 1); }
         } else {
             for (int j = 0; j < n_local; ++j) {
+                prefetch_res(j);
                 epi1(j);
                 epi_out(j);
             }

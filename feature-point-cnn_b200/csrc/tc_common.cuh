@@ -236,6 +236,21 @@ __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// round two floats to a packed 16-bit pair with ReLU fused into the conversion (cvt.rn.relu: negative -> +0)
+template <typename T>
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2_relu<__half>(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));      // first source -> upper half
+    return r;
+}
+template <>
+__device__ __forceinline__ uint32_t pack2_relu<__nv_bfloat16>(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 template <typename T>
 __device__ __forceinline__ float2 unpack2(uint32_t v);
 template <>
