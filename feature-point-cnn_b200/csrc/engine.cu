@@ -33,47 +33,47 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
-// Host-buffer pipeline state of detect_host: three streams (upload, compute, download), two slots of device
-// input / output buffers, pinned count mirrors, and pinned staging used only when the caller's buffers are pageable.
+// Host-buffer pipeline state of detect_host: three streams (upload, compute, download), whole-batch device input /
+// output buffers cut into chunks, one event pair and one pinned count mirror per chunk, and pinned staging used only
+// when the caller's buffers are pageable.
 struct Engine::HostStage {
+    static constexpr int kMaxChunks = 64;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-    float* d_img[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_comp[kMaxChunks] = {};
+    float* d_img = nullptr;
     size_t d_img_bytes = 0;
-    int* d_count[2] = {nullptr, nullptr};
-    int* d_xy[2] = {nullptr, nullptr};
-    float* d_conf[2] = {nullptr, nullptr};
-    float* d_desc[2] = {nullptr, nullptr};
-    int* h_count[2] = {nullptr, nullptr};      // pinned
+    int* d_count = nullptr;
+    int* d_xy = nullptr;
+    float* d_conf = nullptr;
+    float* d_desc = nullptr;
+    int* h_count = nullptr;        // pinned [B]
     int d_B = 0, d_cap = 0;
     // pageable callers
-    float* h_img[2] = {nullptr, nullptr};      // pinned
+    float* h_img = nullptr;        // pinned, whole batch
     size_t h_img_bytes = 0;
-    int* h_xy[2] = {nullptr, nullptr};
-    float* h_conf[2] = {nullptr, nullptr};
-    float* h_desc[2] = {nullptr, nullptr};
-    size_t h_out_cap[2] = {0, 0};              // keypoints the pinned output staging of a slot holds
+    int* h_xy = nullptr;
+    float* h_conf = nullptr;
+    float* h_desc = nullptr;
+    size_t h_out_cap = 0;          // keypoints the pinned output staging holds
     void init() {
         SPB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
         SPB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         SPB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMaxChunks; ++i) {
             SPB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
             SPB_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-            SPB_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
         }
     }
     ~HostStage() {
-        for (int i = 0; i < 2; ++i) {
-            cudaFree(d_img[i]); cudaFree(d_count[i]); cudaFree(d_xy[i]); cudaFree(d_conf[i]); cudaFree(d_desc[i]);
-            if (h_count[i]) cudaFreeHost(h_count[i]);
-            if (h_img[i]) cudaFreeHost(h_img[i]);
-            if (h_xy[i]) cudaFreeHost(h_xy[i]);
-            if (h_conf[i]) cudaFreeHost(h_conf[i]);
-            if (h_desc[i]) cudaFreeHost(h_desc[i]);
+        cudaFree(d_img); cudaFree(d_count); cudaFree(d_xy); cudaFree(d_conf); cudaFree(d_desc);
+        if (h_count) cudaFreeHost(h_count);
+        if (h_img) cudaFreeHost(h_img);
+        if (h_xy) cudaFreeHost(h_xy);
+        if (h_conf) cudaFreeHost(h_conf);
+        if (h_desc) cudaFreeHost(h_desc);
+        for (int i = 0; i < kMaxChunks; ++i) {
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
             if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
-            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
         }
         if (s_in) cudaStreamDestroy(s_in);
         if (s_comp) cudaStreamDestroy(s_comp);
@@ -690,116 +690,111 @@ void Engine::detect_host(const float* img, int B, int C, int H, int W, int cap, 
     {
         int want = 16;
         if (const char* e = std::getenv("SPB200_HOST_CHUNK")) want = std::max(1, std::atoi(e));
-        if (B > want && B % want == 0) Bc = want;
+        if (B > want && B % want == 0 && B / want <= HostStage::kMaxChunks) Bc = want;
     }
     const int nc = B / Bc;
     const bool pin_in = is_pinned_host(img);
     const bool pin_out = is_pinned_host(xy) && is_pinned_host(conf) && is_pinned_host(desc);
-    const size_t img_elems = (size_t)Bc * C * H * W, img_bytes = sizeof(float) * img_elems;
+    const size_t chunk_elems = (size_t)Bc * C * H * W, chunk_bytes = sizeof(float) * chunk_elems;
+    const size_t img_bytes = chunk_bytes * nc;
 
-    if (img_bytes > s.d_img_bytes || Bc > s.d_B || cap > s.d_cap) {
+    if (img_bytes > s.d_img_bytes || B > s.d_B || cap > s.d_cap) {
         SPB_CUDA(cudaDeviceSynchronize());
-        for (int i = 0; i < 2; ++i) {
-            cudaFree(s.d_img[i]); cudaFree(s.d_count[i]); cudaFree(s.d_xy[i]); cudaFree(s.d_conf[i]); cudaFree(s.d_desc[i]);
-            if (s.h_count[i]) cudaFreeHost(s.h_count[i]);
-            SPB_CUDA(cudaMalloc((void**)&s.d_img[i], img_bytes));
-            s.d_count[i] = dev_alloc<int>(Bc);
-            s.d_xy[i] = dev_alloc<int>((size_t)Bc * cap * 2);
-            s.d_conf[i] = dev_alloc<float>((size_t)Bc * cap);
-            s.d_desc[i] = dev_alloc<float>((size_t)Bc * cap * 128);
-            SPB_CUDA(cudaHostAlloc((void**)&s.h_count[i], sizeof(int) * Bc, cudaHostAllocDefault));
-        }
-        s.d_img_bytes = img_bytes; s.d_B = Bc; s.d_cap = cap;
+        cudaFree(s.d_img); cudaFree(s.d_count); cudaFree(s.d_xy); cudaFree(s.d_conf); cudaFree(s.d_desc);
+        if (s.h_count) cudaFreeHost(s.h_count);
+        const int nb = std::max(B, s.d_B), ncap = std::max(cap, s.d_cap);
+        const size_t nbytes = std::max(img_bytes, s.d_img_bytes);
+        SPB_CUDA(cudaMalloc((void**)&s.d_img, nbytes));
+        s.d_count = dev_alloc<int>(nb);
+        s.d_xy = dev_alloc<int>((size_t)nb * ncap * 2);
+        s.d_conf = dev_alloc<float>((size_t)nb * ncap);
+        s.d_desc = dev_alloc<float>((size_t)nb * ncap * 128);
+        SPB_CUDA(cudaHostAlloc((void**)&s.h_count, sizeof(int) * nb, cudaHostAllocDefault));
+        s.d_img_bytes = nbytes; s.d_B = nb; s.d_cap = ncap;
     }
     if (!pin_in && img_bytes > s.h_img_bytes) {
         SPB_CUDA(cudaDeviceSynchronize());
-        for (int i = 0; i < 2; ++i) {
-            if (s.h_img[i]) cudaFreeHost(s.h_img[i]);
-            SPB_CUDA(cudaHostAlloc((void**)&s.h_img[i], img_bytes, cudaHostAllocDefault));
-        }
+        if (s.h_img) cudaFreeHost(s.h_img);
+        SPB_CUDA(cudaHostAlloc((void**)&s.h_img, img_bytes, cudaHostAllocDefault));
         s.h_img_bytes = img_bytes;
     }
     const int dcap = s.d_cap;
 
-    auto enqueue_chunk = [&](int k) {
-        const int slot = k & 1;
-        const float* src = img + (size_t)k * img_elems;
-        if (k >= 2) SPB_CUDA(cudaStreamWaitEvent(s.s_in, s.ev_comp[slot], 0));     // compute(k-2) has read d_img[slot]
-        if (!pin_in) {
-            if (k >= 2) SPB_CUDA(cudaEventSynchronize(s.ev_in[slot]));             // upload(k-2) has left the staging
-            std::memcpy(s.h_img[slot], src, img_bytes);
-            src = s.h_img[slot];
-        }
-        SPB_CUDA(cudaMemcpyAsync(s.d_img[slot], src, img_bytes, cudaMemcpyHostToDevice, s.s_in));
-        SPB_CUDA(cudaEventRecord(s.ev_in[slot], s.s_in));
-        SPB_CUDA(cudaStreamWaitEvent(s.s_comp, s.ev_in[slot], 0));
-        if (k >= 2) SPB_CUDA(cudaStreamWaitEvent(s.s_comp, s.ev_out[slot], 0));    // download(k-2) has read the output slot
-        detect(s.d_img[slot], Bc, C, H, W, dcap, s.d_count[slot], s.d_xy[slot], s.d_conf[slot], desc ? s.d_desc[slot] : nullptr,
-               nullptr, s.s_comp);
-        SPB_CUDA(cudaMemcpyAsync(s.h_count[slot], s.d_count[slot], sizeof(int) * Bc, cudaMemcpyDeviceToHost, s.s_comp));
-        SPB_CUDA(cudaEventRecord(s.ev_comp[slot], s.s_comp));
-    };
-    // pageable outputs: copy a finished slot's staging to the caller's arrays
-    auto drain_staging = [&](int k) {
-        const int slot = k & 1;
-        SPB_CUDA(cudaEventSynchronize(s.ev_out[slot]));
-        size_t off = 0;
-        for (int b = 0; b < Bc; ++b) {
-            const size_t g = (size_t)k * Bc + b, n = (size_t)count[g];
-            std::memcpy(xy + g * cap * 2, s.h_xy[slot] + off * 2, sizeof(int) * 2 * n);
-            std::memcpy(conf + g * cap, s.h_conf[slot] + off, sizeof(float) * n);
-            if (desc) std::memcpy(desc + g * cap * 128, s.h_desc[slot] + off * 128, sizeof(float) * 128 * n);
-            off += n;
-        }
-    };
-
-    enqueue_chunk(0);
+    // 1. everything the GPU has to do is enqueued up front: chunk k's upload on the copy stream, its network +
+    //    post-processing on the compute stream behind the upload's event, its counts copied to the pinned mirror
     for (int k = 0; k < nc; ++k) {
-        const int slot = k & 1;
-        if (k + 1 < nc) enqueue_chunk(k + 1);
-        SPB_CUDA(cudaEventSynchronize(s.ev_comp[slot]));                            // counts of chunk k are on the host
+        const float* src = img + (size_t)k * chunk_elems;
+        float* d_in = s.d_img + (size_t)k * chunk_elems;
+        if (!pin_in) {
+            std::memcpy(s.h_img + (size_t)k * chunk_elems, src, chunk_bytes);
+            src = s.h_img + (size_t)k * chunk_elems;
+        }
+        SPB_CUDA(cudaMemcpyAsync(d_in, src, chunk_bytes, cudaMemcpyHostToDevice, s.s_in));
+        SPB_CUDA(cudaEventRecord(s.ev_in[k], s.s_in));
+        SPB_CUDA(cudaStreamWaitEvent(s.s_comp, s.ev_in[k], 0));
+        const size_t o = (size_t)k * Bc;
+        detect(d_in, Bc, C, H, W, dcap, s.d_count + o, s.d_xy + o * dcap * 2, s.d_conf + o * dcap,
+               desc ? s.d_desc + o * dcap * 128 : nullptr, nullptr, s.s_comp);
+        SPB_CUDA(cudaMemcpyAsync(s.h_count + o, s.d_count + o, sizeof(int) * Bc, cudaMemcpyDeviceToHost, s.s_comp));
+        SPB_CUDA(cudaEventRecord(s.ev_comp[k], s.s_comp));
+    }
+    // 2. as each chunk's counts arrive, its keypoints and descriptors (count[b] rows per image, nothing else) are
+    //    downloaded on the third stream while the later chunks compute
+    size_t staged = 0;
+    std::vector<size_t> stage_off;
+    if (!pin_out) stage_off.assign((size_t)B, 0);
+    for (int k = 0; k < nc; ++k) {
+        SPB_CUDA(cudaEventSynchronize(s.ev_comp[k]));
         size_t total = 0;
         for (int b = 0; b < Bc; ++b) {
-            const int n = std::min(std::max(s.h_count[slot][b], 0), cap);
-            count[(size_t)k * Bc + b] = n;
-            total += (size_t)n;
+            const size_t g = (size_t)k * Bc + b;
+            count[g] = std::min(std::max(s.h_count[g], 0), cap);
+            total += (size_t)count[g];
         }
-        if (!pin_out) {
-            if (k >= 2) drain_staging(k - 2);
-            if (total > s.h_out_cap[slot]) {
-                if (s.h_xy[slot]) cudaFreeHost(s.h_xy[slot]);
-                if (s.h_conf[slot]) cudaFreeHost(s.h_conf[slot]);
-                if (s.h_desc[slot]) cudaFreeHost(s.h_desc[slot]);
-                const size_t n = total + total / 2 + 1024;
-                SPB_CUDA(cudaHostAlloc((void**)&s.h_xy[slot], sizeof(int) * 2 * n, cudaHostAllocDefault));
-                SPB_CUDA(cudaHostAlloc((void**)&s.h_conf[slot], sizeof(float) * n, cudaHostAllocDefault));
-                SPB_CUDA(cudaHostAlloc((void**)&s.h_desc[slot], sizeof(float) * 128 * n, cudaHostAllocDefault));
-                s.h_out_cap[slot] = n;
+        if (!pin_out && staged + total > s.h_out_cap) {
+            // grow the pinned staging; what is already in flight must land first, then it is copied over
+            SPB_CUDA(cudaStreamSynchronize(s.s_out));
+            const size_t n = (staged + total) * 2 + 1024;
+            int* nxy = nullptr; float* ncf = nullptr; float* nds = nullptr;
+            SPB_CUDA(cudaHostAlloc((void**)&nxy, sizeof(int) * 2 * n, cudaHostAllocDefault));
+            SPB_CUDA(cudaHostAlloc((void**)&ncf, sizeof(float) * n, cudaHostAllocDefault));
+            SPB_CUDA(cudaHostAlloc((void**)&nds, sizeof(float) * 128 * n, cudaHostAllocDefault));
+            if (staged) {
+                std::memcpy(nxy, s.h_xy, sizeof(int) * 2 * staged);
+                std::memcpy(ncf, s.h_conf, sizeof(float) * staged);
+                if (desc) std::memcpy(nds, s.h_desc, sizeof(float) * 128 * staged);
             }
+            if (s.h_xy) cudaFreeHost(s.h_xy);
+            if (s.h_conf) cudaFreeHost(s.h_conf);
+            if (s.h_desc) cudaFreeHost(s.h_desc);
+            s.h_xy = nxy; s.h_conf = ncf; s.h_desc = nds; s.h_out_cap = n;
         }
-        size_t off = 0;
         for (int b = 0; b < Bc; ++b) {
             const size_t g = (size_t)k * Bc + b, n = (size_t)count[g];
+            if (!pin_out) stage_off[g] = staged;
             if (n) {
-                int* dxy = pin_out ? xy + g * cap * 2 : s.h_xy[slot] + off * 2;
-                float* dcf = pin_out ? conf + g * cap : s.h_conf[slot] + off;
-                SPB_CUDA(cudaMemcpyAsync(dxy, s.d_xy[slot] + (size_t)b * dcap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s.s_out));
-                SPB_CUDA(cudaMemcpyAsync(dcf, s.d_conf[slot] + (size_t)b * dcap, sizeof(float) * n, cudaMemcpyDeviceToHost, s.s_out));
+                int* dxy = pin_out ? xy + g * cap * 2 : s.h_xy + staged * 2;
+                float* dcf = pin_out ? conf + g * cap : s.h_conf + staged;
+                SPB_CUDA(cudaMemcpyAsync(dxy, s.d_xy + g * dcap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s.s_out));
+                SPB_CUDA(cudaMemcpyAsync(dcf, s.d_conf + g * dcap, sizeof(float) * n, cudaMemcpyDeviceToHost, s.s_out));
                 if (desc) {
-                    float* dds = pin_out ? desc + g * cap * 128 : s.h_desc[slot] + off * 128;
-                    SPB_CUDA(cudaMemcpyAsync(dds, s.d_desc[slot] + (size_t)b * dcap * 128, sizeof(float) * 128 * n, cudaMemcpyDeviceToHost, s.s_out));
+                    float* dds = pin_out ? desc + g * cap * 128 : s.h_desc + staged * 128;
+                    SPB_CUDA(cudaMemcpyAsync(dds, s.d_desc + g * dcap * 128, sizeof(float) * 128 * n, cudaMemcpyDeviceToHost, s.s_out));
                 }
             }
-            off += n;
+            if (!pin_out) staged += n;
         }
-        SPB_CUDA(cudaEventRecord(s.ev_out[slot], s.s_out));
-    }
-    if (!pin_out) {
-        if (nc >= 2) drain_staging(nc - 2);
-        drain_staging(nc - 1);
     }
     SPB_CUDA(cudaStreamSynchronize(s.s_out));
     SPB_CUDA(cudaStreamSynchronize(s.s_comp));
+    if (!pin_out) {
+        for (size_t g = 0; g < (size_t)B; ++g) {
+            const size_t n = (size_t)count[g], off = stage_off[g];
+            std::memcpy(xy + g * cap * 2, s.h_xy + off * 2, sizeof(int) * 2 * n);
+            std::memcpy(conf + g * cap, s.h_conf + off, sizeof(float) * n);
+            if (desc) std::memcpy(desc + g * cap * 128, s.h_desc + off * 128, sizeof(float) * 128 * n);
+        }
+    }
 }
 
 }  // namespace spb200
