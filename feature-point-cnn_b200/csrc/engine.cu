@@ -95,6 +95,8 @@ Engine::Engine(int device) : device_(device) {
     fuse_blocks_ = !(nf && nf[0] == '1');
     const char* nh = std::getenv("SPB200_NO_HALO");
     use_halo_ = !(nh && nh[0] == '1');
+    const char* os = std::getenv("SPB200_OLD_STEM");
+    use_planes_ = !(os && os[0] == '1');
     buf_.fill(nullptr);
 }
 
@@ -114,6 +116,7 @@ void Engine::release_workspace() {
     }
     for (auto& p : buf_) { cudaFree(p); p = nullptr; }
     cudaFree(d_prob_); d_prob_ = nullptr;
+    cudaFree(d_planes_); d_planes_ = nullptr;
     wsB_ = wsH_ = wsW_ = 0;
 }
 
@@ -133,6 +136,10 @@ void Engine::release_weights() {
         stem_plan_[i] = nullptr;
         cudaFree(d_stem_w16_[i]);
         d_stem_w16_[i] = nullptr;
+    }
+    if (stem_planes_) {
+        stem_planes_plan_destroy(stem_planes_);
+        stem_planes_ = nullptr;
     }
 }
 
@@ -368,6 +375,7 @@ void Engine::build_ops() {
                         }
             d_stem_w16_[v] = dev_upload(w16);
             stem_plan_[v] = stem_tc_plan_create(d_stem_w16_[v], d_stem_b_, cin, precision_, num_sms_);
+            if (v == 0) stem_planes_ = stem_planes_plan_create(d_stem_w16_[0], d_stem_b_, precision_, num_sms_);
         }
     }
 }
@@ -409,6 +417,7 @@ void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
         SPB_CUDA(cudaMemset(buf_[i], 0, bytes));     // padded channels stay zero forever
     }
     d_prob_ = dev_alloc<float>((size_t)B * H * W);
+    if (precision_ != PREC_FP32) SPB_CUDA(cudaMalloc(&d_planes_, (size_t)B * H * W * 2));
     wsB_ = B; wsH_ = H; wsW_ = W;
     if (precision_ != PREC_FP32) {
         for (size_t i = 0; i < ops_.size(); ++i) {
@@ -541,10 +550,19 @@ double Engine::op_flops(const OpSpec& op) const {
 void Engine::run_network(const float* img, int B, int C, int H, int W, cudaStream_t st) {
     ensure_workspace(B, C, H, W, st);
     // gray-folded stem: 49 MACs per output (the reference's 3-channel stem does 147 on replicated input)
+    const bool planes = precision_ != PREC_FP32 && C == 1 && use_planes_;
+    if (planes) {
+        prof_open("image_planes", 0.0, (double)B * H * W * (4 + 2), st);
+        launch_planes(img, 0, d_planes_, precision_, B, H, W, st);
+        prof_close(st);
+        ++launches_;
+    }
     prof_open("stem_pool", 2.0 * B * (H / 2) * (W / 2) * 64.0 * 49.0 * C,
-              (double)B * C * H * W * 4 + (double)B * (H / 4) * (W / 4) * 64 * (precision_ == PREC_FP32 ? 4 : 2), st);
+              (double)B * C * H * W * (planes ? 2 : 4) + (double)B * (H / 4) * (W / 4) * 64 * (precision_ == PREC_FP32 ? 4 : 2), st);
     if (precision_ == PREC_FP32)
         launch_stem_pool(img, B, C, H, W, d_stem_w_[C == 1 ? 0 : 1], d_stem_b_, buf_[BUF_POOL], precision_, st);
+    else if (planes)
+        launch_stem_planes(stem_planes_, d_planes_, buf_[BUF_POOL], B, H, W, st);
     else
         launch_stem_tc(stem_plan_[C == 1 ? 0 : 1], img, buf_[BUF_POOL], B, H, W, st);
     prof_close(st);

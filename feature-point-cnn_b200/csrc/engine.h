@@ -140,6 +140,9 @@ private:
     float* d_stem_b_ = nullptr;
     void* d_stem_w16_[2] = {nullptr, nullptr};     // tensor-core stem: [64][nchunk*64] 16-bit, K-major
     StemTcPlan* stem_plan_[2] = {nullptr, nullptr};
+    StemPlanesPlan* stem_planes_ = nullptr;        // gray stem fed by TMA from parity planes (stem_planes.cu)
+    bool use_planes_ = true;      // SPB200_OLD_STEM=1 keeps the im2col-in-shared-memory stem
+    void* d_planes_ = nullptr;    // [B][2][H/2][W] 16-bit image x255, per workspace shape
 
     // workspace
     int wsB_ = 0, wsH_ = 0, wsW_ = 0;

@@ -36,6 +36,15 @@ StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int
 void stem_tc_plan_destroy(StemTcPlan* plan);
 void launch_stem_tc(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st);
 
+// ---- stem_planes.cu ------------------------------------------------------------------------------
+// Gray stem fed by TMA from 16-bit row-parity planes of the image (no im2col pass).
+struct StemPlanesPlan;
+StemPlanesPlan* stem_planes_plan_create(const void* w16, const float* bias, int operand_type, int num_sms);
+void stem_planes_plan_destroy(StemPlanesPlan* plan);
+// img: [B][H][W] fp32 in [0,1] (img_is_u8 = 0) or 8-bit (1) -> planes [B][2][H/2][W] 16-bit, value x255
+void launch_planes(const void* img, int img_is_u8, void* planes, int operand_type, int B, int H, int W, cudaStream_t st);
+void launch_stem_planes(StemPlanesPlan* plan, const void* planes, void* dst, int B, int H, int W, cudaStream_t st);
+
 // ---- postproc.cu ---------------------------------------------------------------------------------
 // Softmax-with-epsilon over 65 channels, drop the dustbin, depth-to-space (reference
 // python/src/superpoint.py:111-114, python/src/netutils.py:64-75).  logits element (b, c, i, j) is at

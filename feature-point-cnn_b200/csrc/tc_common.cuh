@@ -280,5 +280,8 @@ __device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, uint32_t b) 
 // 128B swizzle, zero fill out of bounds.
 void tc_encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
                      const cuuint64_t* strides_bytes, const cuuint32_t* box);
+// the same with the swizzle mode selectable (false: CU_TENSOR_MAP_SWIZZLE_NONE, the box lands row after row)
+void tc_encode_tiled_ex(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                        const cuuint64_t* strides_bytes, const cuuint32_t* box, bool swizzle128);
 
 }  // namespace spb200

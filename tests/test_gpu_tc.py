@@ -242,3 +242,33 @@ def test_other_checkpoints_harsh_and_magicpoint(tmp_path):
     print('[harsh fp16] keypoints %d/%d' % (hit, tot))
     assert hit >= 0.97 * tot
     e.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('prec', ['fp16', 'bf16'])
+@pytest.mark.parametrize('shape', [(1, 240, 320), (3, 480, 640), (2, 64, 48), (2, 272, 1920 // 4)])
+def test_plane_fed_stem_is_bit_identical_to_im2col_stem(prec, shape, monkeypatch):
+    """stem_planes.cu (TMA-fed, no im2col pass) against stem_tc.cu (im2col in shared memory): the same products in
+    the same K order with the same fp32 epilogue, so the pooled tensors must be equal bit for bit - odd tile
+    counts, edge tiles and batches included."""
+    b, h, w = shape
+    g = torch.Generator().manual_seed(h * 7 + w)
+    img = torch.rand((b, 1, h, w), generator=g)
+    img[0, 0, : h // 2] = (img[0, 0, : h // 2] * 255).round() / 255          # an 8-bit half
+    outs = []
+    for old in ('1', '0'):
+        monkeypatch.setenv('SPB200_OLD_STEM', old)
+        e = load_spb().Engine(0)
+        e.load_checkpoint(CKPT)
+        e.finalize(prec)
+        e.set_params()
+        e.forward(img.cuda())
+        outs.append(e.export_activation('pool', b).cpu())
+        e.close()
+    assert outs[0].abs().max() > 0
+    bad = int((outs[0] != outs[1]).sum())
+    if bad:
+        idx = torch.nonzero(outs[0] != outs[1])
+        print('[stem planes %s %s] %d of %d differ, first (b,c,y,x): %s, max diff %.4g' %
+              (prec, shape, bad, outs[0].numel(), idx[:6].tolist(), float((outs[0] - outs[1]).abs().max())))
+    assert bad == 0
