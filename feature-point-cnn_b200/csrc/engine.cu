@@ -104,7 +104,7 @@ Engine::~Engine() {
     cudaSetDevice(device_);
     release_workspace();
     release_weights();
-    cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und);
+    cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und); cudaFree(nms_.ukey);
     cudaFree(d_gtab_);
 }
 
@@ -444,7 +444,7 @@ void Engine::ensure_nms(int B, int H, int W) {
     const int r = params_.nms_dist;
     if (B <= nmsB_ && H == nmsH_ && W == nmsW_ && r == nmsR_) return;
     SPB_CUDA(cudaDeviceSynchronize());
-    cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und);
+    cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und); cudaFree(nms_.ukey);
     nms_.kcap = max_keypoints(H, W, r);
     nms_.mask_w = (W + 31) / 32;
     nms_.keys = dev_alloc<unsigned long long>((size_t)B * nms_.kcap);
@@ -452,6 +452,7 @@ void Engine::ensure_nms(int B, int H, int W) {
     nms_.counters = dev_alloc<int>((size_t)B * 8);
     nms_.mask = dev_alloc<unsigned>((size_t)B * H * nms_.mask_w);
     nms_.und = dev_alloc<unsigned>((size_t)B * H * W);
+    nms_.ukey = dev_alloc<unsigned>((size_t)B * H * W);
     nmsB_ = B; nmsH_ = H; nmsW_ = W; nmsR_ = r;
 }
 
@@ -618,19 +619,21 @@ void Engine::detect(const float* img, int B, int C, int H, int W, int cap, int* 
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
     run_network(img, B, C, H, W, st);
     const int Hc = H / 8, Wc = W / 8;
-    float* heat = prob ? prob : d_prob_;
-    prof_open("heatmap", 0.0, (double)B * (65.0 * Hc * Wc * 4 + (double)H * W * 4), st);
-    launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc, heat, st);
-    prof_close(st);
-    ++launches_;
+    // the heatmap is written only when the caller wants it: round 0 of the NMS computes the softmax values itself
+    const bool from_logits = nms_logits_supported(params_.nms_dist);
+    if (prob || !from_logits) {
+        prof_open("heatmap", 0.0, (double)B * (65.0 * Hc * Wc * 4 + (double)H * W * 4), st);
+        launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc, prob ? prob : d_prob_, st);
+        prof_close(st);
+        ++launches_;
+    }
     ensure_nms(B, H, W);
-    prof_open("nms", 0.0, (double)B * H * W * 4, st);            // + 8 B per survivor, added by the caller
-    launch_nms(heat, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
+    // algorithmic bytes: the logits (65 channels) or the heatmap in; + 8 B per survivor in and 12 B out (added by the caller)
+    prof_open("nms_sort", 0.0, from_logits ? (double)B * 65.0 * Hc * Wc * 4 : (double)B * H * W * 4, st);
+    launch_nms(from_logits ? nullptr : (prob ? prob : d_prob_), (const float*)buf_[BUF_LOGITS], det_c_, B, H, W, params_.conf_thresh,
+               params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_, count, xy, conf, st);
     prof_close(st);
-    prof_open("sort_topk", 0.0, 0.0, st);                        // 8 B in + 12 B out per survivor (caller)
-    launch_sort_emit(B, W, params_.top_k, cap, nms_, count, xy, conf, st);
-    prof_close(st);
-    launches_ += 3;
+    launches_ += 2;
     if (desc) {
         if (params_.descriptor_enabled) {
             prof_open("descriptors", 0.0, 0.0, st);              // bytes depend on the keypoint count (caller)
@@ -656,9 +659,9 @@ void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, in
     SPB_CUDA(cudaSetDevice(device_));
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
     ensure_nms(B, H, W);
-    launch_nms(prob, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
-    launch_sort_emit(B, W, params_.top_k, cap, nms_, count, xy, conf, st);
-    launches_ += 3;
+    launch_nms(prob, nullptr, 0, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_,
+               count, xy, conf, st);
+    launches_ += 2;
 }
 
 void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int W, int cap, const int* count,

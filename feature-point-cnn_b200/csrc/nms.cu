@@ -1,5 +1,6 @@
-// K4: grid NMS, the exact parallel form of the reference's greedy sweep (python/src/nms.py:4-53 with the
-// threshold of python/src/netutils.py:59 and the border removal of netutils.py:95-99).
+// K3-K5 on the detect path: grid NMS, the exact parallel form of the reference's greedy sweep (python/src/nms.py:4-53
+// with the threshold of python/src/netutils.py:59 and the border removal of netutils.py:95-99), followed by the
+// descending sort (netutils.py:92-93) - two launches per batch.
 //
 // The reference visits candidates (heat >= thresh) by descending confidence; a live candidate is kept
 // and kills every candidate of its (2r+1)^2 window; a killed candidate kills nothing.  Equivalent
@@ -9,28 +10,28 @@
 // and, had one been kept, the maximum would have been suppressed with it.)  Equal confidences are
 // ordered by ascending pixel index, the oracle's tie rule.
 //
-// Round 0 (nms_round0_kernel) works on 64x64-pixel tiles with a 2r halo in shared memory: one dense pass
-// thresholds the tile into sortable keys and compacts the candidates, then the window scans run per
-// candidate (early exit), keeper flags are row bitmasks and suppression is a shifted-word test; it emits
-// the keepers, a bit-per-pixel mask of the still-undecided candidates and their compact list.  After it
-// only a few percent of the candidates are left, so the remaining rounds
-// (nms_rounds_kernel, one 8-CTA cluster per image) work on the compact list: a warp per candidate
-// scans its window through the bitmask (heat is read only where a bit is set), keepers clear their
-// window bits with atomics, the list is compacted, two cluster barriers per round.
-#include <cooperative_groups.h>
-
+// Round 0 (nms_round0_kernel) works on 64x64-pixel tiles with a 2r halo in shared memory.  On the detect path it
+// reads the LOGITS (10x10 cells x 65 channels per tile) and computes the softmax / depth-to-space values itself,
+// with the arithmetic of heatmap_kernel (python/src/superpoint.py:111-114, python/src/netutils.py:64-75): the
+// full-resolution heatmap is never written unless the caller asks for it.  The tile becomes sortable keys, the
+// candidates are compacted, the window scans run per candidate (early exit), keeper flags are row bitmasks and
+// suppression is a shifted-word test; it emits the keepers, a bit-per-pixel mask of the still-undecided candidates,
+// their keys (scattered into a dense side array) and their compact list.
+// After it only a few percent of the candidates are left: nms_finish_kernel, ONE 1024-thread CTA per image, keeps
+// them in registers (a thread per candidate scans its window through the bitmask and looks keys up only where a
+// bit is set; keepers clear their window bits with atomics; two block barriers per round), then sorts the
+// survivors in shared memory (LSD radix, 8-bit digits, constant digits skipped) and emits (x, y), confidence, count.
 #include "kernels.h"
 #include "sortkey.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace spb200 {
 
 constexpr int kN0TW = 64, kN0TH = 64;        // interior tile of round 0 (two mask words per row)
 constexpr int kN0Threads = 256;
 constexpr int kNmsMaxR = 8;
-constexpr int kNmsCluster = 8;
-constexpr int kRoundsThreads = 256;
+constexpr int kFinThreads = 1024;
+constexpr int kFinRegEntries = 8;            // undecided candidates a thread keeps in registers
+constexpr int kSortSmemKeys = 10240;         // survivors per image sorted in shared memory (2 x 80 KB ping-pong)
 
 // ------------------------------------------------------------------------------------------------
 // Round 0
@@ -39,11 +40,12 @@ constexpr int kRoundsThreads = 256;
 // tile (+ 2R halo) into sortable keys and compacts the candidates of the evaluation region (interior + R), the
 // window scans run per CANDIDATE with early exit on the first stronger neighbour, keepers become bits, and a
 // candidate is suppressed when a keeper bit lies in its window (nine shifted word tests).
-template <int R>
+// LOGITS: src = detector logits, channels last, `cell_stride` floats per cell (65 real), needs R <= 4 (one halo cell).
+template <int R, bool LOGITS>
 __global__ void __launch_bounds__(kN0Threads)
-nms_round0_kernel(const float* __restrict__ heat, int H, int W, float thresh, int border, int kcap,
+nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, float thresh, int border, int kcap,
                   unsigned long long* __restrict__ keys, int* __restrict__ counters, unsigned* __restrict__ mask,
-                  int mask_w, unsigned* __restrict__ und) {
+                  int mask_w, unsigned* __restrict__ und, unsigned* __restrict__ ukey) {
     constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R;      // loaded region (halo 2R)
     constexpr int EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;      // region where keepers are evaluated (halo R)
     constexpr int KW = (EW + 31) / 32 + 1;                     // keeper bit words per E row (+1 so a 64-bit window read stays inside)
@@ -58,69 +60,112 @@ nms_round0_kernel(const float* __restrict__ heat, int H, int W, float thresh, in
     unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_keep + kMaxKeep);               // [EH*EW] ey << 8 | ex
     __shared__ int s_ncand, s_nund, s_nkeep, s_base_und, s_base_keep;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int ty0 = blockIdx.y * kN0TH, tx0 = blockIdx.x * kN0TW;
-    const float* hmap = heat + (size_t)b * H * W;
     if (tid == 0) { s_ncand = 0; s_nund = 0; s_nkeep = 0; }
     for (int i = tid; i < EH * KW; i += kN0Threads) s_kb[i] = 0u;
     for (int i = tid; i < kN0TH * 2; i += kN0Threads) s_ub[i] = 0u;
-    __syncthreads();
 
-    // 1. keys of the loaded region, four pixels (one 16-byte load) per thread and step; candidates of the evaluation
-    //    region are appended to the list through a warp prefix sum (one shared atomic per warp and step)
-    constexpr int LQ = (LW + 3) / 4;                           // float4 groups per loaded row
-    // groups are then 16-byte aligned and never straddle the image edge
-    const bool vec_ok = ((2 * R) % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(hmap) & 15) == 0);
-    for (int i0 = 0; i0 < LH * LQ; i0 += kN0Threads) {
-        const int i = i0 + tid;
-        unsigned key[4] = {0u, 0u, 0u, 0u};
-        int ly = 0, lx = 0;
-        if (i < LH * LQ) {
-            ly = i / LQ; lx = (i % LQ) * 4;
-            const int gy = ty0 - 2 * R + ly, gx = tx0 - 2 * R + lx;
-            if (gy >= 0 && gy < H) {
-                const float* src = hmap + (size_t)gy * W + gx;
-                float h[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // outside the image: never a candidate
-                if (vec_ok) {
-                    if (gx >= 0 && gx < W) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
-                        h[0] = v.x; h[1] = v.y; h[2] = v.z; h[3] = v.w;
-                    }
-                } else {
+    // 1. keys of the loaded region
+    if (LOGITS) {
+        // a warp per cell, four cells (twelve loads per lane) in flight: lane owns channels lane and lane + 32, lane 0
+        // the dustbin; exp, sum (the summation order of heatmap_kernel), + 1e-5, divide
+        static_assert(!LOGITS || R <= 4, "one halo cell");
+        const int Hc = H / 8, Wc = W / 8;
+        const float* lb = src + (size_t)b * Hc * Wc * cell_stride;
+        constexpr int kOff = 8 - 2 * R;                        // window origin inside the 10x10-cell region
+        for (int c0 = warp; c0 < 100; c0 += 32) {
+            float l0[4], l1[4], l2[4];
+            bool in[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (gx + e >= 0 && gx + e < W) h[e] = __ldg(src + e);
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 8 * u;
+                const int gcy = (int)blockIdx.y * 8 - 1 + c / 10, gcx = (int)blockIdx.x * 8 - 1 + c % 10;
+                in[u] = c < 100 && gcy >= 0 && gcy < Hc && gcx >= 0 && gcx < Wc;
+                l0[u] = l1[u] = l2[u] = 0.f;
+                if (in[u]) {
+                    const float* p = lb + (size_t)(gcy * Wc + gcx) * cell_stride;
+                    l0[u] = __ldg(p + lane);
+                    l1[u] = __ldg(p + lane + 32);
+                    if (lane == 0) l2[u] = __ldg(p + 64);
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (h[e] >= thresh) key[e] = sortable_bits(h[e]);
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (lx + e < LW) s_key[ly * LW + lx + e] = key[e];
-        }
-        unsigned flags = 0u;
-        if (ly >= R && ly < R + EH) {
+            for (int u = 0; u < 4; ++u) {
+                const int c = c0 + 8 * u;
+                if (c >= 100) break;
+                unsigned k0 = 0u, k1 = 0u;
+                if (in[u]) {
+                    const float e0 = expf(l0[u]), e1 = expf(l1[u]);
+                    float s = e0 + e1 + (lane == 0 ? expf(l2[u]) : 0.f);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (key[e] != 0u && lx + e >= R && lx + e < R + EW) flags |= 1u << e;
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    const float den = s + 0.00001f;
+                    const float h0 = e0 / den, h1 = e1 / den;
+                    if (h0 >= thresh) k0 = sortable_bits(h0);
+                    if (h1 >= thresh) k1 = sortable_bits(h1);
+                }
+                const int ly = (c / 10) * 8 + (lane >> 3) - kOff, lx = (c % 10) * 8 + (lane & 7) - kOff;
+                if (lx >= 0 && lx < LW) {
+                    if (ly >= 0 && ly < LH) s_key[ly * LW + lx] = k0;
+                    if (ly + 4 >= 0 && ly + 4 < LH) s_key[(ly + 4) * LW + lx] = k1;
+                }
+            }
         }
-        const int mine = __popc(flags);
-        int incl = mine;
+    } else {
+        // four pixels (one 16-byte load) per thread and step, every load of the thread issued before the first use
+        const float* hmap = src + (size_t)b * H * W;
+        constexpr int LQ = (LW + 3) / 4;                       // float4 groups per loaded row
+        constexpr int kIters = (LH * LQ + kN0Threads - 1) / kN0Threads;
+        // groups are then 16-byte aligned and never straddle the image edge
+        const bool vec_ok = ((2 * R) % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(hmap) & 15) == 0);
+        float4 v[kIters];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+        for (int it = 0; it < kIters; ++it) {
+            const int i = it * kN0Threads + tid;
+            v[it] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);      // outside the image: never a candidate
+            if (i < LH * LQ) {
+                const int ly = i / LQ, lx = (i % LQ) * 4;
+                const int gy = ty0 - 2 * R + ly, gx = tx0 - 2 * R + lx;
+                if (gy >= 0 && gy < H) {
+                    const float* p = hmap + (size_t)gy * W + gx;
+                    if (vec_ok) {
+                        if (gx >= 0 && gx < W) v[it] = __ldg(reinterpret_cast<const float4*>(p));
+                    } else {
+                        if (gx >= 0 && gx < W) v[it].x = __ldg(p);
+                        if (gx + 1 >= 0 && gx + 1 < W) v[it].y = __ldg(p + 1);
+                        if (gx + 2 >= 0 && gx + 2 < W) v[it].z = __ldg(p + 2);
+                        if (gx + 3 >= 0 && gx + 3 < W) v[it].w = __ldg(p + 3);
+                    }
+                }
+            }
         }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total) {
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            const int i = it * kN0Threads + tid;
+            if (i < LH * LQ) {
+                const int ly = i / LQ, lx = (i % LQ) * 4;
+                const float h[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (lx + e < LW) s_key[ly * LW + lx + e] = h[e] >= thresh ? sortable_bits(h[e]) : 0u;
+            }
+        }
+    }
+    __syncthreads();
+
+    // 1b. candidates of the evaluation region, compacted with one ballot and one shared atomic per warp and step
+    for (int i0 = 0; i0 < EH * EW; i0 += kN0Threads) {
+        const int i = i0 + tid;
+        const int ey = i / EW, ex = i - ey * EW;
+        const bool c = i < EH * EW && s_key[(ey + R) * LW + ex + R] != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, c);
+        if (bal) {
             int base = 0;
-            if (lane == 31) base = atomicAdd(&s_ncand, total);
-            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (flags & (1u << e)) s_cand[base++] = (unsigned short)(((ly - R) << 8) | (lx + e - R));
+            if (lane == 0) base = atomicAdd(&s_ncand, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (c) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((ey << 8) | ex);
         }
     }
     __syncthreads();
@@ -146,6 +191,7 @@ nms_round0_kernel(const float* __restrict__ heat, int H, int W, float thresh, in
 
     // 3. interior candidates: kept / suppressed by a keeper in the window / still undecided
     int* cnt = counters + b * kNmsCounters;
+    unsigned* uk = ukey + (size_t)b * H * W;
     for (int c = tid; c < ncand; c += kN0Threads) {
         const int ey = s_cand[c] >> 8, ex = s_cand[c] & 255;
         const int iy = ey - R, ix = ex - R;
@@ -153,18 +199,18 @@ nms_round0_kernel(const float* __restrict__ heat, int H, int W, float thresh, in
         const int gy = ty0 + iy, gx = tx0 + ix;
         const bool keep = (s_kb[ey * KW + (ex >> 5)] >> (ex & 31)) & 1u;
         const unsigned pix = (unsigned)(gy * W + gx);
+        const unsigned me = s_key[(ey + R) * LW + ex + R];
         if (keep) {
             if (!(gx < border || gx >= W - border || gy < border || gy >= H - border)) {
                 const int pos = atomicAdd(&s_nkeep, 1);
-                if (pos < kMaxKeep) s_keep[pos] = survivor_key(s_key[(ey + R) * LW + ex + R], pix);
+                if (pos < kMaxKeep) s_keep[pos] = survivor_key(me, pix);
             }
             continue;
         }
-        // window columns ex-R .. ex+R of rows ey-R .. ey+R (E coordinates; rows/cols outside E hold no keeper
-        // that could matter: a keeper more than R outside the interior cannot cover an interior pixel... but one
-        // within R can, which is why keepers are evaluated on the whole E region)
+        // window columns ex-R .. ex+R of rows ey-R .. ey+R in E coordinates (keepers are evaluated on the whole E
+        // region because one within R outside the interior can cover an interior pixel)
         unsigned any = 0u;
-        const int x0 = ex - R;                                  // may be negative by at most R for ix < R? no: ex >= R here
+        const int x0 = ex - R;
 #pragma unroll
         for (int dy = -R; dy <= R; ++dy) {
             const int yy = ey + dy;
@@ -177,6 +223,7 @@ nms_round0_kernel(const float* __restrict__ heat, int H, int W, float thresh, in
         if (!any) {
             atomicOr(&s_ub[iy * 2 + (ix >> 5)], 1u << (ix & 31));
             s_und[atomicAdd(&s_nund, 1)] = pix;
+            uk[pix] = me;
         }
     }
     __syncthreads();
@@ -201,159 +248,279 @@ nms_round0_kernel(const float* __restrict__ heat, int H, int W, float thresh, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// Rounds >= 1 on the compact list
+// Rounds >= 1, sort, emit: one CTA per image
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRoundsThreads)
-nms_rounds_kernel(const float* __restrict__ heat, int H, int W, int r, int border, int kcap,
-                  unsigned long long* __restrict__ keys, int* __restrict__ counters, unsigned* __restrict__ mask,
-                  int mask_w, unsigned* __restrict__ und) {
-    cg::cluster_group cluster = cg::this_cluster();
-    __shared__ int s_warp_tot[kRoundsThreads / 32];
-    __shared__ int s_total;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x / kNmsCluster;
-    const int rank = (int)cluster.block_rank();
-    int* cnt = counters + b * kNmsCounters;
-    const long n0 = min((long)__ldcg(cnt + 1), (long)H * W);
-    if (n0 == 0) return;                                     // uniform over the cluster
-    const long seg0 = rank * n0 / kNmsCluster, seg1 = (rank + 1) * n0 / kNmsCluster;
-    unsigned* list = und + (size_t)b * H * W + seg0;
-    int m = (int)(seg1 - seg0);
-    const float* hmap = heat + (size_t)b * H * W;
-    unsigned* mrow = mask + (size_t)b * H * mask_w;
-    unsigned long long* kout = keys + (size_t)b * kcap;
-    const int side = 2 * r + 1;
+constexpr unsigned kDead = 0xffffffffu;
 
-    for (int k = 1; k < (1 << 30); ++k) {
-        // ---- phase A: is the candidate the maximum of the undecided candidates of its window? ----
-        for (int i = warp; i < m; i += kRoundsThreads / 32) {
-            const unsigned p = list[i] & 0x7fffffffu;
-            const int y = (int)(p / (unsigned)W), x = (int)(p % (unsigned)W);
-            const unsigned kp = sortable_bits(__ldg(hmap + p));
-            bool beaten = false;
-            for (int t = lane; t < side * side; t += 32) {
-                const int qy = y + t / side - r, qx = x + t % side - r;
-                if (qy < 0 || qy >= H || qx < 0 || qx >= W || (qy == y && qx == x)) continue;
-                const unsigned word = __ldcg(mrow + (size_t)qy * mask_w + (qx >> 5));
-                if ((word >> (qx & 31)) & 1u) {
-                    const unsigned q = (unsigned)(qy * W + qx);
-                    const unsigned kq = sortable_bits(__ldg(hmap + q));
-                    if (kq > kp || (kq == kp && q < p)) beaten = true;
-                }
-            }
-            const bool any = __any_sync(0xffffffffu, beaten);
-            if (lane == 0 && !any) list[i] = p | 0x80000000u;
+// REGS: the thread's candidates live in registers (n0 <= kFinRegEntries * kFinThreads); otherwise they are re-read
+// from the list, where a decided entry is overwritten with kDead.  New survivors are appended to the image's keys.
+template <bool REGS>
+__device__ __forceinline__ void finish_rounds(int n0, int H, int W, int r, int border, int kcap, unsigned* __restrict__ list,
+                                              unsigned* __restrict__ mrow, int mask_w, const unsigned* __restrict__ uk,
+                                              unsigned long long* __restrict__ kdst, int* s_n) {
+    const int tid = threadIdx.x;
+    const int per = REGS ? kFinRegEntries : (n0 + kFinThreads - 1) / kFinThreads;
+    unsigned ent[kFinRegEntries];
+    if (REGS) {
+#pragma unroll
+        for (int k = 0; k < kFinRegEntries; ++k) {
+            const int idx = tid + k * kFinThreads;
+            ent[k] = idx < n0 ? __ldcg(list + idx) : kDead;
         }
-        __syncthreads();
-        cluster.sync();
-        if (k > 1 && __ldcg(cnt + 2 + (k - 1) % 3) == 0) break;            // nothing was left after the last round
-        // ---- phase B: new keepers clear their window in the mask and are emitted ----
-        for (int i = warp; i < m; i += kRoundsThreads / 32) {
-            const unsigned e = list[i];
-            if (!(e >> 31)) continue;
-            const unsigned p = e & 0x7fffffffu;
-            const int y = (int)(p / (unsigned)W), x = (int)(p % (unsigned)W);
-            if (lane < side) {
-                const int qy = y + lane - r;
-                if (qy >= 0 && qy < H) {
-                    const int x0 = max(x - r, 0), x1 = min(x + r, W - 1);
-                    const int w0 = x0 >> 5, w1 = x1 >> 5;
-                    const unsigned lo = 0xffffffffu << (x0 & 31), hi = 0xffffffffu >> (31 - (x1 & 31));
-                    if (w0 == w1) atomicAnd(mrow + (size_t)qy * mask_w + w0, ~(lo & hi));
-                    else { atomicAnd(mrow + (size_t)qy * mask_w + w0, ~lo); atomicAnd(mrow + (size_t)qy * mask_w + w1, ~hi); }
+    }
+    for (int round = 1; round < (1 << 30); ++round) {
+        // ---- phase A: suppressed since the last round?  the maximum of the undecided candidates of its window? ----
+        unsigned keepers = 0u;          // REGS: bit k = entry k is a new keeper
+        bool live = false;
+#pragma unroll
+        for (int k = 0; k < kFinRegEntries; ++k) {
+            if (!REGS && k > 0) break;
+            for (int kk = 0; kk < (REGS ? 1 : per); ++kk) {
+                const int idx = REGS ? 0 : tid + kk * kFinThreads;
+                unsigned p = REGS ? ent[k] : (idx < n0 ? __ldcg(list + idx) : kDead);
+                if (p == kDead) continue;
+                p &= 0x7fffffffu;
+                const int y = (int)(p / (unsigned)W), x = (int)(p - (unsigned)y * (unsigned)W);
+                const int x0 = max(x - r, 0), x1 = min(x + r, W - 1);
+                const int w0 = x0 >> 5, w1 = x1 >> 5, sh = x0 & 31;
+                const unsigned long long wmask = (1ull << (x1 - x0 + 1)) - 1ull;
+                const unsigned* mr = mrow + (size_t)y * mask_w;
+                unsigned long long two = (unsigned long long)__ldcg(mr + w0);
+                if (w1 != w0) two |= (unsigned long long)__ldcg(mr + w1) << 32;
+                const unsigned own_row = (unsigned)((two >> sh) & wmask);
+                if (!((own_row >> (x - x0)) & 1u)) {               // a keeper of the previous round cleared it
+                    if (REGS) ent[k] = kDead; else list[idx] = kDead;
+                    continue;
+                }
+                const unsigned kp = __ldcg(uk + p);
+                bool beaten = false;
+                for (int dy = -r; dy <= r; ++dy) {
+                    const int qy = y + dy;
+                    if (qy < 0 || qy >= H) continue;
+                    unsigned bits = own_row & ~(1u << (x - x0));
+                    if (dy != 0) {
+                        const unsigned* qr = mrow + (size_t)qy * mask_w;
+                        unsigned long long t2 = (unsigned long long)__ldcg(qr + w0);
+                        if (w1 != w0) t2 |= (unsigned long long)__ldcg(qr + w1) << 32;
+                        bits = (unsigned)((t2 >> sh) & wmask);
+                    }
+                    while (bits) {
+                        const int t = __ffs(bits) - 1;
+                        bits &= bits - 1u;
+                        const unsigned q = (unsigned)(qy * W + x0 + t);
+                        const unsigned kq = __ldcg(uk + q);
+                        if (kq > kp || (kq == kp && q < p)) beaten = true;
+                    }
+                }
+                if (!beaten) {
+                    if (REGS) keepers |= 1u << k; else list[idx] = p | 0x80000000u;
+                } else {
+                    live = true;
                 }
             }
-            if (lane == 0 && !(x < border || x >= W - border || y < border || y >= H - border)) {
-                const int pos = atomicAdd(cnt, 1);
-                if (pos < kcap) kout[pos] = survivor_key(sortable_bits(__ldg(hmap + p)), p);
+        }
+        __syncthreads();                 // every test of the round precedes every clearing
+        // ---- phase B: new keepers clear their window in the mask and are emitted ----
+#pragma unroll
+        for (int k = 0; k < kFinRegEntries; ++k) {
+            if (!REGS && k > 0) break;
+            for (int kk = 0; kk < (REGS ? 1 : per); ++kk) {
+                const int idx = REGS ? 0 : tid + kk * kFinThreads;
+                unsigned p;
+                if (REGS) {
+                    if (!((keepers >> k) & 1u)) continue;
+                    p = ent[k] & 0x7fffffffu;
+                    ent[k] = kDead;
+                } else {
+                    if (idx >= n0) continue;
+                    const unsigned e = list[idx];
+                    if (e == kDead || !(e >> 31)) continue;
+                    p = e & 0x7fffffffu;
+                    list[idx] = kDead;
+                }
+                const int y = (int)(p / (unsigned)W), x = (int)(p - (unsigned)y * (unsigned)W);
+                const int x0 = max(x - r, 0), x1 = min(x + r, W - 1);
+                const int w0 = x0 >> 5, w1 = x1 >> 5;
+                const unsigned lo = 0xffffffffu << (x0 & 31), hi = 0xffffffffu >> (31 - (x1 & 31));
+                for (int qy = max(y - r, 0); qy <= min(y + r, H - 1); ++qy) {
+                    unsigned* qr = mrow + (size_t)qy * mask_w;
+                    if (w0 == w1) atomicAnd(qr + w0, ~(lo & hi));
+                    else { atomicAnd(qr + w0, ~lo); atomicAnd(qr + w1, ~hi); }
+                }
+                if (!(x < border || x >= W - border || y < border || y >= H - border)) {
+                    const int pos = atomicAdd(s_n, 1);
+                    if (pos < kcap) kdst[pos] = survivor_key(__ldcg(uk + p), p);
+                }
             }
         }
         __threadfence();
-        __syncthreads();
-        cluster.sync();
-        // ---- compaction: keep the entries whose own bit survived ----
-        int new_m = 0;
-        for (int base = 0; base < m; base += kRoundsThreads) {
-            const int i = base + tid;
-            unsigned p = 0u;
-            bool alive = false;
-            if (i < m) {
-                const unsigned e = list[i];
-                p = e & 0x7fffffffu;
-                if (!(e >> 31)) {
-                    const int y = (int)(p / (unsigned)W), x = (int)(p % (unsigned)W);
-                    alive = (__ldcg(mrow + (size_t)y * mask_w + (x >> 5)) >> (x & 31)) & 1u;
-                }
-            }
-            const unsigned ab = __ballot_sync(0xffffffffu, alive);
-            if (lane == 0) s_warp_tot[warp] = __popc(ab);
-            __syncthreads();
-            int off = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < kRoundsThreads / 32; ++w) {
-                const int c = s_warp_tot[w];
-                if (w < warp) off += c;
-                tot += c;
-            }
-            if (alive) list[new_m + off + __popc(ab & ((1u << lane) - 1u))] = p;
-            new_m += tot;
-            __syncthreads();
-        }
-        m = new_m;
-        if (tid == 0) {
-            if (m) atomicAdd(cnt + 2 + k % 3, m);
-            if (rank == 0) cnt[2 + (k + 1) % 3] = 0;
-            __threadfence();
-        }
-        (void)s_total;
+        if (!__syncthreads_or(live ? 1 : 0)) break;
     }
 }
 
-template <int R>
-static void launch_round0_t(const float* heat, int B, int H, int W, float thresh, int border, const NmsWorkspace& ws,
-                            cudaStream_t st) {
+__global__ void __launch_bounds__(kFinThreads, 1)
+nms_finish_kernel(int H, int W, int r, int border, int kcap, unsigned long long* __restrict__ keys,
+                  unsigned long long* __restrict__ keys_alt, int* __restrict__ counters, unsigned* __restrict__ mask,
+                  int mask_w, unsigned* __restrict__ und, const unsigned* __restrict__ ukey, int cap_out, int top_k,
+                  int* __restrict__ count, int* __restrict__ xy, float* __restrict__ conf) {
+    extern __shared__ __align__(16) unsigned char fin_smem[];
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(fin_smem);       // [2][kSortSmemKeys]
+    __shared__ unsigned s_hist[8][256];
+    __shared__ unsigned s_base[256];
+    __shared__ unsigned s_wcnt[32][256];
+    __shared__ unsigned s_warp_tot[8];
+    __shared__ int s_n;
+    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const int b = blockIdx.x;
+    int* cnt = counters + b * kNmsCounters;
+    const int nkeep0 = min(__ldcg(cnt), kcap);
+    const int n0 = (int)min((long)__ldcg(cnt + 1), (long)H * W);
+    unsigned long long* gkeys = keys + (size_t)b * kcap;
+
+    for (int i = tid; i < 8 * 256; i += kFinThreads) (&s_hist[0][0])[i] = 0;
+    for (int i = tid; i < 32 * 256; i += kFinThreads) (&s_wcnt[0][0])[i] = 0;
+    if (tid == 0) s_n = nkeep0;
+    __syncthreads();
+
+    if (n0 > 0) {
+        unsigned* list = und + (size_t)b * H * W;
+        unsigned* mrow = mask + (size_t)b * H * mask_w;
+        const unsigned* uk = ukey + (size_t)b * H * W;
+        if (n0 <= kFinRegEntries * kFinThreads) finish_rounds<true>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
+        else finish_rounds<false>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
+        __syncthreads();
+    }
+    const int n = min(s_n, kcap);
+    const bool smemk = n <= kSortSmemKeys;                 // the usual case: the whole sort stays in shared memory
+    if (smemk)
+        for (int i = tid; i < n; i += kFinThreads) s_keys[i] = __ldcg(gkeys + i);
+    __syncthreads();
+    unsigned long long* src = smemk ? s_keys : gkeys;
+    unsigned long long* dst = smemk ? s_keys + kSortSmemKeys : keys_alt + (size_t)b * kcap;
+
+    // ---- LSD radix sort by descending key ----
+    for (int i = tid; i < n; i += kFinThreads) {
+        const unsigned long long v = ~src[i];          // ascending on ~key == descending on key
+#pragma unroll
+        for (int d = 0; d < 8; ++d) atomicAdd(&s_hist[d][(unsigned)(v >> (8 * d)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 8 && n > 1; ++pass) {
+        // skip a digit position on which every key agrees (block-uniform decision)
+        const int hit = (tid < 256 && s_hist[pass][tid] == (unsigned)n) ? 1 : 0;
+        if (__syncthreads_or(hit)) continue;
+        // exclusive scan of the 256-bin histogram
+        if (tid < 256) {
+            const unsigned v = s_hist[pass][tid];
+            unsigned inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_warp_tot[warp] = inc;
+            s_base[tid] = inc - v;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            unsigned add = 0;
+            for (int w = 0; w < warp; ++w) add += s_warp_tot[w];
+            s_base[tid] += add;
+        }
+        __syncthreads();
+        const int shift = 8 * pass;
+        for (int r0 = 0; r0 < n; r0 += kFinThreads) {
+            const int i = r0 + tid;
+            const bool valid = i < n;
+            const unsigned long long key = valid ? src[i] : 0ull;
+            const int dig = valid ? (int)((unsigned)((~key) >> shift) & 255u) : 256 + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, dig);
+            const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank_in_warp == 0) s_wcnt[warp][dig] = __popc(peers);
+            __syncthreads();
+            if (tid < 256) {
+                unsigned off = s_base[tid];
+                for (int w = 0; w < 32; ++w) {
+                    const unsigned c = s_wcnt[w][tid];
+                    if (c) {                   // untouched entries must stay 0: only a group's leader resets its entry
+                        s_wcnt[w][tid] = off;
+                        off += c;
+                    }
+                }
+                s_base[tid] = off;
+            }
+            __syncthreads();
+            if (valid) dst[s_wcnt[warp][dig] + rank_in_warp] = key;
+            __syncwarp();
+            if (valid && rank_in_warp == 0) s_wcnt[warp][dig] = 0;
+            __syncthreads();
+        }
+        unsigned long long* t = src; src = dst; dst = t;
+        __syncthreads();
+    }
+
+    int nout = min(n, cap_out);
+    if (top_k > 0) nout = min(nout, top_k);
+    for (int i = tid; i < nout; i += kFinThreads) {
+        const unsigned long long key = src[i];
+        const unsigned pix = ~(unsigned)(key & 0xffffffffull);
+        xy[((size_t)b * cap_out + i) * 2 + 0] = (int)(pix % (unsigned)W);
+        xy[((size_t)b * cap_out + i) * 2 + 1] = (int)(pix / (unsigned)W);
+        conf[(size_t)b * cap_out + i] = from_sortable_bits((unsigned)(key >> 32));
+    }
+    if (tid == 0) count[b] = nout;
+}
+
+template <int R, bool LOGITS>
+static void launch_round0_t(const float* src, int cell_stride, int B, int H, int W, float thresh, int border,
+                            const NmsWorkspace& ws, cudaStream_t st) {
     constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R, EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;
     constexpr int KW = (EW + 31) / 32 + 1;
     constexpr int kMaxKeep = ((kN0TW + R) / (R + 1) + 1) * ((kN0TH + R) / (R + 1) + 1);
     const size_t smem = sizeof(unsigned) * ((size_t)LH * LW + EH * KW + kN0TH * 2 + kN0TH * kN0TW) + sizeof(unsigned long long) * kMaxKeep +
                         sizeof(unsigned short) * ((size_t)EH * EW) + 16;
-    auto kern = nms_round0_kernel<R>;
+    auto kern = nms_round0_kernel<R, LOGITS>;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((W + kN0TW - 1) / kN0TW, (H + kN0TH - 1) / kN0TH, B);
-    kern<<<grid, kN0Threads, smem, st>>>(heat, H, W, thresh, border, ws.kcap, ws.keys, ws.counters, ws.mask, ws.mask_w, ws.und);
+    kern<<<grid, kN0Threads, smem, st>>>(src, cell_stride, H, W, thresh, border, ws.kcap, ws.keys, ws.counters, ws.mask, ws.mask_w,
+                                         ws.und, ws.ukey);
     SPB_CHECK_LAUNCH();
 }
 
-void launch_nms(const float* heat, int B, int H, int W, float thresh, int radius, int border, const NmsWorkspace& ws,
-                cudaStream_t st) {
+bool nms_logits_supported(int radius) { return radius >= 0 && radius <= 4; }
+
+void launch_nms(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
+                int border, int top_k, int cap, const NmsWorkspace& ws, int* count, int* xy, float* conf, cudaStream_t st) {
     if (radius < 0 || radius > kNmsMaxR) throw std::invalid_argument("nms_dist must be in [0, 8]");
     if ((long)H * W >= (1l << 31)) throw std::invalid_argument("image too large");
+    if (!heat && !(logits && nms_logits_supported(radius))) throw std::invalid_argument("nms: no heatmap given");
     SPB_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * kNmsCounters * B, st));
-    switch (radius) {
-        case 0: launch_round0_t<0>(heat, B, H, W, thresh, border, ws, st); break;
-        case 1: launch_round0_t<1>(heat, B, H, W, thresh, border, ws, st); break;
-        case 2: launch_round0_t<2>(heat, B, H, W, thresh, border, ws, st); break;
-        case 3: launch_round0_t<3>(heat, B, H, W, thresh, border, ws, st); break;
-        case 4: launch_round0_t<4>(heat, B, H, W, thresh, border, ws, st); break;
-        case 5: launch_round0_t<5>(heat, B, H, W, thresh, border, ws, st); break;
-        case 6: launch_round0_t<6>(heat, B, H, W, thresh, border, ws, st); break;
-        case 7: launch_round0_t<7>(heat, B, H, W, thresh, border, ws, st); break;
-        default: launch_round0_t<8>(heat, B, H, W, thresh, border, ws, st); break;
+    if (!heat) {
+        switch (radius) {
+            case 0: launch_round0_t<0, true>(logits, cell_stride, B, H, W, thresh, border, ws, st); break;
+            case 1: launch_round0_t<1, true>(logits, cell_stride, B, H, W, thresh, border, ws, st); break;
+            case 2: launch_round0_t<2, true>(logits, cell_stride, B, H, W, thresh, border, ws, st); break;
+            case 3: launch_round0_t<3, true>(logits, cell_stride, B, H, W, thresh, border, ws, st); break;
+            default: launch_round0_t<4, true>(logits, cell_stride, B, H, W, thresh, border, ws, st); break;
+        }
+    } else {
+        switch (radius) {
+            case 0: launch_round0_t<0, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            case 1: launch_round0_t<1, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            case 2: launch_round0_t<2, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            case 3: launch_round0_t<3, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            case 4: launch_round0_t<4, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            case 5: launch_round0_t<5, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            case 6: launch_round0_t<6, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            case 7: launch_round0_t<7, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            default: launch_round0_t<8, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+        }
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(B * kNmsCluster);
-    cfg.blockDim = dim3(kRoundsThreads);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kNmsCluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SPB_CUDA(cudaLaunchKernelEx(&cfg, nms_rounds_kernel, heat, H, W, radius, border, ws.kcap, ws.keys, ws.counters, ws.mask,
-                                ws.mask_w, ws.und));
+    const size_t smem = sizeof(unsigned long long) * 2 * kSortSmemKeys;
+    SPB_CUDA(cudaFuncSetAttribute(nms_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_finish_kernel<<<B, kFinThreads, smem, st>>>(H, W, radius, border, ws.kcap, ws.keys, ws.keys_alt, ws.counters, ws.mask,
+                                                    ws.mask_w, ws.und, ws.ukey, cap, top_k, count, xy, conf);
+    SPB_CHECK_LAUNCH();
 }
 
 }  // namespace spb200

@@ -3,8 +3,8 @@
 //  K3 heatmap_kernel      softmax-with-epsilon over 65 channels, drop dustbin, depth-to-space
 //                         (reference python/src/superpoint.py:111-114, python/src/netutils.py:64-75)
 //  K4 (nms.cu)            exact parallel form of the reference's greedy grid NMS
-//  K5 sort_emit_kernel    block-wide LSD radix sort of the survivors by descending confidence
-//                         (python/src/netutils.py:92-93) + top-k truncation
+//  K5 (nms.cu)            block-wide LSD radix sort of the survivors by descending confidence
+//                         (python/src/netutils.py:92-93) + top-k truncation, fused with the last NMS rounds
 //  K6 sample_desc_kernel  bilinear sampling (align_corners=True) + L2 normalisation
 //                         (python/src/netutils.py:103-121), one warp per keypoint, 128-bit loads
 #include <type_traits>
@@ -63,108 +63,6 @@ void launch_heatmap(const float* logits, long batch_stride, long chan_stride, lo
                     float* heat, cudaStream_t st) {
     dim3 grid((Wc + kHeatCells - 1) / kHeatCells, Hc, B);
     heatmap_kernel<<<grid, 256, 0, st>>>(logits, batch_stride, chan_stride, cell_stride, Hc, Wc, heat);
-    SPB_CHECK_LAUNCH();
-}
-
-// ================================================================================================
-// K5: one block per image: LSD radix sort (8-bit digits) of the survivor keys by descending key,
-// then emit (x, y), confidence and the count.  Digit positions on which all keys agree are skipped.
-// ================================================================================================
-constexpr int kSortThreads = 1024;
-
-__global__ void __launch_bounds__(kSortThreads)
-sort_emit_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ keys_alt,
-                 int* __restrict__ counters, int kcap, int W, int cap_out, int top_k, int* __restrict__ count,
-                 int* __restrict__ xy, float* __restrict__ conf) {
-    __shared__ unsigned s_hist[8][256];
-    __shared__ unsigned s_base[256];
-    __shared__ unsigned s_wcnt[32][256];
-    __shared__ unsigned s_warp_tot[8];
-    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
-    const int b = blockIdx.x;
-    const int n = min(counters[b * kNmsCounters], kcap);
-    unsigned long long* src = keys + (size_t)b * kcap;
-    unsigned long long* dst = keys_alt + (size_t)b * kcap;
-
-    for (int i = tid; i < 8 * 256; i += kSortThreads) (&s_hist[0][0])[i] = 0;
-    for (int i = tid; i < 32 * 256; i += kSortThreads) (&s_wcnt[0][0])[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += kSortThreads) {
-        const unsigned long long v = ~src[i];          // ascending on ~key == descending on key
-#pragma unroll
-        for (int d = 0; d < 8; ++d) atomicAdd(&s_hist[d][(unsigned)(v >> (8 * d)) & 255u], 1u);
-    }
-    __syncthreads();
-
-    for (int pass = 0; pass < 8 && n > 1; ++pass) {
-        // skip a digit position on which every key agrees (block-uniform decision)
-        const int hit = (tid < 256 && s_hist[pass][tid] == (unsigned)n) ? 1 : 0;
-        if (__syncthreads_or(hit)) continue;
-        // exclusive scan of the 256-bin histogram
-        if (tid < 256) {
-            const unsigned v = s_hist[pass][tid];
-            unsigned inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) s_warp_tot[warp] = inc;
-            s_base[tid] = inc - v;
-        }
-        __syncthreads();
-        if (tid < 256) {
-            unsigned add = 0;
-            for (int w = 0; w < warp; ++w) add += s_warp_tot[w];
-            s_base[tid] += add;
-        }
-        __syncthreads();
-        const int shift = 8 * pass;
-        for (int r0 = 0; r0 < n; r0 += kSortThreads) {
-            const int i = r0 + tid;
-            const bool valid = i < n;
-            const unsigned long long key = valid ? src[i] : 0ull;
-            const int dig = valid ? (int)((unsigned)((~key) >> shift) & 255u) : 256 + lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, dig);
-            const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-            if (valid && rank_in_warp == 0) s_wcnt[warp][dig] = __popc(peers);
-            __syncthreads();
-            if (tid < 256) {
-                unsigned off = s_base[tid];
-                for (int w = 0; w < 32; ++w) {
-                    const unsigned c = s_wcnt[w][tid];
-                    if (c) {                   // untouched entries must stay 0: only a group's leader resets its entry
-                        s_wcnt[w][tid] = off;
-                        off += c;
-                    }
-                }
-                s_base[tid] = off;
-            }
-            __syncthreads();
-            if (valid) dst[s_wcnt[warp][dig] + rank_in_warp] = key;
-            __syncwarp();
-            if (valid && rank_in_warp == 0) s_wcnt[warp][dig] = 0;
-            __syncthreads();
-        }
-        unsigned long long* t = src; src = dst; dst = t;
-        __syncthreads();
-    }
-
-    int nout = min(n, cap_out);
-    if (top_k > 0) nout = min(nout, top_k);
-    for (int i = tid; i < nout; i += kSortThreads) {
-        const unsigned long long key = src[i];
-        const unsigned pix = ~(unsigned)(key & 0xffffffffull);
-        xy[((size_t)b * cap_out + i) * 2 + 0] = (int)(pix % (unsigned)W);
-        xy[((size_t)b * cap_out + i) * 2 + 1] = (int)(pix / (unsigned)W);
-        conf[(size_t)b * cap_out + i] = from_sortable_bits((unsigned)(key >> 32));
-    }
-    if (tid == 0) count[b] = nout;
-}
-
-void launch_sort_emit(int B, int W, int top_k, int cap, const NmsWorkspace& ws, int* count, int* xy, float* conf,
-                      cudaStream_t st) {
-    sort_emit_kernel<<<B, kSortThreads, 0, st>>>(ws.keys, ws.keys_alt, ws.counters, ws.kcap, W, cap, top_k, count, xy, conf);
     SPB_CHECK_LAUNCH();
 }
 
