@@ -276,8 +276,10 @@ def main():
     for name, a in agg.items():
         kms = a['ms'] / a['n']
         by = a['bytes']
-        if name == 'nms_sort':
-            by += 28.0 * n_kp            # survivors: 8 B key written + read by the sort, 12 B (x, y, conf) out
+        if name == 'nms_round0':
+            by += 8.0 * n_kp             # survivor keys out
+        if name == 'nms_finish_sort':
+            by = 20.0 * n_kp             # survivor keys in, (x, y, conf) out
         if name == 'descriptors':
             by = n_kp * (4 * 128 * esz + 8 + 512)
         row = {'kernel': name, 'ms': kms, 'share': kms / total_ms if total_ms else 0.0}
@@ -306,7 +308,7 @@ def main():
         if top_ai is not None:
             roofline['algorithmic_intensity_flop_per_byte'] = top_ai
             roofline['ridge_flop_per_byte'] = ridge
-    ncu_name = {'stem_pool': 'stem_planes_kernel', 'nms_sort': 'nms_round0_kernel', 'descriptors': 'sample_desc', 'heatmap': 'heatmap_kernel',
+    ncu_name = {'stem_pool': 'stem_planes_kernel', 'nms_round0': 'nms_round0_kernel', 'nms_finish_sort': 'nms_finish_kernel', 'descriptors': 'sample_desc', 'heatmap': 'heatmap_kernel',
                 'image_planes': 'planes_kernel'}.get(top['kernel'])
     roofline['traffic'] = ncu_traffic(ncu_name) if ncu_name and B == 64 and H == 480 and W == 640 else None
     roofline['traffic_source'] = 'ncu --set full capture of the same workload committed under profiles/ (dram bytes read + written per launch)'

@@ -628,10 +628,14 @@ void Engine::detect(const float* img, int B, int C, int H, int W, int cap, int* 
         ++launches_;
     }
     ensure_nms(B, H, W);
-    // algorithmic bytes: the logits (65 channels) or the heatmap in; + 8 B per survivor in and 12 B out (added by the caller)
-    prof_open("nms_sort", 0.0, from_logits ? (double)B * 65.0 * Hc * Wc * 4 : (double)B * H * W * 4, st);
-    launch_nms(from_logits ? nullptr : (prob ? prob : d_prob_), (const float*)buf_[BUF_LOGITS], det_c_, B, H, W, params_.conf_thresh,
-               params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_, count, xy, conf, st);
+    // algorithmic bytes: the logits (65 channels) or the heatmap in; per survivor 8 B key out, then 8 B in and 12 B out
+    // in the finish kernel (added by the caller, who knows the keypoint count)
+    prof_open("nms_round0", 0.0, from_logits ? (double)B * 65.0 * Hc * Wc * 4 : (double)B * H * W * 4, st);
+    launch_nms_round0(from_logits ? nullptr : (prob ? prob : d_prob_), (const float*)buf_[BUF_LOGITS], det_c_, B, H, W,
+                      params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
+    prof_close(st);
+    prof_open("nms_finish_sort", 0.0, 0.0, st);
+    launch_nms_finish(B, H, W, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_, count, xy, conf, st);
     prof_close(st);
     launches_ += 2;
     if (desc) {
@@ -659,8 +663,8 @@ void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, in
     SPB_CUDA(cudaSetDevice(device_));
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
     ensure_nms(B, H, W);
-    launch_nms(prob, nullptr, 0, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_,
-               count, xy, conf, st);
+    launch_nms_round0(prob, nullptr, 0, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
+    launch_nms_finish(B, H, W, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_, count, xy, conf, st);
     launches_ += 2;
 }
 

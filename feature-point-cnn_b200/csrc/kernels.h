@@ -63,13 +63,17 @@ struct NmsWorkspace {
     unsigned* ukey;                // [B][H*W] sortable key of a pixel, valid where its undecided bit is (or was) set
 };
 // Greedy-equivalent grid NMS + border removal (reference python/src/nms.py:4-53, python/src/netutils.py:59,95-99),
-// descending sort (netutils.py:92-93) and top-k truncation.  Two launches.  Input: `heat` [B][H][W], or - when heat
-// is null and nms_logits_supported(radius) - the detector logits (channels last, cell_stride floats per cell), from
-// which round 0 computes the softmax / depth-to-space values itself.  Outputs per image: count (clamped to cap
-// and top_k), xy int32 [cap][2] as (x, y), conf fp32 [cap].
+// descending sort (netutils.py:92-93) and top-k truncation, as two launches.
+// launch_nms_round0: input `heat` [B][H][W], or - when heat is null and nms_logits_supported(radius) - the detector
+// logits (channels last, cell_stride floats per cell), from which it computes the softmax / depth-to-space values
+// itself; leaves the first keepers, the undecided candidates and their bit mask in the workspace.
+// launch_nms_finish: remaining rounds, sort, outputs per image: count (clamped to cap and top_k), xy int32 [cap][2]
+// as (x, y), conf fp32 [cap].
 bool nms_logits_supported(int radius);
-void launch_nms(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
-                int border, int top_k, int cap, const NmsWorkspace& ws, int* count, int* xy, float* conf, cudaStream_t st);
+void launch_nms_round0(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
+                       int border, const NmsWorkspace& ws, cudaStream_t st);
+void launch_nms_finish(int B, int H, int W, int radius, int border, int top_k, int cap, const NmsWorkspace& ws, int* count,
+                       int* xy, float* conf, cudaStream_t st);
 
 // Bilinear sampling (align_corners=True) of the descriptor map at the keypoints + L2 normalisation
 // (reference python/src/netutils.py:103-121).  map element (b, c, i, j) is at

@@ -19,8 +19,10 @@
 // their keys (scattered into a dense side array) and their compact list.
 // After it only a few percent of the candidates are left: nms_finish_kernel, ONE 1024-thread CTA per image, keeps
 // them in registers (a thread per candidate scans its window through the bitmask and looks keys up only where a
-// bit is set; keepers clear their window bits with atomics; two block barriers per round), then sorts the
-// survivors in shared memory (LSD radix, 8-bit digits, constant digits skipped) and emits (x, y), confidence, count.
+// bit is set - the mask is copied to shared memory when it fits; keepers clear their window bits with atomics; two
+// block barriers per round), then sorts the survivors (LSD radix sort, 8-bit digits, keys in registers, one
+// scatter/gather through shared memory per pass, constant digits skipped; through global memory when there are
+// more than 8192) and emits (x, y), confidence, count.
 #include "kernels.h"
 #include "sortkey.cuh"
 
@@ -31,7 +33,8 @@ constexpr int kN0Threads = 256;
 constexpr int kNmsMaxR = 8;
 constexpr int kFinThreads = 1024;
 constexpr int kFinRegEntries = 8;            // undecided candidates a thread keeps in registers
-constexpr int kSortSmemKeys = 10240;         // survivors per image sorted in shared memory (2 x 80 KB ping-pong)
+constexpr int kSortSmemKeys = 8192;          // survivors per image sorted in registers + shared memory (8 per thread)
+constexpr int kFinMaskWords = 16384;         // undecided-bit mask words per image held in shared memory (64 KB)
 
 // ------------------------------------------------------------------------------------------------
 // Round 0
@@ -252,9 +255,101 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned kDead = 0xffffffffu;
 
+// The usual case: candidates (and their keys) in registers, the mask in shared memory, radius known at compile time.
+// The window rows are fetched first, then every neighbour key is loaded under its mask bit - up to (2R+1)^2
+// independent predicated loads, so a round costs about one L2 round trip instead of one per undecided neighbour.
+template <int R>
+__device__ __forceinline__ void finish_rounds_fast(int n0, int H, int W, int border, int kcap, const unsigned* __restrict__ list,
+                                                   unsigned* s_mask, int mask_w, const unsigned* __restrict__ uk,
+                                                   unsigned long long* __restrict__ kdst, int* s_n) {
+    constexpr int S = 2 * R + 1;
+    const int tid = threadIdx.x;
+    unsigned ent[kFinRegEntries], kp[kFinRegEntries];
+#pragma unroll
+    for (int k = 0; k < kFinRegEntries; ++k) {
+        const int idx = tid + k * kFinThreads;
+        ent[k] = idx < n0 ? __ldcg(list + idx) : kDead;
+    }
+#pragma unroll
+    for (int k = 0; k < kFinRegEntries; ++k) kp[k] = ent[k] != kDead ? __ldcg(uk + ent[k]) : 0u;
+    for (int round = 1; round < (1 << 30); ++round) {
+        unsigned keepers = 0u;
+        bool live = false;
+#pragma unroll
+        for (int k = 0; k < kFinRegEntries; ++k) {
+            if (ent[k] == kDead) continue;
+            const unsigned p = ent[k];
+            const int y = (int)(p / (unsigned)W), x = (int)(p - (unsigned)y * (unsigned)W);
+            const int x0 = max(x - R, 0), x1 = min(x + R, W - 1);
+            const int w0 = x0 >> 5, w1 = x1 >> 5, sh = x0 & 31;
+            const unsigned long long wmask = (1ull << (x1 - x0 + 1)) - 1ull;
+            unsigned rows[S];
+#pragma unroll
+            for (int d = 0; d < S; ++d) {
+                const int qy = y + d - R;
+                rows[d] = 0u;
+                if (qy >= 0 && qy < H) {
+                    const unsigned* mr = s_mask + qy * mask_w;
+                    unsigned long long two = (unsigned long long)mr[w0];
+                    if (w1 != w0) two |= (unsigned long long)mr[w1] << 32;
+                    rows[d] = (unsigned)((two >> sh) & wmask);
+                }
+            }
+            if (!((rows[R] >> (x - x0)) & 1u)) {               // a keeper of the previous round cleared it
+                ent[k] = kDead;
+                continue;
+            }
+            rows[R] &= ~(1u << (x - x0));
+            unsigned beaten = 0u;
+#pragma unroll
+            for (int d = 0; d < S; ++d) {
+                if (rows[d] == 0u) continue;
+                const unsigned qrow = (unsigned)((y + d - R) * W + x0);
+                unsigned kq[S];
+#pragma unroll
+                for (int t = 0; t < S; ++t) kq[t] = 0u;
+#pragma unroll
+                for (int t = 0; t < S; ++t)
+                    if ((rows[d] >> t) & 1u) kq[t] = __ldcg(uk + qrow + t);      // the row's loads are independent
+#pragma unroll
+                for (int t = 0; t < S; ++t)                                     // kq = 0 (bit clear) never beats: kp > 0
+                    beaten |= (unsigned)(kq[t] > kp[k]) | ((unsigned)(kq[t] == kp[k]) & (unsigned)(qrow + t < p));
+            }
+            if (!beaten) keepers |= 1u << k; else live = true;
+        }
+        __syncthreads();                 // every test of the round precedes every clearing
+#pragma unroll
+        for (int k = 0; k < kFinRegEntries; ++k) {
+            if (!((keepers >> k) & 1u)) continue;
+            const unsigned p = ent[k];
+            ent[k] = kDead;
+            const int y = (int)(p / (unsigned)W), x = (int)(p - (unsigned)y * (unsigned)W);
+            const int x0 = max(x - R, 0), x1 = min(x + R, W - 1);
+            const int w0 = x0 >> 5, w1 = x1 >> 5;
+            const unsigned lo = 0xffffffffu << (x0 & 31), hi = 0xffffffffu >> (31 - (x1 & 31));
+            for (int qy = max(y - R, 0); qy <= min(y + R, H - 1); ++qy) {
+                unsigned* qr = s_mask + qy * mask_w;
+                if (w0 == w1) atomicAnd(qr + w0, ~(lo & hi));
+                else { atomicAnd(qr + w0, ~lo); atomicAnd(qr + w1, ~hi); }
+            }
+            if (!(x < border || x >= W - border || y < border || y >= H - border)) {
+                const int pos = atomicAdd(s_n, 1);
+                if (pos < kcap) kdst[pos] = survivor_key(kp[k], p);
+            }
+        }
+        if (!__syncthreads_or(live ? 1 : 0)) break;
+    }
+}
+
 // REGS: the thread's candidates live in registers (n0 <= kFinRegEntries * kFinThreads); otherwise they are re-read
-// from the list, where a decided entry is overwritten with kDead.  New survivors are appended to the image's keys.
-template <bool REGS>
+// from the list, where a decided entry is overwritten with kDead.  SMASK: the undecided-bit mask of the image is a
+// copy in shared memory.  New survivors are appended to the image's keys.
+template <bool SMASK>
+__device__ __forceinline__ unsigned ld_mask(const unsigned* p) {
+    return SMASK ? *reinterpret_cast<const volatile unsigned*>(p) : __ldcg(p);
+}
+
+template <bool REGS, bool SMASK>
 __device__ __forceinline__ void finish_rounds(int n0, int H, int W, int r, int border, int kcap, unsigned* __restrict__ list,
                                               unsigned* __restrict__ mrow, int mask_w, const unsigned* __restrict__ uk,
                                               unsigned long long* __restrict__ kdst, int* s_n) {
@@ -285,8 +380,8 @@ __device__ __forceinline__ void finish_rounds(int n0, int H, int W, int r, int b
                 const int w0 = x0 >> 5, w1 = x1 >> 5, sh = x0 & 31;
                 const unsigned long long wmask = (1ull << (x1 - x0 + 1)) - 1ull;
                 const unsigned* mr = mrow + (size_t)y * mask_w;
-                unsigned long long two = (unsigned long long)__ldcg(mr + w0);
-                if (w1 != w0) two |= (unsigned long long)__ldcg(mr + w1) << 32;
+                unsigned long long two = (unsigned long long)ld_mask<SMASK>(mr + w0);
+                if (w1 != w0) two |= (unsigned long long)ld_mask<SMASK>(mr + w1) << 32;
                 const unsigned own_row = (unsigned)((two >> sh) & wmask);
                 if (!((own_row >> (x - x0)) & 1u)) {               // a keeper of the previous round cleared it
                     if (REGS) ent[k] = kDead; else list[idx] = kDead;
@@ -300,8 +395,8 @@ __device__ __forceinline__ void finish_rounds(int n0, int H, int W, int r, int b
                     unsigned bits = own_row & ~(1u << (x - x0));
                     if (dy != 0) {
                         const unsigned* qr = mrow + (size_t)qy * mask_w;
-                        unsigned long long t2 = (unsigned long long)__ldcg(qr + w0);
-                        if (w1 != w0) t2 |= (unsigned long long)__ldcg(qr + w1) << 32;
+                        unsigned long long t2 = (unsigned long long)ld_mask<SMASK>(qr + w0);
+                        if (w1 != w0) t2 |= (unsigned long long)ld_mask<SMASK>(qr + w1) << 32;
                         bits = (unsigned)((t2 >> sh) & wmask);
                     }
                     while (bits) {
@@ -364,41 +459,189 @@ nms_finish_kernel(int H, int W, int r, int border, int kcap, unsigned long long*
                   int mask_w, unsigned* __restrict__ und, const unsigned* __restrict__ ukey, int cap_out, int top_k,
                   int* __restrict__ count, int* __restrict__ xy, float* __restrict__ conf) {
     extern __shared__ __align__(16) unsigned char fin_smem[];
-    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(fin_smem);       // [2][kSortSmemKeys]
+    unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(fin_smem);       // [kSortSmemKeys], after the rounds
+    unsigned* s_mask = reinterpret_cast<unsigned*>(fin_smem);                          // [H][mask_w], during the rounds
     __shared__ unsigned s_hist[8][256];
     __shared__ unsigned s_base[256];
     __shared__ unsigned s_wcnt[32][256];
     __shared__ unsigned s_warp_tot[8];
     __shared__ int s_n;
+    __shared__ unsigned s_orand[4];
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     const int b = blockIdx.x;
     int* cnt = counters + b * kNmsCounters;
     const int nkeep0 = min(__ldcg(cnt), kcap);
     const int n0 = (int)min((long)__ldcg(cnt + 1), (long)H * W);
     unsigned long long* gkeys = keys + (size_t)b * kcap;
-
-    for (int i = tid; i < 8 * 256; i += kFinThreads) (&s_hist[0][0])[i] = 0;
-    for (int i = tid; i < 32 * 256; i += kFinThreads) (&s_wcnt[0][0])[i] = 0;
     if (tid == 0) s_n = nkeep0;
-    __syncthreads();
 
     if (n0 > 0) {
         unsigned* list = und + (size_t)b * H * W;
         unsigned* mrow = mask + (size_t)b * H * mask_w;
         const unsigned* uk = ukey + (size_t)b * H * W;
-        if (n0 <= kFinRegEntries * kFinThreads) finish_rounds<true>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
-        else finish_rounds<false>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
-        __syncthreads();
+        const bool regs = n0 <= kFinRegEntries * kFinThreads;
+        if (regs && H * mask_w <= kFinMaskWords) {
+            for (int i = tid; i < H * mask_w; i += kFinThreads) s_mask[i] = __ldcg(mrow + i);
+            __syncthreads();
+            if (r == 4) finish_rounds_fast<4>(n0, H, W, border, kcap, list, s_mask, mask_w, uk, gkeys, &s_n);
+            else finish_rounds<true, true>(n0, H, W, r, border, kcap, list, s_mask, mask_w, uk, gkeys, &s_n);
+        } else {
+            __syncthreads();
+            if (regs) finish_rounds<true, false>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
+            else finish_rounds<false, false>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
+        }
     }
-    const int n = min(s_n, kcap);
-    const bool smemk = n <= kSortSmemKeys;                 // the usual case: the whole sort stays in shared memory
-    if (smemk)
-        for (int i = tid; i < n; i += kFinThreads) s_keys[i] = __ldcg(gkeys + i);
     __syncthreads();
-    unsigned long long* src = smemk ? s_keys : gkeys;
-    unsigned long long* dst = smemk ? s_keys + kSortSmemKeys : keys_alt + (size_t)b * kcap;
+    const int n = min(s_n, kcap);
+    unsigned long long* src = gkeys;
+    bool inverted = false;
 
-    // ---- LSD radix sort by descending key ----
+    if (n <= kSortSmemKeys) {
+        // ---- the usual case: LSD radix sort with the keys in registers (striped: warp w owns positions
+        //      [256 w, 256 w + 256), item i of lane l is position 256 w + 32 i + l, so walking the items in order is
+        //      stable), ranks from match_any + per-warp digit counters, one scatter and one gather through shared
+        //      memory per pass; only the confidence bytes are sorted (constant ones skipped), a fix-up orders the rare
+        //      runs of equal confidence by pixel index.  Keys are held inverted (ascending sort of ~key = descending
+        //      sort of key).
+        constexpr int IPT = kSortSmemKeys / kFinThreads;
+        // a digit position is constant when the OR and the AND of all keys agree on it
+        if (tid < 4) s_orand[tid] = tid < 2 ? 0u : 0xffffffffu;
+        __syncthreads();
+        unsigned long long key[IPT];
+        unsigned or_lo = 0u, or_hi = 0u, and_lo = 0xffffffffu, and_hi = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const int pos = warp * (32 * IPT) + i * 32 + lane;
+            key[i] = pos < n ? ~__ldcg(gkeys + pos) : ~0ull;
+            if (pos < n) {
+                or_lo |= (unsigned)key[i]; or_hi |= (unsigned)(key[i] >> 32);
+                and_lo &= (unsigned)key[i]; and_hi &= (unsigned)(key[i] >> 32);
+            }
+        }
+        or_lo = __reduce_or_sync(0xffffffffu, or_lo); or_hi = __reduce_or_sync(0xffffffffu, or_hi);
+        and_lo = __reduce_and_sync(0xffffffffu, and_lo); and_hi = __reduce_and_sync(0xffffffffu, and_hi);
+        if (lane == 0) {
+            atomicOr(&s_orand[0], or_lo); atomicOr(&s_orand[1], or_hi);
+            atomicAnd(&s_orand[2], and_lo); atomicAnd(&s_orand[3], and_hi);
+        }
+        __syncthreads();
+        const unsigned long long varying = (((unsigned long long)s_orand[1] << 32) | s_orand[0]) ^
+                                           (((unsigned long long)s_orand[3] << 32) | s_orand[2]);
+        bool in_smem = false;
+        for (int pass = 4; pass < 8 && n > 1; ++pass) {
+            if (!((varying >> (8 * pass)) & 255ull)) continue;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) (&s_wcnt[0][0])[tid + i * kFinThreads] = 0u;
+            __syncthreads();
+            const int shift = 8 * pass;
+            unsigned rank[IPT];
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const int pos = warp * (32 * IPT) + i * 32 + lane;
+                if (pos - lane >= n) break;                         // the rest of the warp's segment is empty
+                const bool valid = pos < n;
+                const unsigned dig = (unsigned)(key[i] >> shift) & 255u;
+                // lanes holding the same digit: eight ballots (MATCH.ANY has a fraction of the ballot throughput)
+                unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+                for (int bit = 0; bit < 8; ++bit) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, (dig >> bit) & 1u);
+                    peers &= ((dig >> bit) & 1u) ? bal : ~bal;
+                }
+                const unsigned before = __popc(peers & ((1u << lane) - 1u));
+                unsigned base = 0u;
+                if (valid) base = s_wcnt[warp][dig];
+                __syncwarp();
+                if (valid && before == 0u) s_wcnt[warp][dig] = base + __popc(peers);
+                __syncwarp();
+                rank[i] = base + before;
+            }
+            __syncthreads();
+            // digit totals -> exclusive offsets: s_wcnt[w][d] becomes the offset of warp w inside digit d, s_base[d] the
+            // offset of digit d
+            if (tid < 256) {
+                unsigned total = 0u;
+#pragma unroll 8
+                for (int w = 0; w < 32; ++w) {
+                    const unsigned c = s_wcnt[w][tid];
+                    s_wcnt[w][tid] = total;
+                    total += c;
+                }
+                unsigned inc = total;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) s_warp_tot[warp] = inc;
+                s_base[tid] = inc - total;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                unsigned add = 0u;
+                for (int w = 0; w < warp; ++w) add += s_warp_tot[w];
+                s_base[tid] += add;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const int pos = warp * (32 * IPT) + i * 32 + lane;
+                if (pos < n) {
+                    const unsigned dig = (unsigned)(key[i] >> shift) & 255u;
+                    s_keys[s_base[dig] + s_wcnt[warp][dig] + rank[i]] = key[i];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const int pos = warp * (32 * IPT) + i * 32 + lane;
+                key[i] = pos < n ? s_keys[pos] : ~0ull;
+            }
+            in_smem = true;
+        }
+        if (!in_smem) {
+#pragma unroll
+            for (int i = 0; i < IPT; ++i) {
+                const int pos = warp * (32 * IPT) + i * 32 + lane;
+                if (pos < n) s_keys[pos] = key[i];
+            }
+        }
+        __syncthreads();
+        // runs of equal confidence (flat image regions give them) are still in arrival order: every element of a run
+        // counts the smaller keys of its run and moves to that rank - ascending inverted key = ascending pixel index
+        {
+            int newpos[IPT];
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const int i = tid + k * kFinThreads;
+                newpos[k] = -1;
+                if (i >= n) continue;
+                const unsigned long long v = s_keys[i];
+                const unsigned c = (unsigned)(v >> 32);
+                const bool left = i > 0 && (unsigned)(s_keys[i - 1] >> 32) == c;
+                const bool right = i + 1 < n && (unsigned)(s_keys[i + 1] >> 32) == c;
+                if (!left && !right) continue;
+                key[k] = v;
+                int lo = i, hi = i, rank = 0;
+                while (lo > 0 && (unsigned)(s_keys[lo - 1] >> 32) == c) { --lo; ++rank; rank -= s_keys[lo] > v ? 1 : 0; }
+                while (hi + 1 < n && (unsigned)(s_keys[hi + 1] >> 32) == c) { ++hi; rank += s_keys[hi] < v ? 1 : 0; }
+                newpos[k] = lo + rank;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < IPT; ++k)
+                if (newpos[k] >= 0) s_keys[newpos[k]] = key[k];
+        }
+        __syncthreads();
+        src = s_keys;
+        inverted = true;
+
+    } else {
+    // ---- very many survivors: LSD radix sort through global memory ----
+    unsigned long long* dst = keys_alt + (size_t)b * kcap;
+    for (int i = tid; i < 8 * 256; i += kFinThreads) (&s_hist[0][0])[i] = 0;
+    for (int i = tid; i < 32 * 256; i += kFinThreads) (&s_wcnt[0][0])[i] = 0;
+    __syncthreads();
     for (int i = tid; i < n; i += kFinThreads) {
         const unsigned long long v = ~src[i];          // ascending on ~key == descending on key
 #pragma unroll
@@ -459,10 +702,12 @@ nms_finish_kernel(int H, int W, int r, int border, int kcap, unsigned long long*
         __syncthreads();
     }
 
+    }
+
     int nout = min(n, cap_out);
     if (top_k > 0) nout = min(nout, top_k);
     for (int i = tid; i < nout; i += kFinThreads) {
-        const unsigned long long key = src[i];
+        const unsigned long long key = inverted ? ~src[i] : src[i];
         const unsigned pix = ~(unsigned)(key & 0xffffffffull);
         xy[((size_t)b * cap_out + i) * 2 + 0] = (int)(pix % (unsigned)W);
         xy[((size_t)b * cap_out + i) * 2 + 1] = (int)(pix / (unsigned)W);
@@ -489,8 +734,8 @@ static void launch_round0_t(const float* src, int cell_stride, int B, int H, int
 
 bool nms_logits_supported(int radius) { return radius >= 0 && radius <= 4; }
 
-void launch_nms(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
-                int border, int top_k, int cap, const NmsWorkspace& ws, int* count, int* xy, float* conf, cudaStream_t st) {
+void launch_nms_round0(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
+                       int border, const NmsWorkspace& ws, cudaStream_t st) {
     if (radius < 0 || radius > kNmsMaxR) throw std::invalid_argument("nms_dist must be in [0, 8]");
     if ((long)H * W >= (1l << 31)) throw std::invalid_argument("image too large");
     if (!heat && !(logits && nms_logits_supported(radius))) throw std::invalid_argument("nms: no heatmap given");
@@ -516,7 +761,11 @@ void launch_nms(const float* heat, const float* logits, int cell_stride, int B, 
             default: launch_round0_t<8, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
         }
     }
-    const size_t smem = sizeof(unsigned long long) * 2 * kSortSmemKeys;
+}
+
+void launch_nms_finish(int B, int H, int W, int radius, int border, int top_k, int cap, const NmsWorkspace& ws, int* count,
+                       int* xy, float* conf, cudaStream_t st) {
+    const size_t smem = sizeof(unsigned long long) * kSortSmemKeys;
     SPB_CUDA(cudaFuncSetAttribute(nms_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_finish_kernel<<<B, kFinThreads, smem, st>>>(H, W, radius, border, ws.kcap, ws.keys, ws.keys_alt, ws.counters, ws.mask,
                                                     ws.mask_w, ws.und, ws.ukey, cap, top_k, count, xy, conf);
