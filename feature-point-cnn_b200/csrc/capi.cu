@@ -115,6 +115,31 @@ int spb200_detect_host(spb200_engine* e, const float* img_host, int B, int C, in
     });
 }
 
+int spb200_detect_u8(spb200_engine* e, const uint8_t* img, int B, int H, int W, int capacity, int* count, int* xy, float* conf,
+                     float* desc, float* prob_map, void* stream) {
+    return guarded(e, [&](spb200::Engine& g) {
+        if (!img || !count || !xy || !conf) throw std::invalid_argument("img, count, xy and conf must not be null");
+        g.detect_u8(img, B, H, W, capacity, count, xy, conf, desc, prob_map, (cudaStream_t)stream);
+    });
+}
+
+int spb200_detect_host_u8(spb200_engine* e, const uint8_t* img_host, int B, int H, int W, int capacity, int* count_host,
+                          int* xy_host, float* conf_host, float* desc_host) {
+    return guarded(e, [&](spb200::Engine& g) {
+        if (!img_host || !count_host || !xy_host || !conf_host) throw std::invalid_argument("img, count, xy and conf must not be null");
+        if (capacity <= 0) throw std::invalid_argument("capacity must be positive");
+        g.detect_host_u8(img_host, B, H, W, capacity, count_host, xy_host, conf_host, desc_host);
+    });
+}
+
+int spb200_match(spb200_engine* e, const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B,
+                 int capacity, int D, float max_dist, int* match_ab, float* dist, void* stream) {
+    return guarded(e, [&](spb200::Engine& g) {
+        if (!desc_a || !count_a || !desc_b || !count_b || !match_ab || !dist) throw std::invalid_argument("match: null argument");
+        g.match(desc_a, count_a, desc_b, count_b, B, capacity, D, max_dist, match_ab, dist, (cudaStream_t)stream);
+    });
+}
+
 int spb200_heatmap_from_logits(spb200_engine* e, const float* logits, int B, int H, int W, float* prob_map, void* stream) {
     return guarded(e, [&](spb200::Engine& g) {
         if (!logits || !prob_map || B <= 0 || H <= 0 || W <= 0) throw std::invalid_argument("bad heatmap arguments");

@@ -271,4 +271,14 @@ void launch_nhwc_to_nchw(const void* src, int src_type, int B, int HW, int Cs, i
     SPB_CHECK_LAUNCH();
 }
 
+__global__ void u8_to_f32_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i] / 255.f;
+}
+
+void launch_u8_to_f32(const uint8_t* src, float* dst, long n, cudaStream_t st) {
+    u8_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+    SPB_CHECK_LAUNCH();
+}
+
 }  // namespace spb200

@@ -106,6 +106,7 @@ Engine::~Engine() {
     release_weights();
     cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und); cudaFree(nms_.ukey);
     cudaFree(d_gtab_);
+    cudaFree(d_match_ws_);
 }
 
 void Engine::release_workspace() {
@@ -117,6 +118,7 @@ void Engine::release_workspace() {
     for (auto& p : buf_) { cudaFree(p); p = nullptr; }
     cudaFree(d_prob_); d_prob_ = nullptr;
     cudaFree(d_planes_); d_planes_ = nullptr;
+    cudaFree(d_imgf_); d_imgf_ = nullptr;
     wsB_ = wsH_ = wsW_ = 0;
 }
 
@@ -548,13 +550,24 @@ double Engine::op_flops(const OpSpec& op) const {
     return 2.0 * rows * k * op.cout_real;
 }
 
-void Engine::run_network(const float* img, int B, int C, int H, int W, cudaStream_t st) {
+void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, int W, cudaStream_t st) {
     ensure_workspace(B, C, H, W, st);
+    if (img_u8 && C != 1) throw std::invalid_argument("8-bit frames must be single-channel (grayscale)");
+    const float* img = static_cast<const float*>(img_any);
+    if (img_u8 && !(precision_ != PREC_FP32 && use_planes_)) {
+        // paths without the plane-fed stem take fp32 images: frame / 255 as the reference's loaders do
+        // (python/src/inference.py:78-80, cpp/src/camera.cc:16-18)
+        if (!d_imgf_) SPB_CUDA(cudaMalloc((void**)&d_imgf_, sizeof(float) * (size_t)B * H * W));
+        launch_u8_to_f32(static_cast<const uint8_t*>(img_any), d_imgf_, (long)B * H * W, st);
+        ++launches_;
+        img = d_imgf_;
+        img_u8 = false;
+    }
     // gray-folded stem: 49 MACs per output (the reference's 3-channel stem does 147 on replicated input)
     const bool planes = precision_ != PREC_FP32 && C == 1 && use_planes_;
     if (planes) {
-        prof_open("image_planes", 0.0, (double)B * H * W * (4 + 2), st);
-        launch_planes(img, 0, d_planes_, precision_, B, H, W, st);
+        prof_open("image_planes", 0.0, (double)B * H * W * ((img_u8 ? 1 : 4) + 2), st);
+        launch_planes(img_any, img_u8 ? 1 : 0, d_planes_, precision_, B, H, W, st);
         prof_close(st);
         ++launches_;
     }
@@ -593,7 +606,7 @@ void Engine::run_network(const float* img, int B, int C, int H, int W, cudaStrea
 void Engine::forward(const float* img, int B, int C, int H, int W, float* prob, float* desc_nchw, float* logits_nchw,
                      cudaStream_t st) {
     SPB_CUDA(cudaSetDevice(device_));
-    run_network(img, B, C, H, W, st);
+    run_network(img, false, B, C, H, W, st);
     const int Hc = H / 8, Wc = W / 8;
     float* heat = prob ? prob : d_prob_;
     launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc, heat, st);
@@ -615,9 +628,19 @@ void Engine::forward(const float* img, int B, int C, int H, int W, float* prob, 
 
 void Engine::detect(const float* img, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                     float* desc, float* prob, cudaStream_t st) {
+    detect_any(img, false, B, C, H, W, cap, count, xy, conf, desc, prob, st);
+}
+
+void Engine::detect_u8(const uint8_t* img, int B, int H, int W, int cap, int* count, int* xy, float* conf, float* desc,
+                       float* prob, cudaStream_t st) {
+    detect_any(img, true, B, 1, H, W, cap, count, xy, conf, desc, prob, st);
+}
+
+void Engine::detect_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                        float* desc, float* prob, cudaStream_t st) {
     SPB_CUDA(cudaSetDevice(device_));
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
-    run_network(img, B, C, H, W, st);
+    run_network(img, img_u8, B, C, H, W, st);
     const int Hc = H / 8, Wc = W / 8;
     // the heatmap is written only when the caller wants it: round 0 of the NMS computes the softmax values itself
     const bool from_logits = nms_logits_supported(params_.nms_dist);
@@ -677,6 +700,24 @@ void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int
     ++launches_;
 }
 
+void Engine::match(const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B, int cap, int D,
+                   float max_dist, int* match_ab, float* dist, cudaStream_t st) {
+    SPB_CUDA(cudaSetDevice(device_));
+    if (B <= 0 || cap <= 0) throw std::invalid_argument("match: batch and capacity must be positive");
+    const size_t need = (size_t)2 * B * cap;
+    if (need > match_ws_elems_) {
+        SPB_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_match_ws_);
+        d_match_ws_ = dev_alloc<unsigned long long>(need);
+        match_ws_elems_ = need;
+    }
+    prof_open("match", 2.0 * B * (double)cap * cap * D, 0.0, st);
+    launch_match(desc_a, count_a, desc_b, count_b, B, cap, D, max_dist, d_match_ws_, d_match_ws_ + (size_t)B * cap, match_ab, dist,
+                 num_sms_, st);
+    prof_close(st);
+    launches_ += 3;
+}
+
 void Engine::buffer_dims(int id, int* C, int* H, int* W) const {
     if (id < 0 || id >= BUF_COUNT) throw std::invalid_argument("bad buffer id");
     *C = bufspec_[id].C; *H = wsH_ / bufspec_[id].div; *W = wsW_ / bufspec_[id].div;
@@ -703,6 +744,17 @@ static bool is_pinned_host(const void* p) {
 
 void Engine::detect_host(const float* img, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                          float* desc) {
+    detect_host_any(img, false, B, C, H, W, cap, count, xy, conf, desc);
+}
+
+void Engine::detect_host_u8(const uint8_t* img, int B, int H, int W, int cap, int* count, int* xy, float* conf, float* desc) {
+    detect_host_any(img, true, B, 1, H, W, cap, count, xy, conf, desc);
+}
+
+void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy,
+                             float* conf, float* desc) {
+    const uint8_t* img = static_cast<const uint8_t*>(img_any);
+    const size_t esz = img_u8 ? 1 : sizeof(float);
     SPB_CUDA(cudaSetDevice(device_));
     if (B <= 0) throw std::invalid_argument("batch must be positive");
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
@@ -720,7 +772,7 @@ void Engine::detect_host(const float* img, int B, int C, int H, int W, int cap, 
     const int nc = B / Bc;
     const bool pin_in = is_pinned_host(img);
     const bool pin_out = is_pinned_host(xy) && is_pinned_host(conf) && is_pinned_host(desc);
-    const size_t chunk_elems = (size_t)Bc * C * H * W, chunk_bytes = sizeof(float) * chunk_elems;
+    const size_t chunk_bytes = esz * (size_t)Bc * C * H * W;
     const size_t img_bytes = chunk_bytes * nc;
 
     if (img_bytes > s.d_img_bytes || B > s.d_B || cap > s.d_cap) {
@@ -748,17 +800,17 @@ void Engine::detect_host(const float* img, int B, int C, int H, int W, int cap, 
     // 1. everything the GPU has to do is enqueued up front: chunk k's upload on the copy stream, its network +
     //    post-processing on the compute stream behind the upload's event, its counts copied to the pinned mirror
     for (int k = 0; k < nc; ++k) {
-        const float* src = img + (size_t)k * chunk_elems;
-        float* d_in = s.d_img + (size_t)k * chunk_elems;
+        const uint8_t* src = img + (size_t)k * chunk_bytes;
+        uint8_t* d_in = reinterpret_cast<uint8_t*>(s.d_img) + (size_t)k * chunk_bytes;
         if (!pin_in) {
-            std::memcpy(s.h_img + (size_t)k * chunk_elems, src, chunk_bytes);
-            src = s.h_img + (size_t)k * chunk_elems;
+            std::memcpy(reinterpret_cast<uint8_t*>(s.h_img) + (size_t)k * chunk_bytes, src, chunk_bytes);
+            src = reinterpret_cast<uint8_t*>(s.h_img) + (size_t)k * chunk_bytes;
         }
         SPB_CUDA(cudaMemcpyAsync(d_in, src, chunk_bytes, cudaMemcpyHostToDevice, s.s_in));
         SPB_CUDA(cudaEventRecord(s.ev_in[k], s.s_in));
         SPB_CUDA(cudaStreamWaitEvent(s.s_comp, s.ev_in[k], 0));
         const size_t o = (size_t)k * Bc;
-        detect(d_in, Bc, C, H, W, dcap, s.d_count + o, s.d_xy + o * dcap * 2, s.d_conf + o * dcap,
+        detect_any(d_in, img_u8, Bc, C, H, W, dcap, s.d_count + o, s.d_xy + o * dcap * 2, s.d_conf + o * dcap,
                desc ? s.d_desc + o * dcap * 128 : nullptr, nullptr, s.s_comp);
         SPB_CUDA(cudaMemcpyAsync(s.h_count + o, s.d_count + o, sizeof(int) * Bc, cudaMemcpyDeviceToHost, s.s_comp));
         SPB_CUDA(cudaEventRecord(s.ev_comp[k], s.s_comp));

@@ -91,11 +91,21 @@ public:
                 float* prob, cudaStream_t st);
     void detect_host(const float* img, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                      float* desc);
+    // the same for 8-bit grayscale frames [B][H][W] (what the reference's loaders divide by 255:
+    // python/src/inference.py:72-85, cpp/src/camera.cc:12-23); value k means k / 255
+    void detect_u8(const uint8_t* img, int B, int H, int W, int cap, int* count, int* xy, float* conf, float* desc,
+                   float* prob, cudaStream_t st);
+    void detect_host_u8(const uint8_t* img, int B, int H, int W, int cap, int* count, int* xy, float* conf, float* desc);
     // stage-level entry points (reference restore_prob_map / get_points / get_descriptors)
     void heatmap_from_logits(const float* logits_nchw, int B, int H, int W, float* prob, cudaStream_t st);
     void nms(const float* prob, int B, int H, int W, int cap, int* count, int* xy, float* conf, cudaStream_t st);
     void sample_descriptors(const float* desc_nchw, int B, int D, int H, int W, int cap, const int* count,
                             const int* xy, float* out, cudaStream_t st);
+
+    // reference get_best_correspondences (python/src/inference.py:88-96): mutual nearest neighbours of two batches of
+    // descriptor sets as spb200_detect returns them; max_dist <= 0 disables the distance gate
+    void match(const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B, int cap, int D,
+               float max_dist, int* match_ab, float* dist, cudaStream_t st);
 
     // intermediate activation (debug / parity tests): copies buffer `id` as NCHW fp32 to dst (device)
     void export_buffer(int id, float* dst_nchw, int channels, cudaStream_t st);
@@ -118,7 +128,11 @@ private:
     void ensure_nms(int B, int H, int W);
     void release_workspace();
     void release_weights();
-    void run_network(const float* img, int B, int C, int H, int W, cudaStream_t st);
+    void run_network(const void* img, bool img_u8, int B, int C, int H, int W, cudaStream_t st);
+    void detect_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                    float* desc, float* prob, cudaStream_t st);
+    void detect_host_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                         float* desc);
     ConvDev make_conv_dev(const OpSpec& op) const;
     const HostConv* fold(const std::string& conv_key, const std::string& bn_key, bool transposed, bool has_bias);
     void add_block(const std::string& prefix, std::vector<std::pair<int, int>> srcs, int y_buf, int dst_buf, int stride,
@@ -143,6 +157,7 @@ private:
     StemPlanesPlan* stem_planes_ = nullptr;        // gray stem fed by TMA from parity planes (stem_planes.cu)
     bool use_planes_ = true;      // SPB200_OLD_STEM=1 keeps the im2col-in-shared-memory stem
     void* d_planes_ = nullptr;    // [B][2][H/2][W] 16-bit image x255, per workspace shape
+    float* d_imgf_ = nullptr;     // 8-bit frames / 255 for the paths without the plane-fed stem
 
     // workspace
     int wsB_ = 0, wsH_ = 0, wsW_ = 0;
@@ -155,6 +170,8 @@ private:
     float* d_gtab_ = nullptr;
     int gtabH_ = 0, gtabW_ = 0;
     const float* grid_table(int H, int W);
+    unsigned long long* d_match_ws_ = nullptr;     // [2][B][cap] best keys of the matcher
+    size_t match_ws_elems_ = 0;
     // detect_host staging
     struct HostStage;
     std::unique_ptr<HostStage> stage_;

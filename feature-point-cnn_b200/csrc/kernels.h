@@ -9,6 +9,8 @@ namespace spb200 {
 void launch_stem_pool(const float* img, int B, int C, int H, int W, const float* w, const float* bias, void* dst,
                       int dst_type, cudaStream_t st);
 void launch_conv_simt(const ConvDev& p, cudaStream_t st);
+// 8-bit frame -> fp32 / 255 (the reference's loaders, python/src/inference.py:78-80)
+void launch_u8_to_f32(const uint8_t* src, float* dst, long n, cudaStream_t st);
 void launch_nhwc_to_nchw(const void* src, int src_type, int B, int HW, int Cs, int C, float* dst, cudaStream_t st);
 
 // ---- conv_tc.cu ----------------------------------------------------------------------------------
@@ -82,5 +84,14 @@ void launch_nms_finish(int B, int H, int W, int radius, int border, int top_k, i
 void launch_sample_descriptors(const void* map, int map_type, long batch_stride, long chan_stride, long cell_stride,
                                int B, int D, int Hc, int Wc, int W, const float* gtab, int cap, const int* count,
                                const int* xy, float* out, cudaStream_t st);
+
+// ---- match.cu ------------------------------------------------------------------------------------
+// Mutual nearest neighbours in L2 distance between the descriptor sets of image pairs (reference
+// python/src/inference.py:88-96, BFMatcher crossCheck; gate: settings.py:6 nn_thresh, 0 = none).
+// desc_a / desc_b: [B][cap][D] fp32 with count_a[b] / count_b[b] valid rows; best_a / best_b: [B][cap] scratch;
+// match[b][i] = index in b of the match of descriptor i of a, or -1; dist[b][i] = distance to its nearest.
+void launch_match(const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B, int cap, int D,
+                  float max_dist, unsigned long long* best_a, unsigned long long* best_b, int* match, float* dist, int num_sms,
+                  cudaStream_t st);
 
 }  // namespace spb200

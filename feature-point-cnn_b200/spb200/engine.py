@@ -130,6 +130,45 @@ class Engine:
                     'spb200_detect_host')
         return out
 
+    def detect_u8(self, img, capacity, want_desc=True, want_prob=False, out=None):
+        """img: uint8 CUDA tensor B*H*W (grayscale frames, value k = k/255).  Same outputs as detect()."""
+        img = img.contiguous()
+        assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_cuda
+        b, h, w = img.shape
+        if out is None:
+            out = self.alloc_outputs(b, capacity, img.device, want_desc, (h, w) if want_prob else None)
+        count, xy, conf, desc, prob = out
+        self._check(self._lib.spb200_detect_u8(self._h, _ptr(img), b, h, w, capacity, _ptr(count), _ptr(xy), _ptr(conf),
+                                               _ptr(desc), _ptr(prob), self._stream()), 'spb200_detect_u8')
+        return out
+
+    def detect_host_u8(self, img, capacity, want_desc=True, out=None):
+        """img: uint8 numpy B*H*W (host).  Returns numpy (count, xy, conf, desc)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        b, h, w = img.shape
+        if out is None:
+            out = (np.zeros((b,), np.int32), np.zeros((b, capacity, 2), np.int32), np.zeros((b, capacity), np.float32),
+                   np.zeros((b, capacity, 128), np.float32) if want_desc else None)
+        count, xy, conf, desc = out
+        self._check(self._lib.spb200_detect_host_u8(self._h, ctypes.c_void_p(img.ctypes.data), b, h, w, capacity,
+                                                    ctypes.c_void_p(count.ctypes.data), ctypes.c_void_p(xy.ctypes.data),
+                                                    ctypes.c_void_p(conf.ctypes.data),
+                                                    ctypes.c_void_p(desc.ctypes.data if desc is not None else 0)),
+                    'spb200_detect_host_u8')
+        return out
+
+    def match(self, desc_a, count_a, desc_b, count_b, max_dist=0.0):
+        """Mutual nearest neighbours (reference get_best_correspondences): desc_* B*cap*D fp32 CUDA tensors, count_* B
+        int32.  Returns (match[B,cap] int32: index in b or -1, dist[B,cap] fp32)."""
+        desc_a, desc_b = desc_a.contiguous(), desc_b.contiguous()
+        b, cap, d = desc_a.shape
+        assert desc_b.shape == desc_a.shape
+        m = torch.empty((b, cap), dtype=torch.int32, device=desc_a.device)
+        dist = torch.empty((b, cap), dtype=torch.float32, device=desc_a.device)
+        self._check(self._lib.spb200_match(self._h, _ptr(desc_a), _ptr(count_a), _ptr(desc_b), _ptr(count_b), b, cap, d,
+                                           float(max_dist), _ptr(m), _ptr(dist), self._stream()), 'spb200_match')
+        return m, dist
+
     # ---- stage-level ---------------------------------------------------------------------------
     def heatmap_from_logits(self, logits, h, w):
         logits = logits.contiguous()

@@ -98,6 +98,15 @@ SPB200_API int spb200_detect(spb200_engine* e, const float* img, int B, int C, i
 SPB200_API int spb200_detect_host(spb200_engine* e, const float* img_host, int B, int C, int H, int W, int capacity,
                        int* count_host, int* xy_host, float* conf_host, float* desc_host);
 
+/* The same two calls for 8-bit grayscale frames, B*H*W bytes, value k meaning k/255: the frame as the camera or
+ * cv2.imread delivers it, before the division the reference's loaders do on the host (python/src/inference.py:72-85
+ * resize -> gray -> /255; cpp/src/camera.cc:12-23 convertTo(CV_32FC1, 1/255)).  A quarter of the upload bytes; with
+ * the tensor-core path the result is bit-identical to passing k/255.f as fp32. */
+SPB200_API int spb200_detect_u8(spb200_engine* e, const uint8_t* img, int B, int H, int W, int capacity, int* count, int* xy,
+                     float* conf, float* desc, float* prob_map, void* stream);
+SPB200_API int spb200_detect_host_u8(spb200_engine* e, const uint8_t* img_host, int B, int H, int W, int capacity,
+                          int* count_host, int* xy_host, float* conf_host, float* desc_host);
+
 /* Stage-level entry points with the reference's tensor layouts (NCHW fp32). */
 /* exp(l)/(sum exp(l)+1e-5), drop dustbin, depth-to-space: superpoint.py:111-114 + restore_prob_map
  * (netutils.py:64-75) / GetPoints (superpoint.cc:154-173).  logits B*65*(H/8)*(W/8) -> prob_map B*H*W. */
@@ -108,6 +117,15 @@ SPB200_API int spb200_nms(spb200_engine* e, const float* prob_map, int B, int H,
 /* get_descriptors (netutils.py:103-121) / AddDescriptors (superpoint.cc:98-152): desc_map B*D*(H/8)*(W/8). */
 SPB200_API int spb200_sample_descriptors(spb200_engine* e, const float* desc_map, int B, int D, int H, int W, int capacity,
                               const int* count, const int* xy, float* desc, void* stream);
+
+/* Descriptor matching, the step that follows the path in both demos: get_best_correspondences (inference.py:88-96,
+ * cv2.BFMatcher(NORM_L2, crossCheck=True)) / SearchKeyFrameCorrespondence (main.cc:9-29) for B image pairs at once,
+ * on the arrays spb200_detect produced.  desc_a, desc_b: B*capacity*D fp32 with count_a[b] / count_b[b] valid rows.
+ * match_ab[b][i] = index in b of the mutual nearest neighbour of descriptor i of a, or -1 (no mutual neighbour, or
+ * its L2 distance is not below max_dist; max_dist <= 0 disables the gate - settings.py:6 nn_thresh = 0.7);
+ * dist[b][i] = L2 distance of descriptor i to its nearest descriptor of b.  Ties go to the lowest index. */
+SPB200_API int spb200_match(spb200_engine* e, const float* desc_a, const int* count_a, const float* desc_b, const int* count_b,
+                 int B, int capacity, int D, float max_dist, int* match_ab, float* dist, void* stream);
 
 /* 128 for these checkpoints (superpoint.py:49-50; the C++ demo's 256, torchutis.h:11, is stale). */
 SPB200_API int spb200_descriptor_dim(const spb200_engine* e);

@@ -1,0 +1,126 @@
+"""GPU tests of the rows next to the hot path: 8-bit frame input (N3) and descriptor matching (N2)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import matching
+from _gpu_common import GOLDEN, LazyEngines, golden_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def engines():
+    e = LazyEngines()
+    yield e
+    e.close()
+
+
+def _frames(names):
+    imgs = np.load(os.path.join(GOLDEN, 'images.npz'))
+    return np.stack([imgs[n] for n in names]).astype(np.uint8)
+
+
+@pytest.mark.parametrize('prec', ['fp16', 'fp32'])
+def test_u8_frames_equal_float_frames(prec, engines):
+    """An 8-bit frame k gives exactly what the reference's loaders feed (k / 255 as fp32): same keypoints, same
+    confidences, same descriptors - bit for bit on the tensor-core path (both become the integer k in the 16-bit
+    operand), and on the fp32 path (the same division on the device)."""
+    u8 = _frames(['s240_0', 's240_1', 's240_2'])
+    e = engines[prec]
+    cap = e.max_keypoints(240, 320)
+    f = torch.from_numpy(u8.astype(np.float32) / 255.)[:, None].cuda()
+    c0, xy0, cf0, d0, p0 = [t.clone() for t in e.detect(f, cap, want_prob=True)]
+    c1, xy1, cf1, d1, p1 = e.detect_u8(torch.from_numpy(u8).cuda(), cap, want_prob=True)
+    assert int(c0.sum()) > 1000
+    assert torch.equal(c0, c1) and torch.equal(p0, p1)
+    for b in range(3):
+        n = int(c0[b])
+        assert torch.equal(xy0[b, :n], xy1[b, :n]) and torch.equal(cf0[b, :n], cf1[b, :n]) and torch.equal(d0[b, :n], d1[b, :n])
+
+
+def test_u8_host_entry_point(engines):
+    u8 = _frames(['s240_0', 's240_1'])
+    e = engines['fp16']
+    cap = e.max_keypoints(240, 320)
+    c0, xy0, cf0, d0, _ = e.detect_u8(torch.from_numpy(u8).cuda(), cap)
+    c1, xy1, cf1, d1 = e.detect_host_u8(u8, cap)
+    assert np.array_equal(c0.cpu().numpy(), c1)
+    for b in range(2):
+        n = int(c1[b])
+        assert np.array_equal(xy0[b, :n].cpu().numpy(), xy1[b, :n]) and np.array_equal(d0[b, :n].cpu().numpy(), d1[b, :n])
+    with pytest.raises(Exception):
+        e.detect_host_u8(u8[:, :100, :100], cap)            # not a multiple of 16
+
+
+def _run_match(e, sets_a, sets_b, max_dist=0.0):
+    b = len(sets_a)
+    cap = max(max(len(s) for s in sets_a), max(len(s) for s in sets_b), 1) + 5
+    da = torch.full((b, cap, 128), 7.0)                      # rows beyond the count hold garbage on purpose
+    db = torch.full((b, cap, 128), -3.0)
+    for i in range(b):
+        da[i, :len(sets_a[i])] = torch.from_numpy(sets_a[i])
+        db[i, :len(sets_b[i])] = torch.from_numpy(sets_b[i])
+    ca = torch.tensor([len(s) for s in sets_a], dtype=torch.int32).cuda()
+    cb = torch.tensor([len(s) for s in sets_b], dtype=torch.int32).cuda()
+    m, d = e.match(da.cuda(), ca, db.cuda(), cb, max_dist)
+    return m.cpu().numpy(), d.cpu().numpy()
+
+
+def test_match_golden_vectors_of_the_reference(engines):
+    """The four golden cases as ONE batch of ragged pairs: identical (queryIdx, trainIdx) to cv2.BFMatcher crossCheck
+    as called by the reference, distances within 1e-5."""
+    k = np.load(os.path.join(GOLDEN, 'match_kat.npz'))
+    names = ['net', 'rand', 'near', 'tiny']
+    m, d = _run_match(engines['fp16'], [k[n + '_q'] for n in names], [k[n + '_t'] for n in names])
+    for i, n in enumerate(names):
+        nq = len(k[n + '_q'])
+        qi = np.nonzero(m[i, :nq] >= 0)[0]
+        assert list(qi) == list(k[n + '_qidx']), n
+        assert list(m[i, qi]) == list(k[n + '_tidx']), n
+        np.testing.assert_allclose(d[i, qi], k[n + '_dist'], atol=1e-5)
+        assert (m[i, nq:] == -1).all()
+
+
+@pytest.mark.parametrize('nq,nt,seed', [(1, 1, 0), (64, 64, 1), (65, 129, 2), (700, 3, 3), (5000, 4800, 4)])
+def test_match_against_oracle(nq, nt, seed, engines):
+    rng = np.random.RandomState(seed)
+    a = rng.randn(nq, 128).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    t = rng.randn(nt, 128).astype(np.float32)
+    n_copy = min(nq, nt) // 2
+    t[:n_copy] = a[rng.permutation(nq)[:n_copy]] + 0.03 * rng.randn(n_copy, 128).astype(np.float32)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    for gate in (0.0, 0.7):                                      # settings.py:6 nn_thresh
+        m, d = _run_match(engines['fp16'], [a], [t], gate)
+        qi, ti, dist = matching.mutual_nearest(a, t, gate)
+        got = np.nonzero(m[0, :nq] >= 0)[0]
+        # a pair whose two nearest candidates are within float rounding of each other may legitimately differ
+        same = len(set(zip(got, m[0, got])) & set(zip(qi, ti)))
+        assert same >= 0.999 * len(qi) and abs(len(got) - len(qi)) <= max(1, len(qi) // 1000)
+        common = np.intersect1d(got, qi)
+        np.testing.assert_allclose(d[0, common], dist[np.searchsorted(qi, common)], atol=2e-5)
+
+
+def test_match_empty_sets_and_linear_pipeline(engines):
+    """count = 0 on either side gives no matches; detect -> match on two frames of the same scene runs end to end
+    and every match is mutual."""
+    e = engines['fp16']
+    a = np.eye(8, 128, dtype=np.float32)
+    m, _ = _run_match(e, [a[:0], a], [a, a[:0]])
+    assert (m == -1).all()
+    u8 = _frames(['s240_0', 's240_0'])
+    u8[1] = np.roll(u8[1], 16, axis=1)                         # the same scene shifted by two cells (the network is
+                                                               # equivariant to shifts by its total stride)
+    cap = e.max_keypoints(240, 320)
+    count, xy, conf, desc, _ = e.detect_u8(torch.from_numpy(u8).cuda(), cap)
+    m, d = e.match(desc[0:1], count[0:1], desc[1:2], count[1:2], 0.7)
+    mb, _ = e.match(desc[1:2], count[1:2], desc[0:1], count[0:1], 0.7)
+    m, mb = m[0].cpu().numpy(), mb[0].cpu().numpy()
+    qi = np.nonzero(m >= 0)[0]
+    assert len(qi) > 100
+    assert (mb[m[qi]] == qi).all()
+    dx = (xy[1, m[qi], 0] - xy[0, qi, 0]).cpu().numpy()
+    assert np.median(dx) == 16
