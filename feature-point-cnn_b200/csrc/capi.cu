@@ -132,6 +132,14 @@ int spb200_detect_host_u8(spb200_engine* e, const uint8_t* img_host, int B, int 
     });
 }
 
+int spb200_homography_adaptation(spb200_engine* e, const float* img, int B, int C, int H, int W, const float* homographies_host,
+                                 int num, int valid_border_margin, int aggregation, float* prob_map, void* stream) {
+    return guarded(e, [&](spb200::Engine& g) {
+        g.homography_adaptation(img, B, C, H, W, homographies_host, num, valid_border_margin, aggregation, prob_map,
+                                (cudaStream_t)stream);
+    });
+}
+
 int spb200_match(spb200_engine* e, const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B,
                  int capacity, int D, float max_dist, int* match_ab, float* dist, void* stream) {
     return guarded(e, [&](spb200::Engine& g) {

@@ -107,6 +107,7 @@ Engine::~Engine() {
     cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und); cudaFree(nms_.ukey);
     cudaFree(d_gtab_);
     cudaFree(d_match_ws_);
+    cudaFree(d_ha_img_); cudaFree(d_ha_prob_); cudaFree(d_ha_coeffs_); cudaFree(d_ha_maps_);
 }
 
 void Engine::release_workspace() {
@@ -697,6 +698,74 @@ void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int
     const int Hc = H / 8, Wc = W / 8;
     launch_sample_descriptors(desc_nchw, PREC_FP32, (long)D * Hc * Wc, (long)Hc * Wc, 1, B, D, Hc, Wc, W, grid_table(H, W), cap,
                               count, xy, out, st);
+    ++launches_;
+}
+
+void Engine::homography_adaptation(const float* img, int B, int C, int H, int W, const float* homographies, int num, int margin,
+                                   int aggregation, float* prob_out, cudaStream_t st) {
+    SPB_CUDA(cudaSetDevice(device_));
+    if (!img || !homographies || !prob_out) throw std::invalid_argument("homography_adaptation: null argument");
+    if (num < 0 || num > 4096) throw std::invalid_argument("homography_adaptation: num must be in [0, 4096]");
+    if (aggregation != 0 && aggregation != 1) throw std::invalid_argument("homography_adaptation: aggregation must be 0 (mean) or 1 (max)");
+    ensure_workspace(B, C, H, W, st);
+    const size_t plane = (size_t)H * W;
+    const size_t img_elems = (size_t)B * C * plane, prob_elems = (size_t)(num + 1) * B * plane, map_bytes = (size_t)4 * num * plane;
+    if (img_elems > ha_img_elems_ || prob_elems > ha_prob_elems_ || map_bytes > ha_map_bytes_ || num > ha_num_) {
+        SPB_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_ha_img_); cudaFree(d_ha_prob_); cudaFree(d_ha_coeffs_); cudaFree(d_ha_maps_);
+        ha_img_elems_ = std::max(img_elems, ha_img_elems_); ha_prob_elems_ = std::max(prob_elems, ha_prob_elems_);
+        ha_map_bytes_ = std::max(map_bytes, ha_map_bytes_); ha_num_ = std::max(num, ha_num_);
+        d_ha_img_ = dev_alloc<float>(ha_img_elems_);
+        d_ha_prob_ = dev_alloc<float>(ha_prob_elems_);
+        d_ha_coeffs_ = dev_alloc<float>((size_t)16 * std::max(ha_num_, 1));
+        SPB_CUDA(cudaMalloc((void**)&d_ha_maps_, std::max(ha_map_bytes_, (size_t)16)));
+    }
+    // forward coefficients, then the inverses (invert_homography, homographies.py:199-203; double precision here)
+    std::vector<float> coeffs((size_t)16 * std::max(num, 1), 0.f);
+    for (int k = 0; k < num; ++k) {
+        const float* h = homographies + (size_t)k * 8;
+        const double m[9] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], 1.0};
+        const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+        if (!(std::fabs(det) > 1e-300)) throw std::invalid_argument("homography_adaptation: singular homography");
+        const double inv[9] = {(m[4] * m[8] - m[5] * m[7]) / det, (m[2] * m[7] - m[1] * m[8]) / det, (m[1] * m[5] - m[2] * m[4]) / det,
+                               (m[5] * m[6] - m[3] * m[8]) / det, (m[0] * m[8] - m[2] * m[6]) / det, (m[2] * m[3] - m[0] * m[5]) / det,
+                               (m[3] * m[7] - m[4] * m[6]) / det, (m[1] * m[6] - m[0] * m[7]) / det, (m[0] * m[4] - m[1] * m[3]) / det};
+        for (int i = 0; i < 8; ++i) {
+            coeffs[(size_t)k * 8 + i] = h[i];
+            coeffs[(size_t)(num + k) * 8 + i] = (float)(inv[i] / inv[8]);
+        }
+    }
+    SPB_CUDA(cudaMemcpyAsync(d_ha_coeffs_, coeffs.data(), sizeof(float) * 16 * std::max(num, 1), cudaMemcpyHostToDevice, st));
+    SPB_CUDA(cudaStreamSynchronize(st));                       // `coeffs` is pageable and goes out of scope
+    uint8_t* raw = d_ha_maps_;
+    uint8_t* eroded = d_ha_maps_ + (size_t)2 * num * plane;
+    if (num) {
+        launch_ha_valid_maps(d_ha_coeffs_, num, H, W, margin, raw, eroded, st);
+        launches_ += margin ? 2 : 1;
+    }
+    // the detector on the image and on every warp of it; the descriptor head is not needed
+    const int desc_was = params_.descriptor_enabled;
+    params_.descriptor_enabled = 0;
+    const int Hc = H / 8, Wc = W / 8;
+    try {
+        for (int k = -1; k < num; ++k) {
+            const float* src = img;
+            if (k >= 0) {
+                launch_ha_warp(img, d_ha_coeffs_ + (size_t)k * 8, B, C, H, W, d_ha_img_, st);
+                ++launches_;
+                src = d_ha_img_;
+            }
+            run_network(src, false, B, C, H, W, st);
+            launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc,
+                           d_ha_prob_ + (size_t)(k + 1) * B * plane, st);
+            ++launches_;
+        }
+    } catch (...) {
+        params_.descriptor_enabled = desc_was;
+        throw;
+    }
+    params_.descriptor_enabled = desc_was;
+    launch_ha_aggregate(d_ha_prob_, eroded, d_ha_coeffs_, num, B, H, W, aggregation, prob_out, st);
     ++launches_;
 }
 

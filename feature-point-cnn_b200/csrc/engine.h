@@ -107,6 +107,11 @@ public:
     void match(const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B, int cap, int D,
                float max_dist, int* match_ab, float* dist, cudaStream_t st);
 
+    // reference homography_adaptation (python/src/homographies.py:250-324): homographies = num flattened transforms
+    // [num][8] on the HOST (sampled by the caller), aggregation 0 = mean ('sum'), 1 = max; prob_out [B][H][W] device
+    void homography_adaptation(const float* img, int B, int C, int H, int W, const float* homographies, int num, int margin,
+                               int aggregation, float* prob_out, cudaStream_t st);
+
     // intermediate activation (debug / parity tests): copies buffer `id` as NCHW fp32 to dst (device)
     void export_buffer(int id, float* dst_nchw, int channels, cudaStream_t st);
     void buffer_dims(int id, int* C, int* H, int* W) const;
@@ -172,6 +177,9 @@ private:
     const float* grid_table(int H, int W);
     unsigned long long* d_match_ws_ = nullptr;     // [2][B][cap] best keys of the matcher
     size_t match_ws_elems_ = 0;
+    // homography adaptation workspace
+    float* d_ha_img_ = nullptr; float* d_ha_prob_ = nullptr; float* d_ha_coeffs_ = nullptr; uint8_t* d_ha_maps_ = nullptr;
+    size_t ha_img_elems_ = 0, ha_prob_elems_ = 0, ha_map_bytes_ = 0; int ha_num_ = 0;
     // detect_host staging
     struct HostStage;
     std::unique_ptr<HostStage> stage_;

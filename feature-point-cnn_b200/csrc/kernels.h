@@ -85,6 +85,14 @@ void launch_sample_descriptors(const void* map, int map_type, long batch_stride,
                                int B, int D, int Hc, int Wc, int W, const float* gtab, int cap, const int* count,
                                const int* xy, float* out, cudaStream_t st);
 
+// ---- homography.cu -------------------------------------------------------------------------------
+// Pieces of homography adaptation (reference python/src/homographies.py:250-324).  coeffs: device [2 num][8], the num
+// forward transforms followed by their inverses.  maps: [2 num][H][W] bytes, map 2k = count_k, 2k + 1 = mask_k.
+void launch_ha_valid_maps(const float* coeffs, int num, int H, int W, int margin, uint8_t* raw, uint8_t* eroded, cudaStream_t st);
+void launch_ha_warp(const float* img, const float* coeffs_k, int B, int C, int H, int W, float* out, cudaStream_t st);
+void launch_ha_aggregate(const float* probs, const uint8_t* maps, const float* coeffs, int num, int B, int H, int W, int use_max,
+                         float* out, cudaStream_t st);
+
 // ---- match.cu ------------------------------------------------------------------------------------
 // Mutual nearest neighbours in L2 distance between the descriptor sets of image pairs (reference
 // python/src/inference.py:88-96, BFMatcher crossCheck; gate: settings.py:6 nn_thresh, 0 = none).

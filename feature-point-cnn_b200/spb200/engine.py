@@ -157,6 +157,17 @@ class Engine:
                     'spb200_detect_host_u8')
         return out
 
+    def homography_adaptation(self, img, homographies, margin=8, aggregation='sum'):
+        """Reference homography_adaptation: img B*C*H*W CUDA fp32, homographies (num, 8) host array.  -> prob B*H*W."""
+        img = self._img(img)
+        b, c, h, w = img.shape
+        hs = np.ascontiguousarray(np.asarray(homographies, dtype=np.float32).reshape(-1, 8))
+        prob = torch.empty((b, h, w), dtype=torch.float32, device=img.device)
+        self._check(self._lib.spb200_homography_adaptation(self._h, _ptr(img), b, c, h, w, ctypes.c_void_p(hs.ctypes.data),
+                                                           hs.shape[0], int(margin), {'sum': 0, 'max': 1}[aggregation],
+                                                           _ptr(prob), self._stream()), 'spb200_homography_adaptation')
+        return prob
+
     def match(self, desc_a, count_a, desc_b, count_b, max_dist=0.0):
         """Mutual nearest neighbours (reference get_best_correspondences): desc_* B*cap*D fp32 CUDA tensors, count_* B
         int32.  Returns (match[B,cap] int32: index in b or -1, dist[B,cap] fp32)."""

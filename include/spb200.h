@@ -118,6 +118,17 @@ SPB200_API int spb200_nms(spb200_engine* e, const float* prob_map, int B, int H,
 SPB200_API int spb200_sample_descriptors(spb200_engine* e, const float* desc_map, int B, int D, int H, int W, int capacity,
                               const int* count, const int* xy, float* desc, void* stream);
 
+/* homography_adaptation (homographies.py:250-324) behind InferenceWrapper.run_with_homography_adaptation
+ * (inferencewrapper.py:48-68) and the COCO pseudo-labelling job (preprocess_coco.py:64-74): the detector runs on the
+ * images and on `num` warps of them, the warped heatmaps are projected back, masked by the eroded validity maps and
+ * averaged (aggregation 0, the reference's 'sum') or maximised (1); pixels seen by fewer than num/3 views are zero.
+ * img: B*C*H*W fp32 on the device; homographies_host: num*8 fp32 on the HOST, the flattened transforms as
+ * sample_homography (homographies.py:79-196) returns them; prob_map: B*H*W fp32 on the device.  The call synchronises
+ * `stream` once (coefficient upload). */
+SPB200_API int spb200_homography_adaptation(spb200_engine* e, const float* img, int B, int C, int H, int W,
+                                 const float* homographies_host, int num, int valid_border_margin, int aggregation,
+                                 float* prob_map, void* stream);
+
 /* Descriptor matching, the step that follows the path in both demos: get_best_correspondences (inference.py:88-96,
  * cv2.BFMatcher(NORM_L2, crossCheck=True)) / SearchKeyFrameCorrespondence (main.cc:9-29) for B image pairs at once,
  * on the arrays spb200_detect produced.  desc_a, desc_b: B*capacity*D fp32 with count_a[b] / count_b[b] valid rows.
