@@ -67,6 +67,28 @@ class InferenceWrapper(object):
             dsc.append(desc[i, :n].t().contiguous().cpu().numpy())
         return pts, dsc
 
+    @torch.no_grad()
+    def run_with_homography_adaptation(self, img, config, homographies=None, rng=None):
+        """python/src/inferencewrapper.py:48-68: N*C*H*W images -> list of per-image points (3, n) from the heatmap
+        aggregated over ``config.num`` random homographies (sampled here unless given as a (num, 8) array)."""
+        from . import homographies as hg
+        self._params()
+        x = self.prepare_input(img).to('cuda:%d' % self.engine.device, torch.float32)
+        b, _, h, w = x.shape
+        hs = hg.sample_homographies((h, w), config, rng) if homographies is None else homographies
+        prob = self.engine.homography_adaptation(x, hs, config.valid_border_margin, config.aggregation)
+        cap = max(self.engine.max_keypoints(h, w, self.settings.nms_dist), 1)
+        count, xy, conf = self.engine.nms(prob, cap)
+        count = count.cpu().numpy()
+        pts = []
+        for i in range(b):
+            n = int(count[i])
+            p = np.zeros((3, n))
+            p[:2] = xy[i, :n].t().cpu().numpy()
+            p[2] = conf[i, :n].cpu().numpy()
+            pts.append(p)
+        return pts
+
     def forward(self, images):
         """The network triple (SuperPoint.forward, python/src/superpoint.py:91-115) for a B*C*H*W tensor."""
         self._params()

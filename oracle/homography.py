@@ -78,6 +78,8 @@ def valid_maps(hs, shape, margin):
             cnt, msk = erode(cnt, margin), erode(msk, margin)
         counts.append(cnt)
         masks.append(msk)
+    if not counts:
+        return np.zeros((0,) + tuple(shape), np.float32), np.zeros((0,) + tuple(shape), np.float32)
     return np.stack(counts), np.stack(masks)
 
 

@@ -124,3 +124,52 @@ def test_match_empty_sets_and_linear_pipeline(engines):
     assert (mb[m[qi]] == qi).all()
     dx = (xy[1, m[qi], 0] - xy[0, qi, 0]).cpu().numpy()
     assert np.median(dx) == 16
+
+
+# ---- N1: homography adaptation --------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['default', 'preprocess'])
+def test_homography_adaptation_matches_reference_golden(name, engines):
+    """spb200_homography_adaptation against the map the REFERENCE's homography_adaptation produced for the same
+    images and the same sampled homographies: fp32 engine within 1e-3 everywhere (bilinear weights and nearest
+    rounding at validity-mask edges are the only differences), fp16 tensor-core engine within the heatmap bar 1e-2."""
+    k = np.load(os.path.join(GOLDEN, 'homography_kat.npz'))
+    imgs = np.load(os.path.join(GOLDEN, 'images.npz'))
+    x = torch.from_numpy(np.stack([imgs[str(i)] for i in k[name + '_ids']]).astype(np.float32) / 255.)[:, None].cuda()
+    num, margin, agg = [int(v) for v in k[name + '_cfg']]
+    ref = k[name + '_prob']
+    for prec, tol in (('fp32', 1e-3), ('fp16', 1e-2)):
+        p = engines[prec].homography_adaptation(x, k[name + '_H'], margin, 'sum' if agg == 0 else 'max').cpu().numpy()
+        d = np.abs(p - ref)
+        print('[homography adaptation %s %s] max abs %.3e, %d px above 1e-4' % (name, prec, float(d.max()), int((d > 1e-4).sum())))
+        assert float(d.max()) <= tol, (name, prec)
+        assert ((p == 0) == (ref == 0)).mean() > 0.9995          # the count >= num // 3 gate
+
+
+def test_homography_adaptation_against_oracle_and_wrapper(engines, tmp_path):
+    """Other sizes / counts against the oracle (incl. num = 0, margin = 0, 'max'), and the drop-in wrapper entry
+    point run_with_homography_adaptation end to end."""
+    from oracle import homography as oh, model, weights
+    from _gpu_common import CKPT, load_spb
+    spb = load_spb()
+    from spb200 import homographies as hg
+    sd = weights.load_state_dict(CKPT)
+    rng = np.random.default_rng(5)
+    e = engines['fp32']
+    for (b, h, w, num, margin, agg) in [(1, 96, 128, 0, 8, 'sum'), (2, 96, 128, 4, 0, 'sum'), (1, 128, 96, 5, 3, 'max')]:
+        x = torch.rand((b, 1, h, w), generator=torch.Generator().manual_seed(h + num))
+        cfg = hg.HomographyConfig()
+        cfg.num = num
+        hs = hg.sample_homographies((h, w), cfg, rng)
+        want = oh.homography_adaptation(x, lambda im: model.forward(im, sd)[0], hs, margin, agg).numpy()
+        got = e.homography_adaptation(x.cuda(), hs, margin, agg).cpu().numpy()
+        assert float(np.abs(got - want).max()) <= 1e-3, (b, h, w, num, margin, agg)
+    settings = spb.SuperPointSettings()
+    settings.precision = 'fp32'
+    wrap = spb.InferenceWrapper(CKPT, settings)
+    cfg = hg.HomographyConfig()
+    cfg.num = 6
+    img = np.repeat(golden_image('shapes240_0').numpy()[:, :, None], 3, axis=2).astype(np.float32)
+    pts = wrap.run_with_homography_adaptation(img, cfg, rng=rng)
+    assert len(pts) == 1 and pts[0].shape[0] == 3 and pts[0].shape[1] > 100
+    assert (np.diff(pts[0][2]) <= 0).all()                        # descending confidence
+    wrap.engine.close()
