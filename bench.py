@@ -321,6 +321,58 @@ def main():
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
         json.dump({'per_kernel': table, 'step_ms_profiled': total_ms, 'keypoints_per_image': kp_mean}, open(args.profile_out, 'w'), indent=1)
 
+    # ---- the rows next to the path, rank 0 at N = 1 only, a few iterations each -------------------------
+    next_rows = None
+    if rank == 0 and world == 1 and args.precision != 'fp32':
+        next_rows = {}
+        # N3: 8-bit frames through the host-buffer entry point (a quarter of the upload bytes)
+        u8 = [(b.squeeze(1) * 255).round().to(torch.uint8).pin_memory().numpy() for b in host_batches]
+        for i in range(2):
+            host_out = eng.detect_host_u8(u8[i % n_rot], cap, out=host_out)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            host_out = eng.detect_host_u8(u8[i % n_rot], cap, out=host_out)
+        torch.cuda.synchronize()
+        next_rows['e2e_u8_frames'] = {'value': B * e2e_steps / (time.perf_counter() - t0), 'unit': UNIT, 'h2d_bytes_per_step': B * H * W,
+                                      'api': 'spb200_detect_host_u8'}
+        # N2: mutual-nearest-neighbour matching of consecutive images of the batch (B / 2 pairs per call)
+        half = B // 2
+        if half:
+            da, db, ca, cb = outs[3][:half], outs[3][half:2 * half], outs[0][:half], outs[0][half:2 * half]
+            eng.match(da, ca, db, cb, 0.7)
+            torch.cuda.synchronize()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for i in range(5):
+                mres = eng.match(da, ca, db, cb, 0.7)
+            m1.record()
+            torch.cuda.synchronize()
+            mms = m0.elapsed_time(m1) / 5
+            nq = float(ca.float().mean().item())
+            next_rows['match'] = {'value': half / (mms * 1e-3), 'unit': 'image pairs/s', 'ms_per_call': mms, 'pairs_per_call': half,
+                                  'keypoints_per_image': nq, 'matched_fraction': float((mres[0] >= 0).float().sum().item() / max(ca.sum().item(), 1)),
+                                  'tflops_fp32': 2.0 * half * nq * nq * 128 / (mms * 1e-3) / 1e12, 'api': 'spb200_match'}
+        # N1: homography adaptation, the reference's default configuration (15 homographies), batch 32 at 240x320
+        from spb200 import homographies as hg
+        cfg = hg.HomographyConfig()
+        hb, hh, hw = 32, 240, 320
+        himg = dev_batches[0][:hb, :, :hh, :hw].contiguous()
+        hs = hg.sample_homographies((hh, hw), cfg, __import__('numpy').random.default_rng(0))
+        eng2 = spb200.Engine(local_rank)                      # its own engine: the workspace is per (B, H, W)
+        eng2.load_checkpoint(CKPT)
+        eng2.finalize(args.precision)
+        eng2.set_params()
+        eng2.homography_adaptation(himg, hs, cfg.valid_border_margin, cfg.aggregation)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(5):
+            eng2.homography_adaptation(himg, hs, cfg.valid_border_margin, cfg.aggregation)
+        torch.cuda.synchronize()
+        hdt = (time.perf_counter() - t0) / 5
+        next_rows['homography_adaptation'] = {'value': hb / hdt, 'unit': 'images/s', 'ms_per_call': hdt * 1e3, 'batch': hb, 'height': hh,
+                                              'width': hw, 'homographies': cfg.num, 'api': 'spb200_homography_adaptation'}
+        eng2.close()
+
     # ---- CPU baseline (rank 0, N = 1 only, bounded sample) -----------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,6 +395,7 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': roofline,
+            'next_rows': next_rows,
             'cpu_baseline': cpu,
         }
         print(json.dumps(out))
