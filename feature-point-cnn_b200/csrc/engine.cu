@@ -95,6 +95,13 @@ Engine::Engine(int device) : device_(device) {
     fuse_blocks_ = !(nf && nf[0] == '1');
     const char* nh = std::getenv("SPB200_NO_HALO");
     use_halo_ = !(nh && nh[0] == '1');
+    const char* ns = std::getenv("SPB200_NO_SIDE");
+    use_side_ = !(ns && ns[0] == '1');
+    for (int i = 0; i < 3; ++i) {
+        SPB_CUDA(cudaStreamCreateWithFlags(&side_stream_[i], cudaStreamNonBlocking));
+        SPB_CUDA(cudaEventCreateWithFlags(&side_join_[i], cudaEventDisableTiming));
+    }
+    SPB_CUDA(cudaEventCreateWithFlags(&side_fork_, cudaEventDisableTiming));
     const char* os = std::getenv("SPB200_OLD_STEM");
     use_planes_ = !(os && os[0] == '1');
     buf_.fill(nullptr);
@@ -105,6 +112,11 @@ Engine::~Engine() {
     release_workspace();
     release_weights();
     cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und); cudaFree(nms_.ukey);
+    for (int i = 0; i < 3; ++i) {
+        if (side_stream_[i]) cudaStreamDestroy(side_stream_[i]);
+        if (side_join_[i]) cudaEventDestroy(side_join_[i]);
+    }
+    if (side_fork_) cudaEventDestroy(side_fork_);
     cudaFree(d_gtab_);
     cudaFree(d_match_ws_);
     cudaFree(d_ha_img_); cudaFree(d_ha_prob_); cudaFree(d_ha_coeffs_); cudaFree(d_ha_maps_);
@@ -301,6 +313,7 @@ void Engine::build_ops() {
             o.segs.push_back(SegSpec{BUF_I1, up, 0, 256, 1, taps});
             o.cout_real = 128; o.cout_pad = 128; o.dst_buf = BUF_UP; o.relu = true;
             o.dst_stride = 2; o.off_y = py; o.off_x = px;
+            o.side = py * 2 + px;
             o.bias = up->b;
             ops_.push_back(std::move(o));
         }
@@ -436,8 +449,15 @@ void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
                 ++i;
             } else {
                 const ConvDev c1 = make_conv_dev(op);
-                if (use_halo_) op.halo = tc_halo_plan_create(c1, nullptr, precision_, op.cout_real, num_sms_);
-                if (!op.halo) op.fused = tc_block_plan_create(c1, nullptr, precision_, op.cout_real, num_sms_);
+                // side-by-side ops share the SMs in proportion to their measured cost (1, 2, 2 and 4 taps of the same
+                // tile count: 21 : 23 : 23 : 30 us when each runs alone)
+                int sms = num_sms_;
+                if (op.side >= 0 && use_side_) {
+                    static const int share[4] = {32, 35, 35, 46};
+                    sms = std::max(1, num_sms_ * share[op.side] / 148);
+                }
+                if (use_halo_) op.halo = tc_halo_plan_create(c1, nullptr, precision_, op.cout_real, sms);
+                if (!op.halo) op.fused = tc_block_plan_create(c1, nullptr, precision_, op.cout_real, sms);
             }
         }
     }
@@ -591,10 +611,37 @@ void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
             launch_conv_simt(make_conv_dev(op), st);
         } else if (op.fused || op.halo) {
             const bool block = i + 1 < ops_.size() && ops_[i + 1].fused_skip;
-            prof_open(block ? op.name.substr(0, op.name.size() - 6) : op.name,
-                      op_flops(op) + (block ? op_flops(ops_[i + 1]) : 0.0), 0.0, st);
-            if (op.halo) launch_halo_tc(op.halo, st);
-            else launch_block_tc(op.fused, st);
+            // a side-by-side group (consecutive ops with side = 0, 1, 2, ...): member 0 runs on the caller's stream, the
+            // others on the side streams, between a fork event recorded before member 0 and one join event per side
+            // stream; the profile times the group as one entry
+            const bool grouped = op.side >= 0 && use_side_;
+            cudaStream_t ls = st;
+            if (grouped) {
+                if (op.side == 0) {
+                    double fl = 0.0;
+                    for (size_t j = i; j < ops_.size() && ops_[j].side >= 0 && (j == i || ops_[j].side > 0); ++j) fl += op_flops(ops_[j]);
+                    prof_open(op.name.substr(0, op.name.rfind('.')), fl, 0.0, st);
+                    SPB_CUDA(cudaEventRecord(side_fork_, st));
+                } else {
+                    ls = side_stream_[op.side - 1];
+                    SPB_CUDA(cudaStreamWaitEvent(ls, side_fork_, 0));
+                }
+            } else {
+                prof_open(block ? op.name.substr(0, op.name.size() - 6) : op.name,
+                          op_flops(op) + (block ? op_flops(ops_[i + 1]) : 0.0), 0.0, st);
+            }
+            if (op.halo) launch_halo_tc(op.halo, ls);
+            else launch_block_tc(op.fused, ls);
+            if (ls != st) {
+                SPB_CUDA(cudaEventRecord(side_join_[op.side - 1], ls));
+                SPB_CUDA(cudaStreamWaitEvent(st, side_join_[op.side - 1], 0));
+            }
+            if (grouped) {
+                ++launches_;
+                const bool last = !(i + 1 < ops_.size() && ops_[i + 1].side > 0);
+                if (last) prof_close(st);
+                continue;
+            }
         } else {
             prof_open(op.name, op_flops(op), 0.0, st);
             launch_conv_tc(op.plan, st);

@@ -55,6 +55,8 @@ struct OpSpec {
     TcBlockPlan* fused = nullptr; // per workspace shape: this op fused with the next one (block) or alone
     TcHaloPlan* halo = nullptr;   // per workspace shape: haloed-tile kernel (preferred over `fused` when it applies)
     bool fused_skip = false;      // executed as the second half of the previous op's fused plan
+    int side = -1;                // >= 0: one of a group of independent ops that run side by side, each on its share
+                                  // of the SMs (the four transposed-convolution phases); index inside the group
 };
 
 enum BufId {
@@ -184,6 +186,10 @@ private:
     struct HostStage;
     std::unique_ptr<HostStage> stage_;
 
+    // fork / join of the side-by-side groups: three extra streams, one event to fork and one per stream to join
+    cudaStream_t side_stream_[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t side_fork_ = nullptr, side_join_[3] = {nullptr, nullptr, nullptr};
+    bool use_side_ = true;        // SPB200_NO_SIDE=1 runs the phases one after the other on all SMs
     long launches_ = 0;
     bool profiling_ = false;
     std::vector<ProfEntry> prof_;
