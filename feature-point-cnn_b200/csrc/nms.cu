@@ -255,10 +255,16 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned kDead = 0xffffffffu;
 
-// The usual case: candidates (and their keys) in registers, the mask in shared memory, radius known at compile time.
+template <bool SMASK>
+__device__ __forceinline__ unsigned ld_mask(const unsigned* p) {
+    return SMASK ? *reinterpret_cast<const volatile unsigned*>(p) : __ldcg(p);
+}
+
+// The usual case: candidates (and their keys) in registers, radius known at compile time; SMASK: the undecided-bit mask
+// of the image is a copy in shared memory (else it is read from L2).
 // The window rows are fetched first, then every neighbour key is loaded under its mask bit - up to (2R+1)^2
 // independent predicated loads, so a round costs about one L2 round trip instead of one per undecided neighbour.
-template <int R>
+template <int R, bool SMASK>
 __device__ __forceinline__ void finish_rounds_fast(int n0, int H, int W, int border, int kcap, const unsigned* __restrict__ list,
                                                    unsigned* s_mask, int mask_w, const unsigned* __restrict__ uk,
                                                    unsigned long long* __restrict__ kdst, int* s_n) {
@@ -289,9 +295,9 @@ __device__ __forceinline__ void finish_rounds_fast(int n0, int H, int W, int bor
                 const int qy = y + d - R;
                 rows[d] = 0u;
                 if (qy >= 0 && qy < H) {
-                    const unsigned* mr = s_mask + qy * mask_w;
-                    unsigned long long two = (unsigned long long)mr[w0];
-                    if (w1 != w0) two |= (unsigned long long)mr[w1] << 32;
+                    const unsigned* mr = s_mask + (size_t)qy * mask_w;
+                    unsigned long long two = (unsigned long long)ld_mask<SMASK>(mr + w0);
+                    if (w1 != w0) two |= (unsigned long long)ld_mask<SMASK>(mr + w1) << 32;
                     rows[d] = (unsigned)((two >> sh) & wmask);
                 }
             }
@@ -328,7 +334,7 @@ __device__ __forceinline__ void finish_rounds_fast(int n0, int H, int W, int bor
             const int w0 = x0 >> 5, w1 = x1 >> 5;
             const unsigned lo = 0xffffffffu << (x0 & 31), hi = 0xffffffffu >> (31 - (x1 & 31));
             for (int qy = max(y - R, 0); qy <= min(y + R, H - 1); ++qy) {
-                unsigned* qr = s_mask + qy * mask_w;
+                unsigned* qr = s_mask + (size_t)qy * mask_w;
                 if (w0 == w1) atomicAnd(qr + w0, ~(lo & hi));
                 else { atomicAnd(qr + w0, ~lo); atomicAnd(qr + w1, ~hi); }
             }
@@ -337,6 +343,7 @@ __device__ __forceinline__ void finish_rounds_fast(int n0, int H, int W, int bor
                 if (pos < kcap) kdst[pos] = survivor_key(kp[k], p);
             }
         }
+        if (!SMASK) __threadfence();     // the cleared bits are read back from L2 in the next round
         if (!__syncthreads_or(live ? 1 : 0)) break;
     }
 }
@@ -344,11 +351,6 @@ __device__ __forceinline__ void finish_rounds_fast(int n0, int H, int W, int bor
 // REGS: the thread's candidates live in registers (n0 <= kFinRegEntries * kFinThreads); otherwise they are re-read
 // from the list, where a decided entry is overwritten with kDead.  SMASK: the undecided-bit mask of the image is a
 // copy in shared memory.  New survivors are appended to the image's keys.
-template <bool SMASK>
-__device__ __forceinline__ unsigned ld_mask(const unsigned* p) {
-    return SMASK ? *reinterpret_cast<const volatile unsigned*>(p) : __ldcg(p);
-}
-
 template <bool REGS, bool SMASK>
 __device__ __forceinline__ void finish_rounds(int n0, int H, int W, int r, int border, int kcap, unsigned* __restrict__ list,
                                               unsigned* __restrict__ mrow, int mask_w, const unsigned* __restrict__ uk,
@@ -483,18 +485,96 @@ nms_finish_kernel(int H, int W, int r, int border, int kcap, unsigned long long*
         if (regs && H * mask_w <= kFinMaskWords) {
             for (int i = tid; i < H * mask_w; i += kFinThreads) s_mask[i] = __ldcg(mrow + i);
             __syncthreads();
-            if (r == 4) finish_rounds_fast<4>(n0, H, W, border, kcap, list, s_mask, mask_w, uk, gkeys, &s_n);
+            if (r == 4) finish_rounds_fast<4, true>(n0, H, W, border, kcap, list, s_mask, mask_w, uk, gkeys, &s_n);
             else finish_rounds<true, true>(n0, H, W, r, border, kcap, list, s_mask, mask_w, uk, gkeys, &s_n);
         } else {
             __syncthreads();
-            if (regs) finish_rounds<true, false>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
+            if (regs && r == 4) finish_rounds_fast<4, false>(n0, H, W, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
+            else if (regs) finish_rounds<true, false>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
             else finish_rounds<false, false>(n0, H, W, r, border, kcap, list, mrow, mask_w, uk, gkeys, &s_n);
         }
     }
     __syncthreads();
-    const int n = min(s_n, kcap);
+    int n = min(s_n, kcap);
     unsigned long long* src = gkeys;
     bool inverted = false;
+
+    // ---- top-k with very many survivors (1080p): keep only the keys that can reach the first top_k places ----
+    // Two histogram levels over the leading 13 + 13 bits of the inverted key (sign, exponent and 17 mantissa bits of the
+    // confidence): at each level the bin in which the running count from the best key reaches the remaining quota
+    // is the cut; keys before the cut prefix, and keys on it (ties included), are compacted into the second key buffer
+    // and sorted by the usual path.
+    if (top_k > 0 && n > kSortSmemKeys && top_k <= kSortSmemKeys / 2) {
+        unsigned* hist = &s_wcnt[0][0];                          // 8192 bins
+        __shared__ int s_cut, s_sel;
+        unsigned prefix = 0u;                                    // cut bins of the levels done so far
+        int quota = top_k, above = 0, sel = 0;                   // `above` keys are better than every key of the cut prefix
+        bool two = false;
+        for (int level = 0; level < 2; ++level) {
+            const int sh_hi = 51 - 13 * level;                   // this level's 13 bits start here
+            for (int i = tid; i < 8192; i += kFinThreads) hist[i] = 0u;
+            if (tid == 0) { s_cut = 8191; s_sel = 0; }
+            __syncthreads();
+            for (int i = tid; i < n; i += kFinThreads) {
+                const unsigned long long k = ~__ldcg(gkeys + i);
+                if (level == 0 || (unsigned)(k >> 51) == prefix) atomicAdd(&hist[(unsigned)(k >> sh_hi) & 8191u], 1u);
+            }
+            __syncthreads();
+            unsigned loc[8], sum = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = hist[tid * 8 + j]; sum += loc[j]; }
+            unsigned inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_base[warp] = inc;
+            __syncthreads();
+            unsigned before = inc - sum;
+            for (int w = 0; w < warp; ++w) before += s_base[w];
+            if (before < (unsigned)quota && before + sum >= (unsigned)quota) {      // exactly one thread
+                unsigned c = before;
+                for (int j = 0; j < 8; ++j) {
+                    if (c + loc[j] >= (unsigned)quota) { s_cut = tid * 8 + j; s_sel = (int)c; break; }
+                    c += loc[j];
+                }
+            }
+            __syncthreads();
+            const int cut = s_cut, better = s_sel;               // keys of this level strictly before the cut bin
+            const int in_cut = (int)hist[cut];
+            __syncthreads();
+            if (level == 0) prefix = (unsigned)cut; else { prefix = (prefix << 13) | (unsigned)cut; two = true; }
+            above += better;
+            quota -= better;
+            sel = above + in_cut;
+            if (sel <= kSortSmemKeys) break;                     // fits: no finer cut needed
+        }
+        if (sel > 0 && sel <= kSortSmemKeys) {
+            unsigned long long* alt = keys_alt + (size_t)b * kcap;
+            const int cmp_shift = two ? 38 : 51;                 // compare the leading 26 or 13 bits with the cut prefix
+            if (tid == 0) s_sel = 0;
+            __syncthreads();
+            for (int i0 = 0; i0 < n; i0 += kFinThreads) {
+                const int i = i0 + tid;
+                const unsigned long long k = i < n ? __ldcg(gkeys + i) : 0ull;
+                bool take = false;
+                if (i < n) take = (unsigned)((~k) >> cmp_shift) <= prefix;
+                const unsigned bal = __ballot_sync(0xffffffffu, take);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_sel, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) alt[base + __popc(bal & ((1u << lane) - 1u))] = k;
+                }
+            }
+            __syncthreads();
+            n = sel;
+            gkeys = alt;
+            src = alt;
+        }
+        __syncthreads();
+    }
 
     if (n <= kSortSmemKeys) {
         // ---- the usual case: LSD radix sort with the keys in registers (striped: warp w owns positions
@@ -638,7 +718,7 @@ nms_finish_kernel(int H, int W, int r, int border, int kcap, unsigned long long*
 
     } else {
     // ---- very many survivors: LSD radix sort through global memory ----
-    unsigned long long* dst = keys_alt + (size_t)b * kcap;
+    unsigned long long* dst = keys_alt + (size_t)b * kcap;            // (the preselection above never leads here: it only swaps buffers when the result fits)
     for (int i = tid; i < 8 * 256; i += kFinThreads) (&s_hist[0][0])[i] = 0;
     for (int i = tid; i < 32 * 256; i += kFinThreads) (&s_wcnt[0][0])[i] = 0;
     __syncthreads();

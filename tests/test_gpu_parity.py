@@ -94,6 +94,27 @@ def test_nms_random_heatmaps_bit_exact(shape, batch, dens, engines):
     e.set_params()
 
 
+@pytest.mark.parametrize('quant', [0, 64, 4096])
+def test_topk_preselection_1080p_bit_exact(quant, engines):
+    """BASELINE config 5 shape: tens of thousands of survivors, top_k = 2048.  The finish kernel keeps only the keys
+    that can reach the first 2048 places (histogram cut) before sorting; quantised confidences put thousands of
+    equal keys into the cut bin (ties by pixel index; with 64 levels the bin overflows and the full sort runs)."""
+    h, w = 1088, 1920
+    g = torch.Generator().manual_seed(quant + 1)
+    heat = torch.rand((1, h, w), generator=g)
+    heat = torch.where(torch.rand((1, h, w), generator=g) < 0.3, heat, torch.zeros(()))
+    if quant:
+        heat = (heat * quant).floor() / quant
+    e = engines['fp32']
+    for top_k in (2048, 1):
+        e.set_params(conf_thresh=0.015, nms_dist=4, border_remove=4, top_k=top_k)
+        count, xy, conf = e.nms(heat.cuda(), e.max_keypoints(h, w))
+        want_all = postproc.get_points(heat[0].numpy(), top_k=0)
+        assert want_all.shape[1] > 8192
+        np.testing.assert_array_equal(points_from(count, xy, conf, 0), want_all[:, :top_k])
+    e.set_params()
+
+
 def test_nms_properties_full_size(engines):
     """Size-independent properties at BASELINE config 3 size (64 x 480 x 640)."""
     b, h, w, r = 64, 480, 640, 4
