@@ -24,6 +24,7 @@
 // scatter/gather through shared memory per pass, constant digits skipped; through global memory when there are
 // more than 8192) and emits (x, y), confidence, count.
 #include "kernels.h"
+#include "softmax_cell.cuh"
 #include "sortkey.cuh"
 
 namespace spb200 {
@@ -72,48 +73,44 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
 
     // 1. keys of the loaded region
     if (LOGITS) {
-        // a warp per cell, four cells (twelve loads per lane) in flight: lane owns channels lane and lane + 32, lane 0
-        // the dustbin; exp, sum (the summation order of heatmap_kernel), + 1e-5, divide
+        // eight lanes per cell (softmax_cell.cuh): lane j owns channels 8j..8j+7 = pixel row j of the cell, so its keys
+        // are eight consecutive entries of one s_key row; the loads of all the thread's cells are issued first
         static_assert(!LOGITS || R <= 4, "one halo cell");
         const int Hc = H / 8, Wc = W / 8;
         const float* lb = src + (size_t)b * Hc * Wc * cell_stride;
         constexpr int kOff = 8 - 2 * R;                        // window origin inside the 10x10-cell region
-        for (int c0 = warp; c0 < 100; c0 += 32) {
-            float l0[4], l1[4], l2[4];
-            bool in[4];
+        constexpr int kTasks = 100 * 8, kIters = (kTasks + kN0Threads - 1) / kN0Threads;
+        float4 la[kIters], lc[kIters];
+        float ld[kIters];
+        bool in[kIters];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c0 + 8 * u;
-                const int gcy = (int)blockIdx.y * 8 - 1 + c / 10, gcx = (int)blockIdx.x * 8 - 1 + c % 10;
-                in[u] = c < 100 && gcy >= 0 && gcy < Hc && gcx >= 0 && gcx < Wc;
-                l0[u] = l1[u] = l2[u] = 0.f;
-                if (in[u]) {
-                    const float* p = lb + (size_t)(gcy * Wc + gcx) * cell_stride;
-                    l0[u] = __ldg(p + lane);
-                    l1[u] = __ldg(p + lane + 32);
-                    if (lane == 0) l2[u] = __ldg(p + 64);
-                }
+        for (int it = 0; it < kIters; ++it) {
+            const int t = it * kN0Threads + tid, c = t >> 3, j = t & 7;
+            const int gcy = (int)blockIdx.y * 8 - 1 + c / 10, gcx = (int)blockIdx.x * 8 - 1 + c % 10;
+            in[it] = t < kTasks && gcy >= 0 && gcy < Hc && gcx >= 0 && gcx < Wc;
+            la[it] = lc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ld[it] = 0.f;
+            if (in[it]) {
+                const float* p = lb + (size_t)(gcy * Wc + gcx) * cell_stride;
+                la[it] = __ldg(reinterpret_cast<const float4*>(p + 8 * j));
+                lc[it] = __ldg(reinterpret_cast<const float4*>(p + 8 * j) + 1);
+                ld[it] = __ldg(p + 64);
             }
+        }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c0 + 8 * u;
-                if (c >= 100) break;
-                unsigned k0 = 0u, k1 = 0u;
-                if (in[u]) {
-                    const float e0 = expf(l0[u]), e1 = expf(l1[u]);
-                    float s = e0 + e1 + (lane == 0 ? expf(l2[u]) : 0.f);
+        for (int it = 0; it < kIters; ++it) {
+            const int t = it * kN0Threads + tid, c = t >> 3, j = t & 7;
+            if (it * kN0Threads + (tid & ~31) >= kTasks) break;          // the whole warp is past the last task
+            const float l[8] = {la[it].x, la[it].y, la[it].z, la[it].w, lc[it].x, lc[it].y, lc[it].z, lc[it].w};
+            float h[8];
+            softmax_cell_octet(l, ld[it], j, h);
+            if (t >= kTasks) continue;
+            const int ly = (c / 10) * 8 + j - kOff, lx0 = (c % 10) * 8 - kOff;
+            if (ly < 0 || ly >= LH) continue;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    const float den = s + 0.00001f;
-                    const float h0 = e0 / den, h1 = e1 / den;
-                    if (h0 >= thresh) k0 = sortable_bits(h0);
-                    if (h1 >= thresh) k1 = sortable_bits(h1);
-                }
-                const int ly = (c / 10) * 8 + (lane >> 3) - kOff, lx = (c % 10) * 8 + (lane & 7) - kOff;
-                if (lx >= 0 && lx < LW) {
-                    if (ly >= 0 && ly < LH) s_key[ly * LW + lx] = k0;
-                    if (ly + 4 >= 0 && ly + 4 < LH) s_key[(ly + 4) * LW + lx] = k1;
-                }
+            for (int k = 0; k < 8; ++k) {
+                const int lx = lx0 + k;
+                if (lx >= 0 && lx < LW) s_key[ly * LW + lx] = (in[it] && h[k] >= thresh) ? sortable_bits(h[k]) : 0u;
             }
         }
     } else {

@@ -10,6 +10,7 @@
 #include <type_traits>
 
 #include "kernels.h"
+#include "softmax_cell.cuh"
 #include "sortkey.cuh"
 
 namespace spb200 {
@@ -17,45 +18,34 @@ namespace spb200 {
 // ================================================================================================
 // K3: logits -> full-resolution heatmap
 // ================================================================================================
-constexpr int kHeatCells = 32;     // cells of one cell-row per block
-constexpr int kHeatPitch = 72;     // smem pitch (floats): 72 % 32 == 8 -> conflict-free depth-to-space reads
+constexpr int kHeatCells = 32;     // cells of one cell-row per block: 8 lanes per cell, 256 threads
 
 __global__ void __launch_bounds__(256)
 heatmap_kernel(const float* __restrict__ logits, long batch_stride, long chan_stride, long cell_stride, int Hc, int Wc,
                float* __restrict__ heat) {
-    __shared__ float s_e[kHeatCells][kHeatPitch];
-    __shared__ float s_den[kHeatCells];
-    const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const int tid = threadIdx.x, cell = tid >> 3, j = tid & 7;
     const int b = blockIdx.z, i = blockIdx.y, j0 = blockIdx.x * kHeatCells;
-    const int ncell = min(kHeatCells, Wc - j0);
-    const float* base = logits + (size_t)b * batch_stride + (size_t)(i * Wc + j0) * cell_stride;
-
-    if (chan_stride == 1) {            // channels-last: walk channels fastest
-        for (int idx = tid; idx < ncell * 65; idx += 256) {
-            const int cell = idx / 65, c = idx % 65;
-            s_e[cell][c] = expf(base[(size_t)cell * cell_stride + c]);
-        }
-    } else {                           // planar: walk cells fastest
-        for (int idx = tid; idx < kHeatCells * 65; idx += 256) {
-            const int c = idx / kHeatCells, cell = idx % kHeatCells;
-            if (cell < ncell) s_e[cell][c] = expf(base[(size_t)c * chan_stride + (size_t)cell * cell_stride]);
-        }
-    }
-    __syncthreads();
-    for (int cell = warp; cell < ncell; cell += 8) {
-        float s = s_e[cell][lane] + s_e[cell][lane + 32] + (lane == 0 ? s_e[cell][64] : 0.f);
+    const bool in = j0 + cell < Wc;                                   // whole octets are in or out
+    const float* p = logits + (size_t)b * batch_stride + (size_t)(i * Wc + min(j0 + cell, Wc - 1)) * cell_stride;
+    float l[8], l64, h[8];
+    if (chan_stride == 1 && (cell_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (batch_stride & 3) == 0) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p + 8 * j)), c = __ldg(reinterpret_cast<const float4*>(p + 8 * j) + 1);
+        l[0] = a.x; l[1] = a.y; l[2] = a.z; l[3] = a.w; l[4] = c.x; l[5] = c.y; l[6] = c.z; l[7] = c.w;
+    } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) s_den[cell] = s + 0.00001f;
+        for (int k = 0; k < 8; ++k) l[k] = __ldg(p + (size_t)(8 * j + k) * chan_stride);
     }
-    __syncthreads();
+    l64 = __ldg(p + (size_t)64 * chan_stride);
+    softmax_cell_octet(l, l64, j, h);
+    if (!in) return;
     const int H = Hc * 8, W = Wc * 8;
-    const int j = tid / 8, dx = tid % 8;
-    if (j < ncell) {
-        const float den = s_den[j];
-        float* orow = heat + ((size_t)b * H + (size_t)i * 8) * W + (size_t)(j0 + j) * 8 + dx;
+    float* o = heat + ((size_t)b * H + (size_t)i * 8 + j) * W + (size_t)(j0 + cell) * 8;      // pixel row j of the cell
+    if ((reinterpret_cast<uintptr_t>(heat) & 15) == 0) {
+        reinterpret_cast<float4*>(o)[0] = make_float4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<float4*>(o)[1] = make_float4(h[4], h[5], h[6], h[7]);
+    } else {
 #pragma unroll
-        for (int dy = 0; dy < 8; ++dy) orow[(size_t)dy * W] = s_e[j][dy * 8 + dx] / den;
+        for (int k = 0; k < 8; ++k) o[k] = h[k];
     }
 }
 
