@@ -70,6 +70,7 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
     if (tid == 0) { s_ncand = 0; s_nund = 0; s_nkeep = 0; }
     for (int i = tid; i < EH * KW; i += kN0Threads) s_kb[i] = 0u;
     for (int i = tid; i < kN0TH * 2; i += kN0Threads) s_ub[i] = 0u;
+    if (LOGITS) __syncthreads();                               // the candidate counter is used while the keys are made
 
     // 1. keys of the loaded region
     if (LOGITS) {
@@ -104,13 +105,36 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
             const float l[8] = {la[it].x, la[it].y, la[it].z, la[it].w, lc[it].x, lc[it].y, lc[it].z, lc[it].w};
             float h[8];
             softmax_cell_octet(l, ld[it], j, h);
-            if (t >= kTasks) continue;
+            // keys of the lane's pixel row; the candidates of the evaluation region go straight to the list (one
+            // warp prefix sum and one shared atomic per step)
             const int ly = (c / 10) * 8 + j - kOff, lx0 = (c % 10) * 8 - kOff;
-            if (ly < 0 || ly >= LH) continue;
+            unsigned flags = 0u;
+            if (t < kTasks && ly >= 0 && ly < LH) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int lx = lx0 + k;
-                if (lx >= 0 && lx < LW) s_key[ly * LW + lx] = (in[it] && h[k] >= thresh) ? sortable_bits(h[k]) : 0u;
+                for (int k = 0; k < 8; ++k) {
+                    const int lx = lx0 + k;
+                    if (lx >= 0 && lx < LW) {
+                        const bool cand = in[it] && h[k] >= thresh;
+                        s_key[ly * LW + lx] = cand ? sortable_bits(h[k]) : 0u;
+                        if (cand && ly >= R && ly < R + EH && lx >= R && lx < R + EW) flags |= 1u << k;
+                    }
+                }
+            }
+            const int mine = __popc(flags);
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                int base = 0;
+                if (lane == 31) base = atomicAdd(&s_ncand, total);
+                base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (flags & (1u << k)) s_cand[base++] = (unsigned short)(((ly - R) << 8) | (lx0 + k - R));
             }
         }
     } else {
@@ -155,8 +179,9 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
     }
     __syncthreads();
 
-    // 1b. candidates of the evaluation region, compacted with one ballot and one shared atomic per warp and step
-    for (int i0 = 0; i0 < EH * EW; i0 += kN0Threads) {
+    // 1b. (heatmap input) candidates of the evaluation region, compacted with one ballot and one shared atomic per warp
+    // and step
+    for (int i0 = 0; i0 < (LOGITS ? 0 : EH * EW); i0 += kN0Threads) {
         const int i = i0 + tid;
         const int ey = i / EW, ex = i - ey * EW;
         const bool c = i < EH * EW && s_key[(ey + R) * LW + ex + R] != 0u;
