@@ -962,6 +962,23 @@ void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int
             if (s.h_desc) cudaFreeHost(s.h_desc);
             s.h_xy = nxy; s.h_conf = ncf; s.h_desc = nds; s.h_out_cap = n;
         }
+        if (pin_out) {
+            // pinned caller arrays: one strided copy per array and chunk (rows = images, width = the largest count of the
+            // chunk) instead of three small copies per image; rows past an image's count receive don't-care values
+            size_t nmax = 0;
+            for (int b = 0; b < Bc; ++b) nmax = std::max(nmax, (size_t)count[(size_t)k * Bc + b]);
+            const size_t g0 = (size_t)k * Bc;
+            if (nmax) {
+                SPB_CUDA(cudaMemcpy2DAsync(xy + g0 * cap * 2, sizeof(int) * 2 * cap, s.d_xy + g0 * dcap * 2, sizeof(int) * 2 * dcap,
+                                           sizeof(int) * 2 * nmax, Bc, cudaMemcpyDeviceToHost, s.s_out));
+                SPB_CUDA(cudaMemcpy2DAsync(conf + g0 * cap, sizeof(float) * cap, s.d_conf + g0 * dcap, sizeof(float) * dcap,
+                                           sizeof(float) * nmax, Bc, cudaMemcpyDeviceToHost, s.s_out));
+                if (desc)
+                    SPB_CUDA(cudaMemcpy2DAsync(desc + g0 * cap * 128, sizeof(float) * 128 * cap, s.d_desc + g0 * dcap * 128,
+                                               sizeof(float) * 128 * dcap, sizeof(float) * 128 * nmax, Bc, cudaMemcpyDeviceToHost, s.s_out));
+            }
+            continue;
+        }
         for (int b = 0; b < Bc; ++b) {
             const size_t g = (size_t)k * Bc + b, n = (size_t)count[g];
             if (!pin_out) stage_off[g] = staged;
