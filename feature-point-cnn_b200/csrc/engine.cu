@@ -119,6 +119,7 @@ Engine::~Engine() {
     if (side_fork_) cudaEventDestroy(side_fork_);
     cudaFree(d_gtab_);
     cudaFree(d_match_ws_);
+    cudaFree(d_match_tc_ws_);
     cudaFree(d_ha_img_); cudaFree(d_ha_prob_); cudaFree(d_ha_coeffs_); cudaFree(d_ha_maps_);
 }
 
@@ -827,11 +828,25 @@ void Engine::match(const float* desc_a, const int* count_a, const float* desc_b,
         d_match_ws_ = dev_alloc<unsigned long long>(need);
         match_ws_elems_ = need;
     }
+    static const bool simt = [] { const char* e = std::getenv("SPB200_MATCH_SIMT"); return e && e[0] == '1'; }();
     prof_open("match", 2.0 * B * (double)cap * cap * D, 0.0, st);
-    launch_match(desc_a, count_a, desc_b, count_b, B, cap, D, max_dist, d_match_ws_, d_match_ws_ + (size_t)B * cap, match_ab, dist,
-                 num_sms_, st);
+    if (D == 128 && !simt) {
+        const size_t wb = match_tc_workspace_bytes(B, cap);
+        if (wb > match_tc_ws_bytes_) {
+            SPB_CUDA(cudaDeviceSynchronize());
+            cudaFree(d_match_tc_ws_);
+            SPB_CUDA(cudaMalloc(&d_match_tc_ws_, wb));
+            match_tc_ws_bytes_ = wb;
+        }
+        launch_match_tc(desc_a, count_a, desc_b, count_b, B, cap, max_dist, d_match_tc_ws_, d_match_ws_, d_match_ws_ + (size_t)B * cap,
+                        match_ab, dist, num_sms_, st);
+        launches_ += 6;
+    } else {
+        launch_match(desc_a, count_a, desc_b, count_b, B, cap, D, max_dist, d_match_ws_, d_match_ws_ + (size_t)B * cap, match_ab, dist,
+                     num_sms_, st);
+        launches_ += 3;
+    }
     prof_close(st);
-    launches_ += 3;
 }
 
 void Engine::buffer_dims(int id, int* C, int* H, int* W) const {

@@ -179,6 +179,8 @@ private:
     const float* grid_table(int H, int W);
     unsigned long long* d_match_ws_ = nullptr;     // [2][B][cap] best keys of the matcher
     size_t match_ws_elems_ = 0;
+    void* d_match_tc_ws_ = nullptr;                // operands + norms of the tensor-core matcher
+    size_t match_tc_ws_bytes_ = 0;
     // homography adaptation workspace
     float* d_ha_img_ = nullptr; float* d_ha_prob_ = nullptr; float* d_ha_coeffs_ = nullptr; uint8_t* d_ha_maps_ = nullptr;
     size_t ha_img_elems_ = 0, ha_prob_elems_ = 0, ha_map_bytes_ = 0; int ha_num_ = 0;

@@ -102,4 +102,12 @@ void launch_match(const float* desc_a, const int* count_a, const float* desc_b, 
                   float max_dist, unsigned long long* best_a, unsigned long long* best_b, int* match, float* dist, int num_sms,
                   cudaStream_t st);
 
+// ---- match_tc.cu ---------------------------------------------------------------------------------
+// The same on the tensor cores for D = 128: split-precision fp16 GEMM (hi.hi + hi.lo + lo.hi, fp32 accumulation) with the
+// row minima taken in the epilogue, run in both directions.  workspace: match_tc_workspace_bytes(B, cap) bytes.
+size_t match_tc_workspace_bytes(int B, int cap);
+void launch_match_tc(const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B, int cap,
+                     float max_dist, void* workspace, unsigned long long* best_a, unsigned long long* best_b, int* match,
+                     float* dist, int num_sms, cudaStream_t st);
+
 }  // namespace spb200

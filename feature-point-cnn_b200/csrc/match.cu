@@ -141,6 +141,17 @@ __global__ void match_finish_kernel(const int* __restrict__ count_a, int cap, co
     dist[(size_t)b * cap + q] = d;
 }
 
+void match_init_launch(unsigned long long* best_a, unsigned long long* best_b, long n, cudaStream_t st) {
+    match_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(best_a, best_b, n);
+    SPB_CHECK_LAUNCH();
+}
+
+void match_finish_launch(const int* count_a, int B, int cap, const unsigned long long* best_a, const unsigned long long* best_b,
+                         float max_dist, int* match, float* dist, cudaStream_t st) {
+    match_finish_kernel<<<dim3((cap + 255) / 256, B), 256, 0, st>>>(count_a, cap, best_a, best_b, max_dist, match, dist);
+    SPB_CHECK_LAUNCH();
+}
+
 void launch_match(const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B, int cap, int D,
                   float max_dist, unsigned long long* best_a, unsigned long long* best_b, int* match, float* dist, int num_sms,
                   cudaStream_t st) {
