@@ -16,6 +16,7 @@
 #define SPB200_SUPERPOINT_H
 
 #include <array>
+#include <cstdint>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -70,14 +71,22 @@ class SuperPoint {
   int descriptor_dim() const { return spb200_descriptor_dim(engine_); }
 
   // frame: rows*cols floats in [0,1] (cv::Mat CV_32FC1, continuous); rows and cols multiples of 16.
-  std::vector<FeaturePoint> ProcessFrame(const float* frame, int rows, int cols) {
+  std::vector<FeaturePoint> ProcessFrame(const float* frame, int rows, int cols) { return Process(frame, nullptr, rows, cols); }
+
+  // frame: rows*cols bytes, the 8-bit grayscale camera frame before the reference's convertTo(CV_32FC1, 1/255)
+  // (cpp/src/camera.cc:12-23); same result as ProcessFrame on frame / 255.f, a quarter of the upload.
+  std::vector<FeaturePoint> ProcessFrame8(const uint8_t* frame, int rows, int cols) { return Process(nullptr, frame, rows, cols); }
+
+ private:
+  std::vector<FeaturePoint> Process(const float* frame, const uint8_t* frame8, int rows, int cols) {
     const int cap = settings_.top_k > 0 ? settings_.top_k : spb200_max_keypoints(rows, cols, settings_.nms_dist);
     const int dim = descriptor_dim();
     xy_.resize((size_t)cap * 2);
     conf_.resize(cap);
     desc_.resize((size_t)cap * dim);
     int count = 0;
-    Check(spb200_detect_host(engine_, frame, 1, 1, rows, cols, cap, &count, xy_.data(), conf_.data(), desc_.data()));
+    if (frame8) Check(spb200_detect_host_u8(engine_, frame8, 1, rows, cols, cap, &count, xy_.data(), conf_.data(), desc_.data()));
+    else Check(spb200_detect_host(engine_, frame, 1, 1, rows, cols, cap, &count, xy_.data(), conf_.data(), desc_.data()));
     feature_points_.resize(count);
     for (int i = 0; i < count; ++i) {
       FeaturePoint& fp = feature_points_[i];
@@ -90,10 +99,12 @@ class SuperPoint {
     return feature_points_;     // a copy, like the reference (superpoint.cc:95)
   }
 
+ public:
 #ifdef OPENCV_CORE_HPP
   std::vector<FeaturePoint> ProcessFrame(const cv::Mat& frame) {
-    if (frame.type() != CV_32FC1) throw std::invalid_argument("ProcessFrame expects CV_32FC1 (torchutis.cc:6)");
     cv::Mat c = frame.isContinuous() ? frame : frame.clone();
+    if (frame.type() == CV_8UC1) return ProcessFrame8(c.ptr<uint8_t>(), c.rows, c.cols);
+    if (frame.type() != CV_32FC1) throw std::invalid_argument("ProcessFrame expects CV_32FC1 (torchutis.cc:6) or CV_8UC1");
     return ProcessFrame(c.ptr<float>(), c.rows, c.cols);
   }
 #endif

@@ -173,3 +173,15 @@ def test_homography_adaptation_against_oracle_and_wrapper(engines, tmp_path):
     assert len(pts) == 1 and pts[0].shape[0] == 3 and pts[0].shape[1] > 100
     assert (np.diff(pts[0][2]) <= 0).all()                        # descending confidence
     wrap.engine.close()
+
+
+def test_cpp_facade_demo_runs_float_and_8bit_frames():
+    """The C++ mirror of the reference's wrapper (cpp/superpoint.h: superpoint::SuperPoint, ProcessFrame, ProcessFrame8)
+    through its headless demo binary: loads the checkpoint, finds keypoints, and the 8-bit frame gives the same ones."""
+    import subprocess
+    from _gpu_common import CKPT
+    exe = os.path.join(os.path.dirname(GOLDEN), '..', 'feature-point-cnn_b200', 'cpp', 'demo')
+    r = subprocess.run([os.path.abspath(exe), CKPT, '240', '320'], capture_output=True, text=True, timeout=120)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0
+    assert 'descriptor dim 128' in r.stdout and 'identical to the float frame' in r.stdout
