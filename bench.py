@@ -28,20 +28,28 @@ METRIC = 'SuperPoint images/sec @480x640 (kpts+desc)'
 UNIT = 'images/s'
 
 
-def ncu_traffic(kernel_substr):
+def ncu_traffic(kernel_substr, longest=False):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the newest committed ncu
-    full-set summary under profiles/ (MB columns of scripts/ncu_summary.py); None when there is none."""
+    full-set summary under profiles/ (MB columns of scripts/ncu_summary.py); None when there is none.  Several
+    launches share a kernel name (one template instance serves several layers): `longest` picks the longest of them
+    instead of the first."""
     import glob
     best = None
     for f in sorted(glob.glob(os.path.join(REPO, 'profiles', '*ncu_full_summary*.txt'))):
+        cand = None
         for line in open(f):
             if kernel_substr in line:
                 parts = line[44:].split()
                 try:
-                    best = (float(parts[1]) + float(parts[2])) * 1e6
+                    us, val = float(parts[0]), (float(parts[1]) + float(parts[2])) * 1e6
                 except Exception:
-                    pass
-                break
+                    continue
+                if cand is None or (longest and us > cand[0]):
+                    cand = (us, val)
+                if not longest:
+                    break
+        if cand is not None:
+            best = cand[1]
     return best
 
 
@@ -176,6 +184,7 @@ def main():
     ap.add_argument('--width', type=int, default=640)
     ap.add_argument('--precision', default='fp16', choices=['fp32', 'fp16', 'bf16'])
     ap.add_argument('--top-k', type=int, default=0)
+    ap.add_argument('--detector-only', action='store_true', help='MagicPoint: heatmap + NMS, descriptor head skipped (BASELINE configs[1])')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel table (json) here')
     args = ap.parse_args()
@@ -201,7 +210,7 @@ def main():
     eng = spb200.Engine(local_rank)
     eng.load_checkpoint(CKPT)
     eng.finalize(args.precision)
-    eng.set_params(top_k=args.top_k)
+    eng.set_params(top_k=args.top_k, descriptor_enabled=not args.detector_only)
     cap = eng.max_keypoints(H, W) if not args.top_k else args.top_k
 
     n_rot = 4                                               # 4 x 78.6 MB of inputs > 126 MB L2
@@ -311,6 +320,9 @@ def main():
     ncu_name = {'stem_pool': 'stem_planes_kernel', 'nms_round0': 'nms_round0_kernel', 'nms_finish_sort': 'nms_finish_kernel', 'descriptors': 'sample_desc', 'heatmap': 'heatmap_kernel',
                 'image_planes': 'planes_kernel'}.get(top['kernel'])
     roofline['traffic'] = ncu_traffic(ncu_name) if ncu_name and B == 64 and H == 480 and W == 640 else None
+    if top['kernel'] == 'descriptor.layer_out.0' and B == 64 and H == 480 and W == 640:
+        # the 256 -> 128 block with the concatenated input: the longest launch of this template instance in the capture
+        roofline['traffic'] = ncu_traffic('halo_tc_kernel<128, 2, 1, 2, 8, 1, 0', longest=True)
     roofline['traffic_source'] = 'ncu --set full capture of the same workload committed under profiles/ (dram bytes read + written per launch)'
     roofline['peak_source'] = peaks['source'] + (', sustained bf16 GEMM figure' if roofline['bound'] == 'tensor' else '')
     roofline['share_of_step'] = top['share']
@@ -386,7 +398,7 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': {'fp32': 'f32', 'fp16': 'f16', 'bf16': 'bf16'}[args.precision], 'data': 'synthetic',
-            'config': {'workload': 'super_point.pt keypoints+descriptors, batch %d per GPU at %dx%d grayscale (BASELINE configs[2])' % (B, H, W),
+            'config': {'workload': ('magic_point-style detector only (heatmap + NMS, descriptor head skipped), batch %d per GPU at %dx%d grayscale (BASELINE configs[1])' if args.detector_only else 'super_point.pt keypoints+descriptors, batch %d per GPU at %dx%d grayscale (BASELINE configs[2])') % (B, H, W),
                        'batch_per_gpu': B, 'height': H, 'width': W, 'top_k': args.top_k, 'parallelism': 'batch-sharded x%d, no collective' % world,
                        'keypoints_per_image': kp_mean, 'weights': 'tests/golden/super_point.pt (synthetic recipe, reference-written)',
                        'l2': 'inputs rotate over %d batches (%.0f MB > 126 MB L2); activations are rewritten every step' % (n_rot, n_rot * B * H * W * 4 / 1e6)},
