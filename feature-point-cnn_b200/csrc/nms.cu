@@ -51,12 +51,13 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
                   unsigned long long* __restrict__ keys, int* __restrict__ counters, unsigned* __restrict__ mask,
                   int mask_w, unsigned* __restrict__ und, unsigned* __restrict__ ukey) {
     constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R;      // loaded region (halo 2R)
+    constexpr int KP = LW | 1;                                 // odd row pitch of s_key: the eight rows a cell's lanes write fall in different banks
     constexpr int EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;      // region where keepers are evaluated (halo R)
     constexpr int KW = (EW + 31) / 32 + 1;                     // keeper bit words per E row (+1 so a 64-bit window read stays inside)
     constexpr int kMaxKeep = ((kN0TW + R) / (R + 1) + 1) * ((kN0TH + R) / (R + 1) + 1);   // keepers are > R apart
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned* s_key = reinterpret_cast<unsigned*>(smem_raw);   // [LH][LW]   sortable key, 0 = not a candidate
-    unsigned* s_kb = s_key + LH * LW;                          // [EH][KW]   keeper bits, bit ex of row ey
+    unsigned* s_key = reinterpret_cast<unsigned*>(smem_raw);   // [LH][KP]   sortable key, 0 = not a candidate
+    unsigned* s_kb = s_key + LH * KP;                          // [EH][KW]   keeper bits, bit ex of row ey
     unsigned* s_ub = s_kb + EH * KW;                           // [TH][2]    undecided bits of the interior
     unsigned* s_und = s_ub + kN0TH * 2;                        // [TH*TW]    undecided pixel indices
     unsigned long long* s_keep = reinterpret_cast<unsigned long long*>(
@@ -115,7 +116,7 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
                     const int lx = lx0 + k;
                     if (lx >= 0 && lx < LW) {
                         const bool cand = in[it] && h[k] >= thresh;
-                        s_key[ly * LW + lx] = cand ? sortable_bits(h[k]) : 0u;
+                        s_key[ly * KP + lx] = cand ? sortable_bits(h[k]) : 0u;
                         if (cand && ly >= R && ly < R + EH && lx >= R && lx < R + EW) flags |= 1u << k;
                     }
                 }
@@ -173,7 +174,7 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
                 const float h[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (lx + e < LW) s_key[ly * LW + lx + e] = h[e] >= thresh ? sortable_bits(h[e]) : 0u;
+                    if (lx + e < LW) s_key[ly * KP + lx + e] = h[e] >= thresh ? sortable_bits(h[e]) : 0u;
             }
         }
     }
@@ -184,7 +185,7 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
     for (int i0 = 0; i0 < (LOGITS ? 0 : EH * EW); i0 += kN0Threads) {
         const int i = i0 + tid;
         const int ey = i / EW, ex = i - ey * EW;
-        const bool c = i < EH * EW && s_key[(ey + R) * LW + ex + R] != 0u;
+        const bool c = i < EH * EW && s_key[(ey + R) * KP + ex + R] != 0u;
         const unsigned bal = __ballot_sync(0xffffffffu, c);
         if (bal) {
             int base = 0;
@@ -199,11 +200,11 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
     // 2. keeper test per candidate: no stronger key in the window, no equal key earlier in raster order
     for (int c = tid; c < ncand; c += kN0Threads) {
         const int ey = s_cand[c] >> 8, ex = s_cand[c] & 255;
-        const unsigned* centre = s_key + (ey + R) * LW + ex + R;
+        const unsigned* centre = s_key + (ey + R) * KP + ex + R;
         const unsigned me = *centre;
         bool keep = true;
         for (int dy = -R; dy <= R && keep; ++dy) {
-            const unsigned* row = centre + dy * LW;
+            const unsigned* row = centre + dy * KP;
 #pragma unroll
             for (int dx = -R; dx <= R; ++dx) {
                 const unsigned v = row[dx];
@@ -224,7 +225,7 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
         const int gy = ty0 + iy, gx = tx0 + ix;
         const bool keep = (s_kb[ey * KW + (ex >> 5)] >> (ex & 31)) & 1u;
         const unsigned pix = (unsigned)(gy * W + gx);
-        const unsigned me = s_key[(ey + R) * LW + ex + R];
+        const unsigned me = s_key[(ey + R) * KP + ex + R];
         if (keep) {
             if (!(gx < border || gx >= W - border || gy < border || gy >= H - border)) {
                 const int pos = atomicAdd(&s_nkeep, 1);
@@ -824,7 +825,7 @@ static void launch_round0_t(const float* src, int cell_stride, int B, int H, int
     constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R, EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;
     constexpr int KW = (EW + 31) / 32 + 1;
     constexpr int kMaxKeep = ((kN0TW + R) / (R + 1) + 1) * ((kN0TH + R) / (R + 1) + 1);
-    const size_t smem = sizeof(unsigned) * ((size_t)LH * LW + EH * KW + kN0TH * 2 + kN0TH * kN0TW) + sizeof(unsigned long long) * kMaxKeep +
+    const size_t smem = sizeof(unsigned) * ((size_t)LH * (LW | 1) + EH * KW + kN0TH * 2 + kN0TH * kN0TW) + sizeof(unsigned long long) * kMaxKeep +
                         sizeof(unsigned short) * ((size_t)EH * EW) + 16;
     auto kern = nms_round0_kernel<R, LOGITS>;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
