@@ -898,7 +898,10 @@ void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int
     {
         int want = 16;
         if (const char* e = std::getenv("SPB200_HOST_CHUNK")) want = std::max(1, std::atoi(e));
-        if (B > want && B % want == 0 && B / want <= HostStage::kMaxChunks) Bc = want;
+        // the largest divisor of B that is at most `want` (and at least a quarter of it, so that chunks stay efficient)
+        if (B > want)
+            for (int c = want; c >= std::max(1, want / 4); --c)
+                if (B % c == 0 && B / c <= HostStage::kMaxChunks) { Bc = c; break; }
     }
     const int nc = B / Bc;
     const bool pin_in = is_pinned_host(img);

@@ -193,10 +193,12 @@ def test_detect_host_matches_device(engines):
 
 
 @pytest.mark.parametrize('pinned', [False, True])
-def test_detect_host_chunked_pipeline(engines, pinned, monkeypatch):
+@pytest.mark.parametrize('chunk', ['2', '4'])
+def test_detect_host_chunked_pipeline(engines, pinned, chunk, monkeypatch):
     """The host entry point cuts the batch into chunks (upload / compute / download overlap): six images in chunks
-    of two, pageable and pinned caller buffers, against the device path image by image."""
-    monkeypatch.setenv('SPB200_HOST_CHUNK', '2')
+    of two - or of three, the largest divisor of the batch below a preferred size of four -, pageable and pinned caller
+    buffers, against the device path image by image."""
+    monkeypatch.setenv('SPB200_HOST_CHUNK', chunk)
     e = engines['fp16']
     names = ['shapes240_0', 'rand240_1', 'shapes240_1', 'shapes240_2', 'rand240_0', 'shapes240_0']
     imgs = torch.stack([golden_image(n) for n in names])[:, None].contiguous()
