@@ -104,6 +104,24 @@ def test_match_against_oracle(nq, nt, seed, engines):
         np.testing.assert_allclose(d[0, common], dist[np.searchsorted(qi, common)], atol=2e-5)
 
 
+def test_match_256_wide_descriptors_cuda_core_kernel(engines):
+    """D = 256 (the stale C++ demo's descriptor width, cpp/src/torchutis.h:11) takes the fp32 CUDA-core kernel."""
+    rng = np.random.RandomState(9)
+    a = rng.randn(300, 256).astype(np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    t = np.vstack([a[rng.permutation(300)[:120]] + 0.02 * rng.randn(120, 256).astype(np.float32), rng.randn(137, 256).astype(np.float32)])
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    e = engines['fp16']
+    cap = 320
+    da, db = torch.zeros((1, cap, 256)), torch.zeros((1, cap, 256))
+    da[0, :300], db[0, :257] = torch.from_numpy(a), torch.from_numpy(t)
+    m, d = e.match(da.cuda(), torch.tensor([300], dtype=torch.int32).cuda(), db.cuda(), torch.tensor([257], dtype=torch.int32).cuda(), 0.7)
+    qi, ti, dist = matching.mutual_nearest(a, t, 0.7)
+    got = np.nonzero(m[0, :300].cpu().numpy() >= 0)[0]
+    assert list(got) == list(qi) and list(m[0, got].cpu().numpy()) == list(ti)
+    np.testing.assert_allclose(d[0, got].cpu().numpy(), dist, atol=2e-5)
+
+
 def test_match_empty_sets_and_linear_pipeline(engines):
     """count = 0 on either side gives no matches; detect -> match on two frames of the same scene runs end to end
     and every match is mutual."""
