@@ -24,7 +24,7 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 #define SPB_CHECK_LAUNCH() ::spb200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
 
 constexpr int kMaxTaps = 9;
-constexpr int kMaxSegs = 3;
+constexpr int kMaxSegs = 5;
 
 // One K segment of an implicit-GEMM convolution: `ntaps` taps over a `cin`-channel NHWC source.
 // Output pixel (oy, ox) reads source pixel (oy*stride + dy[t], ox*stride + dx[t]); pixels outside
@@ -37,6 +37,8 @@ struct SegDev {
     int ntaps;
     int stride;
     int koff;             // first K index of this segment in the packed weights
+    int view;             // > 1: src / H / W describe every `view`-th pixel of a full_H x full_W buffer in both axes (src points
+    int full_H, full_W;   //      at the phase's first pixel): a stride-2 convolution read as stride-1 convolutions over four phases
     int8_t dy[kMaxTaps], dx[kMaxTaps];
 };
 

@@ -102,6 +102,8 @@ Engine::Engine(int device) : device_(device) {
         SPB_CUDA(cudaEventCreateWithFlags(&side_join_[i], cudaEventDisableTiming));
     }
     SPB_CUDA(cudaEventCreateWithFlags(&side_fork_, cudaEventDisableTiming));
+    const char* np = std::getenv("SPB200_NO_PHASES");
+    use_phases_ = !(np && np[0] == '1');
     const char* os = std::getenv("SPB200_OLD_STEM");
     use_planes_ = !(os && os[0] == '1');
     buf_.fill(nullptr);
@@ -241,10 +243,29 @@ void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> sr
         throw std::runtime_error("unexpected downsample shape in block " + p);
     const int cout_pad = bufspec_[y_buf].C;
 
+    // A stride-2 block on the tensor-core path with one source and at most 128 output channels is read as stride-1
+    // convolutions over the four pixel phases of its input (row parity a, column parity b): output (oy, ox) takes
+    // input row 2 oy + ky - 1, i.e. phase a = 1 at row oy - 1 (ky = 0), a = 0 at oy (ky = 1), a = 1 at oy (ky = 2), and
+    // the same along x.  Each phase is then ONE haloed tile for the halo kernel instead of nine per-tap tiles.
+    const bool phases = stride == 2 && precision_ != PREC_FP32 && use_halo_ && fuse_blocks_ && srcs.size() == 1 &&
+                        cout_pad <= 128 && bufspec_[srcs[0].first].C == 64 && has_ds && use_phases_;
     OpSpec a;
     a.name = p + ".conv1";
     int off = 0;
+    if (phases) {
+        for (int pa = 0; pa < 2; ++pa)
+            for (int pb = 0; pb < 2; ++pb) {
+                std::vector<TapSpec> taps;
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int kx = 0; kx < 3; ++kx)
+                        if ((ky != 1) == (pa == 1) && (kx != 1) == (pb == 1)) taps.push_back({ky == 0 ? -1 : 0, kx == 0 ? -1 : 0, ky, kx});
+                SegSpec sg{srcs[0].first, c1, 0, srcs[0].second, 1, taps};
+                sg.view = 2; sg.vy = pa; sg.vx = pb;
+                a.segs.push_back(sg);
+            }
+    }
     for (auto& s : srcs) {
+        if (phases) break;
         a.segs.push_back(SegSpec{s.first, c1, off, s.second, stride, taps3x3()});
         off += s.second;
     }
@@ -261,7 +282,9 @@ void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> sr
     if (cd) {
         off = 0;
         for (auto& s : srcs) {
-            b.segs.push_back(SegSpec{s.first, cd, off, s.second, stride, {TapSpec{0, 0, 0, 0}}});
+            SegSpec sg{s.first, cd, off, s.second, phases ? 1 : stride, {TapSpec{0, 0, 0, 0}}};
+            if (phases) sg.view = 2;                 // the 1x1 stride-2 shortcut reads phase (0, 0)
+            b.segs.push_back(sg);
             off += s.second;
         }
         for (int i = 0; i < cout; ++i) b.bias[i] += cd->b[i];
@@ -445,6 +468,7 @@ void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
             if (is_conv1 && i + 1 < ops_.size()) {
                 const ConvDev c1 = make_conv_dev(op), c2 = make_conv_dev(ops_[i + 1]);
                 if (use_halo_) op.halo = tc_halo_plan_create(c1, &c2, precision_, op.cout_real, num_sms_);
+                if (!op.halo && op.segs[0].view > 1) throw std::runtime_error("internal: no haloed-tile plan for the phase form of " + op.name);
                 if (!op.halo) op.fused = tc_block_plan_create(c1, &c2, precision_, op.cout_real, num_sms_);
                 ops_[i + 1].fused_skip = true;
                 ++i;
@@ -512,6 +536,12 @@ ConvDev Engine::make_conv_dev(const OpSpec& op) const {
         SegDev& sd = d.seg[i];
         sd.src = buf_[s.src_buf];
         sd.H = wsH_ / bs.div; sd.W = wsW_ / bs.div; sd.C = bs.C;
+        sd.view = s.view; sd.full_H = sd.H; sd.full_W = sd.W;
+        if (s.view > 1) {
+            const size_t esz = (bs.fp32 || precision_ == PREC_FP32) ? 4 : 2;
+            sd.src = static_cast<const char*>(buf_[s.src_buf]) + ((size_t)s.vy * sd.full_W + s.vx) * bs.C * esz;
+            sd.H /= s.view; sd.W /= s.view;
+        }
         sd.cin = bs.C;
         sd.cin_real = s.cin_real;
         sd.ntaps = (int)s.taps.size();

@@ -36,6 +36,7 @@ struct SegSpec {
     int ci_off, cin_real;
     int stride;
     std::vector<TapSpec> taps;
+    int view = 1, vy = 0, vx = 0;   // view > 1: the segment reads the pixels (view*y + vy, view*x + vx) of its source
 };
 
 struct OpSpec {
@@ -191,6 +192,7 @@ private:
     // fork / join of the side-by-side groups: three extra streams, one event to fork and one per stream to join
     cudaStream_t side_stream_[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t side_fork_ = nullptr, side_join_[3] = {nullptr, nullptr, nullptr};
+    bool use_phases_ = true;      // SPB200_NO_PHASES=1 keeps stride-2 blocks on the per-tap kernel
     bool use_side_ = true;        // SPB200_NO_SIDE=1 runs the phases one after the other on all SMs
     long launches_ = 0;
     bool profiling_ = false;

@@ -550,8 +550,8 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     p.has_ds = c2 && c2->nseg > 1;
     if (c2) {
         if (c2->nseg < 1 || c2->seg[0].ntaps != 1 || c2->seg[0].cin != N) return nullptr;
-        if (p.has_ds && c2->nseg - 1 != c1.nseg) return nullptr;
     }
+    int ds_used = 0;
 
     int nsteps = 0, nchunks = 0;
     const int ring = plan->variant == 0 ? kHaloResidentSlabs : (plan->variant == 1 ? kHaloRing1 : kHaloRing2);
@@ -565,12 +565,17 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         const int nch = sg.cin / 64;
         const int kk_last = kk_of(sg.cin_real > 0 ? sg.cin_real : sg.cin, nch);
         if (sg.koff % 64) return nullptr;
+        // the shortcut convolution of this source, if it has one (a phase-form block has it on phase (0, 0) only)
         const SegDev* ds = nullptr;
         if (p.has_ds) {
-            ds = &c2->seg[s + 1];
-            if (ds->src != sg.src || ds->ntaps != 1 || ds->dy[0] != 0 || ds->dx[0] != 0 || ds->stride != 1 || ds->cin != sg.cin ||
-                ds->koff % 64)
-                return nullptr;
+            for (int j = 1; j < c2->nseg; ++j)
+                if (c2->seg[j].src == sg.src) ds = &c2->seg[j];
+            if (ds) {
+                if (ds->ntaps != 1 || ds->dy[0] != 0 || ds->dx[0] != 0 || ds->stride != 1 || ds->cin != sg.cin || ds->koff % 64 ||
+                    ds->view != sg.view)
+                    return nullptr;
+                ++ds_used;
+            }
         }
         for (int c = 0; c < nch; ++c) {
             if (nchunks >= kMaxChunks) return nullptr;
@@ -589,19 +594,21 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
                 first_ds = false;
             }
         }
-        // activations: dims {C, group axis, slow axis, image}
-        const cuuint64_t C = sg.C, W = sg.W, H = sg.H;
+        // activations: dims {C, group axis, slow axis, image}; a phase view steps `view` pixels of the full buffer
+        const cuuint64_t C = sg.C, W = sg.W, H = sg.H, V = sg.view > 1 ? sg.view : 1;
+        const cuuint64_t FW = sg.view > 1 ? sg.full_W : sg.W, FH = sg.view > 1 ? sg.full_H : sg.H;
         cuuint32_t box[4] = {64, (cuuint32_t)kHaloG, (cuuint32_t)kHaloS, 1};
         if (p.orient == 0) {
             cuuint64_t dims[4] = {C, W, H, (cuuint64_t)c1.B};
-            cuuint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+            cuuint64_t str[3] = {V * C * 2, V * FW * C * 2, FH * FW * C * 2};
             tc_encode_tiled(&p.tmA[s], dt, 4, sg.src, dims, str, box);
         } else {
             cuuint64_t dims[4] = {C, H, W, (cuuint64_t)c1.B};
-            cuuint64_t str[3] = {W * C * 2, C * 2, H * W * C * 2};
+            cuuint64_t str[3] = {V * FW * C * 2, V * C * 2, FH * FW * C * 2};
             tc_encode_tiled(&p.tmA[s], dt, 4, sg.src, dims, str, box);
         }
     }
+    if (p.has_ds && ds_used != c2->nseg - 1) return nullptr;          // a shortcut segment without its source among the inputs
     for (int s = c1.nseg; s < kMaxSegs; ++s) p.tmA[s] = p.tmA[0];
     p.nchunks = nchunks;
     p.n1steps = nsteps;
