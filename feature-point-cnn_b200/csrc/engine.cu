@@ -253,8 +253,10 @@ void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> sr
     a.name = p + ".conv1";
     int off = 0;
     if (phases) {
-        for (int pa = 0; pa < 2; ++pa)
-            for (int pb = 0; pb < 2; ++pb) {
+        // phase (0, 0), the one the shortcut convolution reads, comes last: its step is then the last of GEMM 1 and
+        // everything before it overlaps the previous tile's final epilogue (halo_tc.cu, lazy wait on the D2 accumulator)
+        for (int pa = 1; pa >= 0; --pa)
+            for (int pb = 1; pb >= 0; --pb) {
                 std::vector<TapSpec> taps;
                 for (int ky = 0; ky < 3; ++ky)
                     for (int kx = 0; kx < 3; ++kx)

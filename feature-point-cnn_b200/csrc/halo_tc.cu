@@ -205,7 +205,11 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 // fused: D1[b] holds Y until GEMM 2 of its previous use has read it, and that GEMM 2 was issued by this
                 // warp before this point (MMAs of one thread execute in order): no barrier needed
                 if (!FUSED) mbar_wait(&d1_empty[b], ph ^ 1u);          // epilogue has drained D1[b]
-                if (FUSED && p.has_ds) mbar_wait(&d2_empty[b], ph ^ 1u);
+                // a block with a shortcut convolution accumulates it into D2 during GEMM 1: D2[b] must have been drained
+                // by the epilogue of its previous use - waited for at the first shortcut step, not here, so that the
+                // steps before it overlap that epilogue (the resident-weight path issues a whole tile at once and waits here)
+                bool d2_ready = !(FUSED && p.has_ds);
+                if (!d2_ready && WRES && j > 0) { mbar_wait(&d2_empty[b], ph ^ 1u); d2_ready = true; }
                 tc_fence_after();
                 if (WRES && j > 0) {
                     // resident weights, nothing left to wait for but the activation chunk (a 64-channel block has one
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     const uint32_t slot = hi & 15u, nkk = (hi >> 6) & 7u, acc0 = (hi >> 11) & 1u;
                     if (hi & (1u << 9)) mbar_wait_a(bar_afull + sa * 8, pha);
                     if (!WRES || j == 0) mbar_wait_a(bar_wfull + slot * 8, (wph >> slot) & 1u);
+                    if (!d2_ready && ((hi >> 4) & 3u) != 0) { mbar_wait(&d2_empty[b], ph ^ 1u); d2_ready = true; }
                     tc_fence_after();
                     const uint32_t alo = a_lo_base + (uint32_t)(sa * T * (kHaloBufBytes >> 4)) + (lo & 0xffffu);
                     const uint32_t blo = w_lo_base + (lo >> 16);
