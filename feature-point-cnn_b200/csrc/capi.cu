@@ -226,6 +226,10 @@ int spb200_checkpoint_tensor(const char* path, const char* key, float* dst, long
     std::string err;
     if (!spb200::read_checkpoint(path, sd, err)) { g_create_error = err; return SPB200_E_RUNTIME; }
     auto it = sd.find(key);
+    if (it == sd.end()) {                               // *_params.pt: keys without their module prefix
+        spb200::restore_module_prefixes(sd);
+        it = sd.find(key);
+    }
     if (it == sd.end()) { g_create_error = std::string("no tensor named ") + key; return SPB200_E_INVALID; }
     const spb200::HostTensor& t = it->second;
     if (t.shape.size() > 8) return SPB200_E_INVALID;

@@ -391,4 +391,23 @@ bool read_checkpoint(const std::string& path, StateDict& out, std::string& err) 
     }
 }
 
+void restore_module_prefixes(StateDict& sd) {
+    for (auto& kv : sd)
+        if (kv.first.compare(0, 8, "encoder.") == 0 || kv.first.compare(0, 9, "detector.") == 0 || kv.first.compare(0, 11, "descriptor.") == 0)
+            return;                                        // a full state_dict
+    static const struct { const char* first; const char* module; } kMap[] = {
+        {"conv1", "encoder."}, {"bn1", "encoder."}, {"layer1", "encoder."}, {"layer2", "encoder."},
+        {"layer", "detector."},
+        {"layer_in", "descriptor."}, {"up_sample", "descriptor."}, {"bn", "descriptor."}, {"layer_out", "descriptor."}};
+    StateDict out;
+    for (auto& kv : sd) {
+        const std::string head = kv.first.substr(0, kv.first.find('.'));
+        std::string key = kv.first;
+        for (auto& m : kMap)
+            if (head == m.first) { key = std::string(m.module) + kv.first; break; }
+        out[key] = std::move(kv.second);
+    }
+    sd = std::move(out);
+}
+
 }  // namespace spb200

@@ -34,4 +34,9 @@ using StateDict = std::map<std::string, HostTensor>;
 // top-level dict when there is no such key).  On failure returns false and sets `err`.
 bool read_checkpoint(const std::string& path, StateDict& out, std::string& err);
 
+// InferenceWrapper.trace writes *_params.pt with the first component of every key stripped
+// (python/src/inferencewrapper.py:89-91: 'encoder.conv1.weight' -> 'conv1.weight', 'detector.layer.0...' ->
+// 'layer.0...').  The stripped names are still unambiguous; this puts the module prefixes back when the dict has none.
+void restore_module_prefixes(StateDict& sd);
+
 }  // namespace spb200

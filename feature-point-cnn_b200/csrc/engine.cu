@@ -165,6 +165,7 @@ void Engine::load_checkpoint(const std::string& path) {
     std::string err;
     StateDict sd;
     if (!read_checkpoint(path, sd, err)) throw std::runtime_error("failed to load checkpoint " + path + ": " + err);
+    restore_module_prefixes(sd);                       // *_params.pt of InferenceWrapper.trace
     sd_ = std::move(sd);
     finalized_ = false;
 }

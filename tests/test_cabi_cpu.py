@@ -95,6 +95,26 @@ def test_checkpoint_reader_variants(lib, tmp_path):
     assert lib.spb200_checkpoint_num_tensors(q.encode()) < 0     # documented: legacy (non-zip) format unsupported
 
 
+def test_params_file_of_inferencewrapper_trace(lib, tmp_path):
+    """InferenceWrapper.trace (python/src/inferencewrapper.py:83-91) saves '<name>_params.pt' with the first component of
+    every key stripped; the loader puts the module prefixes back (the weights half of it)."""
+    sd = torch.load(os.path.join(GOLDEN, 'super_point.pt'), map_location='cpu', weights_only=False)['model_state_dict']
+    stripped = {('.'.join(k.split('.')[1:])): v for k, v in sd.items()}           # the reference's own expression
+    assert len(stripped) == len(sd)                                                # still unambiguous
+    p = str(tmp_path / 'super_point_params.pt')
+    torch.save(stripped, p, _use_new_zipfile_serialization=True)
+    assert lib.spb200_checkpoint_num_tensors(p.encode()) == 163
+    shape = (ctypes.c_int64 * 8)()
+    rank = ctypes.c_int()
+    for key in ('encoder.conv1.weight', 'encoder.bn1.running_var', 'detector.layer.1.bn2.bias', 'descriptor.up_sample.bias',
+                'descriptor.bn.weight', 'descriptor.layer_out.0.identity_downsample.0.weight'):
+        t = sd[key]
+        buf = np.empty(t.numel(), np.float32)
+        assert lib.spb200_checkpoint_tensor(p.encode(), key.encode(), ctypes.c_void_p(buf.ctypes.data), buf.size, shape,
+                                            ctypes.byref(rank)) == 0, key
+        np.testing.assert_array_equal(buf, t.to(torch.float32).reshape(-1).numpy(), err_msg=key)
+
+
 def test_dropin_module_has_reference_state_dict_keys():
     import spb200
     from oracle import weights

@@ -203,3 +203,24 @@ def test_cpp_facade_demo_runs_float_and_8bit_frames():
     print(r.stdout, r.stderr)
     assert r.returncode == 0
     assert 'descriptor dim 128' in r.stdout and 'identical to the float frame' in r.stdout
+
+
+def test_engine_loads_params_file_of_the_reference_export(tmp_path):
+    """N4 (weights half): the '<name>_params.pt' InferenceWrapper.trace writes (python/src/inferencewrapper.py:89-91,
+    keys without their module prefix) gives the same network as the full checkpoint."""
+    from _gpu_common import CKPT, load_spb
+    spb = load_spb()
+    sd = torch.load(CKPT, map_location='cpu', weights_only=False)['model_state_dict']
+    p = str(tmp_path / 'super_point_params.pt')
+    torch.save({('.'.join(k.split('.')[1:])): v for k, v in sd.items()}, p, _use_new_zipfile_serialization=True)
+    img = golden_image('shapes240_0')[None, None].cuda()
+    outs = []
+    for path in (CKPT, p):
+        e = spb.Engine(0)
+        e.load_checkpoint(path)
+        e.finalize('fp16')
+        e.set_params()
+        outs.append([t.clone() for t in e.forward(img)])
+        e.close()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
