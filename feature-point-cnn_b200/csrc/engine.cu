@@ -125,24 +125,41 @@ Engine::~Engine() {
     cudaFree(d_ha_img_); cudaFree(d_ha_prob_); cudaFree(d_ha_coeffs_); cudaFree(d_ha_maps_);
 }
 
-void Engine::release_workspace() {
-    for (auto& op : ops_) {
-        if (op.plan) { tc_plan_destroy(op.plan); op.plan = nullptr; }
-        if (op.fused) { tc_block_plan_destroy(op.fused); op.fused = nullptr; }
-        if (op.halo) { tc_halo_plan_destroy(op.halo); op.halo = nullptr; }
+void Engine::destroy_plan_cache() {
+    for (auto& kv : plan_cache_)
+        for (auto& pl : kv.second) {
+            if (pl.plan) tc_plan_destroy(pl.plan);
+            if (pl.fused) tc_block_plan_destroy(pl.fused);
+            if (pl.halo) tc_halo_plan_destroy(pl.halo);
+        }
+    plan_cache_.clear();
+}
+
+// the current plans go (back) into the cache under the batch size they were built for
+void Engine::stash_plans() {
+    if (wsB_ <= 0 || precision_ == PREC_FP32) return;
+    std::vector<OpPlans>& v = plan_cache_[wsB_];
+    v.resize(ops_.size());
+    for (size_t i = 0; i < ops_.size(); ++i) {
+        v[i] = OpPlans{ops_[i].plan, ops_[i].fused, ops_[i].halo, ops_[i].fused_skip};
+        ops_[i].plan = nullptr; ops_[i].fused = nullptr; ops_[i].halo = nullptr;
     }
+}
+
+void Engine::release_workspace() {
+    stash_plans();
+    destroy_plan_cache();
     for (auto& p : buf_) { cudaFree(p); p = nullptr; }
     cudaFree(d_prob_); d_prob_ = nullptr;
     cudaFree(d_planes_); d_planes_ = nullptr;
     cudaFree(d_imgf_); d_imgf_ = nullptr;
-    wsB_ = wsH_ = wsW_ = 0;
+    wsB_ = wsH_ = wsW_ = capB_ = 0;
 }
 
 void Engine::release_weights() {
+    stash_plans();
+    destroy_plan_cache();
     for (auto& op : ops_) {
-        if (op.plan) tc_plan_destroy(op.plan);
-        if (op.fused) tc_block_plan_destroy(op.fused);
-        if (op.halo) tc_halo_plan_destroy(op.halo);
         cudaFree(op.d_bias); cudaFree(op.d_w32); cudaFree(op.d_w16);
     }
     ops_.clear();
@@ -448,20 +465,42 @@ void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
         throw std::invalid_argument("image height and width must be positive multiples of 16");
     if (C != 1 && C != 3) throw std::invalid_argument("images must have 1 or 3 channels");
     if (B == wsB_ && H == wsH_ && W == wsW_) return;
+    if (B <= capB_ && H == wsH_ && W == wsW_) {
+        // the buffers are large enough: only the plans change (from the cache when this batch size was seen before)
+        stash_plans();
+        wsB_ = B;
+        auto it = plan_cache_.find(B);
+        if (it != plan_cache_.end()) {
+            for (size_t i = 0; i < ops_.size(); ++i) {
+                ops_[i].plan = it->second[i].plan; ops_[i].fused = it->second[i].fused; ops_[i].halo = it->second[i].halo;
+                ops_[i].fused_skip = it->second[i].fused_skip;
+            }
+            plan_cache_.erase(it);
+        } else {
+            build_plans();
+        }
+        return;
+    }
     SPB_CUDA(cudaStreamSynchronize(st));
     SPB_CUDA(cudaDeviceSynchronize());
+    const int cap = (H == wsH_ && W == wsW_) ? std::max(B, capB_) : B;
     release_workspace();
     const size_t esz = precision_ == PREC_FP32 ? 4 : 2;
     for (int i = 0; i < BUF_COUNT; ++i) {
         const BufSpec& bs = bufspec_[i];
-        const size_t n = (size_t)B * (H / bs.div) * (W / bs.div) * bs.C;
+        const size_t n = (size_t)cap * (H / bs.div) * (W / bs.div) * bs.C;
         const size_t bytes = n * (bs.fp32 ? 4 : esz);
         SPB_CUDA(cudaMalloc(&buf_[i], bytes));
         SPB_CUDA(cudaMemset(buf_[i], 0, bytes));     // padded channels stay zero forever
     }
-    d_prob_ = dev_alloc<float>((size_t)B * H * W);
-    if (precision_ != PREC_FP32) SPB_CUDA(cudaMalloc(&d_planes_, (size_t)B * H * W * 2));
-    wsB_ = B; wsH_ = H; wsW_ = W;
+    d_prob_ = dev_alloc<float>((size_t)cap * H * W);
+    if (precision_ != PREC_FP32) SPB_CUDA(cudaMalloc(&d_planes_, (size_t)cap * H * W * 2));
+    wsB_ = B; wsH_ = H; wsW_ = W; capB_ = cap;
+    build_plans();
+}
+
+// tensor-core plans of every op for the batch size wsB_ (tile counts, tensor maps over the workspace buffers)
+void Engine::build_plans() {
     if (precision_ != PREC_FP32) {
         for (size_t i = 0; i < ops_.size(); ++i) {
             OpSpec& op = ops_[i];
@@ -612,7 +651,7 @@ void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
     if (img_u8 && !(precision_ != PREC_FP32 && use_planes_)) {
         // paths without the plane-fed stem take fp32 images: frame / 255 as the reference's loaders do
         // (python/src/inference.py:78-80, cpp/src/camera.cc:16-18)
-        if (!d_imgf_) SPB_CUDA(cudaMalloc((void**)&d_imgf_, sizeof(float) * (size_t)B * H * W));
+        if (!d_imgf_) SPB_CUDA(cudaMalloc((void**)&d_imgf_, sizeof(float) * (size_t)capB_ * H * W));
         launch_u8_to_f32(static_cast<const uint8_t*>(img_any), d_imgf_, (long)B * H * W, st);
         ++launches_;
         img = d_imgf_;
@@ -936,11 +975,27 @@ void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int
             for (int c = want; c >= std::max(1, want / 4); --c)
                 if (B % c == 0 && B / c <= HostStage::kMaxChunks) { Bc = c; break; }
     }
-    const int nc = B / Bc;
+    // chunk sizes: uniform.  SPB200_HOST_SPLIT=1 cuts the first and the last chunk in two (the download, the longest of
+    // the three stages, then starts after half a chunk of upload + compute, and the last download, which nothing
+    // overlaps, is half as long; the workspace keeps its plans per batch size, so alternating sizes costs nothing) -
+    // measured 3 % slower at batch 64: eight images use the GPU too poorly, so it is off by default.
+    std::vector<int> csize, cstart;
+    {
+        const int n_uniform = B / Bc;
+        const bool split = n_uniform >= 3 && Bc % 2 == 0 && Bc >= 8 && n_uniform + 2 <= HostStage::kMaxChunks &&
+                           std::getenv("SPB200_HOST_SPLIT") != nullptr;
+        for (int k = 0; k < n_uniform; ++k) {
+            if (split && (k == 0 || k == n_uniform - 1)) { csize.push_back(Bc / 2); csize.push_back(Bc / 2); }
+            else csize.push_back(Bc);
+        }
+        int acc = 0;
+        for (int c : csize) { cstart.push_back(acc); acc += c; }
+    }
+    const int nc = (int)csize.size();
+    const size_t img_elem_bytes = esz * (size_t)C * H * W;
     const bool pin_in = is_pinned_host(img);
     const bool pin_out = is_pinned_host(xy) && is_pinned_host(conf) && is_pinned_host(desc);
-    const size_t chunk_bytes = esz * (size_t)Bc * C * H * W;
-    const size_t img_bytes = chunk_bytes * nc;
+    const size_t img_bytes = img_elem_bytes * B;
 
     if (img_bytes > s.d_img_bytes || B > s.d_B || cap > s.d_cap) {
         SPB_CUDA(cudaDeviceSynchronize());
@@ -967,19 +1022,21 @@ void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int
     // 1. everything the GPU has to do is enqueued up front: chunk k's upload on the copy stream, its network +
     //    post-processing on the compute stream behind the upload's event, its counts copied to the pinned mirror
     for (int k = 0; k < nc; ++k) {
-        const uint8_t* src = img + (size_t)k * chunk_bytes;
-        uint8_t* d_in = reinterpret_cast<uint8_t*>(s.d_img) + (size_t)k * chunk_bytes;
+        const int Bk = csize[k];
+        const size_t coff = (size_t)cstart[k] * img_elem_bytes, chunk_bytes = (size_t)Bk * img_elem_bytes;
+        const uint8_t* src = img + coff;
+        uint8_t* d_in = reinterpret_cast<uint8_t*>(s.d_img) + coff;
         if (!pin_in) {
-            std::memcpy(reinterpret_cast<uint8_t*>(s.h_img) + (size_t)k * chunk_bytes, src, chunk_bytes);
-            src = reinterpret_cast<uint8_t*>(s.h_img) + (size_t)k * chunk_bytes;
+            std::memcpy(reinterpret_cast<uint8_t*>(s.h_img) + coff, src, chunk_bytes);
+            src = reinterpret_cast<uint8_t*>(s.h_img) + coff;
         }
         SPB_CUDA(cudaMemcpyAsync(d_in, src, chunk_bytes, cudaMemcpyHostToDevice, s.s_in));
         SPB_CUDA(cudaEventRecord(s.ev_in[k], s.s_in));
         SPB_CUDA(cudaStreamWaitEvent(s.s_comp, s.ev_in[k], 0));
-        const size_t o = (size_t)k * Bc;
-        detect_any(d_in, img_u8, Bc, C, H, W, dcap, s.d_count + o, s.d_xy + o * dcap * 2, s.d_conf + o * dcap,
+        const size_t o = (size_t)cstart[k];
+        detect_any(d_in, img_u8, Bk, C, H, W, dcap, s.d_count + o, s.d_xy + o * dcap * 2, s.d_conf + o * dcap,
                desc ? s.d_desc + o * dcap * 128 : nullptr, nullptr, s.s_comp);
-        SPB_CUDA(cudaMemcpyAsync(s.h_count + o, s.d_count + o, sizeof(int) * Bc, cudaMemcpyDeviceToHost, s.s_comp));
+        SPB_CUDA(cudaMemcpyAsync(s.h_count + o, s.d_count + o, sizeof(int) * Bk, cudaMemcpyDeviceToHost, s.s_comp));
         SPB_CUDA(cudaEventRecord(s.ev_comp[k], s.s_comp));
     }
     // 2. as each chunk's counts arrive, its keypoints and descriptors (count[b] rows per image, nothing else) are
@@ -989,9 +1046,11 @@ void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int
     if (!pin_out) stage_off.assign((size_t)B, 0);
     for (int k = 0; k < nc; ++k) {
         SPB_CUDA(cudaEventSynchronize(s.ev_comp[k]));
+        const int Bk = csize[k];
+        const size_t g0 = (size_t)cstart[k];
         size_t total = 0;
-        for (int b = 0; b < Bc; ++b) {
-            const size_t g = (size_t)k * Bc + b;
+        for (int b = 0; b < Bk; ++b) {
+            const size_t g = g0 + b;
             count[g] = std::min(std::max(s.h_count[g], 0), cap);
             total += (size_t)count[g];
         }
@@ -1017,21 +1076,20 @@ void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int
             // pinned caller arrays: one strided copy per array and chunk (rows = images, width = the largest count of the
             // chunk) instead of three small copies per image; rows past an image's count receive don't-care values
             size_t nmax = 0;
-            for (int b = 0; b < Bc; ++b) nmax = std::max(nmax, (size_t)count[(size_t)k * Bc + b]);
-            const size_t g0 = (size_t)k * Bc;
+            for (int b = 0; b < Bk; ++b) nmax = std::max(nmax, (size_t)count[g0 + b]);
             if (nmax) {
                 SPB_CUDA(cudaMemcpy2DAsync(xy + g0 * cap * 2, sizeof(int) * 2 * cap, s.d_xy + g0 * dcap * 2, sizeof(int) * 2 * dcap,
-                                           sizeof(int) * 2 * nmax, Bc, cudaMemcpyDeviceToHost, s.s_out));
+                                           sizeof(int) * 2 * nmax, Bk, cudaMemcpyDeviceToHost, s.s_out));
                 SPB_CUDA(cudaMemcpy2DAsync(conf + g0 * cap, sizeof(float) * cap, s.d_conf + g0 * dcap, sizeof(float) * dcap,
-                                           sizeof(float) * nmax, Bc, cudaMemcpyDeviceToHost, s.s_out));
+                                           sizeof(float) * nmax, Bk, cudaMemcpyDeviceToHost, s.s_out));
                 if (desc)
                     SPB_CUDA(cudaMemcpy2DAsync(desc + g0 * cap * 128, sizeof(float) * 128 * cap, s.d_desc + g0 * dcap * 128,
-                                               sizeof(float) * 128 * dcap, sizeof(float) * 128 * nmax, Bc, cudaMemcpyDeviceToHost, s.s_out));
+                                               sizeof(float) * 128 * dcap, sizeof(float) * 128 * nmax, Bk, cudaMemcpyDeviceToHost, s.s_out));
             }
             continue;
         }
-        for (int b = 0; b < Bc; ++b) {
-            const size_t g = (size_t)k * Bc + b, n = (size_t)count[g];
+        for (int b = 0; b < Bk; ++b) {
+            const size_t g = g0 + b, n = (size_t)count[g];
             if (!pin_out) stage_off[g] = staged;
             if (n) {
                 int* dxy = pin_out ? xy + g * cap * 2 : s.h_xy + staged * 2;

@@ -5,6 +5,7 @@
 // kernel launches on the caller's stream.  Not thread-safe per instance; instances are independent.
 #pragma once
 #include <array>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -167,8 +168,14 @@ private:
     void* d_planes_ = nullptr;    // [B][2][H/2][W] 16-bit image x255, per workspace shape
     float* d_imgf_ = nullptr;     // 8-bit frames / 255 for the paths without the plane-fed stem
 
-    // workspace
-    int wsB_ = 0, wsH_ = 0, wsW_ = 0;
+    // workspace: buffers sized for capB_ images of wsH_ x wsW_; the tensor-core plans (tile counts, tensor maps) depend on
+    // the batch actually run, wsB_ <= capB_, and are kept per batch size so that alternating sizes costs nothing
+    int wsB_ = 0, wsH_ = 0, wsW_ = 0, capB_ = 0;
+    struct OpPlans { TcConvPlan* plan = nullptr; TcBlockPlan* fused = nullptr; TcHaloPlan* halo = nullptr; bool fused_skip = false; };
+    std::map<int, std::vector<OpPlans>> plan_cache_;
+    void build_plans();
+    void stash_plans();
+    void destroy_plan_cache();
     std::array<void*, BUF_COUNT> buf_{};
     float* d_prob_ = nullptr;
     // nms workspace

@@ -221,6 +221,36 @@ def test_detect_host_chunked_pipeline(engines, pinned, chunk, monkeypatch):
             np.testing.assert_array_equal(hdsc[i, :n], dsc[i, :n].cpu().numpy())
 
 
+def test_detect_host_split_end_chunks_and_batch_switching(engines, monkeypatch):
+    """24 images in chunks of 8 run as 4 + 4 + 8 + 4 + 4 (SPB200_HOST_SPLIT cuts the end chunks in two): the workspace switches between two
+    batch sizes inside one call and the result is that of the device path; then other batch sizes on the same engine."""
+    monkeypatch.setenv('SPB200_HOST_CHUNK', '8')
+    monkeypatch.setenv('SPB200_HOST_SPLIT', '1')
+    e = engines['fp16']
+    names = ['shapes240_0', 'rand240_1', 'shapes240_1', 'shapes240_2', 'rand240_0', 'shapes240_0']
+    imgs = torch.stack([golden_image(n) for n in names * 4])[:, None].contiguous()
+    cap = e.max_keypoints(240, 320)
+    count, xy, conf, dsc, _ = [t.clone() if t is not None else None for t in e.detect(imgs.cuda(), cap)]
+    host_in = imgs.pin_memory().numpy()
+    out = (np.zeros((24,), np.int32), torch.zeros((24, cap, 2), dtype=torch.int32).pin_memory().numpy(),
+           torch.zeros((24, cap), dtype=torch.float32).pin_memory().numpy(),
+           torch.zeros((24, cap, 128), dtype=torch.float32).pin_memory().numpy())
+    for _ in range(2):
+        hc, hxy, hconf, hdsc = e.detect_host(host_in, cap, out=out)
+        np.testing.assert_array_equal(hc, count.cpu().numpy())
+        for i in range(24):
+            n = int(hc[i])
+            np.testing.assert_array_equal(hxy[i, :n], xy[i, :n].cpu().numpy())
+            np.testing.assert_array_equal(hconf[i, :n], conf[i, :n].cpu().numpy())
+            np.testing.assert_array_equal(hdsc[i, :n], dsc[i, :n].cpu().numpy())
+    for b in (3, 24, 1, 8, 3):                                   # plans come back from the per-batch cache
+        c2, xy2, conf2, d2, _ = e.detect(imgs[:b].cuda(), cap)
+        assert torch.equal(c2, count[:b])
+        for i in range(b):
+            n = int(c2[i])
+            assert torch.equal(xy2[i, :n], xy[i, :n]) and torch.equal(d2[i, :n], dsc[i, :n])
+
+
 def test_other_checkpoints_harsh_and_magicpoint(tmp_path):
     """Synthetic 'harsh' preset + a magic_point.pt written in the reference's checkpoint format."""
     spb = load_spb()
