@@ -827,9 +827,14 @@ void Engine::homography_adaptation(const float* img, int B, int C, int H, int W,
     if (!img || !homographies || !prob_out) throw std::invalid_argument("homography_adaptation: null argument");
     if (num < 0 || num > 4096) throw std::invalid_argument("homography_adaptation: num must be in [0, 4096]");
     if (aggregation != 0 && aggregation != 1) throw std::invalid_argument("homography_adaptation: aggregation must be 0 (mean) or 1 (max)");
-    ensure_workspace(B, C, H, W, st);
+    // views (the image and its num warps) go through the network in groups of G: one batch of G * B images per forward
+    // uses the GPU far better than G forwards of B (the workspace grows to G * B once; smaller batches on the same
+    // engine keep using it, the plans are cached per batch size)
+    const int views = num + 1;
+    int G = std::max(1, std::min(views, 256 / std::max(B, 1)));
+    if (const char* e = std::getenv("SPB200_HA_GROUP")) G = std::max(1, std::min(views, std::atoi(e)));
     const size_t plane = (size_t)H * W;
-    const size_t img_elems = (size_t)B * C * plane, prob_elems = (size_t)(num + 1) * B * plane, map_bytes = (size_t)4 * num * plane;
+    const size_t img_elems = (size_t)G * B * C * plane, prob_elems = (size_t)(num + 1) * B * plane, map_bytes = (size_t)4 * num * plane;
     if (img_elems > ha_img_elems_ || prob_elems > ha_prob_elems_ || map_bytes > ha_map_bytes_ || num > ha_num_) {
         SPB_CUDA(cudaDeviceSynchronize());
         cudaFree(d_ha_img_); cudaFree(d_ha_prob_); cudaFree(d_ha_coeffs_); cudaFree(d_ha_maps_);
@@ -868,16 +873,20 @@ void Engine::homography_adaptation(const float* img, int B, int C, int H, int W,
     params_.descriptor_enabled = 0;
     const int Hc = H / 8, Wc = W / 8;
     try {
-        for (int k = -1; k < num; ++k) {
+        for (int v0 = 0; v0 < views; v0 += G) {                    // view 0 = the image itself, view k + 1 = homography k
+            const int g = std::min(G, views - v0);
             const float* src = img;
-            if (k >= 0) {
-                launch_ha_warp(img, d_ha_coeffs_ + (size_t)k * 8, B, C, H, W, d_ha_img_, st);
-                ++launches_;
+            if (!(g == 1 && v0 == 0)) {
+                for (int v = v0; v < v0 + g; ++v) {
+                    float* slot = d_ha_img_ + (size_t)(v - v0) * B * C * plane;
+                    if (v == 0) SPB_CUDA(cudaMemcpyAsync(slot, img, sizeof(float) * (size_t)B * C * plane, cudaMemcpyDeviceToDevice, st));
+                    else { launch_ha_warp(img, d_ha_coeffs_ + (size_t)(v - 1) * 8, B, C, H, W, slot, st); ++launches_; }
+                }
                 src = d_ha_img_;
             }
-            run_network(src, false, B, C, H, W, st);
-            launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc,
-                           d_ha_prob_ + (size_t)(k + 1) * B * plane, st);
+            run_network(src, false, g * B, C, H, W, st);
+            launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, g * B, Hc, Wc,
+                           d_ha_prob_ + (size_t)v0 * B * plane, st);
             ++launches_;
         }
     } catch (...) {
