@@ -30,7 +30,7 @@
 namespace spb200 {
 
 constexpr int kN0TW = 64, kN0TH = 64;        // interior tile of round 0 (two mask words per row)
-constexpr int kN0Threads = 256;
+constexpr int kN0Threads = 512;
 constexpr int kNmsMaxR = 8;
 constexpr int kFinThreads = 1024;
 constexpr int kFinRegEntries = 8;            // undecided candidates a thread keeps in registers
