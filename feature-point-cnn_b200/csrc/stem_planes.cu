@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
     constexpr uint32_t kIdesc = (1u << 4) | (OperandFmt<T>::value << 7) | (OperandFmt<T>::value << 10) |
                                 ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ uint8_t dyn_smem[];
-    __shared__ __align__(8) uint64_t bar_w, bar_rfull[2], bar_rempty[2], bar_cfull[2], bar_cempty[2], bar_afull[2], bar_aempty[2];
+    __shared__ __align__(8) uint64_t bar_w, bar_rfull[2], bar_rempty[2], bar_cfull[2], bar_cempty[2], bar_afull[8], bar_aempty[8];
     __shared__ uint32_t tmem_slot;
 
     uint8_t* base = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
@@ -112,8 +112,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
             mbar_init(&bar_rempty[i], kSpShiftWarps);
             mbar_init(&bar_cfull[i], kSpShiftWarps);
             mbar_init(&bar_cempty[i], 1);
-            mbar_init(&bar_afull[i], 1);
-            mbar_init(&bar_aempty[i], 8);
+            for (int k = 0; k < 4; ++k) { mbar_init(&bar_afull[4 * i + k], 1); mbar_init(&bar_aempty[4 * i + k], 8); }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -162,23 +161,26 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
                     load_tile(ahead, stage);
                 }
                 mbar_wait(&bar_cfull[stage], par);
+                // accumulators are handed over per (M-tile, phase): the MMAs of the next tile start as soon as the epilogue
+                // has read one phase of this one, so the tensor core's shared-memory traffic spreads over the whole tile
+                // instead of piling up behind the vertical pooling pass
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    if (it >= 1) mbar_wait(&bar_aempty[t], (it - 1) & 1);
-                    tc_fence_after();
+                for (int t = 0; t < 2; ++t)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int s = 0; s < 4; ++s) {
+                        if (it >= 1) mbar_wait(&bar_aempty[t * 4 + s], (it - 1) & 1);
+                        tc_fence_after();
 #pragma unroll
-                        for (int part = 0; part < 2; ++part)
+                        for (int j = 0; j < 4; ++j)
 #pragma unroll
-                            for (int s = 0; s < 4; ++s) {
+                            for (int part = 0; part < 2; ++part) {
                                 const uint32_t a_addr = cp_addr + stage * kSpStage + s * 2 * kSpCopy + (16 * t + j) * 128;
                                 const uint32_t a = ((a_addr >> 4) & 0x3fffu) | kLboA;
                                 const uint32_t w = w_lo + (uint32_t)((part * 8192 + j * 32) >> 4);
                                 umma_f16_w(tmem + t * 256 + s * 64, a, kHiA, w, kHiW, kIdesc, (j > 0 || part > 0) ? 1u : 0u);
                             }
-                    umma_commit(&bar_afull[t]);
-                }
+                        umma_commit(&bar_afull[t * 4 + s]);
+                    }
                 umma_commit(&bar_cempty[stage]);
             }
         }
@@ -241,16 +243,19 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
             for (int t = 0; t < 2; ++t) {
                 const int c = 16 * t + crow, cy = cy0 + c;
                 const bool rowok = cy >= 0 && cy < CH;
-                mbar_wait(&bar_afull[t], it & 1);
-                tc_fence_after();
                 uint32_t E[16], Q[16];
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     uint32_t r[32];
+                    mbar_wait(&bar_afull[t * 4 + s], it & 1);
+                    tc_fence_after();
                     tmem_ld_32x32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + s * 64 + h * 32), r);
                     const int cx = cx0 + 4 * mp + s;
                     const uint32_t m = (rowok && cx >= 0 && cx < CW) ? 0xffffffffu : 0u;   // outside the conv output: 0 (neutral under ReLU)
                     tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_aempty[t * 4 + s]);
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const uint32_t v = pack2<T>(fmaf(__uint_as_float(r[2 * e]), 1.f / 255.f, bias[2 * e]),
@@ -261,9 +266,6 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
                         else Q[e] = max2<T>(Q[e], v);
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_aempty[t]);
                 if (c < 31) {
                     uint8_t* xe = s_x + (c * 16 + 2 * mp) * 128;
 #pragma unroll
