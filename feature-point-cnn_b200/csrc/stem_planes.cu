@@ -277,22 +277,30 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            // vertical half of the pooling: pooled row k of the tile = conv rows 2k, 2k+1, 2k+2 of the tile; max with 0 = ReLU
-            for (int i = tid; i < kSpP * kSpP * 8; i += 256) {
-                const int chunk = i & 7, pix = i >> 3;
-                const int k = pix / kSpP, l = pix - k * kSpP;
-                const int py = p0 + k, px = q0 + l;
-                if (py >= PH || px >= PW) continue;
-                const uint8_t* src = s_x + ((2 * k) * 16 + l) * 128 + ((chunk ^ (l >> 1)) << 4);
-                const uint4 a = *reinterpret_cast<const uint4*>(src);
-                const uint4 bq = *reinterpret_cast<const uint4*>(src + 2048);
-                const uint4 cq = *reinterpret_cast<const uint4*>(src + 4096);
-                uint4 m;
-                m.x = max2<T>(max2<T>(max2<T>(0u, a.x), bq.x), cq.x);
-                m.y = max2<T>(max2<T>(max2<T>(0u, a.y), bq.y), cq.y);
-                m.z = max2<T>(max2<T>(max2<T>(0u, a.z), bq.z), cq.z);
-                m.w = max2<T>(max2<T>(max2<T>(0u, a.w), bq.w), cq.w);
-                *reinterpret_cast<uint4*>(out + ((size_t)(b * PH + py) * PW + px) * 64 + chunk * 8) = m;
+            // vertical half of the pooling: pooled row k of the tile = conv rows 2k, 2k+1, 2k+2 of the tile; max with 0 = ReLU.
+            // A thread owns one (pooled column, 8-channel chunk) and walks down half of the pooled rows with a running
+            // row: two shared loads per output instead of three and no per-item index arithmetic (this pass shares the
+            // shared-memory pipe with the next tile's MMA operand fetch, every load less shortens it).
+            if (tid < 2 * kSpP * 8) {
+                const int chunk = tid & 7, l = (tid >> 3) % kSpP, g = tid / (kSpP * 8);       // g = 0: pooled rows 0..7, 1: 8..14
+                const int k0 = g * 8, k1 = g == 0 ? 8 : kSpP;
+                const int px = q0 + l;
+                const uint8_t* src = s_x + ((2 * k0) * 16 + l) * 128 + ((chunk ^ (l >> 1)) << 4);
+                T* dst = out + ((size_t)(b * PH + p0 + k0) * PW + px) * 64 + chunk * 8;
+                uint4 ev = *reinterpret_cast<const uint4*>(src);                               // conv row 2k
+                for (int k = k0; k < k1; ++k) {
+                    const uint4 od = *reinterpret_cast<const uint4*>(src + 2048);              // conv row 2k + 1
+                    const uint4 nx = *reinterpret_cast<const uint4*>(src + 4096);              // conv row 2k + 2
+                    uint4 m;
+                    m.x = max2<T>(max2<T>(max2<T>(0u, ev.x), od.x), nx.x);
+                    m.y = max2<T>(max2<T>(max2<T>(0u, ev.y), od.y), nx.y);
+                    m.z = max2<T>(max2<T>(max2<T>(0u, ev.z), od.z), nx.z);
+                    m.w = max2<T>(max2<T>(max2<T>(0u, ev.w), od.w), nx.w);
+                    if (p0 + k < PH && px < PW) *reinterpret_cast<uint4*>(dst) = m;
+                    ev = nx;
+                    src += 4096;
+                    dst += (size_t)PW * 64;
+                }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
