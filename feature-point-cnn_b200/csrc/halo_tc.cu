@@ -43,7 +43,9 @@ constexpr int kHaloBufBytes = 23552;                        // rounded up to a m
 constexpr int kHaloSbo = kHaloG * 128;                      // 8-pixel groups are one haloed row apart
 constexpr int kMaxSteps = 48;
 constexpr int kMaxChunks = 8;
-__host__ __device__ constexpr int halo_threads(int T) { return (2 + T + 8) * 32; }   // 2 producers, T MMA issuers, 8 epilogue warps
+__host__ __device__ constexpr int halo_threads(int T) { return (2 + T + 8) * 32; }
+__host__ __device__ constexpr int halo_out_slots(int N, bool fused) { return fused ? (N == 128 ? 2 : 1) : 0; }
+constexpr int kHaloOutBox = 16384;                          // one staged output box: 128 pixel rows x 128 B   // 2 producers, T MMA issuers, 8 epilogue warps
 
 // One weight slab [N x 64 K] and the MMAs that consume it, packed into 64 bits so that the issuing warps fetch a
 // step with one constant load and a few bit-field extracts (their instruction count is the bottleneck):
@@ -65,6 +67,7 @@ __host__ __device__ constexpr HaloStep halo_step(unsigned a_lo, unsigned w_lo, u
 struct HaloParams {
     CUtensorMap tmA[kMaxSegs];
     CUtensorMap tmW1, tmW2;
+    CUtensorMap tmD;               // destination, for the TMA stores of the fused variants (box = 32 pixels x 128 B)
     HaloStep steps[kMaxSteps + 1];   // one spare entry: the issuing loop prefetches step e + 1
     int nsteps, n1steps;           // all slabs; slabs of GEMM 1 + shortcut (they come first)
     int chunk_seg[kMaxChunks], chunk_c0[kMaxChunks], nchunks;
@@ -79,6 +82,8 @@ struct HaloParams {
     void* dst;
     int res_C, dst_H, dst_W, dst_C, dst_stride, dst_off_y, dst_off_x;
     int relu, dst_fp32, n_mma;
+    int tma_store;                 // fused variants: the output leaves through shared memory and TMA stores
+    long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
 };
 
 template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, typename Tp>
@@ -100,6 +105,10 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     // 32-bit addresses) instead of falling back to generic loads
     uint8_t* a_ring = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
     uint8_t* w_ring = a_ring + SA * T * kHaloBufBytes;
+    // output staging of the fused variants: per tile kOutSlots boxes of 128 pixel rows x 128 B (16 KB), each epilogue warp
+    // owns the 4 KB of its 32 rows in every box
+    constexpr int kOutSlots = halo_out_slots(N, FUSED);
+    uint8_t* out_stage = w_ring + SW * kWBytes;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the role loops below run on the
     // uniform datapath (loop counters, ring state, descriptors in uniform registers) instead of R2UR round trips
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
@@ -123,6 +132,9 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         if (FUSED) prefetch_tmap(&p.tmW2);
     }
     if (warp == 2) tmem_alloc(&tmem_slot, kTmemCols);
+    for (int i = threadIdx.x; i < T * kOutSlots * kHaloOutBox / 16; i += halo_threads(T))
+        reinterpret_cast<uint4*>(out_stage)[i] = make_uint4(0u, 0u, 0u, 0u);      // channels beyond n_mma leave as zeros
+    if (kOutSlots > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int i = threadIdx.x; i < N; i += halo_threads(T)) {
         s_bias1[i] = p.bias1[i];
         s_bias2[i] = FUSED ? p.bias2[i] : 0.f;
@@ -199,6 +211,8 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);                // SBO = 1024 (dense tile)
         constexpr int LAG = (FUSED && NBUF == 2) ? 1 : 0;
         for (int j = 0; j < n_local + LAG; ++j) {
+            const bool dbg_on = p.dbg && blockIdx.x == 0 && mt == 0 && lane == 0 && j < 16;
+            if (dbg_on) p.dbg[j * 8 + 0] = clock64();
             if (j < n_local) {
                 const int b = j % NBUF;
                 const uint32_t ph = (uint32_t)(j / NBUF) & 1u;
@@ -258,6 +272,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     if (hi & (1u << 10)) { if (++sa == SA) { sa = 0; pha ^= 1u; } }
                 }
                 if (!(WRES && j > 0) && elect_one()) umma_commit(&d1_full[b]);
+                if (dbg_on) p.dbg[j * 8 + 1] = clock64();
             }
             if (FUSED && j >= LAG) {
                 const int jj = j - LAG;
@@ -266,6 +281,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 mbar_wait(&y_full[b], ph);                 // Y written by the epilogue warps
                 if (!p.has_ds) mbar_wait(&d2_empty[b], ph ^ 1u);
                 tc_fence_after();
+                if (dbg_on) p.dbg[j * 8 + 2] = clock64();
                 for (int e = p.n1steps; e < p.nsteps; ++e) {
                     const HaloStep s = p.steps[e];
                     const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
@@ -286,6 +302,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     if (!WRES) wph ^= 1u << slot;
                 }
                 if (elect_one()) umma_commit(&d2_full[b]);
+                if (dbg_on) p.dbg[j * 8 + 3] = clock64();
             }
         }
         __syncwarp();
@@ -325,6 +342,8 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             const uint32_t tmem_d1 = tmem_base + (uint32_t)((b * T + t) * N) + lane_off;
             mbar_wait(&d1_full[b], ph);
             tc_fence_after();
+            const bool dbg_on = p.dbg && blockIdx.x == 0 && warp == 2 + T && lane == 0 && jt < 16;
+            if (dbg_on) p.dbg[jt * 8 + 4] = clock64();
 #pragma unroll 1
             for (int blk = blk_lo; blk < blk_hi; ++blk) {
                 const int c0 = blk * 32;
@@ -347,6 +366,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&y_full[b]);
+            if (dbg_on) p.dbg[jt * 8 + 5] = clock64();
         };
         // the identity-shortcut operand of a tile, fetched long before it is needed (the call sites put a whole first
         // epilogue or the accumulator wait between this and its use)
@@ -372,8 +392,32 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             const bool has_res = p.residual != nullptr && px.valid;
             const uint32_t tmem_out = tmem_base + (uint32_t)((b * T + t) * N) + lane_off + (FUSED ? kAccCols : 0u);
             const float* sb = FUSED ? s_bias2 : s_bias1;
+            // TMA-store path (fused variants): a warp stages its 32 pixel rows (128 B per row and box, 128-byte swizzle: the
+            // eight lanes of a store phase hit eight different 16-byte columns) and one lane sends the 4 KB sub-box; the
+            // box is clipped at the image border by the TMA unit.  Direct 16-byte stores from the accumulator layout
+            // (one pixel row per lane) touch 32 lines per instruction and were measured to slow the MMAs' own
+            // shared-memory reads: 18.3 k -> 12.3 k cycles per tile pair with the stores removed.
+            const bool ts = kOutSlots > 0 && p.tma_store;
+            int tc_img = 0, tc_s = 0, tc_g = 0;
+            bool tile_ok = false;
+            uint32_t stg = 0;
+            if (ts) {
+                const int tile_raw = (blockIdx.x + jt * gridDim.x) * T + t;
+                tile_ok = tile_raw < p.total_tiles;
+                const int tile = min(tile_raw, p.total_tiles - 1);
+                const int tt = tile % p.tiles_per_img;
+                tc_img = tile / p.tiles_per_img;
+                tc_s = (tt / p.tiles_g) * 16 + q * 4;
+                tc_g = (tt % p.tiles_g) * 8;
+                stg = smem_u32(out_stage) + (uint32_t)(t * kOutSlots * kHaloOutBox + q * 4096);
+                if (lane == 0) tma_store_wait_read<0>();          // the previous tile's boxes have left shared memory
+                __syncwarp();
+            }
+            int nbox = 0;
             mbar_wait(FUSED ? &d2_full[b] : &d1_full[b], ph);
             tc_fence_after();
+            const bool dbg_on = p.dbg && blockIdx.x == 0 && warp == 2 + T && lane == 0 && jt < 16;
+            if (dbg_on) p.dbg[jt * 8 + 6] = clock64();
 #pragma unroll
             for (int blk = 0; blk < kResBlk; ++blk) {
                 if (blk < blk_lo || blk >= blk_hi) continue;
@@ -387,7 +431,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
                 }
                 tmem_ld_wait();
-                if (px.valid) {
+                if (px.valid || ts) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
                     if (has_res) {
@@ -406,7 +450,43 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (p.dst_fp32) {
+                    if (ts) {
+                        const uint32_t sw = (uint32_t)(lane & 7);
+                        if (p.dst_fp32) {
+                            // one box per block of 32 fp32 channels; the two slots alternate
+                            const uint32_t box = stg + (uint32_t)((nbox & 1) * kHaloOutBox);
+                            if (nbox >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj)
+                                st_shared_v4(box + (uint32_t)lane * 128u + (((uint32_t)jj ^ sw) << 4), __float_as_uint(v[jj * 4]),
+                                             __float_as_uint(v[jj * 4 + 1]), __float_as_uint(v[jj * 4 + 2]), __float_as_uint(v[jj * 4 + 3]));
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0 && tile_ok) { tma_store_4d(&p.tmD, box, c0, tc_g, tc_s, tc_img); tma_store_commit(); }
+                            ++nbox;
+                        } else {
+                            // 32 16-bit channels = half a box row; the box (64 channels) leaves after its second half
+                            const uint32_t box = stg + (uint32_t)((blk >> 1) * kHaloOutBox);
+                            const uint32_t half = (uint32_t)(blk & 1) * 4u;
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                uint32_t w0, w1, w2, w3;
+                                if (p.relu) {
+                                    w0 = pack2_relu<Tp>(v[jj * 8], v[jj * 8 + 1]); w1 = pack2_relu<Tp>(v[jj * 8 + 2], v[jj * 8 + 3]);
+                                    w2 = pack2_relu<Tp>(v[jj * 8 + 4], v[jj * 8 + 5]); w3 = pack2_relu<Tp>(v[jj * 8 + 6], v[jj * 8 + 7]);
+                                } else {
+                                    w0 = pack2<Tp>(v[jj * 8], v[jj * 8 + 1]); w1 = pack2<Tp>(v[jj * 8 + 2], v[jj * 8 + 3]);
+                                    w2 = pack2<Tp>(v[jj * 8 + 4], v[jj * 8 + 5]); w3 = pack2<Tp>(v[jj * 8 + 6], v[jj * 8 + 7]);
+                                }
+                                st_shared_v4(box + (uint32_t)lane * 128u + (((half + (uint32_t)jj) ^ sw) << 4), w0, w1, w2, w3);
+                            }
+                            if ((blk & 1) || blk == blk_hi - 1) {
+                                fence_async_smem();
+                                __syncwarp();
+                                if (lane == 0 && tile_ok) { tma_store_4d(&p.tmD, box, (blk >> 1) * 64, tc_g, tc_s, tc_img); tma_store_commit(); }
+                            }
+                        }
+                    } else if (p.dst_fp32) {
                         float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.dst) + px.dpix * p.dst_C + c0);
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) dp[jj] = make_float4(v[jj * 4], v[jj * 4 + 1], v[jj * 4 + 2], v[jj * 4 + 3]);
@@ -428,6 +508,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(FUSED ? &d2_empty[b] : &d1_empty[b]);
+            if (dbg_on) p.dbg[jt * 8 + 7] = clock64();
         };
         if (!FUSED) {
             for (int j = 0; j < n_local; ++j) { prefetch_res(j); epi_out(j); }
@@ -447,6 +528,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 epi_out(j);
             }
         }
+        if (kOutSlots > 0 && lane == 0) tma_store_wait_all();
     }
     __syncthreads();
     if (warp == 2) {
@@ -458,6 +540,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
 // ------------------------------------------------------------------------------------------------
 // Host
 // ------------------------------------------------------------------------------------------------
+static long long* g_halo_dbg = nullptr;
 struct TcHaloPlan {
     HaloParams params;
     int variant;       // 0: N=64 fused, resident weights; 1: N=128 fused, T=2; 2: N=128 single convolution, T=2
@@ -467,7 +550,7 @@ struct TcHaloPlan {
 template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, typename Tp>
 static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
     auto kern = halo_tc_kernel<N, T, NBUF, SA, SW, FUSED, WRES, Tp>;
-    const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + 1024;
+    const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + (size_t)T * halo_out_slots(N, FUSED) * kHaloOutBox + 1024;
     static bool configured = false;       // per instantiation
     if (!configured) {
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -478,7 +561,7 @@ static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
 }
 
 constexpr int kHaloResidentSlabs = 11;   // variant 0: every slab of a 64-channel block stays in shared memory
-constexpr int kHaloRing1 = 8;            // variant 1: weight ring slots (16 KB each)
+constexpr int kHaloRing1 = 4;            // variant 1: weight ring slots (16 KB each; 8 slots measured no faster)
 constexpr int kHaloRing2 = 6;            // variant 2
 
 template <typename Tp>
@@ -652,7 +735,44 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     p.res_C = last.res_C; p.dst_H = last.dst_H; p.dst_W = last.dst_W; p.dst_C = last.dst_C;
     p.dst_stride = last.dst_stride; p.dst_off_y = last.dst_off_y; p.dst_off_x = last.dst_off_x;
     p.relu = last.relu; p.dst_fp32 = last.dst_fp32;
+    // fused variants store through shared memory: destination tensor {C, group axis, slow axis, image}, one box = the 32
+    // pixel rows of an epilogue warp (8 along the group axis x 4 slow rows) x 128 B of channels
+    p.tma_store = 0;
+    if (c2 && last.dst_stride == 1 && last.dst_off_y == 0 && last.dst_off_x == 0 && last.dst_H == c1.OH && last.dst_W == c1.OW &&
+        last.dst_C % (last.dst_fp32 ? 32 : 64) == 0 && last.dst_C >= (last.dst_fp32 ? p.n_mma : (p.n_mma + 63) / 64 * 64) &&
+        !std::getenv("SPB200_NO_TMA_STORE")) {
+        const cuuint64_t es = last.dst_fp32 ? 4 : 2;
+        const cuuint64_t C = last.dst_C, W = last.dst_W, H = last.dst_H;
+        cuuint32_t box[4] = {(cuuint32_t)(128 / es), 8, 4, 1};
+        const CUtensorMapDataType ddt = last.dst_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt;
+        if (p.orient == 0) {
+            cuuint64_t dims[4] = {C, W, H, (cuuint64_t)c1.B};
+            cuuint64_t str[3] = {C * es, W * C * es, H * W * C * es};
+            tc_encode_tiled(&p.tmD, ddt, 4, last.dst, dims, str, box);
+        } else {
+            cuuint64_t dims[4] = {C, H, W, (cuuint64_t)c1.B};
+            cuuint64_t str[3] = {W * C * es, C * es, H * W * C * es};
+            tc_encode_tiled(&p.tmD, ddt, 4, last.dst, dims, str, box);
+        }
+        p.tma_store = 1;
+    }
+    {
+        static int v_count[3] = {0, 0, 0};
+        const char* d = std::getenv("SPB200_HALO_DBG");         // "<variant><index>", e.g. 11 = second plan of variant 1
+        if (d && d[0] - '0' == plan->variant && v_count[plan->variant]++ == atoi(d + 1)) {
+            cudaMalloc(&g_halo_dbg, 16 * 8 * sizeof(long long));
+            cudaMemset(g_halo_dbg, 0, 16 * 8 * sizeof(long long));
+            p.dbg = g_halo_dbg;
+            fprintf(stderr, "halo dbg on plan OH=%d OW=%d n_mma=%d nsteps=%d n1=%d has_ds=%d fp32=%d\n", p.OH, p.OW, p.n_mma, p.nsteps, p.n1steps, p.has_ds, p.dst_fp32);
+        }
+    }
     return plan.release();
 }
 
 }  // namespace spb200
+extern "C" __attribute__((visibility("default"))) int spb200_debug_halo(long long* host) {
+    if (!spb200::g_halo_dbg) return 1;
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, spb200::g_halo_dbg, 16 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+    return 0;
+}
