@@ -67,9 +67,11 @@ __host__ __device__ constexpr HaloStep halo_step(unsigned a_lo, unsigned w_lo, u
 struct HaloParams {
     CUtensorMap tmA[kMaxSegs];
     CUtensorMap tmW1, tmW2;
+    CUtensorMap tmR;               // identity-shortcut operand, fetched into the same staging boxes
     CUtensorMap tmD;               // destination, for the TMA stores of the fused variants (box = 32 pixels x 128 B)
     HaloStep steps[kMaxSteps + 1];   // one spare entry: the issuing loop prefetches step e + 1
     int nsteps, n1steps;           // all slabs; slabs of GEMM 1 + shortcut (they come first)
+    int first_ds_step;             // first shortcut slab (n1steps when there is none)
     int chunk_seg[kMaxChunks], chunk_c0[kMaxChunks], nchunks;
     int lo_s, lo_g;                // origin of the haloed box relative to the tile origin
     int orient;                    // 0: group axis = x (tile 16 rows x 8 cols); 1: group axis = y (8 rows x 16 cols)
@@ -82,6 +84,7 @@ struct HaloParams {
     void* dst;
     int res_C, dst_H, dst_W, dst_C, dst_stride, dst_off_y, dst_off_x;
     int relu, dst_fp32, n_mma;
+    int tma_res;                   // the identity shortcut arrives by TMA (needs tma_store)
     int tma_store;                 // fused variants: the output leaves through shared memory and TMA stores
     long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
 };
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full[SW], w_empty[SW];
     __shared__ __align__(8) uint64_t d1_full[NBUF], d1_empty[NBUF], y_full[NBUF], d2_full[NBUF], d2_empty[NBUF];
+    __shared__ __align__(8) uint64_t res_full[8];          // one per epilogue warp: its shortcut sub-boxes have landed
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_bias1[N], s_bias2[N];
 
@@ -119,6 +123,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     if (threadIdx.x == 0) {
         for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], T); }
         for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], T); }
+        for (int w = 0; w < 8; ++w) mbar_init(&res_full[w], 1);
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(&d1_full[b], T); mbar_init(&d2_full[b], T);
             mbar_init(&d1_empty[b], 8); mbar_init(&y_full[b], 8); mbar_init(&d2_empty[b], 8);
@@ -223,16 +228,18 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 // by the epilogue of its previous use - waited for at the first shortcut step, not here, so that the
                 // steps before it overlap that epilogue (the resident-weight path issues a whole tile at once and waits here)
                 bool d2_ready = !(FUSED && p.has_ds);
-                if (!d2_ready && WRES && j > 0) { mbar_wait(&d2_empty[b], ph ^ 1u); d2_ready = true; }
                 tc_fence_after();
                 if (WRES && j > 0) {
                     // resident weights, nothing left to wait for but the activation chunk (a 64-channel block has one
-                    // chunk): the whole tile is issued from one elect region with no barrier traffic between MMAs
+                    // chunk): the tile is issued from elect regions with no barrier traffic between MMAs.  The steps
+                    // before the first shortcut step do not touch D2 and go first; D2[b] is drained by the second
+                    // epilogue of tile j - 2, which runs AFTER the first epilogue of tile j - 1 - waiting for it up
+                    // front cost 1.9 k of the 6.8 k cycles per tile pair (timeline of CTA 0).
                     mbar_wait_a(bar_afull + sa * 8, pha);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a0 = a_lo_base + (uint32_t)(sa * T * (kHaloBufBytes >> 4));
-                        for (int e = 0; e < p.n1steps; ++e) {
+                    const uint32_t a0 = a_lo_base + (uint32_t)(sa * T * (kHaloBufBytes >> 4));
+                    auto issue = [&](int e0, int e1) {
+                        for (int e = e0; e < e1; ++e) {
                             const HaloStep s = p.steps[e];
                             const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
                             const uint32_t alo = a0 + (lo & 0xffffu), blo = w_lo_base + (lo >> 16);
@@ -242,9 +249,19 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                             umma_f16_w(d, alo + 4, kHiA, blo + 4, kHiB, idesc, 1u);
                             umma_f16_w(d, alo + 6, kHiA, blo + 6, kHiB, idesc, 1u);
                         }
+                    };
+                    const int e_ds = d2_ready ? p.n1steps : p.first_ds_step;
+                    if (elect_one()) issue(0, e_ds);
+                    if (e_ds < p.n1steps) {
+                        mbar_wait(&d2_empty[b], ph ^ 1u);
+                        tc_fence_after();
+                        if (elect_one()) issue(e_ds, p.n1steps);
+                    }
+                    if (elect_one()) {
                         umma_commit_a(bar_aempty + sa * 8);
                         umma_commit(&d1_full[b]);
                     }
+                    d2_ready = true;
                     if (++sa == SA) { sa = 0; pha ^= 1u; }
                 }
                 HaloStep rec = p.steps[0];
@@ -371,8 +388,31 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         // the identity-shortcut operand of a tile, fetched long before it is needed (the call sites put a whole first
         // epilogue or the accumulator wait between this and its use)
         uint4 res[kResBlk][4];
+        const int ew = warp - (2 + T);                         // epilogue warp 0..7
+        uint32_t rph = 0;
+        struct TileAt { int img, s, g; bool ok; };
+        auto tile_at = [&](int jt) {                           // origin of this warp's 32 pixels (warp-uniform)
+            const int tile_raw = (blockIdx.x + jt * gridDim.x) * T + t;
+            const int tile = min(tile_raw, p.total_tiles - 1);
+            const int tt = tile % p.tiles_per_img;
+            return TileAt{tile / p.tiles_per_img, (tt / p.tiles_g) * 16 + q * 4, (tt % p.tiles_g) * 8, tile_raw < p.total_tiles};
+        };
         auto prefetch_res = [&](int jt) {
             if (p.residual == nullptr) return;
+            if (kOutSlots > 0 && p.tma_res) {
+                // by TMA into the staging boxes the output will overwrite in place: issued as soon as the previous tile's
+                // stores have read them, a whole first epilogue and accumulator wait before the use
+                const TileAt ta = tile_at(jt);
+                if (lane == 0) {
+                    tma_store_wait_read<0>();
+                    const int nb = (p.n_mma + 63) / 64;
+                    mbar_expect_tx(&res_full[ew], (uint32_t)(nb * 4096));
+                    for (int k = 0; k < nb; ++k)
+                        tma_load_4d(out_stage + (t * kOutSlots + k) * kHaloOutBox + q * 4096, &p.tmR, &res_full[ew], k * 64, ta.g, ta.s, ta.img);
+                }
+                __syncwarp();
+                return;
+            }
             const Pix px = pixel_of(jt);
             if (!px.valid) return;
             const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const Tp*>(p.residual) + px.gpix * p.res_C);
@@ -389,7 +429,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             const int b = jt % NBUF;
             const uint32_t ph = (uint32_t)(jt / NBUF) & 1u;
             const Pix px = pixel_of(jt);
-            const bool has_res = p.residual != nullptr && px.valid;
+            const bool has_res = p.residual != nullptr && (px.valid || (kOutSlots > 0 && p.tma_res));
             const uint32_t tmem_out = tmem_base + (uint32_t)((b * T + t) * N) + lane_off + (FUSED ? kAccCols : 0u);
             const float* sb = FUSED ? s_bias2 : s_bias1;
             // TMA-store path (fused variants): a warp stages its 32 pixel rows (128 B per row and box, 128-byte swizzle: the
@@ -398,24 +438,23 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             // (one pixel row per lane) touch 32 lines per instruction and were measured to slow the MMAs' own
             // shared-memory reads: 18.3 k -> 12.3 k cycles per tile pair with the stores removed.
             const bool ts = kOutSlots > 0 && p.tma_store;
+            const bool tr = ts && p.tma_res && p.residual != nullptr;
             int tc_img = 0, tc_s = 0, tc_g = 0;
             bool tile_ok = false;
             uint32_t stg = 0;
             if (ts) {
-                const int tile_raw = (blockIdx.x + jt * gridDim.x) * T + t;
-                tile_ok = tile_raw < p.total_tiles;
-                const int tile = min(tile_raw, p.total_tiles - 1);
-                const int tt = tile % p.tiles_per_img;
-                tc_img = tile / p.tiles_per_img;
-                tc_s = (tt / p.tiles_g) * 16 + q * 4;
-                tc_g = (tt % p.tiles_g) * 8;
+                const TileAt ta = tile_at(jt);
+                tc_img = ta.img; tc_s = ta.s; tc_g = ta.g; tile_ok = ta.ok;
                 stg = smem_u32(out_stage) + (uint32_t)(t * kOutSlots * kHaloOutBox + q * 4096);
-                if (lane == 0) tma_store_wait_read<0>();          // the previous tile's boxes have left shared memory
-                __syncwarp();
+                if (!tr) {
+                    if (lane == 0) tma_store_wait_read<0>();      // the previous tile's boxes have left shared memory
+                    __syncwarp();
+                }
             }
             int nbox = 0;
             mbar_wait(FUSED ? &d2_full[b] : &d1_full[b], ph);
             tc_fence_after();
+            if (tr) { mbar_wait(&res_full[ew], rph); rph ^= 1u; }
             const bool dbg_on = p.dbg && blockIdx.x == 0 && warp == 2 + T && lane == 0 && jt < 16;
             if (dbg_on) p.dbg[jt * 8 + 6] = clock64();
 #pragma unroll
@@ -437,7 +476,10 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     if (has_res) {
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
-                            const uint32_t w[4] = {res[blk][jj].x, res[blk][jj].y, res[blk][jj].z, res[blk][jj].w};
+                            const uint4 rv = tr ? ld_shared_v4(stg + (uint32_t)((blk >> 1) * kHaloOutBox) + (uint32_t)lane * 128u +
+                                                               ((((uint32_t)(blk & 1) * 4u + (uint32_t)jj) ^ (uint32_t)(lane & 7)) << 4))
+                                                : res[blk][jj];
+                            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 f = unpack2<Tp>(w[e]);
@@ -700,6 +742,9 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     for (int s = c1.nseg; s < kMaxSegs; ++s) p.tmA[s] = p.tmA[0];
     p.nchunks = nchunks;
     p.n1steps = nsteps;
+    p.first_ds_step = nsteps;
+    for (int e = nsteps - 1; e >= 0; --e)
+        if (((p.steps[e] >> 36) & 3u) == 1u) p.first_ds_step = e;
     {
         cuuint64_t dims[2] = {(cuuint64_t)c1.K, (cuuint64_t)N};
         cuuint64_t str[1] = {(cuuint64_t)c1.K * 2};
@@ -755,6 +800,21 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
             tc_encode_tiled(&p.tmD, ddt, 4, last.dst, dims, str, box);
         }
         p.tma_store = 1;
+        if (last.residual && !last.dst_fp32 && last.res_C % 64 == 0 && last.res_C >= (p.n_mma + 63) / 64 * 64 &&
+            !std::getenv("SPB200_NO_TMA_RES")) {
+            const cuuint64_t RC = last.res_C;
+            cuuint32_t rbox[4] = {64, 8, 4, 1};
+            if (p.orient == 0) {
+                cuuint64_t dims[4] = {RC, W, H, (cuuint64_t)c1.B};
+                cuuint64_t str[3] = {RC * 2, W * RC * 2, H * W * RC * 2};
+                tc_encode_tiled(&p.tmR, dt, 4, last.residual, dims, str, rbox);
+            } else {
+                cuuint64_t dims[4] = {RC, H, W, (cuuint64_t)c1.B};
+                cuuint64_t str[3] = {W * RC * 2, RC * 2, H * W * RC * 2};
+                tc_encode_tiled(&p.tmR, dt, 4, last.residual, dims, str, rbox);
+            }
+            p.tma_res = 1;
+        }
     }
     {
         static int v_count[3] = {0, 0, 0};
