@@ -32,6 +32,7 @@ struct BlkSeg {
 struct BlkParams {
     CUtensorMap tmA[kMaxSegs];
     CUtensorMap tmW1, tmW2;
+    CUtensorMap tmD, tmR;      // destination / identity shortcut, box = the 32 pixel rows of an epilogue warp x 64 channels
     BlkSeg seg[kMaxSegs];
     int nseg;                  // GEMM 1 segments
     int nds;                   // GEMM 2 shortcut segments (0 = identity or none); they reuse tmA[0..nds)
@@ -45,6 +46,7 @@ struct BlkParams {
     void* dst;
     int res_C, dst_H, dst_W, dst_C, dst_stride, dst_off_y, dst_off_x;
     int relu, dst_fp32, n_mma;
+    int tma_store, tma_res;    // the output leaves (the shortcut arrives) through the Y buffer and TMA, see halo_tc.cu
 };
 
 constexpr int kBlkThreads = 192;
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
     __shared__ __align__(8) uint64_t d1_full, d1_empty, y_full, y_empty, d2_full, d2_empty;
+    __shared__ __align__(8) uint64_t res_full[4];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias1[BLOCK_N], s_bias2[BLOCK_N];
 
@@ -77,6 +80,7 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&d1_full, 1); mbar_init(&y_empty, 1); mbar_init(&d2_full, 1);
         mbar_init(&d1_empty, 4); mbar_init(&y_full, 4); mbar_init(&d2_empty, 4);
+        for (int w = 0; w < 4; ++w) mbar_init(&res_full[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -239,9 +243,13 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
         const int q = warp % 4;
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        uint32_t tph = 0;
+        uint32_t tph = 0, rph = 0;
+        // TMA-store path (fused blocks): the second epilogue writes the output tile over Y (same swizzled [chunk][row]
+        // layout, each warp its own 32 rows) and sends it as 4 KB sub-boxes; an identity shortcut arrives the same way
+        const bool ts = fused && p.tma_store, tr = ts && p.tma_res;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, tph ^= 1u) {
             const int img = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
+            const int bx = (tt % p.tiles_x) * p.tw, by = (tt / p.tiles_x) * p.th + (q * 32) / p.tw;   // this warp's sub-box
             const int oy = (tt / p.tiles_x) * p.th + row / p.tw, ox = (tt % p.tiles_x) * p.tw + row % p.tw;
             const bool valid = oy < p.OH && ox < p.OW;
             const size_t gpix = ((size_t)img * p.OH + oy) * p.OW + ox;
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
             tc_fence_after();
             if (fused) {
                 mbar_wait(&y_empty, tph ^ 1u);             // GEMM 2 of the previous tile has finished reading Y
+                if (ts) { if (lane == 0) tma_store_wait_read<0>(); __syncwarp(); }   // and its output has left the buffer
                 uint8_t* yrow = s_y + row * 128;
 #pragma unroll 1
                 for (int c0 = 0; c0 < p.n_mma; c0 += 32) {
@@ -274,6 +283,15 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                 if (lane == 0) { mbar_arrive(&d1_empty); mbar_arrive(&y_full); }
                 mbar_wait(&d2_full, tph);
                 tc_fence_after();
+                if (tr) {
+                    if (lane == 0) {
+                        const int nb = (p.n_mma + 63) / 64;
+                        mbar_expect_tx(&res_full[q], (uint32_t)(nb * 4096));
+                        for (int k = 0; k < nb; ++k) tma_load_4d(s_y + k * kBlkABytes + q * 4096, &p.tmR, &res_full[q], k * 64, bx, by, img);
+                    }
+                    mbar_wait(&res_full[q], rph);
+                    rph ^= 1u;
+                }
             }
             const uint32_t tmem_out = fused ? tmem_d2 : tmem_d1;
             const float* sb = fused ? s_bias2 : s_bias1;
@@ -282,15 +300,17 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_out + lane_off + (uint32_t)c0, r);
                 tmem_ld_wait();
-                if (valid) {
+                if (valid || ts) {
                     float v[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + sb[c0 + i];
+                    const uint32_t orow = smem_u32(s_y) + (uint32_t)((c0 >> 6) * kBlkABytes + row * 128);
+                    const uint32_t half = (uint32_t)(c0 & 63) >> 3, sw = (uint32_t)(row & 7);
                     if (p.residual) {
                         const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const T*>(p.residual) + gpix * p.res_C + c0);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint4 u = __ldg(rp + j);
+                            const uint4 u = tr ? ld_shared_v4(orow + (((half + (uint32_t)j) ^ sw) << 4)) : __ldg(rp + j);
                             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -304,7 +324,20 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (p.dst_fp32) {
+                    if (ts) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            st_shared_v4(orow + (((half + (uint32_t)j) ^ sw) << 4), pack2<T>(v[j * 8], v[j * 8 + 1]), pack2<T>(v[j * 8 + 2], v[j * 8 + 3]),
+                                         pack2<T>(v[j * 8 + 4], v[j * 8 + 5]), pack2<T>(v[j * 8 + 6], v[j * 8 + 7]));
+                        if ((c0 & 32) || c0 + 32 >= p.n_mma) {
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_4d(&p.tmD, smem_u32(s_y) + (uint32_t)((c0 >> 6) * kBlkABytes + q * 4096), (c0 >> 6) * 64, bx, by, img);
+                                tma_store_commit();
+                            }
+                        }
+                    } else if (p.dst_fp32) {
                         float4* dp = reinterpret_cast<float4*>(static_cast<float*>(p.dst) + dpix * p.dst_C + c0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) dp[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
@@ -321,6 +354,7 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(fused ? &d2_empty : &d1_empty);
         }
+        if (ts && lane == 0) tma_store_wait_all();
     }
     __syncthreads();
     if (warp == 1) {
@@ -466,6 +500,22 @@ TcBlockPlan* tc_block_plan_create(const ConvDev& c1, const ConvDev* c2, int oper
     p.res_C = last.res_C; p.dst_H = last.dst_H; p.dst_W = last.dst_W; p.dst_C = last.dst_C;
     p.dst_stride = last.dst_stride; p.dst_off_y = last.dst_off_y; p.dst_off_x = last.dst_off_x;
     p.relu = last.relu; p.dst_fp32 = last.dst_fp32;
+    const int n64 = (p.n_mma + 63) / 64 * 64;
+    if (c2 && !last.dst_fp32 && last.dst_stride == 1 && last.dst_off_y == 0 && last.dst_off_x == 0 && last.dst_H == c1.OH &&
+        last.dst_W == c1.OW && p.tw <= 32 && last.dst_C % 64 == 0 && last.dst_C >= n64 && n64 <= N && !std::getenv("SPB200_NO_TMA_STORE")) {
+        cuuint32_t box[4] = {64, (cuuint32_t)p.tw, (cuuint32_t)(32 / p.tw), 1};
+        auto encode = [&](CUtensorMap* m, const void* base, int C) {
+            cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)c1.OW, (cuuint64_t)c1.OH, (cuuint64_t)c1.B};
+            cuuint64_t str[3] = {(cuuint64_t)C * 2, (cuuint64_t)c1.OW * C * 2, (cuuint64_t)c1.OH * c1.OW * C * 2};
+            tc_encode_tiled(m, dt, 4, base, dims, str, box);
+        };
+        encode(&p.tmD, last.dst, last.dst_C);
+        p.tma_store = 1;
+        if (last.residual && last.res_C % 64 == 0 && last.res_C >= n64 && !std::getenv("SPB200_NO_TMA_RES")) {
+            encode(&p.tmR, last.residual, last.res_C);
+            p.tma_res = 1;
+        }
+    }
     return plan.release();
 }
 

@@ -44,7 +44,7 @@ constexpr int kHaloSbo = kHaloG * 128;                      // 8-pixel groups ar
 constexpr int kMaxSteps = 48;
 constexpr int kMaxChunks = 8;
 __host__ __device__ constexpr int halo_threads(int T) { return (2 + T + 8) * 32; }
-__host__ __device__ constexpr int halo_out_slots(int N, bool fused) { return fused ? (N == 128 ? 2 : 1) : 0; }
+__host__ __device__ constexpr int halo_out_slots(int N, bool) { return N == 128 ? 2 : 1; }
 constexpr int kHaloOutBox = 16384;                          // one staged output box: 128 pixel rows x 128 B   // 2 producers, T MMA issuers, 8 epilogue warps
 
 // One weight slab [N x 64 K] and the MMAs that consume it, packed into 64 bits so that the issuing warps fetch a
@@ -604,7 +604,7 @@ static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
 
 constexpr int kHaloResidentSlabs = 11;   // variant 0: every slab of a 64-channel block stays in shared memory
 constexpr int kHaloRing1 = 4;            // variant 1: weight ring slots (16 KB each; 8 slots measured no faster)
-constexpr int kHaloRing2 = 6;            // variant 2
+constexpr int kHaloRing2 = 4;            // variant 2
 
 template <typename Tp>
 static void launch_halo_v(const TcHaloPlan* plan, cudaStream_t st) {
@@ -783,24 +783,28 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     // fused variants store through shared memory: destination tensor {C, group axis, slow axis, image}, one box = the 32
     // pixel rows of an epilogue warp (8 along the group axis x 4 slow rows) x 128 B of channels
     p.tma_store = 0;
-    if (c2 && last.dst_stride == 1 && last.dst_off_y == 0 && last.dst_off_x == 0 && last.dst_H == c1.OH && last.dst_W == c1.OW &&
+    if (last.dst_stride >= 1 && (c1.OH - 1) * last.dst_stride + last.dst_off_y < last.dst_H &&
+        (c1.OW - 1) * last.dst_stride + last.dst_off_x < last.dst_W &&
         last.dst_C % (last.dst_fp32 ? 32 : 64) == 0 && last.dst_C >= (last.dst_fp32 ? p.n_mma : (p.n_mma + 63) / 64 * 64) &&
         !std::getenv("SPB200_NO_TMA_STORE")) {
+        // a strided destination (the output phases of the transposed convolution) is the same map over every
+        // dst_stride-th pixel, starting at the phase offset
         const cuuint64_t es = last.dst_fp32 ? 4 : 2;
-        const cuuint64_t C = last.dst_C, W = last.dst_W, H = last.dst_H;
+        const cuuint64_t C = last.dst_C, W = c1.OW, H = c1.OH, S = last.dst_stride, FW = last.dst_W, FH = last.dst_H;
+        const uint8_t* base = static_cast<const uint8_t*>(last.dst) + ((size_t)last.dst_off_y * FW + last.dst_off_x) * C * es;
         cuuint32_t box[4] = {(cuuint32_t)(128 / es), 8, 4, 1};
         const CUtensorMapDataType ddt = last.dst_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : dt;
         if (p.orient == 0) {
             cuuint64_t dims[4] = {C, W, H, (cuuint64_t)c1.B};
-            cuuint64_t str[3] = {C * es, W * C * es, H * W * C * es};
-            tc_encode_tiled(&p.tmD, ddt, 4, last.dst, dims, str, box);
+            cuuint64_t str[3] = {S * C * es, S * FW * C * es, FH * FW * C * es};
+            tc_encode_tiled(&p.tmD, ddt, 4, base, dims, str, box);
         } else {
             cuuint64_t dims[4] = {C, H, W, (cuuint64_t)c1.B};
-            cuuint64_t str[3] = {W * C * es, C * es, H * W * C * es};
-            tc_encode_tiled(&p.tmD, ddt, 4, last.dst, dims, str, box);
+            cuuint64_t str[3] = {S * FW * C * es, S * C * es, FH * FW * C * es};
+            tc_encode_tiled(&p.tmD, ddt, 4, base, dims, str, box);
         }
         p.tma_store = 1;
-        if (last.residual && !last.dst_fp32 && last.res_C % 64 == 0 && last.res_C >= (p.n_mma + 63) / 64 * 64 &&
+        if (last.residual && last.dst_stride == 1 && last.dst_off_y == 0 && last.dst_off_x == 0 && !last.dst_fp32 && last.res_C % 64 == 0 && last.res_C >= (p.n_mma + 63) / 64 * 64 &&
             !std::getenv("SPB200_NO_TMA_RES")) {
             const cuuint64_t RC = last.res_C;
             cuuint32_t rbox[4] = {64, 8, 4, 1};
