@@ -84,6 +84,7 @@ struct HaloParams {
     void* dst;
     int res_C, dst_H, dst_W, dst_C, dst_stride, dst_off_y, dst_off_x;
     int relu, dst_fp32, n_mma;
+    int w_bytes;                   // bytes of one weight slab as loaded: n_mma rows x 128 B
     int tma_res;                   // the identity shortcut arrives by TMA (needs tma_store)
     int tma_store;                 // fused variants: the output leaves through shared memory and TMA stores
     long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 const uint32_t hi = (uint32_t)(s >> 32), slot = hi & 15u;
                 if (!WRES) { mbar_wait_a(bar_empty + slot * 8, ((eph >> slot) & 1u) ^ 1u); eph ^= 1u << slot; }
                 if (elect_one()) {
-                    mbar_expect_tx_a(bar_full + slot * 8, (uint32_t)kWBytes);
+                    mbar_expect_tx_a(bar_full + slot * 8, (uint32_t)p.w_bytes);
                     tma_load_2d_a(ring + slot * kWBytes, ((hi >> 4) & 3u) == 0 ? &p.tmW1 : &p.tmW2, bar_full + slot * 8,
                                   (int)((hi >> 16) & 0xfffu) * 64, 0);
                 }
@@ -742,13 +743,14 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     for (int s = c1.nseg; s < kMaxSegs; ++s) p.tmA[s] = p.tmA[0];
     p.nchunks = nchunks;
     p.n1steps = nsteps;
+    p.w_bytes = p.n_mma * 128;
     p.first_ds_step = nsteps;
     for (int e = nsteps - 1; e >= 0; --e)
         if (((p.steps[e] >> 36) & 3u) == 1u) p.first_ds_step = e;
     {
         cuuint64_t dims[2] = {(cuuint64_t)c1.K, (cuuint64_t)N};
         cuuint64_t str[1] = {(cuuint64_t)c1.K * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)N};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.n_mma};        // rows beyond n_mma are never read by the MMAs
         tc_encode_tiled(&p.tmW1, dt, 2, c1.w, dims, str, box);
     }
     p.bias1 = c1.bias;
@@ -762,7 +764,7 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         }
         cuuint64_t dims[2] = {(cuuint64_t)c2->K, (cuuint64_t)N};
         cuuint64_t str[1] = {(cuuint64_t)c2->K * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)N};
+        cuuint32_t box[2] = {64, (cuuint32_t)p.n_mma};        // rows beyond n_mma are never read by the MMAs
         tc_encode_tiled(&p.tmW2, dt, 2, c2->w, dims, str, box);
         p.bias2 = c2->bias;
     } else {

@@ -127,6 +127,16 @@ def test_path_fp16_tensor_cores_meets_bars(engines, golden_sd):
     assert hit >= 0.99 * tot
 
 
+@pytest.mark.parametrize('shape', [(208, 272), (112, 400)])
+def test_path_fp16_ragged_tile_geometry(shape, engines, golden_sd):
+    """Sizes whose feature maps do not divide into the kernels' 16x8-pixel tiles anywhere (52x68 / 26x34 / 13x17 and
+    28x100 / 14x50 / 7x25): the TMA stores and shortcut loads of the residual blocks are clipped at both image edges,
+    the last tile pair of an image is half empty.  Same bars as the golden set."""
+    h, w = shape
+    for i, gray in enumerate([weights.shapes_image(3, h, w), weights.rand_image(11, h, w)]):
+        compare_path(engines['fp16'], gray, golden_sd, 1e-2, 0.985, 0.999, 'fp16 ragged %dx%d #%d' % (h, w, i))
+
+
 def test_block_outputs_fp16_vs_fp32(engines):
     """Per-stage comparison of the tensor-core path with the fp32 CUDA-core path on the device."""
     img = golden_image('shapes240_0')[None, None].cuda()
