@@ -252,9 +252,24 @@ void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> sr
     const bool has_ds = sd_.count(p + ".identity_downsample.0.weight") > 0;
     const HostConv* c1 = fold(p + ".conv1", p + ".bn1", false, false);
     const HostConv* c2 = fold(p + ".conv2", p + ".bn2", false, false);
-    const HostConv* cd = has_ds ? fold(p + ".identity_downsample.0", p + ".identity_downsample.1", false, false) : nullptr;
+    const HostConv* cd_folded = has_ds ? fold(p + ".identity_downsample.0", p + ".identity_downsample.1", false, false) : nullptr;
     int cin_total = 0;
     for (auto& s : srcs) cin_total += s.second;
+    // A 64-channel identity block on the tensor-core path adds its shortcut ON the tensor core, as x . I into the second
+    // accumulator (exact: 16-bit x times 1.0, fp32 accumulation): four more MMAs per tile, but the second epilogue then
+    // neither waits for the shortcut tile to land in its staging box nor reads it (halo_tc.cu keeps ONE box per tile at
+    // N = 64, shared memory is full; encoder.layer1.1 121 -> see DESIGN.md section 9).
+    const HostConv* cd = cd_folded;
+    if (!cd && precision_ != PREC_FP32 && use_halo_ && fuse_blocks_ && srcs.size() == 1 && stride == 1 && cout == 64 &&
+        cin_total == 64 && bufspec_[y_buf].C == 64 && bufspec_[srcs[0].first].C == 64 && !std::getenv("SPB200_NO_IDENTITY_MMA")) {
+        auto hc = std::make_unique<HostConv>();
+        hc->cout = hc->cin = cout; hc->kh = hc->kw = 1;
+        hc->w.assign((size_t)cout * cout, 0.f);
+        for (int i = 0; i < cout; ++i) hc->w[(size_t)i * cout + i] = 1.f;
+        hc->b.assign(cout, 0.f);
+        convs_.push_back(std::move(hc));
+        cd = convs_.back().get();
+    }
     if (c1->cin != cin_total || c1->cout != cout || c1->kh != 3 || c2->cin != cout || c2->cout != cout || c2->kh != 1)
         throw std::runtime_error("unexpected convolution shapes in block " + p);
     if (cd && (cd->cin != cin_total || cd->cout != cout || cd->kh != 1))
