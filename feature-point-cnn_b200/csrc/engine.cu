@@ -264,6 +264,7 @@ void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> sr
         cin_total == 64 && bufspec_[y_buf].C == 64 && bufspec_[srcs[0].first].C == 64 && !std::getenv("SPB200_NO_IDENTITY_MMA")) {
         auto hc = std::make_unique<HostConv>();
         hc->cout = hc->cin = cout; hc->kh = hc->kw = 1;
+        hc->synthetic = true;
         hc->w.assign((size_t)cout * cout, 0.f);
         for (int i = 0; i < cout; ++i) hc->w[(size_t)i * cout + i] = 1.f;
         hc->b.assign(cout, 0.f);
@@ -655,7 +656,8 @@ double Engine::op_flops(const OpSpec& op) const {
     const BufSpec& ds = bufspec_[op.dst_buf];
     const double rows = (double)wsB_ * (wsH_ / ds.div / op.dst_stride) * (wsW_ / ds.div / op.dst_stride);
     double k = 0;
-    for (auto& s : op.segs) k += (double)s.taps.size() * s.cin_real;
+    for (auto& s : op.segs)
+        if (!(s.conv && s.conv->synthetic)) k += (double)s.taps.size() * s.cin_real;
     return 2.0 * rows * k * op.cout_real;
 }
 

@@ -25,6 +25,7 @@ struct Params {
 
 struct HostConv {                 // BatchNorm-folded convolution, [cout][cin][kh][kw]
     int cout = 0, cin = 0, kh = 0, kw = 0;
+    bool synthetic = false;       // not a convolution of the reference (an identity shortcut run as MMAs): no algorithmic FLOPs
     std::vector<float> w, b;
     float at(int co, int ci, int y, int x) const { return w[(((size_t)co * cin + ci) * kh + y) * kw + x]; }
 };
