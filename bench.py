@@ -322,7 +322,7 @@ def main():
     roofline['traffic'] = ncu_traffic(ncu_name) if ncu_name and B == 64 and H == 480 and W == 640 else None
     if top['kernel'] == 'descriptor.layer_out.0' and B == 64 and H == 480 and W == 640:
         # the 256 -> 128 block with the concatenated input: the longest launch of this template instance in the capture
-        roofline['traffic'] = ncu_traffic('halo_tc_kernel<128, 2, 1, 2, 8, 1, 0', longest=True)
+        roofline['traffic'] = ncu_traffic('halo_tc_kernel<128, 2, 1, 2, ', longest=True)
     roofline['traffic_source'] = 'ncu --set full capture of the same workload committed under profiles/ (dram bytes read + written per launch)'
     roofline['peak_source'] = peaks['source'] + (', sustained bf16 GEMM figure' if roofline['bound'] == 'tensor' else '')
     roofline['share_of_step'] = top['share']
