@@ -22,6 +22,15 @@
 // TMA producer, warps 2-3 = MMA issuers (one per tile of the pair; warp 2 also owns the TMEM allocation),
 // warps 4-11 = epilogue (two warps per TMEM lane quarter, one per tile).  With NBUF = 2 (transposed-conv
 // phases) the accumulator is double buffered, so the next tile pair runs under the epilogue of this one.
+//
+// The output leaves through shared memory: an epilogue warp owns 32 pixel rows of its tile (8 pixels along the
+// group axis x 4 slow rows), writes them as 128-byte swizzled rows into its 4 KB share of a staging box and sends
+// the sub-box with one TMA store per 64 channels (per 32 for fp32 output), clipped at the image border by the TMA
+// unit; an identity shortcut is fetched into the same sub-boxes by TMA as soon as the previous tile's stores have
+// read them and is overwritten in place.  No cross-warp synchronisation is involved.  Global loads and stores
+// issued from the accumulator layout (one pixel row per lane, 32 lines per instruction) go through the same
+// L1 / shared-memory pipe as the MMAs' operand reads and were measured to stretch a tile pair of the 128-channel
+// block from 12.3 k to 18.3 k cycles.
 #include <cuda.h>
 
 #include <algorithm>
