@@ -8,7 +8,9 @@
 //   (3) the producer side: both CTAs fetch their operands by TMA (.cta_group::2) and complete the transaction bytes on
 //       ONE barrier in the leader CTA (address mapped with mapa); the epilogue warps of both CTAs arrive on a barrier
 //       of the leader (mbarrier.arrive.shared::cluster) - the hand-overs the paired kernel needs.  All waits of (3) are
-//       bounded, a hand-over that never happens is reported instead of hanging.
+//       bounded, a hand-over that never happens is reported instead of hanging;
+//   (4) the second GEMM of a fused block on the pair: Y = fp16(D1[:, 0:64]) packed into each CTA's own tensor memory by
+//       its epilogue warps, D2 = Y . B2^T with the A operand read from tensor memory (TS form of the pair MMA).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -o mma_pair mma_pair.cu ; run under `timeout 20`.
 #include <cstdio>
 #include <cstdint>
@@ -226,6 +228,126 @@ kpair_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 0) { tc_fence_after(); tmem_dealloc2(tm, 512); }
 }
 
+__device__ __forceinline__ void umma2_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__host__ __device__ inline int b2_val(int n, int k) { return (n + 5 * k) % 3 - 1; }
+
+// N = 128: D1 (columns 0..127) = A . B^T;  Y (columns 256..287, 64 packed fp16) = D1[:, 0:64];  D2 (columns 384..511) = Y . B2^T
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) kpair_ts(int* errs, int* flags) {
+    constexpr int N = 128, nb = 64;
+    extern __shared__ uint8_t dyn[];
+    __shared__ __align__(8) uint64_t bar, bar2, yfull;
+    __shared__ uint32_t slot;
+    uint8_t* base = dyn + ((1024u - (smem_u32(dyn) & 1023u)) & 1023u);
+    uint8_t* s_a = base;
+    uint8_t* s_b = base + 16384;
+    uint8_t* s_b2 = base + 24576;
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int rank = (int)cluster_ctarank();
+    for (int i = threadIdx.x; i < 128 * 64; i += 128) {
+        const int r = i / 64, k = i % 64;
+        const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)k >> 3) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)k & 7u) * 2u;
+        *reinterpret_cast<__half*>(s_a + off) = __int2half_rn(a_val(rank * 128 + r, k));
+        if (r < nb) {
+            *reinterpret_cast<__half*>(s_b + off) = __int2half_rn(b_val(rank * nb + r, k));
+            *reinterpret_cast<__half*>(s_b2 + off) = __int2half_rn(b2_val(rank * nb + r, k));
+        }
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_init(&bar2, 1);
+        mbar_init(&yfull, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 0) tmem_alloc2(&slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tm = slot;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    if (rank == 0 && warp == 0) {
+        const uint32_t alo = umma_desc_lo(smem_u32(s_a)), blo = umma_desc_lo(smem_u32(s_b));
+        if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma2_f16_w(tm, alo + kk * 2, hi, blo + kk * 2, hi, idesc, kk ? 1u : 0u);
+            umma2_commit_mc(&bar, 3);
+        }
+        __syncwarp();
+    }
+    bool ok = mbar_wait_bounded(&bar, 0, 300000);
+    if (!ok && threadIdx.x == 0) flags[rank] = 1;
+    tc_fence_after();
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    if (ok) {
+        for (int blk = 0; blk < 2; ++blk) {
+            uint32_t r[32], y[16];
+            tmem_ld_32x32(tm + lane_off + (uint32_t)(blk * 32), r);
+            tmem_ld_wait();
+            for (int e = 0; e < 16; ++e) y[e] = pack2<__half>(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
+            tmem_st_32x16(tm + lane_off + 256u + (uint32_t)(blk * 16), y);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&yfull), 0));
+    if (rank == 0 && warp == 0) {
+        const bool yok = mbar_wait_bounded(&yfull, 0, 300000);
+        if (!yok && lane == 0) flags[2] = 1;
+        tc_fence_after();
+        if (yok) {
+            const uint32_t b2lo = umma_desc_lo(smem_u32(s_b2));
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) umma2_f16_ts(tm + 384u, tm + 256u + (uint32_t)(kk * 8), b2lo + kk * 2, hi, idesc, kk ? 1u : 0u);
+                umma2_commit_mc(&bar2, 3);
+            }
+            __syncwarp();
+        }
+    }
+    const bool ok2 = mbar_wait_bounded(&bar2, 0, 300000);
+    if (!ok2 && threadIdx.x == 0) flags[3] = 1;
+    tc_fence_after();
+    if (ok2) {
+        const int m = rank * 128 + warp * 32 + lane;
+        int yv[64];
+        for (int k = 0; k < 64; ++k) {
+            int v = 0;
+            for (int kk = 0; kk < 64; ++kk) v += a_val(m, kk) * b_val(k, kk);
+            yv[k] = v;
+        }
+        int bad = 0;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tm + lane_off + 384u + (uint32_t)c0, r);
+            tmem_ld_wait();
+            for (int j = 0; j < 32; ++j) {
+                int want = 0;
+                for (int k = 0; k < 64; ++k) want += yv[k] * b2_val(c0 + j, k);
+                if (__uint_as_float(r[j]) != (float)want) ++bad;
+            }
+        }
+        if (bad) atomicAdd(errs + rank, bad);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc2(tm, 512); }
+}
+
 int main() {
     unsigned long long* d_cyc;
     int* d_err;
@@ -304,6 +426,20 @@ int main() {
                f[2] ? "NO" : "yes", f[3] ? "NO" : "yes", h[0], h[1], ad[0], ad[1], ad[2], ad[3]);
         fflush(stdout);
         delete[] hA; delete[] hB; cudaFree(dA); cudaFree(dB);
+    }
+    // (4) second GEMM with A from tensor memory
+    cudaFuncSetAttribute(kpair_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaMemset(d_err, 0, 2 * sizeof(int));
+    cudaMemset(d_flags, 0, 4 * sizeof(int));
+    kpair_ts<<<2, 128, smem>>>(d_err, d_flags);
+    {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("TS pair: error %s\n", cudaGetErrorString(e)); return 1; }
+        int h[2], f[4];
+        cudaMemcpy(h, d_err, sizeof(h), cudaMemcpyDeviceToHost);
+        cudaMemcpy(f, d_flags, sizeof(f), cudaMemcpyDeviceToHost);
+        printf("N=128  TS pair (Y from each CTA's tensor memory): GEMM 1 seen leader %s peer %s, Y hand-over %s, GEMM 2 seen %s; wrong D2 values leader %d peer %d (of 16384 each)\n",
+               f[0] ? "NO" : "yes", f[1] ? "NO" : "yes", f[2] ? "NO" : "yes", f[3] ? "NO" : "yes", h[0], h[1]);
     }
     return 0;
 }
