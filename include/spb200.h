@@ -177,6 +177,12 @@ SPB200_API int spb200_test_conv_tc(int precision, const void* x, const void* w, 
 SPB200_API int spb200_test_conv_kernel(int kernel, int precision, const void* x, const void* w, const float* bias, void* y, int B,
                             int H, int W, int cin, int cout, int taps, int stride, int relu, int out_fp32, void* stream);
 
+/* Diagnostic: with SPB200_HALO_DBG=<variant><index> in the environment one haloed-tile plan records clock stamps of
+ * its CTA 0 (16 tile pairs x 8 stamps: MMA issuer start / GEMM 1 issued / Y seen / GEMM 2 issued, first epilogue warp
+ * accumulator 1 seen / epilogue 1 done / accumulator 2 seen / epilogue 2 done).  Copies the 128 stamps to `host`;
+ * returns 1 when no plan was instrumented.  Read by scripts/halo_dbg.py; no counterpart in the reference. */
+SPB200_API int spb200_debug_halo(long long* host);
+
 #ifdef __cplusplus
 }
 #endif
