@@ -14,6 +14,7 @@ _c = ctypes
 _P = _c.c_void_p
 SYMBOLS = {
     'spb200_create': (_c.c_int, [_c.c_int, _c.POINTER(_P)]),
+    'spb200_debug_halo': (_c.c_int, [_P]),
     'spb200_destroy': (None, [_P]),
     'spb200_last_error': (_c.c_char_p, [_P]),
     'spb200_load_checkpoint': (_c.c_int, [_P, _c.c_char_p]),

@@ -14,7 +14,7 @@ for i in range(3): out = e.detect(img, cap)
 torch.cuda.synchronize()
 lib = e._lib
 buf = (ctypes.c_longlong * 128)()
-print('rc', lib.spb200_debug_halo(buf))
+print('rc', lib.spb200_debug_halo(ctypes.cast(buf, ctypes.c_void_p)))
 a = np.array(list(buf), dtype=np.int64).reshape(16, 8)
 t0 = a[0, 0]
 names = ['m:start', 'm:g1issued', 'm:yfull', 'm:g2issued', 'e:d1full', 'e:epi1done', 'e:d2full', 'e:epi2done']
