@@ -79,6 +79,10 @@ int spb200_finalize_weights(spb200_engine* e, int precision) {
     return guarded(e, [&](spb200::Engine& g) { g.finalize(precision); });
 }
 
+int spb200_finalize_weights_split(spb200_engine* e, int precision, int split_level) {
+    return guarded(e, [&](spb200::Engine& g) { g.finalize(precision, split_level); });
+}
+
 int spb200_set_params(spb200_engine* e, float conf_thresh, int nms_dist, int border_remove, int top_k, int descriptor_enabled) {
     return guarded(e, [&](spb200::Engine& g) {
         if (nms_dist < 0 || nms_dist > 8) throw std::invalid_argument("nms_dist must be in [0, 8]");

@@ -39,6 +39,13 @@ struct SegDev {
     int koff;             // first K index of this segment in the packed weights
     int view;             // > 1: src / H / W describe every `view`-th pixel of a full_H x full_W buffer in both axes (src points
     int full_H, full_W;   //      at the phase's first pixel): a stride-2 convolution read as stride-1 convolutions over four phases
+    // Split-precision source (tensor-core path only): every 32 real channels are stored as 64 16-bit values
+    // [hi 0..31 | lo 0..31] with value = hi + lo, so C and cin count STORED values (2 x the padded real channels) and a
+    // 64-value K chunk carries a.hi and a.lo of 32 channels.  The packed weights hold w.hi at both halves of the chunk
+    // from `koff` (a.hi w.hi + a.lo w.hi) and w.lo at the hi half from `koff_lo` (a.hi w.lo; < 0: no such range, the
+    // weights are exact in 16 bits).
+    int split;
+    int koff_lo;
     int8_t dy[kMaxTaps], dx[kMaxTaps];
 };
 
@@ -57,6 +64,7 @@ struct ConvDev {
     int res_C;
     int relu;
     int dst_fp32;         // tensor-core path: store fp32 instead of the 16-bit operand type
+    int split_out;        // tensor-core path: store hi + lo in the split layout described at SegDev (dst_C counts stored values)
 };
 
 }  // namespace spb200

@@ -120,11 +120,8 @@ static void launch_stem_t(const float* img, int B, int H, int W, const float* w,
                           cudaStream_t st) {
     auto kern = stem_pool_kernel<TOut, CIN>;
     const size_t smem = stem_smem_bytes(CIN);
-    static bool configured = false;   // per template instance
-    if (!configured) {
-        SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // function attributes are per device: set on every launch (a process may hold engines on several GPUs)
+    SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((W / 4 + kStemPT - 1) / kStemPT, (H / 4 + kStemPT - 1) / kStemPT, B);
     kern<<<grid, 256, smem, st>>>(img, w, bias, (TOut*)dst, H, W);
     SPB_CHECK_LAUNCH();
@@ -268,6 +265,53 @@ void launch_nhwc_to_nchw(const void* src, int src_type, int B, int HW, int Cs, i
     if (src_type == PREC_FP32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, st>>>((const float*)src, dst, HW, Cs, C);
     else if (src_type == PREC_FP16) nhwc_to_nchw_kernel<__half><<<grid, 256, 0, st>>>((const __half*)src, dst, HW, Cs, C);
     else nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, dst, HW, Cs, C);
+    SPB_CHECK_LAUNCH();
+}
+
+// Split-layout source (common.cuh, SegDev): channel c of a pixel = hi + lo, hi at (c / 32) * 64 + c % 32, lo 32 further.
+template <typename T>
+__global__ void __launch_bounds__(256) split_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int HW, int Cs, int C) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+    for (int i = ty; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + tx;
+        float v = 0.f;
+        if (p < HW && c < C) {
+            const T* px = src + ((size_t)b * HW + p) * Cs + (c / 32) * 64 + c % 32;
+            v = to_float(px[0]) + to_float(px[32]);
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + tx;
+        if (p < HW && c < C) dst[((size_t)b * C + c) * HW + p] = tile[tx][i];
+    }
+}
+
+void launch_split_to_nchw(const void* src, int src_type, int B, int HW, int Cs, int C, float* dst, cudaStream_t st) {
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+    if (src_type == PREC_FP16) split_to_nchw_kernel<__half><<<grid, 256, 0, st>>>((const __half*)src, dst, HW, Cs, C);
+    else if (src_type == PREC_BF16) split_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, dst, HW, Cs, C);
+    else throw std::invalid_argument("split layout: 16-bit element types only");
+    SPB_CHECK_LAUNCH();
+}
+
+// one thread = 16 bytes (8 hi values); a pixel has C / 8 of them
+__global__ void __launch_bounds__(256) split_hi_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long total, int c8) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long pix = i / c8;
+    const int k = (int)(i % c8);                       // 16-byte piece of the plain pixel: chunk k / 4, piece k % 4 of its hi half
+    dst[i] = __ldg(src + pix * (2 * c8) + (k >> 2) * 8 + (k & 3));
+}
+
+void launch_split_hi(const void* src, void* dst, long npix, int C, cudaStream_t st) {
+    if (C % 32) throw std::invalid_argument("split layout: channels must be a multiple of 32");
+    const long total = npix * (C / 8);
+    split_hi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, total, C / 8);
     SPB_CHECK_LAUNCH();
 }
 

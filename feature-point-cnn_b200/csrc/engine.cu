@@ -260,8 +260,11 @@ void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> sr
     // neither waits for the shortcut tile to land in its staging box nor reads it (halo_tc.cu keeps ONE box per tile at
     // N = 64, shared memory is full; encoder.layer1.1 121 -> see DESIGN.md section 9).
     const HostConv* cd = cd_folded;
-    if (!cd && precision_ != PREC_FP32 && use_halo_ && fuse_blocks_ && srcs.size() == 1 && stride == 1 && cout == 64 &&
-        cin_total == 64 && bufspec_[y_buf].C == 64 && bufspec_[srcs[0].first].C == 64 && !std::getenv("SPB200_NO_IDENTITY_MMA")) {
+    // split-precision blocks (their source is stored as hi + lo) always do: x.hi . I + x.lo . I is the exact fp32-grade shortcut
+    const bool split_in = bufspec_[srcs[0].first].split;
+    if (!cd && ((split_in && srcs.size() == 1 && stride == 1 && cin_total == cout) ||
+                (precision_ != PREC_FP32 && use_halo_ && fuse_blocks_ && srcs.size() == 1 && stride == 1 && cout == 64 &&
+                 cin_total == 64 && bufspec_[y_buf].C == 64 && bufspec_[srcs[0].first].C == 64 && !std::getenv("SPB200_NO_IDENTITY_MMA")))) {
         auto hc = std::make_unique<HostConv>();
         hc->cout = hc->cin = cout; hc->kh = hc->kw = 1;
         hc->synthetic = true;
@@ -275,7 +278,7 @@ void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> sr
         throw std::runtime_error("unexpected convolution shapes in block " + p);
     if (cd && (cd->cin != cin_total || cd->cout != cout || cd->kh != 1))
         throw std::runtime_error("unexpected downsample shape in block " + p);
-    const int cout_pad = bufspec_[y_buf].C;
+    const int cout_pad = cout_pad_of(cout, y_buf);
 
     // A stride-2 block on the tensor-core path with one source and at most 128 output channels is read as stride-1
     // convolutions over the four pixel phases of its input (row parity a, column parity b): output (oy, ox) takes
@@ -334,13 +337,21 @@ void Engine::add_block(const std::string& p, std::vector<std::pair<int, int>> sr
 
 void Engine::build_ops() {
     const int dc = det_c_;
-    bufspec_[BUF_POOL] = {4, 64, false};
-    for (int b : {BUF_L1A_Y, BUF_L1A, BUF_L1B_Y, BUF_L1B}) bufspec_[b] = {4, 64, false};
-    for (int b : {BUF_L2A_Y, BUF_L2A, BUF_L2B_Y, BUF_FEAT}) bufspec_[b] = {8, 128, false};
-    for (int b : {BUF_D0_Y, BUF_D0, BUF_D1_Y}) bufspec_[b] = {8, dc, false};
-    bufspec_[BUF_LOGITS] = {8, dc, true};
-    for (int b : {BUF_I0_Y, BUF_I0, BUF_I1_Y, BUF_I1}) bufspec_[b] = {16, 256, false};
-    for (int b : {BUF_UP, BUF_O0_Y, BUF_O0, BUF_O1_Y, BUF_DESC}) bufspec_[b] = {8, 128, false};
+    // a buffer is stored in the split layout when the stage that READS it runs split-precision convolutions
+    const int L = precision_ == PREC_FP32 ? (int)SPLIT_NONE : split_level_;
+    const bool s1 = L >= SPLIT_LAYER1, s2 = L >= SPLIT_LAYER2, s3 = L >= SPLIT_DETECTOR;
+    bufspec_[BUF_POOL] = {4, 64, false, s1};
+    for (int b : {BUF_L1A_Y, BUF_L1A, BUF_L1B_Y}) bufspec_[b] = {4, 64, false, s1};
+    bufspec_[BUF_L1B] = {4, 64, false, s2};
+    for (int b : {BUF_L2A_Y, BUF_L2A, BUF_L2B_Y}) bufspec_[b] = {8, 128, false, s2};
+    bufspec_[BUF_FEAT] = {8, 128, false, s3};
+    // 65 detector channels: 128 per pixel (the kernels' N), or 3 split chunks of 32
+    for (int b : {BUF_D0_Y, BUF_D0, BUF_D1_Y}) bufspec_[b] = {8, s3 ? 96 : dc, false, s3};
+    bufspec_[BUF_LOGITS] = {8, dc, true, false};
+    for (int b : {BUF_I0_Y, BUF_I0, BUF_I1_Y, BUF_I1}) bufspec_[b] = {16, 256, false, false};
+    for (int b : {BUF_UP, BUF_O0_Y, BUF_O0, BUF_O1_Y, BUF_DESC}) bufspec_[b] = {8, 128, false, false};
+    bufspec_[BUF_FEAT_HI] = {8, s3 ? 128 : 0, false, false};
+    const int feat_desc = s3 ? BUF_FEAT_HI : BUF_FEAT;               // what the descriptor head reads
 
     // encoder (reference python/src/superpoint.py:16-17), detector (:32), descriptor (:43-50)
     add_block("encoder.layer1.0", {{BUF_POOL, 64}}, BUF_L1A_Y, BUF_L1A, 1, 64, false);
@@ -350,7 +361,7 @@ void Engine::build_ops() {
     add_block("detector.layer.0", {{BUF_FEAT, 128}}, BUF_D0_Y, BUF_D0, 1, 65, false);
     add_block("detector.layer.1", {{BUF_D0, 65}}, BUF_D1_Y, BUF_LOGITS, 1, 65, true);
     const size_t first_desc_op = ops_.size();
-    add_block("descriptor.layer_in.0", {{BUF_FEAT, 128}}, BUF_I0_Y, BUF_I0, 2, 256, false);
+    add_block("descriptor.layer_in.0", {{feat_desc, 128}}, BUF_I0_Y, BUF_I0, 2, 256, false);
     add_block("descriptor.layer_in.1", {{BUF_I0, 256}}, BUF_I1_Y, BUF_I1, 1, 256, false);
     // ConvTranspose2d(256,128,k3,s2,p1,op1)+bias -> BN -> ReLU (python/src/superpoint.py:45-47,55-57) as four
     // output phases: out[2m+py, 2n+px]; even outputs use kernel index 1 from input m, odd outputs kernel
@@ -377,24 +388,47 @@ void Engine::build_ops() {
             o.bias = up->b;
             ops_.push_back(std::move(o));
         }
-    add_block("descriptor.layer_out.0", {{BUF_UP, 128}, {BUF_FEAT, 128}}, BUF_O0_Y, BUF_O0, 1, 128, false);
+    add_block("descriptor.layer_out.0", {{BUF_UP, 128}, {feat_desc, 128}}, BUF_O0_Y, BUF_O0, 1, 128, false);
     add_block("descriptor.layer_out.1", {{BUF_O0, 128}}, BUF_O1_Y, BUF_DESC, 1, 128, false);
     (void)first_desc_op;
 
     // pack and upload
+    auto round16 = [&](float f) {
+        return precision_ == PREC_FP16 ? __half2float(__float2half_rn(f)) : __bfloat162float(__float2bfloat16_rn(f));
+    };
     for (auto& op : ops_) {
         int K = 0;
-        for (auto& s : op.segs) K += (int)s.taps.size() * bufspec_[s.src_buf].C;
-        op.K = K;
+        bool any_split = false;
+        for (auto& s : op.segs) {
+            K += (int)s.taps.size() * bufspec_[s.src_buf].stored();
+            any_split = any_split || bufspec_[s.src_buf].split;
+        }
+        for (auto& s : op.segs)
+            if (bufspec_[s.src_buf].split != any_split) throw std::runtime_error("internal: mixed split / plain sources in " + op.name);
+        op.K_main = K;
+        op.K = any_split ? 2 * K : K;        // split sources: the lo-weight ranges mirror the main ranges
+        K = op.K;
         std::vector<float> w32((size_t)K * op.cout_pad, 0.f);
         int koff = 0;
         for (auto& s : op.segs) {
-            const int cpad = bufspec_[s.src_buf].C;
+            const int cpad = bufspec_[s.src_buf].stored();
             for (size_t t = 0; t < s.taps.size(); ++t)
                 for (int ci = 0; ci < s.cin_real; ++ci)
-                    for (int co = 0; co < op.cout_real; ++co)
-                        w32[(size_t)(koff + (int)t * cpad + ci) * op.cout_pad + co] =
-                            s.conv->at(co, s.ci_off + ci, s.taps[t].kh, s.taps[t].kw);
+                    for (int co = 0; co < op.cout_real; ++co) {
+                        const float w = s.conv->at(co, s.ci_off + ci, s.taps[t].kh, s.taps[t].kw);
+                        if (!any_split) {
+                            w32[(size_t)(koff + (int)t * cpad + ci) * op.cout_pad + co] = w;
+                            continue;
+                        }
+                        // split layout (common.cuh, SegDev): channel ci sits at (ci / 32) * 64 + ci % 32 (hi) and + 32 (lo);
+                        // w.hi multiplies both, w.lo - kept only where the weight is not exact in 16 bits - the hi half
+                        const int j = (ci / 32) * 64 + ci % 32;
+                        const size_t row = (size_t)(koff + (int)t * cpad + j);
+                        const float hi = round16(w);
+                        w32[row * op.cout_pad + co] = hi;
+                        w32[(row + 32) * op.cout_pad + co] = hi;
+                        if (!s.conv->synthetic) w32[(row + (size_t)op.K_main) * op.cout_pad + co] = w - hi;
+                    }
             koff += (int)s.taps.size() * cpad;
         }
         op.d_bias = dev_upload(op.bias);
@@ -456,15 +490,24 @@ void Engine::build_ops() {
     }
 }
 
-void Engine::finalize(int precision) {
+int Engine::cout_pad_of(int cout, int y_buf) const {
+    return precision_ == PREC_FP32 ? bufspec_[y_buf].C : round_up(cout, 64);
+}
+
+void Engine::finalize(int precision, int split_level) {
     if (precision != PREC_FP32 && precision != PREC_FP16 && precision != PREC_BF16)
         throw std::invalid_argument("precision must be 0 (fp32 CUDA cores), 1 (fp16 tcgen05) or 2 (bf16 tcgen05)");
+    if (split_level < SPLIT_NONE || split_level > SPLIT_DETECTOR)
+        throw std::invalid_argument("split level must be 0 (none), 1 (stem + layer1), 2 (+ layer2) or 3 (+ detector)");
+    if (split_level != SPLIT_NONE && (precision == PREC_FP32 || !use_halo_ || !fuse_blocks_))
+        throw std::invalid_argument("split-precision stages need the fused tensor-core path (precision fp16 / bf16)");
     if (sd_.empty()) throw std::runtime_error("no weights loaded");
     SPB_CUDA(cudaSetDevice(device_));
     SPB_CUDA(cudaDeviceSynchronize());
     release_workspace();
     release_weights();
     precision_ = precision;
+    split_level_ = split_level;
     det_c_ = precision == PREC_FP32 ? 80 : 128;
     build_ops();
     finalized_ = true;
@@ -504,8 +547,9 @@ void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
     const size_t esz = precision_ == PREC_FP32 ? 4 : 2;
     for (int i = 0; i < BUF_COUNT; ++i) {
         const BufSpec& bs = bufspec_[i];
-        const size_t n = (size_t)cap * (H / bs.div) * (W / bs.div) * bs.C;
+        const size_t n = (size_t)cap * (H / bs.div) * (W / bs.div) * bs.stored();
         const size_t bytes = n * (bs.fp32 ? 4 : esz);
+        if (bytes == 0) continue;
         SPB_CUDA(cudaMalloc(&buf_[i], bytes));
         SPB_CUDA(cudaMemset(buf_[i], 0, bytes));     // padded channels stay zero forever
     }
@@ -527,6 +571,7 @@ void Engine::build_plans() {
                 const ConvDev c1 = make_conv_dev(op), c2 = make_conv_dev(ops_[i + 1]);
                 if (use_halo_) op.halo = tc_halo_plan_create(c1, &c2, precision_, op.cout_real, num_sms_);
                 if (!op.halo && op.segs[0].view > 1) throw std::runtime_error("internal: no haloed-tile plan for the phase form of " + op.name);
+                if (!op.halo && bufspec_[op.segs[0].src_buf].split) throw std::runtime_error("internal: no split-precision plan for " + op.name);
                 if (!op.halo) op.fused = tc_block_plan_create(c1, &c2, precision_, op.cout_real, num_sms_);
                 ops_[i + 1].fused_skip = true;
                 ++i;
@@ -593,28 +638,31 @@ ConvDev Engine::make_conv_dev(const OpSpec& op) const {
         const BufSpec& bs = bufspec_[s.src_buf];
         SegDev& sd = d.seg[i];
         sd.src = buf_[s.src_buf];
-        sd.H = wsH_ / bs.div; sd.W = wsW_ / bs.div; sd.C = bs.C;
+        sd.H = wsH_ / bs.div; sd.W = wsW_ / bs.div; sd.C = bs.stored();
         sd.view = s.view; sd.full_H = sd.H; sd.full_W = sd.W;
         if (s.view > 1) {
             const size_t esz = (bs.fp32 || precision_ == PREC_FP32) ? 4 : 2;
-            sd.src = static_cast<const char*>(buf_[s.src_buf]) + ((size_t)s.vy * sd.full_W + s.vx) * bs.C * esz;
+            sd.src = static_cast<const char*>(buf_[s.src_buf]) + ((size_t)s.vy * sd.full_W + s.vx) * bs.stored() * esz;
             sd.H /= s.view; sd.W /= s.view;
         }
-        sd.cin = bs.C;
+        sd.cin = bs.stored();
         sd.cin_real = s.cin_real;
+        sd.split = bs.split ? 1 : 0;
+        sd.koff_lo = (bs.split && !(s.conv && s.conv->synthetic)) ? op.K_main + koff : -1;
         sd.ntaps = (int)s.taps.size();
         sd.stride = s.stride;
         sd.koff = koff;
         for (int t = 0; t < sd.ntaps; ++t) { sd.dy[t] = (int8_t)s.taps[t].dy; sd.dx[t] = (int8_t)s.taps[t].dx; }
-        koff += sd.ntaps * bs.C;
+        koff += sd.ntaps * bs.stored();
     }
     d.w = precision_ == PREC_FP32 ? (const void*)op.d_w32 : (const void*)op.d_w16;
     d.bias = op.d_bias;
     d.residual = op.res_buf >= 0 ? buf_[op.res_buf] : nullptr;
-    d.res_C = op.res_buf >= 0 ? bufspec_[op.res_buf].C : 0;
+    d.res_C = op.res_buf >= 0 ? bufspec_[op.res_buf].stored() : 0;
     d.dst = buf_[op.dst_buf];
     d.B = wsB_;
-    d.dst_H = wsH_ / ds.div; d.dst_W = wsW_ / ds.div; d.dst_C = ds.C;
+    d.dst_H = wsH_ / ds.div; d.dst_W = wsW_ / ds.div; d.dst_C = ds.stored();
+    d.split_out = ds.split ? 1 : 0;
     d.dst_stride = op.dst_stride; d.dst_off_y = op.off_y; d.dst_off_x = op.off_x;
     d.OH = d.dst_H / op.dst_stride; d.OW = d.dst_W / op.dst_stride;
     d.K = op.K; d.cout_pad = op.cout_pad;
@@ -665,7 +713,8 @@ void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
     ensure_workspace(B, C, H, W, st);
     if (img_u8 && C != 1) throw std::invalid_argument("8-bit frames must be single-channel (grayscale)");
     const float* img = static_cast<const float*>(img_any);
-    if (img_u8 && !(precision_ != PREC_FP32 && use_planes_)) {
+    const bool wide_stem = bufspec_[BUF_POOL].split;      // split level >= 1: image hi + lo, three MMAs per product (stem_tc.cu)
+    if (img_u8 && !(precision_ != PREC_FP32 && use_planes_ && !wide_stem)) {
         // paths without the plane-fed stem take fp32 images: frame / 255 as the reference's loaders do
         // (python/src/inference.py:78-80, cpp/src/camera.cc:16-18)
         if (!d_imgf_) SPB_CUDA(cudaMalloc((void**)&d_imgf_, sizeof(float) * (size_t)capB_ * H * W));
@@ -675,7 +724,7 @@ void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
         img_u8 = false;
     }
     // gray-folded stem: 49 MACs per output (the reference's 3-channel stem does 147 on replicated input)
-    const bool planes = precision_ != PREC_FP32 && C == 1 && use_planes_;
+    const bool planes = precision_ != PREC_FP32 && C == 1 && use_planes_ && !wide_stem;
     if (planes) {
         prof_open("image_planes", 0.0, (double)B * H * W * ((img_u8 ? 1 : 4) + 2), st);
         launch_planes(img_any, img_u8 ? 1 : 0, d_planes_, precision_, B, H, W, st);
@@ -686,16 +735,28 @@ void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
               (double)B * C * H * W * (planes ? 2 : 4) + (double)B * (H / 4) * (W / 4) * 64 * (precision_ == PREC_FP32 ? 4 : 2), st);
     if (precision_ == PREC_FP32)
         launch_stem_pool(img, B, C, H, W, d_stem_w_[C == 1 ? 0 : 1], d_stem_b_, buf_[BUF_POOL], precision_, st);
+    else if (wide_stem)
+        launch_stem_wide(stem_plan_[C == 1 ? 0 : 1], img, buf_[BUF_POOL], B, H, W, st);
     else if (planes)
         launch_stem_planes(stem_planes_, d_planes_, buf_[BUF_POOL], B, H, W, st);
     else
         launch_stem_tc(stem_plan_[C == 1 ? 0 : 1], img, buf_[BUF_POOL], B, H, W, st);
     prof_close(st);
     ++launches_;
+    bool feat_hi_done = !bufspec_[BUF_FEAT].split;
     for (size_t i = 0; i < ops_.size(); ++i) {
         OpSpec& op = ops_[i];
         if (!params_.descriptor_enabled && op.name.compare(0, 11, "descriptor.") == 0) continue;
         if (op.fused_skip) continue;
+        if (!feat_hi_done && op.name.compare(0, 11, "descriptor.") == 0) {
+            // the descriptor head is not split: it reads the hi halves of the encoder features as a plain tensor
+            const long npix = (long)B * (H / 8) * (W / 8);
+            prof_open("features_hi", 0.0, (double)npix * 128 * 2 * 3, st);
+            launch_split_hi(buf_[BUF_FEAT], buf_[BUF_FEAT_HI], npix, 128, st);
+            prof_close(st);
+            ++launches_;
+            feat_hi_done = true;
+        }
         if (precision_ == PREC_FP32) {
             prof_open(op.name, op_flops(op), 0.0, st);
             launch_conv_simt(make_conv_dev(op), st);
@@ -955,8 +1016,11 @@ void Engine::buffer_dims(int id, int* C, int* H, int* W) const {
 void Engine::export_buffer(int id, float* dst_nchw, int channels, cudaStream_t st) {
     if (id < 0 || id >= BUF_COUNT || !buf_[id]) throw std::invalid_argument("bad buffer id or no workspace");
     const BufSpec& bs = bufspec_[id];
-    launch_nhwc_to_nchw(buf_[id], bs.fp32 ? PREC_FP32 : precision_, wsB_, (wsH_ / bs.div) * (wsW_ / bs.div), bs.C,
-                        channels, dst_nchw, st);
+    if (bs.split)
+        launch_split_to_nchw(buf_[id], precision_, wsB_, (wsH_ / bs.div) * (wsW_ / bs.div), bs.stored(), channels, dst_nchw, st);
+    else
+        launch_nhwc_to_nchw(buf_[id], bs.fp32 ? PREC_FP32 : precision_, wsB_, (wsH_ / bs.div) * (wsW_ / bs.div), bs.C,
+                            channels, dst_nchw, st);
 }
 
 // Host-buffer entry point: what ProcessFrame / InferenceWrapper.run do around the network (H2D of the frames, D2H

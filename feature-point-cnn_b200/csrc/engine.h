@@ -48,7 +48,8 @@ struct OpSpec {
     int dst_buf = -1, res_buf = -1;
     bool relu = true, dst_fp32 = false;
     int dst_stride = 1, off_y = 0, off_x = 0;
-    int K = 0;
+    int K = 0;                    // packed K: every segment's taps x stored channels, then (split sources) the lo-weight ranges
+    int K_main = 0;               // K without the lo-weight ranges
     std::vector<float> bias;      // [cout_pad]
     // device
     float* d_bias = nullptr;
@@ -66,10 +67,19 @@ enum BufId {
     BUF_POOL, BUF_L1A_Y, BUF_L1A, BUF_L1B_Y, BUF_L1B, BUF_L2A_Y, BUF_L2A, BUF_L2B_Y, BUF_FEAT,
     BUF_D0_Y, BUF_D0, BUF_D1_Y, BUF_LOGITS,
     BUF_I0_Y, BUF_I0, BUF_I1_Y, BUF_I1, BUF_UP, BUF_O0_Y, BUF_O0, BUF_O1_Y, BUF_DESC,
+    BUF_FEAT_HI,                  // the hi halves of a split BUF_FEAT as a plain 16-bit tensor: what the descriptor head reads
     BUF_COUNT
 };
 
-struct BufSpec { int div; int C; bool fp32; };
+// C: channels per pixel (padded); split: stored in the split-precision layout (common.cuh, SegDev), 2 C values per pixel
+struct BufSpec {
+    int div; int C; bool fp32; bool split;
+    int stored() const { return split ? 2 * C : C; }
+};
+
+// Stages whose convolutions run with split-precision operands (three MMAs per product, fp32-grade results).  Only
+// prefixes of the network are accepted: the stem, + layer1, + layer2, + the detector head.
+enum SplitLevel { SPLIT_NONE = 0, SPLIT_LAYER1 = 1, SPLIT_LAYER2 = 2, SPLIT_DETECTOR = 3 };
 
 class Engine {
 public:
@@ -80,7 +90,8 @@ public:
 
     void load_checkpoint(const std::string& path);
     void load_tensor(const std::string& key, const float* data, const int64_t* shape, int rank);
-    void finalize(int precision);
+    void finalize(int precision, int split_level = SPLIT_NONE);
+    int split_level() const { return split_level_; }
     void set_params(const Params& p) { params_ = p; }
     const Params& params() const { return params_; }
     int precision() const { return precision_; }
@@ -150,6 +161,7 @@ private:
 
     int device_;
     int precision_ = PREC_FP32;
+    int split_level_ = SPLIT_NONE;
     bool finalized_ = false;
     Params params_;
     StateDict sd_;
@@ -164,6 +176,7 @@ private:
     float* d_stem_b_ = nullptr;
     void* d_stem_w16_[2] = {nullptr, nullptr};     // tensor-core stem: [64][nchunk*64] 16-bit, K-major
     StemTcPlan* stem_plan_[2] = {nullptr, nullptr};
+    int cout_pad_of(int cout, int y_buf) const;
     StemPlanesPlan* stem_planes_ = nullptr;        // gray stem fed by TMA from parity planes (stem_planes.cu)
     bool use_planes_ = true;      // SPB200_OLD_STEM=1 keeps the im2col-in-shared-memory stem
     void* d_planes_ = nullptr;    // [B][2][H/2][W] 16-bit image x255, per workspace shape

@@ -50,10 +50,10 @@ constexpr int kHaloS = 18;                                  // 16 + 2 rows along
 constexpr int kHaloLoadBytes = kHaloS * kHaloG * 128;       // 23040 B landed by one TMA box
 constexpr int kHaloBufBytes = 23552;                        // rounded up to a multiple of 1024
 constexpr int kHaloSbo = kHaloG * 128;                      // 8-pixel groups are one haloed row apart
-constexpr int kMaxSteps = 48;
+constexpr int kMaxSteps = 96;
 constexpr int kMaxChunks = 8;
 __host__ __device__ constexpr int halo_threads(int T) { return (2 + T + 8) * 32; }
-__host__ __device__ constexpr int halo_out_slots(int N, bool) { return N == 128 ? 2 : 1; }
+__host__ __device__ constexpr int halo_out_slots(int N, bool split) { return (N == 128 || split) ? 2 : 1; }
 constexpr int kHaloOutBox = 16384;                          // one staged output box: 128 pixel rows x 128 B   // 2 producers, T MMA issuers, 8 epilogue warps
 
 // One weight slab [N x 64 K] and the MMAs that consume it, packed into 64 bits so that the issuing warps fetch a
@@ -96,10 +96,14 @@ struct HaloParams {
     int w_bytes;                   // bytes of one weight slab as loaded: n_mma rows x 128 B
     int tma_res;                   // the identity shortcut arrives by TMA (needs tma_store)
     int tma_store;                 // fused variants: the output leaves through shared memory and TMA stores
+    int split_out;                 // SPLIT kernels: the output is stored as [hi 32 | lo 32] per 32 channels (common.cuh, SegDev)
     long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
 };
 
-template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, typename Tp>
+// SPLIT: split-precision operands (three MMAs per product, common.cuh SegDev): the activation chunks and the weight slabs
+// arrive in the split layout - which only the host-built step list knows about -, the first epilogue writes Y back as
+// [hi | lo] and the second one can store the block output the same way.
+template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, bool SPLIT, typename Tp>
 __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __grid_constant__ HaloParams p) {
     constexpr int kWBytes = N * 128;
     constexpr uint32_t kAccCols = NBUF * T * N;
@@ -107,6 +111,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     static_assert(kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
     static_assert(!(FUSED && NBUF == 2) || WRES, "pipelined GEMM 2 needs resident weights (slab order)");
     static_assert(T == 2 || !FUSED, "the in-place Y write-back assumes one epilogue warp per lane quarter and tile");
+    static_assert(!SPLIT || (FUSED && !WRES), "split precision: fused blocks with streamed weights");
 
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full[SW], w_empty[SW];
@@ -121,7 +126,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     uint8_t* w_ring = a_ring + SA * T * kHaloBufBytes;
     // output staging of the fused variants: per tile kOutSlots boxes of 128 pixel rows x 128 B (16 KB), each epilogue warp
     // owns the 4 KB of its 32 rows in every box
-    constexpr int kOutSlots = halo_out_slots(N, FUSED);
+    constexpr int kOutSlots = halo_out_slots(N, SPLIT);
     uint8_t* out_stage = w_ring + SW * kWBytes;
     // warp index through a shuffle: tells the compiler it is warp-uniform, so the role loops below run on the
     // uniform datapath (loop counters, ring state, descriptors in uniform registers) instead of R2UR round trips
@@ -384,10 +389,25 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 }
                 tmem_ld_wait();
                 uint32_t y[16];
+                if (SPLIT) {
+                    // the 32 fp32 columns of the block become 16 columns of hi pairs + 16 columns of lo pairs, in place
+                    uint32_t yl[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    y[e] = pack2_relu<Tp>(__uint_as_float(r[2 * e]) + bb[2 * e], __uint_as_float(r[2 * e + 1]) + bb[2 * e + 1]);
-                tmem_st_32x16(tmem_d1 + (uint32_t)(c0 >> 1), y);
+                    for (int e = 0; e < 16; ++e) {
+                        const float a = fmaxf(__uint_as_float(r[2 * e]) + bb[2 * e], 0.f);
+                        const float c = fmaxf(__uint_as_float(r[2 * e + 1]) + bb[2 * e + 1], 0.f);
+                        y[e] = pack2<Tp>(a, c);
+                        const float2 f = unpack2<Tp>(y[e]);
+                        yl[e] = pack2<Tp>(a - f.x, c - f.y);
+                    }
+                    tmem_st_32x16(tmem_d1 + (uint32_t)c0, y);
+                    tmem_st_32x16(tmem_d1 + (uint32_t)(c0 + 16), yl);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        y[e] = pack2_relu<Tp>(__uint_as_float(r[2 * e]) + bb[2 * e], __uint_as_float(r[2 * e + 1]) + bb[2 * e + 1]);
+                    tmem_st_32x16(tmem_d1 + (uint32_t)(c0 >> 1), y);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
@@ -502,7 +522,33 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
 #pragma unroll
                         for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (ts) {
+                    if (SPLIT && ts && p.split_out) {
+                        // one 128-byte box row per block of 32 channels: 64 B of hi pairs, 64 B of lo pairs; the two
+                        // slots alternate as on the fp32 path
+                        const uint32_t sw = (uint32_t)(lane & 7);
+                        const uint32_t box = stg + (uint32_t)((nbox & 1) * kHaloOutBox);
+                        if (nbox >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
+                        uint32_t hw[16], lw[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float a = p.relu ? fmaxf(v[2 * e], 0.f) : v[2 * e];
+                            const float c = p.relu ? fmaxf(v[2 * e + 1], 0.f) : v[2 * e + 1];
+                            hw[e] = pack2<Tp>(a, c);
+                            const float2 f = unpack2<Tp>(hw[e]);
+                            lw[e] = pack2<Tp>(a - f.x, c - f.y);
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            st_shared_v4(box + (uint32_t)lane * 128u + (((uint32_t)jj ^ sw) << 4), hw[jj * 4], hw[jj * 4 + 1], hw[jj * 4 + 2],
+                                         hw[jj * 4 + 3]);
+                            st_shared_v4(box + (uint32_t)lane * 128u + (((uint32_t)(4 + jj) ^ sw) << 4), lw[jj * 4], lw[jj * 4 + 1],
+                                         lw[jj * 4 + 2], lw[jj * 4 + 3]);
+                        }
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && tile_ok) { tma_store_4d(&p.tmD, box, blk * 64, tc_g, tc_s, tc_img); tma_store_commit(); }
+                        ++nbox;
+                    } else if (ts) {
                         const uint32_t sw = (uint32_t)(lane & 7);
                         if (p.dst_fp32) {
                             // one box per block of 32 fp32 channels; the two slots alternate
@@ -1008,19 +1054,16 @@ static long long* g_halo_dbg = nullptr;
 struct TcHaloPlan {
     HaloParams params;
     int variant;       // 0: N=64 fused, resident weights; 1: N=128 fused, T=2; 2: N=128 single convolution, T=2;
-                       // 3: N=128 fused on CTA pairs (SPB200_PAIR=1, not yet run on a GPU)
+                       // 3: N=128 fused on CTA pairs (SPB200_PAIR=1); 4 / 5: split precision, N = 64 / 128 fused
     int operand_type, grid;
 };
 
-template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, typename Tp>
+template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, bool SPLIT, typename Tp>
 static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
-    auto kern = halo_tc_kernel<N, T, NBUF, SA, SW, FUSED, WRES, Tp>;
-    const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + (size_t)T * halo_out_slots(N, FUSED) * kHaloOutBox + 1024;
-    static bool configured = false;       // per instantiation
-    if (!configured) {
-        SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    auto kern = halo_tc_kernel<N, T, NBUF, SA, SW, FUSED, WRES, SPLIT, Tp>;
+    const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + (size_t)T * halo_out_slots(N, SPLIT) * kHaloOutBox + 1024;
+    // function attributes are per device: set on every launch (a process may hold engines on several GPUs)
+    SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<plan->grid, halo_threads(T), smem, st>>>(plan->params);
     SPB_CHECK_LAUNCH();
 }
@@ -1028,20 +1071,20 @@ static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
 constexpr int kHaloResidentSlabs = 11;   // variant 0: every slab of a 64-channel block stays in shared memory
 constexpr int kHaloRing1 = 4;            // variant 1: weight ring slots (16 KB each; 8 slots measured no faster)
 constexpr int kHaloRing2 = 4;            // variant 2
+constexpr int kHaloRing4 = 8;            // variant 4: split precision, N = 64 (8 KB slabs)
+constexpr int kHaloRing5 = 4;            // variant 5: split precision, N = 128
 
 template <typename Tp>
 static void launch_halo_v(const TcHaloPlan* plan, cudaStream_t st) {
     switch (plan->variant) {
-        case 0: launch_halo_t<64, 2, 2, 2, kHaloResidentSlabs, true, true, Tp>(plan, st); break;
-        case 1: launch_halo_t<128, 2, 1, 2, kHaloRing1, true, false, Tp>(plan, st); break;
-        case 2: launch_halo_t<128, 2, 2, 2, kHaloRing2, false, false, Tp>(plan, st); break;
+        case 0: launch_halo_t<64, 2, 2, 2, kHaloResidentSlabs, true, true, false, Tp>(plan, st); break;
+        case 1: launch_halo_t<128, 2, 1, 2, kHaloRing1, true, false, false, Tp>(plan, st); break;
+        case 2: launch_halo_t<128, 2, 2, 2, kHaloRing2, false, false, false, Tp>(plan, st); break;
+        case 4: launch_halo_t<64, 2, 1, 2, kHaloRing4, true, false, true, Tp>(plan, st); break;
+        case 5: launch_halo_t<128, 2, 1, 2, kHaloRing5, true, false, true, Tp>(plan, st); break;
         case 3: {
             auto kern = halo_pair_kernel<Tp>;
-            static bool configured = false;
-            if (!configured) {
-                SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
-                configured = true;
-            }
+            SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
             kern<<<plan->grid, kPairThreads, kPairSmem, st>>>(plan->params);
             SPB_CHECK_LAUNCH();
             break;
@@ -1065,9 +1108,13 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     const int N = c1.cout_pad;
     if (N != 64 && N != 128) return nullptr;
     if (N == 64 && !c2) return nullptr;
+    // split-precision block (common.cuh, SegDev): every source in the split layout, fused form only
+    const bool split = c1.nseg > 0 && c1.seg[0].split != 0;
+    if (split && !c2) return nullptr;
     int min_dy = 127, max_dy = -127, min_dx = 127, max_dx = -127;
     for (int s = 0; s < c1.nseg; ++s) {
         const SegDev& sg = c1.seg[s];
+        if ((sg.split != 0) != split) return nullptr;
         if (sg.stride != 1 || sg.cin % 64 != 0 || sg.C % 64 != 0 || sg.cin != sg.C) return nullptr;
         if (sg.H != c1.OH || sg.W != c1.OW) return nullptr;
         for (int t = 0; t < sg.ntaps; ++t) {
@@ -1086,7 +1133,7 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     std::memset(&p, 0, sizeof(p));
     const CUtensorMapDataType dt = operand_type == PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     plan->operand_type = operand_type;
-    plan->variant = N == 64 ? 0 : (c2 ? 1 : 2);
+    plan->variant = split ? (N == 64 ? 4 : 5) : (N == 64 ? 0 : (c2 ? 1 : 2));
     const int T = 2;
 
     // tile orientation: 16 x 8 (group axis = x) or 8 x 16 (group axis = y), whichever needs fewer tiles
@@ -1113,22 +1160,32 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     };
     p.has_ds = c2 && c2->nseg > 1;
     if (c2) {
-        if (c2->nseg < 1 || c2->seg[0].ntaps != 1 || c2->seg[0].cin != N) return nullptr;
+        if (c2->nseg < 1 || c2->seg[0].ntaps != 1) return nullptr;
+        // the second GEMM reads Y from tensor memory: N values per row, or 2 N in the split layout (the packed weights
+        // may cover fewer 64-value chunks when the real output channels end earlier)
+        if (!split && c2->seg[0].cin != N) return nullptr;
+        if (split && (c2->seg[0].split == 0 || c2->seg[0].cin % 64 != 0 || c2->seg[0].cin < (real_cout + 31) / 32 * 64)) return nullptr;
     }
     int ds_used = 0;
 
     int nsteps = 0, nchunks = 0;
-    const int ring = plan->variant == 0 ? kHaloResidentSlabs : (plan->variant == 1 ? kHaloRing1 : kHaloRing2);
+    const int ring = plan->variant == 0 ? kHaloResidentSlabs
+                   : plan->variant == 1 ? kHaloRing1 : plan->variant == 2 ? kHaloRing2 : plan->variant == 4 ? kHaloRing4 : kHaloRing5;
     bool first_g1 = true, first_ds = true;
     auto add_step = [&](unsigned a_lo, unsigned gemm, unsigned nkk, bool first, bool last, bool acc0, int kcoord) {
         const unsigned slot = (unsigned)(nsteps % ring);
         p.steps[nsteps++] = halo_step(a_lo, slot * (unsigned)(N * 128 / 16), slot, gemm, nkk, first, last, acc0, (unsigned)kcoord);
     };
+    // K = 16 steps of a split-layout chunk holding `real` (1..32) channels: the main slab spans the hi half and the
+    // lo half (a.hi w.hi + a.lo w.hi), the lo-weight slab the hi half only (a.hi w.lo)
+    auto kk_split_main = [](int real) { return 2 + (std::min(real, 32) + 15) / 16; };
+    auto kk_split_lo = [](int real) { return (std::min(real, 32) + 15) / 16; };
     for (int s = 0; s < c1.nseg; ++s) {
         const SegDev& sg = c1.seg[s];
         const int nch = sg.cin / 64;
         const int kk_last = kk_of(sg.cin_real > 0 ? sg.cin_real : sg.cin, nch);
         if (sg.koff % 64) return nullptr;
+        if (split && sg.koff_lo >= 0 && sg.koff_lo % 64) return nullptr;
         // the shortcut convolution of this source, if it has one (a phase-form block has it on phase (0, 0) only)
         const SegDev* ds = nullptr;
         if (p.has_ds) {
@@ -1136,26 +1193,35 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
                 if (c2->seg[j].src == sg.src) ds = &c2->seg[j];
             if (ds) {
                 if (ds->ntaps != 1 || ds->dy[0] != 0 || ds->dx[0] != 0 || ds->stride != 1 || ds->cin != sg.cin || ds->koff % 64 ||
-                    ds->view != sg.view)
+                    ds->view != sg.view || (ds->split != 0) != split || (split && ds->koff_lo >= 0 && ds->koff_lo % 64))
                     return nullptr;
                 ++ds_used;
             }
         }
         for (int c = 0; c < nch; ++c) {
+            const int real_here = (sg.cin_real > 0 ? sg.cin_real : sg.cin / 2) - 32 * c;      // split layout: real channels in this chunk
+            if (split && real_here <= 0) continue;                                        // a chunk of padding only
             if (nchunks >= kMaxChunks) return nullptr;
             p.chunk_seg[nchunks] = s;
             p.chunk_c0[nchunks] = c * 64;
             ++nchunks;
-            const int nkk = c == nch - 1 ? kk_last : 4;
-            for (int t = 0; t < sg.ntaps; ++t) {
-                if (nsteps >= kMaxSteps) return nullptr;
-                add_step(view16(sg.dy[t], sg.dx[t]), 0, nkk, t == 0, t == sg.ntaps - 1 && !ds, !first_g1, sg.koff / 64 + t * nch + c);
-                first_g1 = false;
-            }
+            // the slabs that read this chunk, in issue order: (view, gemm, K steps, K coordinate)
+            struct Use { unsigned view, gemm, nkk; int kcoord; };
+            std::vector<Use> uses;
+            const int nkk = split ? kk_split_main(real_here) : (c == nch - 1 ? kk_last : 4);
+            for (int t = 0; t < sg.ntaps; ++t) uses.push_back({view16(sg.dy[t], sg.dx[t]), 0u, (unsigned)nkk, sg.koff / 64 + t * nch + c});
+            if (split && sg.koff_lo >= 0)
+                for (int t = 0; t < sg.ntaps; ++t)
+                    uses.push_back({view16(sg.dy[t], sg.dx[t]), 0u, (unsigned)kk_split_lo(real_here), sg.koff_lo / 64 + t * nch + c});
             if (ds) {
+                uses.push_back({view16(0, 0), 1u, (unsigned)nkk, ds->koff / 64 + c});
+                if (split && ds->koff_lo >= 0) uses.push_back({view16(0, 0), 1u, (unsigned)kk_split_lo(real_here), ds->koff_lo / 64 + c});
+            }
+            for (size_t u = 0; u < uses.size(); ++u) {
                 if (nsteps >= kMaxSteps) return nullptr;
-                add_step(view16(0, 0), 1, nkk, 0, 1, !first_ds, ds->koff / 64 + c);
-                first_ds = false;
+                const bool acc = uses[u].gemm == 0 ? !first_g1 : !first_ds;
+                add_step(uses[u].view, uses[u].gemm, uses[u].nkk, u == 0, u + 1 == uses.size(), acc, uses[u].kcoord);
+                (uses[u].gemm == 0 ? first_g1 : first_ds) = false;
             }
         }
         // activations: dims {C, group axis, slow axis, image}; a phase view steps `view` pixels of the full buffer
@@ -1191,7 +1257,18 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         const int ych = N / 64;
         const int y_kk_last = kk_of(real_cout, ych);
         if (c2->seg[0].koff != 0) return nullptr;
-        for (int c = 0; c < ych; ++c) {
+        if (split) {
+            // Y sits in tensor memory as [hi 16 columns | lo 16 columns] per block of 32 channels = one 64-value K chunk
+            const int ych_split = (real_cout + 31) / 32;
+            if (c2->seg[0].koff_lo < 0 || c2->seg[0].koff_lo % 64) return nullptr;
+            for (int c = 0; c < ych_split; ++c) {
+                if (nsteps + 2 > kMaxSteps) return nullptr;
+                const int real_here = real_cout - 32 * c;
+                add_step((unsigned)(c * 32), 2, (unsigned)kk_split_main(real_here), 0, 0, p.has_ds || c > 0, c);
+                add_step((unsigned)(c * 32), 2, (unsigned)kk_split_lo(real_here), 0, 0, true, c2->seg[0].koff_lo / 64 + c);
+            }
+        }
+        for (int c = 0; c < ych && !split; ++c) {
             if (nsteps >= kMaxSteps) return nullptr;
             add_step((unsigned)(c * 32), 2, c == ych - 1 ? y_kk_last : 4, 0, 0, p.has_ds || c > 0, c);
         }
@@ -1215,13 +1292,17 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     p.res_C = last.res_C; p.dst_H = last.dst_H; p.dst_W = last.dst_W; p.dst_C = last.dst_C;
     p.dst_stride = last.dst_stride; p.dst_off_y = last.dst_off_y; p.dst_off_x = last.dst_off_x;
     p.relu = last.relu; p.dst_fp32 = last.dst_fp32;
+    p.split_out = (split && last.split_out && !last.dst_fp32) ? 1 : 0;
+    if (last.split_out && !p.split_out) return nullptr;
+    if (split && last.residual) return nullptr;                      // split blocks add their shortcut on the tensor core (x . I)
     // fused variants store through shared memory: destination tensor {C, group axis, slow axis, image}, one box = the 32
     // pixel rows of an epilogue warp (8 along the group axis x 4 slow rows) x 128 B of channels
     p.tma_store = 0;
     if (last.dst_stride >= 1 && (c1.OH - 1) * last.dst_stride + last.dst_off_y < last.dst_H &&
         (c1.OW - 1) * last.dst_stride + last.dst_off_x < last.dst_W &&
-        last.dst_C % (last.dst_fp32 ? 32 : 64) == 0 && last.dst_C >= (last.dst_fp32 ? p.n_mma : (p.n_mma + 63) / 64 * 64) &&
-        !std::getenv("SPB200_NO_TMA_STORE")) {
+        last.dst_C % (last.dst_fp32 ? 32 : 64) == 0 &&
+        last.dst_C >= (last.dst_fp32 ? p.n_mma : (p.split_out ? 2 * p.n_mma : (p.n_mma + 63) / 64 * 64)) &&
+        (split || !std::getenv("SPB200_NO_TMA_STORE"))) {
         // a strided destination (the output phases of the transposed convolution) is the same map over every
         // dst_stride-th pixel, starting at the phase offset
         const cuuint64_t es = last.dst_fp32 ? 4 : 2;
@@ -1255,7 +1336,9 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
             p.tma_res = 1;
         }
     }
-    if (plan->variant == 1 && p.tma_store && p.n_mma % 32 == 0 && std::getenv("SPB200_PAIR")) {
+    if (split && !p.tma_store) return nullptr;                       // the split epilogue only stores through shared memory
+    const char* pair_env = std::getenv("SPB200_PAIR");
+    if (plan->variant == 1 && p.tma_store && p.n_mma % 32 == 0 && pair_env && pair_env[0] == '1') {
         // CTA pairs: every CTA loads its half of the rows of a weight slab; one cluster per tile pair
         plan->variant = 3;
         const cuuint32_t hbox[2] = {64, (cuuint32_t)(p.n_mma / 2)};

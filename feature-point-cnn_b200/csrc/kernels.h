@@ -12,6 +12,10 @@ void launch_conv_simt(const ConvDev& p, cudaStream_t st);
 // 8-bit frame -> fp32 / 255 (the reference's loaders, python/src/inference.py:78-80)
 void launch_u8_to_f32(const uint8_t* src, float* dst, long n, cudaStream_t st);
 void launch_nhwc_to_nchw(const void* src, int src_type, int B, int HW, int Cs, int C, float* dst, cudaStream_t st);
+// the same for a 16-bit source in the split layout (common.cuh, SegDev): channel c = hi + lo
+void launch_split_to_nchw(const void* src, int src_type, int B, int HW, int Cs, int C, float* dst, cudaStream_t st);
+// hi halves of a split-layout tensor [npix][2 C] as a plain 16-bit tensor [npix][C] (C a multiple of 32)
+void launch_split_hi(const void* src, void* dst, long npix, int C, cudaStream_t st);
 
 // ---- conv_tc.cu ----------------------------------------------------------------------------------
 struct TcConvPlan;   // tensor maps + launch geometry of one tcgen05 convolution (conv_tc.cu)
@@ -37,6 +41,8 @@ struct StemTcPlan;
 StemTcPlan* stem_tc_plan_create(const void* w16, const float* bias, int cin, int operand_type, int num_sms);
 void stem_tc_plan_destroy(StemTcPlan* plan);
 void launch_stem_tc(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st);
+// split-precision variant: image hi + lo, three MMAs per product, fp32 pooling; dst [B][H/4][W/4][128] in the split layout
+void launch_stem_wide(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st);
 
 // ---- stem_planes.cu ------------------------------------------------------------------------------
 // Gray stem fed by TMA from 16-bit row-parity planes of the image (no im2col pass).

@@ -264,6 +264,184 @@ __global__ void __launch_bounds__(kStThreads, CIN == 1 ? 4 : 1) stem_tc_kernel(c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split-precision stem (the first stage of the engine's split levels): the same tile scheme with
+//   * the image x 255 kept as hi + lo 16-bit parts (an fp32 image in [0, 1] is then represented to 2^-22),
+//   * three MMAs per product, a.hi w.hi + a.hi w.lo + a.lo w.hi, one input channel (= one 64-wide K chunk) at a time,
+//   * the convolution tile staged and pooled in fp32,
+//   * the pooled tensor stored in the split layout of common.cuh (SegDev): per 32 channels [hi 32 | lo 32].
+// ------------------------------------------------------------------------------------------------
+template <int CIN, typename T>
+__global__ void __launch_bounds__(kStThreads, 1) stem_wide_kernel(const __grid_constant__ StemParams p) {
+    constexpr int kATile = 128 * 128;                                 // bytes of one M-tile of one part
+    constexpr uint32_t kIdesc = (1u << 4) | (OperandFmt<T>::value << 7) | (OperandFmt<T>::value << 10) |
+                                ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    extern __shared__ uint8_t dyn_smem[];
+    __shared__ __align__(8) uint64_t bar_w, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_bias[64];
+
+    uint8_t* base = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
+    uint8_t* s_a = base;                                              // [2 M-tiles][hi, lo][128 rows][128 B]
+    uint8_t* s_w = s_a + 4 * kATile;                                  // [hi, lo][CIN][64 rows][128 B]
+    constexpr int kPatch = CIN * kStIH * kStIWp;
+    T* s_in = reinterpret_cast<T*>(s_w + 2 * CIN * 64 * 128);         // [hi, lo][CIN][27][48], image * 255
+    float* s_conv = reinterpret_cast<float*>(s_a);                    // aliases A after the MMAs: [16 channel quads][231 rows][4] fp32
+
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
+    const int H = p.H, W = p.W, CH = H / 2, CW = W / 2, PH = H / 4, PW = W / 4;
+
+    if (tid == 0) {
+        mbar_init(&bar_w, 1);
+        mbar_init(&bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        prefetch_tmap(&p.tmW);
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    if (tid < 64) s_bias[tid] = p.bias[tid];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_slot;
+
+    if (tid == 0) {
+        mbar_expect_tx(&bar_w, 2 * CIN * 64 * 128);
+        for (int c = 0; c < 2 * CIN; ++c) tma_load_2d(s_w + c * 64 * 128, &p.tmW, &bar_w, c * 64, 0);
+    }
+    uint32_t mma_phase = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
+        const int py0 = (tt / p.tiles_x) * kStPH, px0 = (tt % p.tiles_x) * kStPW;
+        const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;
+        const int iy0 = 4 * py0 - 5, ix0 = 4 * px0 - 5;
+        // ---- input patch as hi + lo parts ----
+        const float* img_b = p.img + (size_t)b * CIN * H * W;
+        for (int i = tid; i < kPatch; i += kStThreads) {
+            const int c = i / (kStIH * kStIWp), r = i % (kStIH * kStIWp);
+            const int y = iy0 + r / kStIWp, x = ix0 + r % kStIWp;
+            float v = 0.f;
+            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img_b + ((size_t)c * H + y) * W + x) * 255.f;
+            const uint32_t hw = pack2<T>(v, 0.f);
+            const float hi = unpack2<T>(hw).x;
+            const uint32_t lw = pack2<T>(v - hi, 0.f);
+            reinterpret_cast<uint16_t*>(s_in)[i] = (uint16_t)(hw & 0xffffu);
+            reinterpret_cast<uint16_t*>(s_in)[kPatch + i] = (uint16_t)(lw & 0xffffu);
+        }
+        __syncthreads();
+        for (int ck = 0; ck < CIN; ++ck) {
+            // ---- im2col rows of channel ck (hi and lo), SWIZZLE_128B K-major, as in stem_tc_kernel ----
+            {
+                const int row = tid;
+                const int mt = row >> 7, rr = row & 127;
+                const bool live = row < kStRows;
+                const int cyl = row / kStCW, cxl = row % kStCW;
+                const int sw = (rr & 7) << 4;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const T* pin = s_in + part * kPatch + ck * kStIH * kStIWp + (2 * cyl) * kStIWp + 2 * cxl;
+                    uint8_t* arow = s_a + (mt * 2 + part) * kATile + rr * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                        if (live && j < 7) {
+                            const uint32_t* q = reinterpret_cast<const uint32_t*>(pin + j * kStIWp);
+                            u = make_uint4(q[0], q[1], q[2], q[3]);
+                        }
+                        *reinterpret_cast<uint4*>(arow + ((j << 4) ^ sw)) = u;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (warp == 0) {
+                if (first) mbar_wait(&bar_w, 0);
+                tc_fence_after();
+                const uint32_t a_lo = umma_desc_lo(smem_u32(s_a)), w_lo = umma_desc_lo(smem_u32(s_w));
+                constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+                if (elect_one()) {
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            const uint32_t ah = a_lo + (uint32_t)(((mt * 2) * kATile + kk * 32) >> 4);
+                            const uint32_t al = a_lo + (uint32_t)(((mt * 2 + 1) * kATile + kk * 32) >> 4);
+                            const uint32_t wh = w_lo + (uint32_t)((ck * 64 * 128 + kk * 32) >> 4);
+                            const uint32_t wl = wh + (uint32_t)((CIN * 64 * 128) >> 4);
+                            umma_f16_w(tmem_acc + mt * 64, ah, kHi, wh, kHi, kIdesc, (ck > 0 || kk > 0) ? 1u : 0u);
+                            umma_f16_w(tmem_acc + mt * 64, ah, kHi, wl, kHi, kIdesc, 1u);
+                            umma_f16_w(tmem_acc + mt * 64, al, kHi, wh, kHi, kIdesc, 1u);
+                        }
+                    umma_commit(&bar_mma);
+                }
+            }
+            __syncwarp();
+            first = false;
+            mbar_wait(&bar_mma, mma_phase);                        // the A tiles may be rebuilt (or aliased by the staging)
+            mma_phase ^= 1u;
+            tc_fence_after();
+        }
+        // ---- epilogue: fp32 conv tile, transposed [channel quad][row] ----
+        {
+            const int mt = warp >> 2, q = warp & 3;
+            const int row = mt * 128 + q * 32 + lane;
+            const int cy = cy0 + row / kStCW, cx = cx0 + row % kStCW;
+            const bool real = row < kStRows && cy >= 0 && cy < CH && cx >= 0 && cx < CW;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * 64 + half * 32), r);
+                tmem_ld_wait();
+                if (row < kStRows) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (real) {
+                            const float* bb = s_bias + half * 32 + 4 * j;
+                            u = make_float4(fmaf(__uint_as_float(r[4 * j]), 1.f / 255.f, bb[0]), fmaf(__uint_as_float(r[4 * j + 1]), 1.f / 255.f, bb[1]),
+                                            fmaf(__uint_as_float(r[4 * j + 2]), 1.f / 255.f, bb[2]), fmaf(__uint_as_float(r[4 * j + 3]), 1.f / 255.f, bb[3]));
+                        }
+                        *reinterpret_cast<float4*>(s_conv + ((size_t)(half * 8 + j) * kStRows + row) * 4) = u;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        // ---- 3x3 / stride-2 max-pool in fp32 (running maximum from 0 = the ReLU), split-layout store ----
+        uint16_t* out = static_cast<uint16_t*>(p.dst);
+        for (int o = tid; o < kStPH * kStPW * 16; o += kStThreads) {
+            const int c4 = o & 15, pp = o >> 4;
+            const int ppy = pp / kStPW, ppx = pp - ppy * kStPW;
+            const int py = py0 + ppy, px = px0 + ppx;
+            if (py >= PH || px >= PW) continue;
+            const float* src = s_conv + ((size_t)c4 * kStRows + (2 * ppy) * kStCW + 2 * ppx) * 4;
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float4 u = *reinterpret_cast<const float4*>(src + (dy * kStCW + dx) * 4);
+                    m.x = fmaxf(m.x, u.x); m.y = fmaxf(m.y, u.y); m.z = fmaxf(m.z, u.z); m.w = fmaxf(m.w, u.w);
+                }
+            const uint32_t h0 = pack2<T>(m.x, m.y), h1 = pack2<T>(m.z, m.w);
+            const float2 f0 = unpack2<T>(h0), f1 = unpack2<T>(h1);
+            const uint32_t l0 = pack2<T>(m.x - f0.x, m.y - f0.y), l1 = pack2<T>(m.z - f1.x, m.w - f1.y);
+            // channels 4 c4 .. 4 c4 + 3 of 64: chunk c4 / 8, hi at (c4 % 8) * 4, lo 32 values further
+            uint16_t* dst = out + ((size_t)(b * PH + py) * PW + px) * 128 + (c4 >> 3) * 64 + (c4 & 7) * 4;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(dst + 32) = make_uint2(l0, l1);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_acc, 128);
+    }
+}
+
 struct StemTcPlan {
     StemParams params;
     int cin, operand_type, num_sms;
@@ -285,6 +463,33 @@ static void launch_stem_tc_t(const StemTcPlan* plan, const float* img, void* dst
     const int grid = std::min(p.total_tiles, plan->num_sms * per_sm);
     kern<<<grid, kStThreads, smem, st>>>(p);
     SPB_CHECK_LAUNCH();
+}
+
+template <int CIN, typename T>
+static void launch_stem_wide_t(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st) {
+    auto kern = stem_wide_kernel<CIN, T>;
+    const size_t smem = (size_t)4 * 128 * 128 + (size_t)2 * CIN * 64 * 128 + (size_t)2 * CIN * kStIH * kStIWp * 2 + 1024;
+    SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StemParams p = plan->params;
+    p.img = img; p.dst = dst; p.H = H; p.W = W;
+    p.tiles_x = (W / 4 + kStPW - 1) / kStPW;
+    p.tiles_per_img = p.tiles_x * ((H / 4 + kStPH - 1) / kStPH);
+    p.total_tiles = p.tiles_per_img * B;
+    const int per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1536))));
+    const int grid = std::min(p.total_tiles, plan->num_sms * per_sm);
+    kern<<<grid, kStThreads, smem, st>>>(p);
+    SPB_CHECK_LAUNCH();
+}
+
+// Split-precision stem: dst is NHWC [B][H/4][W/4][128] 16-bit in the split layout (64 channels as hi + lo).
+void launch_stem_wide(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st) {
+    if (plan->operand_type == PREC_FP16) {
+        if (plan->cin == 1) launch_stem_wide_t<1, __half>(plan, img, dst, B, H, W, st);
+        else launch_stem_wide_t<3, __half>(plan, img, dst, B, H, W, st);
+    } else {
+        if (plan->cin == 1) launch_stem_wide_t<1, __nv_bfloat16>(plan, img, dst, B, H, W, st);
+        else launch_stem_wide_t<3, __nv_bfloat16>(plan, img, dst, B, H, W, st);
+    }
 }
 
 void launch_stem_tc(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st) {

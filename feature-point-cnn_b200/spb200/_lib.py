@@ -20,6 +20,7 @@ SYMBOLS = {
     'spb200_load_checkpoint': (_c.c_int, [_P, _c.c_char_p]),
     'spb200_load_tensor': (_c.c_int, [_P, _c.c_char_p, _P, _c.POINTER(_c.c_int64), _c.c_int]),
     'spb200_finalize_weights': (_c.c_int, [_P, _c.c_int]),
+    'spb200_finalize_weights_split': (_c.c_int, [_P, _c.c_int, _c.c_int]),
     'spb200_set_params': (_c.c_int, [_P, _c.c_float, _c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     'spb200_forward': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'spb200_detect': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P, _P, _P]),

@@ -7,10 +7,12 @@ import torch
 from . import _lib
 
 PRECISIONS = {'fp32': 0, 'fp16': 1, 'bf16': 2}
+# split-precision stages (include/spb200.h SPB200_SPLIT_*): a precision string may carry the level as a suffix
+SPLIT_LEVELS = {'none': 0, 'layer1': 1, 'layer2': 2, 'encoder': 2, 'detector': 3, 'all': 3}
 
 # activation buffer ids (csrc/engine.h BufId) for spb200_export_activation
 BUFFERS = ['pool', 'l1a_y', 'l1a', 'l1b_y', 'l1b', 'l2a_y', 'l2a', 'l2b_y', 'feat', 'd0_y', 'd0', 'd1_y', 'logits',
-           'i0_y', 'i0', 'i1_y', 'i1', 'up', 'o0_y', 'o0', 'o1_y', 'desc']
+           'i0_y', 'i0', 'i1_y', 'i1', 'up', 'o0_y', 'o0', 'o1_y', 'desc', 'feat_hi']
 
 
 class Spb200Error(RuntimeError):
@@ -66,9 +68,19 @@ class Engine:
             self._check(self._lib.spb200_load_tensor(self._h, k.encode(), ctypes.c_void_p(a.ctypes.data), shape, a.ndim),
                         'spb200_load_tensor(%s)' % k)
 
-    def finalize(self, precision='fp16'):
-        self._check(self._lib.spb200_finalize_weights(self._h, PRECISIONS[precision]), 'spb200_finalize_weights')
+    def finalize(self, precision='fp16', split=None):
+        """precision: 'fp32' | 'fp16' | 'bf16', optionally with the split level as a suffix ('fp16+all', 'fp16+encoder',
+        'fp16+layer1'); split: the same level as a separate argument (name or 0..3)."""
+        if '+' in precision:
+            precision, split = precision.split('+', 1)
+        level = SPLIT_LEVELS[split] if isinstance(split, str) else int(split or 0)
+        if level:
+            self._check(self._lib.spb200_finalize_weights_split(self._h, PRECISIONS[precision], level),
+                        'spb200_finalize_weights_split')
+        else:
+            self._check(self._lib.spb200_finalize_weights(self._h, PRECISIONS[precision]), 'spb200_finalize_weights')
         self.precision = precision
+        self.split_level = level
 
     def set_params(self, conf_thresh=0.015, nms_dist=4, border_remove=4, top_k=0, descriptor_enabled=True):
         self._check(self._lib.spb200_set_params(self._h, float(conf_thresh), int(nms_dist), int(border_remove),

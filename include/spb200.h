@@ -73,6 +73,21 @@ SPB200_API int spb200_load_tensor(spb200_engine* e, const char* key, const float
  * (strict loading, saveutils.py:9-14). */
 SPB200_API int spb200_finalize_weights(spb200_engine* e, int precision);
 
+/* Split-precision stages: the guaranteed-parity mode of the tensor-core path (no counterpart in the reference, whose
+ * arithmetic is fp32 throughout: superpoint.py:91-115).  In a split stage activations and weights are kept as 16-bit
+ * hi + lo pairs and every product is three MMAs (a.hi w.hi + a.hi w.lo + a.lo w.hi, fp32 accumulation): results agree
+ * with the fp32 network to ~1e-4 on the logits instead of ~5e-2, at three times the tensor work of the stage.  Errors
+ * of early layers are amplified by the later ones, so only prefixes of the network are accepted. */
+enum {
+    SPB200_SPLIT_NONE = 0,      /* what spb200_finalize_weights does                                     */
+    SPB200_SPLIT_LAYER1 = 1,    /* stem (image as hi + lo) + encoder.layer1                              */
+    SPB200_SPLIT_LAYER2 = 2,    /* + encoder.layer2: the whole encoder                                   */
+    SPB200_SPLIT_DETECTOR = 3   /* + detector head: every layer the heatmap depends on                   */
+};
+/* Same as spb200_finalize_weights with the stages up to `split_level` in split precision; precision must be
+ * SPB200_PREC_FP16 or SPB200_PREC_BF16 when split_level != 0.  The descriptor head is never split. */
+SPB200_API int spb200_finalize_weights_split(spb200_engine* e, int precision, int split_level);
+
 /* settings.py:3-8 / settings.h:27-31.  top_k = 0 returns every survivor (the reference's behaviour);
  * descriptor_enabled = 0 is SuperPoint.disable_descriptor (superpoint.py:74-78, MagicPoint). */
 SPB200_API int spb200_set_params(spb200_engine* e, float conf_thresh, int nms_dist, int border_remove, int top_k,
