@@ -182,13 +182,14 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='images per GPU per step')
     ap.add_argument('--height', type=int, default=480)
     ap.add_argument('--width', type=int, default=640)
-    ap.add_argument('--precision', default='fp16', choices=['fp32', 'fp16', 'bf16'])
+    ap.add_argument('--precision', default='fp16', help="fp32 | fp16 | bf16, optionally with split-precision stages: fp16+layer1 | fp16+encoder | fp16+all")
     ap.add_argument('--top-k', type=int, default=0)
     ap.add_argument('--detector-only', action='store_true', help='MagicPoint: heatmap + NMS, descriptor head skipped (BASELINE configs[1])')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel table (json) here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    base_prec = args.precision.split('+')[0]
 
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -274,7 +275,7 @@ def main():
         eng.detect(dev_batches[i % n_rot], cap, out=outs)
     entries = eng.profile_end()
     n_kp = float(outs[0].sum().item())
-    esz = 4 if args.precision == 'fp32' else 2
+    esz = 4 if base_prec == 'fp32' else 2
     agg = {}
     for name, kms, fl, by in entries:
         a = agg.setdefault(name, {'ms': 0.0, 'flops': fl, 'bytes': by, 'n': 0})
@@ -335,7 +336,7 @@ def main():
 
     # ---- the rows next to the path, rank 0 at N = 1 only, a few iterations each -------------------------
     next_rows = None
-    if rank == 0 and world == 1 and args.precision != 'fp32':
+    if rank == 0 and world == 1 and base_prec != 'fp32':
         next_rows = {}
         # N3: 8-bit frames through the host-buffer entry point (a quarter of the upload bytes)
         u8 = [(b.squeeze(1) * 255).round().to(torch.uint8).pin_memory().numpy() for b in host_batches]
@@ -397,9 +398,9 @@ def main():
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': {'fp32': 'f32', 'fp16': 'f16', 'bf16': 'bf16'}[args.precision], 'data': 'synthetic',
+            'dtype': {'fp32': 'f32', 'fp16': 'f16', 'bf16': 'bf16'}[base_prec], 'data': 'synthetic',
             'config': {'workload': ('magic_point-style detector only (heatmap + NMS, descriptor head skipped), batch %d per GPU at %dx%d grayscale (BASELINE configs[1])' if args.detector_only else 'super_point.pt keypoints+descriptors, batch %d per GPU at %dx%d grayscale (BASELINE configs[2])') % (B, H, W),
-                       'batch_per_gpu': B, 'height': H, 'width': W, 'top_k': args.top_k, 'parallelism': 'batch-sharded x%d, no collective' % world,
+                       'batch_per_gpu': B, 'height': H, 'width': W, 'top_k': args.top_k, 'precision': args.precision, 'parallelism': 'batch-sharded x%d, no collective' % world,
                        'keypoints_per_image': kp_mean, 'weights': 'tests/golden/super_point.pt (synthetic recipe, reference-written)',
                        'l2': 'inputs rotate over %d batches (%.0f MB > 126 MB L2); activations are rewritten every step' % (n_rot, n_rot * B * H * W * 4 / 1e6)},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * H * W * 4, 'd2h_bytes_per_step': d2h // e2e_steps,

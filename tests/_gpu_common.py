@@ -83,3 +83,49 @@ def compare_path(e, gray, sd, heat_tol, kp_frac, cos_min, tag):
     return dh, frac, cos, inter, len(pset(pts_o))
 
 
+
+
+def unexplained_differences(pts_a, heat_a, pts_b, heat_b, thresh=0.015, radius=4):
+    """Keypoint-set differences that are NOT ties or threshold-edge cases (the only differences the north star allows).
+
+    pts_*: (3, N) keypoints of two runs of get_points on heat_* (H, W).  A point kept in one run and not in the other is
+    either a candidate in one map only (threshold edge), or was suppressed by a point that is itself kept in one run only:
+    the differing points form chains of window neighbours, and the chain ends at a threshold-edge point or at two
+    neighbours whose ORDER differs between the two maps (a near tie, |difference| <= 2 max|heat_a - heat_b|).  Returns the
+    number of connected components (Chebyshev distance <= radius) of the symmetric difference without such a root cause.
+    """
+    a, b = pset(pts_a), pset(pts_b)
+    diff = sorted(a ^ b)
+    if not diff:
+        return 0
+    parent = list(range(len(diff)))
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+
+    for i in range(len(diff)):
+        for j in range(i + 1, len(diff)):
+            if abs(diff[i][0] - diff[j][0]) <= radius and abs(diff[i][1] - diff[j][1]) <= radius:
+                parent[find(i)] = find(j)
+    comps = {}
+    for i in range(len(diff)):
+        comps.setdefault(find(i), []).append(diff[i])
+    bad = 0
+    for pts in comps.values():
+        ok = False
+        for (x, y) in pts:
+            if (heat_a[y, x] >= thresh) != (heat_b[y, x] >= thresh):
+                ok = True
+        for i in range(len(pts)):
+            for j in range(i + 1, len(pts)):
+                (x0, y0), (x1, y1) = pts[i], pts[j]
+                if abs(x0 - x1) <= radius and abs(y0 - y1) <= radius:
+                    da = float(heat_a[y0, x0]) - float(heat_a[y1, x1])
+                    db = float(heat_b[y0, x0]) - float(heat_b[y1, x1])
+                    if da * db <= 0:
+                        ok = True
+        bad += 0 if ok else 1
+    return bad
