@@ -40,62 +40,82 @@ class HomographyConfig(object):
         self.patch_ratio = 0.85
 
 
-def _truncated_normal(rng, n, mean, std):
-    """Normal(mean, std) restricted to mean +- 2 std (rejection sampling)."""
-    out = np.empty((n,), np.float64)
-    i = 0
-    while i < n:
-        v = rng.normal(mean, std, size=2 * (n - i) + 4) if std > 0 else np.full((n - i,), mean)
-        v = v[np.abs(v - mean) <= 2 * std]
-        take = min(len(v), n - i)
-        out[i:i + take] = v[:take]
-        i += take
-    return out
+class NumpyDraws(object):
+    """The three kinds of random draws sample_homography makes, from a numpy Generator.  Tests replay the reference's
+    own draws (scipy truncnorm on numpy's global state, torch.randint, torch Uniform) through the same interface."""
+
+    def __init__(self, rng=None):
+        self.rng = np.random.default_rng() if rng is None else rng
+
+    def truncated_normal(self, n, mean, std):
+        # homographies.py:64-67 hands mean -+ 2 std to scipy's truncnorm as STANDARDISED bounds (loc 0, scale 1 are left
+        # at their defaults): the draw is a standard normal restricted to [mean - 2 std, mean + 2 std] - for the small
+        # amplitudes used here nearly uniform on that interval.  Followed as written.
+        from scipy.stats import truncnorm
+        return np.atleast_1d(truncnorm(mean - 2 * std, mean + 2 * std).rvs(n, random_state=self.rng)).astype(np.float64)
+
+    def integer(self, high):
+        return int(self.rng.integers(high))
+
+    def uniform(self, low, high):
+        return float(self.rng.uniform(low, high))
 
 
-def _uniform(rng, low, high):
+def _uniform(draws, low, high):
+    """random_uniform (homographies.py:70-75)."""
     if low > high:
         low, high = high, low
     if low == high:
         high = low + 0.00001
-    return rng.uniform(low, high)
+    return draws.uniform(low, high)
 
 
-def sample_homography(shape, config=None, rng=None, **kw):
-    """A random homography between a patch of the image and the full frame, as the reference samples it: a centred
-    crop of ``patch_ratio`` is perturbed in perspective, scaled, translated and rotated (each step keeping the patch
-    inside the image unless ``allow_artifacts``), then the transform mapping the unit-square corners of the crop to
-    the perturbed corners is solved for.  ``shape`` = (H, W).  Returns a float32 array [8]."""
+def sample_homography(shape, config=None, rng=None, draws=None, **kw):
+    """A random homography between a patch of the image and the full frame, as the reference samples it
+    (homographies.py:79-196): a centred crop of ``patch_ratio`` is perturbed in perspective, scaled, translated and
+    rotated (each step keeping the patch inside the image unless ``allow_artifacts``), then the transform mapping the
+    source corners to the perturbed corners is solved for.  ``shape`` = (H, W).  Returns a float32 array [8].
+
+    The reference starts with ``pts2 = pts1`` - ONE tensor under two names - and perturbs ``pts2`` in place until a step
+    rebinds it (the scaling and rotation steps do, perspective and translation do not).  Its source corners therefore
+    carry the perspective perturbation, and the translation too when scaling is off; with neither scaling nor rotation
+    both names still mean the same tensor at the end and the transform is the identity.  Followed as written."""
     cfg = HomographyConfig() if config is None else config
     g = lambda k: kw.get(k, getattr(cfg, k))          # noqa: E731
-    rng = np.random.default_rng() if rng is None else rng
+    d = draws if draws is not None else NumpyDraws(rng)
     ratio = g('patch_ratio')
     margin = (1 - ratio) / 2
     src = margin + np.array([[0, 0], [0, ratio], [ratio, ratio], [ratio, 0]], np.float64)
-    dst = src.copy()
+    dst = src
+    aliased = True                                    # dst is src (homographies.py:117)
     if g('perspective'):
         ax, ay = g('perspective_amplitude_x'), g('perspective_amplitude_y')
         if not g('allow_artifacts'):
             ax, ay = min(ax, margin), min(ay, margin)
-        py = _truncated_normal(rng, 1, 0., ay / 2)[0]
-        left = _truncated_normal(rng, 1, 0., ax / 2)[0]
-        right = _truncated_normal(rng, 1, 0., ax / 2)[0]
+        py = d.truncated_normal(1, 0., ay / 2)[0]
+        left = d.truncated_normal(1, 0., ax / 2)[0]
+        right = d.truncated_normal(1, 0., ax / 2)[0]
         dst = dst + np.array([[left, py], [left, -py], [right, py], [right, -py]])
+        if aliased:
+            src = dst                                 # in-place += on the shared tensor (homographies.py:127)
     if g('scaling'):
         n = g('n_scales')
-        scales = np.concatenate([[1.], _truncated_normal(rng, n, 1, g('scaling_amplitude') / 2)])
+        scales = np.concatenate([[1.], d.truncated_normal(n, 1, g('scaling_amplitude') / 2)])
         centre = dst.mean(0, keepdims=True)
         cand = (dst - centre)[None] * scales[:, None, None] + centre
         if g('allow_artifacts'):
             valid = np.arange(n)                                    # the reference's quirk: indices 0 .. n-1
         else:
             valid = np.nonzero(((cand >= 0.) & (cand < 1.)).sum((1, 2)))[0]
-        dst = cand[valid[rng.integers(len(valid))]]
+        dst = cand[valid[d.integer(len(valid))]]
+        aliased = False                               # rebinding (homographies.py:145)
     if g('translation'):
         t_min, t_max = dst.min(0), (1. - dst).min(0)
         if g('allow_artifacts'):
             t_min, t_max = t_min + g('translation_overflow'), t_max + g('translation_overflow')
-        dst = dst + np.array([[_uniform(rng, -t_min[0], t_max[0]), _uniform(rng, -t_min[1], t_max[1])]])
+        dst = dst + np.array([[_uniform(d, -t_min[0], t_max[0]), _uniform(d, -t_min[1], t_max[1])]])
+        if aliased:
+            src = dst                                 # homographies.py:154 is an in-place += as well
     if g('rotation'):
         n = g('n_angles')
         angles = np.concatenate([[0.], np.linspace(-g('max_angle'), g('max_angle'), n)])
@@ -106,9 +126,12 @@ def sample_homography(shape, config=None, rng=None, **kw):
             valid = np.arange(n)
         else:
             valid = np.nonzero(((cand >= 0.) & (cand < 1.)).sum((1, 2)))[0]
-        dst = cand[valid[rng.integers(len(valid))]]
+        dst = cand[valid[d.integer(len(valid))]]
+        aliased = False
     size = np.array([shape[1], shape[0]], np.float64)             # (x, y) order
-    p, q = src * size, dst * size
+    # `pts1 *= shape; pts2 *= shape` (homographies.py:177-178): a tensor still shared is scaled twice - source and target
+    # stay equal, the solution below is the identity either way
+    p, q = (src * size * size, dst * size * size) if aliased else (src * size, dst * size)
     a = np.zeros((8, 8))
     rhs = np.zeros((8,))
     for i in range(4):
@@ -118,6 +141,7 @@ def sample_homography(shape, config=None, rng=None, **kw):
     return np.linalg.solve(a, rhs).astype(np.float32)
 
 
-def sample_homographies(shape, config, rng=None):
+def sample_homographies(shape, config, rng=None, draws=None):
     """config.num homographies [num, 8] for one call of homography adaptation."""
-    return np.stack([sample_homography(shape, config, rng) for _ in range(config.num)]) if config.num else np.zeros((0, 8), np.float32)
+    d = draws if draws is not None else NumpyDraws(rng)
+    return np.stack([sample_homography(shape, config, draws=d) for _ in range(config.num)]) if config.num else np.zeros((0, 8), np.float32)

@@ -85,19 +85,23 @@ def compare_path(e, gray, sd, heat_tol, kp_frac, cos_min, tag):
 
 
 
-def unexplained_differences(pts_a, heat_a, pts_b, heat_b, thresh=0.015, radius=4):
-    """Keypoint-set differences that are NOT ties or threshold-edge cases (the only differences the north star allows).
+def unexplained_differences(heat_a, heat_b, thresh=0.015, radius=4):
+    """Keypoint-set differences between two heatmaps that are NOT ties or threshold-edge cases (the only differences the
+    north star allows).
 
-    pts_*: (3, N) keypoints of two runs of get_points on heat_* (H, W).  A point kept in one run and not in the other is
-    either a candidate in one map only (threshold edge), or was suppressed by a point that is itself kept in one run only:
-    the differing points form chains of window neighbours, and the chain ends at a threshold-edge point or at two
-    neighbours whose ORDER differs between the two maps (a near tie, |difference| <= 2 max|heat_a - heat_b|).  Returns the
-    number of connected components (Chebyshev distance <= radius) of the symmetric difference without such a root cause.
+    The greedy NMS (python/src/nms.py:4-53) is run on both maps WITHOUT border removal (a suppressor inside the border is
+    invisible in the final lists).  A point kept on one map and not on the other is either a candidate on one map only
+    (threshold edge), or was suppressed by a point that is itself kept on one map only: the differing points form chains
+    of window neighbours, and a chain ends at a threshold-edge point or at two neighbours whose ORDER differs between the
+    maps (a near tie: |difference| <= 2 max|heat_a - heat_b|).  Returns the number of connected components (Chebyshev
+    distance <= radius) of the symmetric difference without such a root cause, and the size of the symmetric difference.
     """
-    a, b = pset(pts_a), pset(pts_b)
+    heat_a, heat_b = np.asarray(heat_a, dtype=np.float32), np.asarray(heat_b, dtype=np.float32)
+    a = pset(postproc.get_points(heat_a, thresh, radius, 0))
+    b = pset(postproc.get_points(heat_b, thresh, radius, 0))
     diff = sorted(a ^ b)
     if not diff:
-        return 0
+        return 0, 0
     parent = list(range(len(diff)))
 
     def find(i):
@@ -128,4 +132,4 @@ def unexplained_differences(pts_a, heat_a, pts_b, heat_b, thresh=0.015, radius=4
                     if da * db <= 0:
                         ok = True
         bad += 0 if ok else 1
-    return bad
+    return bad, len(diff)

@@ -57,3 +57,59 @@ def test_inverse_and_sampler_properties():
     assert hs.shape == (cfg.num, 8)
     ident = hg.sample_homography((h, w), cfg, rng, perspective=False, scaling=False, rotation=False, translation=False, patch_ratio=1.0)
     np.testing.assert_allclose(ident, [1, 0, 0, 0, 1, 0, 0, 0], atol=1e-5)
+
+
+class ReferenceDraws(object):
+    """The reference's own random draws, in its call order: scipy truncnorm on numpy's global state (truncated_normal,
+    homographies.py:64-67), torch.randint (:144,:172) and torch's Uniform.sample (random_uniform, :70-75)."""
+
+    def truncated_normal(self, n, mean, std):
+        from scipy.stats import truncnorm
+        return np.asarray(torch.tensor(truncnorm(mean - 2 * std, mean + 2 * std).rvs([n]), dtype=torch.float32), dtype=np.float64)
+
+    def integer(self, high):
+        return int(torch.randint(high=high, size=()))
+
+    def uniform(self, low, high):
+        return float(torch.distributions.uniform.Uniform(low, high).sample(()))
+
+
+@pytest.mark.parametrize('name,seed', [('default', 11), ('preprocess', 12)])
+def test_sampler_replays_the_reference_draw_for_draw(name, seed):
+    """tests/golden/homography_kat.npz holds the homographies the reference's sample_homography returned under
+    np.random.seed / torch.manual_seed(seed) (make_homography_golden.py).  Fed the same draws, the mirror must return the
+    same transforms: this pins the quirks it follows - source corners that carry the perspective perturbation
+    (pts2 = pts1 aliasing, homographies.py:117-178), standardised truncnorm bounds, 'valid' indices under allow_artifacts."""
+    from spb200 import homographies as hg
+    k = np.load(os.path.join(GOLDEN, 'homography_kat.npz'))
+    cfg = hg.HomographyConfig()
+    if name == 'preprocess':
+        cfg.init_for_preprocess()
+    cfg.num = int(k[name + '_cfg'][0])
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    got = hg.sample_homographies((240, 320), cfg, draws=ReferenceDraws())
+    want = k[name + '_H']
+    assert got.shape == want.shape
+    # float32 corner arithmetic in the reference, float64 here: the coefficients agree to ~1e-4 relative
+    # float32 corner arithmetic in the reference, float64 here: compared by where the transforms send the image
+    worst = 0.0
+    for g, w_ in zip(got.astype(np.float64), want.astype(np.float64)):
+        for x, y in ((0, 0), (319, 0), (0, 239), (319, 239), (160, 120)):
+            pg = np.array([g[0] * x + g[1] * y + g[2], g[3] * x + g[4] * y + g[5]]) / (g[6] * x + g[7] * y + 1)
+            pw = np.array([w_[0] * x + w_[1] * y + w_[2], w_[3] * x + w_[4] * y + w_[5]]) / (w_[6] * x + w_[7] * y + 1)
+            worst = max(worst, float(np.abs(pg - pw).max()))
+    print('[homography replay %s] largest displacement between the two transforms %.2e px' % (name, worst))
+    assert worst <= 1e-2
+
+
+def test_sampler_aliasing_quirks():
+    from spb200 import homographies as hg
+    rng = np.random.default_rng(5)
+    # neither scaling nor rotation: source and target corners are the same tensor to the end -> identity
+    c = hg.sample_homography((240, 320), hg.HomographyConfig(), rng, scaling=False, rotation=False)
+    np.testing.assert_allclose(c, [1, 0, 0, 0, 1, 0, 0, 0], atol=1e-5)
+    # perspective only + scaling: the perspective perturbation is in the source corners too, what is left is a pure
+    # scaling about the perturbed centre: no projective terms
+    c = hg.sample_homography((240, 320), hg.HomographyConfig(), rng, rotation=False, translation=False)
+    assert abs(c[6]) < 1e-6 and abs(c[7]) < 1e-6 and abs(c[1]) < 1e-6 and abs(c[3]) < 1e-6
