@@ -49,13 +49,23 @@ struct Settings {                       // cpp/src/settings.h:27-31 == python/sr
 class SuperPoint {
  public:
   // file_name: snapshots/super_point.pt or magic_point.pt (the torch.save checkpoint of
-  // python/src/saveutils.py:54-63, or a bare state_dict).  load_script is accepted for source
-  // compatibility and ignored: TorchScript modules are not loaded.
-  explicit SuperPoint(const std::string& file_name, bool /*load_script*/ = false, const Settings& settings = Settings())
+  // python/src/saveutils.py:54-63, a bare state_dict, or the <name>_params.pt of InferenceWrapper.trace).
+  // load_script = true is the reference's "<name>_script.pt" mode (cpp/src/superpoint.cc:11-26): this engine executes no
+  // TorchScript, so the weights are taken from the "<name>_params.pt" that the same trace() call wrote next to the script;
+  // any other script path fails with a message that says so.
+  explicit SuperPoint(const std::string& file_name, bool load_script = false, const Settings& settings = Settings())
       : settings_(settings) {
+    std::string weights = file_name;
+    if (load_script) {
+      const std::string tail = "_script.pt";
+      if (weights.size() <= tail.size() || weights.compare(weights.size() - tail.size(), tail.size(), tail) != 0)
+        throw std::invalid_argument("load_script: expected a '<name>_script.pt' path; TorchScript modules are not executed, the "
+                                    "weights are read from '<name>_params.pt' (InferenceWrapper.trace writes both)");
+      weights = weights.substr(0, weights.size() - tail.size()) + "_params.pt";
+    }
     if (spb200_create(settings_.device, &engine_) != SPB200_OK) throw std::runtime_error(spb200_last_error(nullptr));
     try {
-      Check(spb200_load_checkpoint(engine_, file_name.c_str()));
+      Check(spb200_load_checkpoint(engine_, weights.c_str()));
       Check(spb200_finalize_weights(engine_, settings_.precision));
       Check(spb200_set_params(engine_, settings_.confidence_thresh, settings_.nms_dist, settings_.border_remove,
                               settings_.top_k, 1));

@@ -159,6 +159,13 @@ int spb200_heatmap_from_logits(spb200_engine* e, const float* logits, int B, int
     });
 }
 
+int spb200_restore_prob_map(spb200_engine* e, const float* softmax, int B, int H, int W, float* prob_map, void* stream) {
+    return guarded(e, [&](spb200::Engine& g) {
+        if (!softmax || !prob_map || B <= 0 || H <= 0 || W <= 0) throw std::invalid_argument("bad restore_prob_map arguments");
+        g.restore_prob_map(softmax, B, H, W, prob_map, (cudaStream_t)stream);
+    });
+}
+
 int spb200_nms(spb200_engine* e, const float* prob_map, int B, int H, int W, int capacity, int* count, int* xy, float* conf,
                void* stream) {
     return guarded(e, [&](spb200::Engine& g) {

@@ -15,6 +15,7 @@ namespace {
 struct ZipEntry {
     uint64_t data_offset = 0;
     uint64_t size = 0;
+    bool stored = true;          // false: deflated (TorchScript code files are); such an entry is listed but never read
 };
 
 struct Archive {
@@ -47,40 +48,47 @@ void open_archive(const std::string& path, Archive& ar) {
     for (int64_t i = (int64_t)n - 22; i >= 0 && i >= (int64_t)n - 22 - 65536; --i)
         if (rd32(b + i) == 0x06054b50u) { eocd = i; break; }
     if (eocd < 0) fail("not a ZIP archive (legacy torch.save format is not supported): " + path);
+    // every offset below comes from the file: compared as `x > n - k` (never `x + k > n`, which wraps for hostile 64-bit values)
     uint64_t count = rd16(b + eocd + 10);
     uint64_t cd_off = rd32(b + eocd + 16);
     if (count == 0xFFFF || cd_off == 0xFFFFFFFFu) {   // ZIP64
         if (eocd < 20 || rd32(b + eocd - 20) != 0x07064b50u) fail("ZIP64 locator missing");
         uint64_t e64 = rd64(b + eocd - 20 + 8);
-        if (e64 + 56 > n || rd32(b + e64) != 0x06064b50u) fail("bad ZIP64 end record");
+        if (n < 56 || e64 > n - 56 || rd32(b + e64) != 0x06064b50u) fail("bad ZIP64 end record");
         count = rd64(b + e64 + 32);
         cd_off = rd64(b + e64 + 48);
     }
+    if (count > n / 46) fail("bad ZIP entry count");
     uint64_t p = cd_off;
     for (uint64_t k = 0; k < count; ++k) {
-        if (p + 46 > n || rd32(b + p) != 0x02014b50u) fail("bad ZIP central directory");
+        if (n < 46 || p > n - 46 || rd32(b + p) != 0x02014b50u) fail("bad ZIP central directory");
         uint16_t method = rd16(b + p + 10);
         uint64_t csize = rd32(b + p + 20), usize = rd32(b + p + 24);
         uint16_t nlen = rd16(b + p + 28), xlen = rd16(b + p + 30), clen = rd16(b + p + 32);
         uint64_t lho = rd32(b + p + 42);
+        if ((uint64_t)nlen + xlen + clen > n - 46 - p) fail("ZIP central directory entry runs past the end of the file");
         std::string name((const char*)b + p + 46, nlen);
         const uint8_t* x = b + p + 46 + nlen;
         const uint8_t* xe = x + xlen;
-        while (x + 4 <= xe) {                          // ZIP64 extended information
+        while (xe - x >= 4) {                          // ZIP64 extended information
             uint16_t id = rd16(x), len = rd16(x + 2);
             const uint8_t* q = x + 4;
+            if (len > xe - q) fail("bad ZIP extra field in " + name);
+            const uint8_t* qe = q + len;
             if (id == 0x0001) {
-                if (usize == 0xFFFFFFFFu) { usize = rd64(q); q += 8; }
-                if (csize == 0xFFFFFFFFu) { csize = rd64(q); q += 8; }
-                if (lho == 0xFFFFFFFFu) { lho = rd64(q); q += 8; }
+                auto take64 = [&](uint64_t& v) { if (qe - q < 8) fail("short ZIP64 extra field in " + name); v = rd64(q); q += 8; };
+                if (usize == 0xFFFFFFFFu) take64(usize);
+                if (csize == 0xFFFFFFFFu) take64(csize);
+                if (lho == 0xFFFFFFFFu) take64(lho);
             }
-            x += 4 + len;
+            x = qe;
         }
-        if (method != 0) fail("compressed ZIP entry '" + name + "' (torch.save writes STORED entries)");
-        if (lho + 30 > n || rd32(b + lho) != 0x04034b50u) fail("bad ZIP local header for " + name);
-        uint64_t data = lho + 30 + rd16(b + lho + 26) + rd16(b + lho + 28);
-        if (data + usize > n) fail("ZIP entry out of bounds: " + name);
-        ar.entries[name] = ZipEntry{data, usize};
+        if (n < 30 || lho > n - 30 || rd32(b + lho) != 0x04034b50u) fail("bad ZIP local header for " + name);
+        const uint64_t hdr = 30 + (uint64_t)rd16(b + lho + 26) + rd16(b + lho + 28);
+        if (hdr > n - lho) fail("bad ZIP local header for " + name);
+        uint64_t data = lho + hdr;
+        if (method == 0 && usize > n - data) fail("ZIP entry out of bounds: " + name);
+        ar.entries[name] = ZipEntry{data, usize, method == 0};
         p += 46 + (uint64_t)nlen + xlen + clen;
     }
 }
@@ -116,11 +124,13 @@ struct Unpickler {
     void need(size_t k) { if ((size_t)(end - p) < k) fail("truncated pickle"); }
     PRef pop() {
         if (stack.empty()) fail("pickle stack underflow");
-        PRef v = stack.back(); stack.pop_back(); return v;
+        PRef v = stack.back(); stack.pop_back();
+        if (!v) fail("empty value on the pickle stack");
+        return v;
     }
     std::vector<PRef> pop_to_mark() {
         size_t m = stack.size();
-        while (m > 0 && stack[m - 1]->kind != PVal::MARK) --m;
+        while (m > 0 && !(stack[m - 1] && stack[m - 1]->kind == PVal::MARK)) --m;
         if (m == 0) fail("pickle MARK not found");
         std::vector<PRef> out(stack.begin() + m, stack.end());
         stack.resize(m - 1);
@@ -146,13 +156,15 @@ struct Unpickler {
         std::vector<int64_t> out;
         if (!t || (t->kind != PVal::TUPLE && t->kind != PVal::LIST)) fail("expected a tuple of ints");
         for (auto& e : t->items) {
-            if (e->kind != PVal::INT) fail("expected int in shape/stride");
+            if (!e || e->kind != PVal::INT) fail("expected int in shape/stride");
             out.push_back(e->i);
         }
         return out;
     }
 
     PRef reduce(const PRef& fn, const PRef& args) {
+        if (!fn || !args) fail("REDUCE on an empty value");
+        for (auto& a : args->items) if (!a) fail("REDUCE argument is empty");
         if (fn->kind == PVal::GLOBAL && args->kind == PVal::TUPLE) {
             const std::string& mod = fn->s;
             const std::string& name = fn->s2;
@@ -160,7 +172,7 @@ struct Unpickler {
                 auto d = mk(PVal::DICT);
                 if (!args->items.empty() && args->items[0]->kind == PVal::LIST)   // OrderedDict([(k, v), ...])
                     for (auto& kv : args->items[0]->items)
-                        if ((kv->kind == PVal::TUPLE || kv->kind == PVal::LIST) && kv->items.size() == 2)
+                        if (kv && (kv->kind == PVal::TUPLE || kv->kind == PVal::LIST) && kv->items.size() == 2)
                             d->dict.emplace_back(kv->items[0], kv->items[1]);
                 return d;
             }
@@ -173,6 +185,13 @@ struct Unpickler {
                 t->offset = args->items[1]->i;
                 t->sizes = int_list(args->items[2]);
                 t->strides = int_list(args->items[3]);
+                if (t->sizes.size() != t->strides.size() || t->sizes.size() > 8) fail("_rebuild_tensor: sizes and strides do not match");
+                int64_t numel = 1;
+                for (int64_t d : t->sizes) {
+                    if (d < 0 || (d > 0 && numel > (int64_t)1 << 40)) fail("_rebuild_tensor: bad size");
+                    numel *= d;
+                }
+                if (numel > (int64_t)1 << 32 || t->offset < 0) fail("_rebuild_tensor: tensor too large or negative offset");
                 return t;
             }
             if (mod == "torch._utils" && name == "_rebuild_parameter" && !args->items.empty())
@@ -183,9 +202,9 @@ struct Unpickler {
 
     PRef persistent(const PRef& pid) {
         // ('storage', <global torch.FloatStorage>, key, location, numel)
-        if (pid->kind != PVal::TUPLE || pid->items.size() < 5 || pid->items[0]->kind != PVal::STR ||
-            pid->items[0]->s != "storage")
-            fail("unsupported persistent id in pickle");
+        if (!pid || pid->kind != PVal::TUPLE || pid->items.size() < 5) fail("unsupported persistent id in pickle");
+        for (auto& it : pid->items) if (!it) fail("unsupported persistent id in pickle");
+        if (pid->items[0]->kind != PVal::STR || pid->items[0]->s != "storage") fail("unsupported persistent id in pickle");
         auto st = mk(PVal::STORAGE);
         const PRef& ty = pid->items[1];
         if (ty->kind == PVal::GLOBAL) st->s = ty->s2;       // e.g. FloatStorage
@@ -238,11 +257,12 @@ struct Unpickler {
                 case 'c': { auto v = mk(PVal::GLOBAL); v->s = line(); v->s2 = line(); stack.push_back(v); break; }   // GLOBAL
                 case 0x93: {                                                          // STACK_GLOBAL
                     PRef name = pop(), mod = pop();
+                    if (name->kind != PVal::STR || mod->kind != PVal::STR) fail("STACK_GLOBAL needs two strings");
                     auto v = mk(PVal::GLOBAL); v->s = mod->s; v->s2 = name->s; stack.push_back(v); break;
                 }
-                case 'q': { need(1); memo[*p] = stack.empty() ? nullptr : stack.back(); p += 1; break; }           // BINPUT
-                case 'r': { need(4); memo[rd32(p)] = stack.empty() ? nullptr : stack.back(); p += 4; break; }      // LONG_BINPUT
-                case 0x94: memo[memo_next++] = stack.empty() ? nullptr : stack.back(); break;                     // MEMOIZE
+                case 'q': { need(1); if (stack.empty()) fail("BINPUT on empty stack"); memo[*p] = stack.back(); p += 1; break; }           // BINPUT
+                case 'r': { need(4); if (stack.empty()) fail("LONG_BINPUT on empty stack"); memo[rd32(p)] = stack.back(); p += 4; break; } // LONG_BINPUT
+                case 0x94: if (stack.empty()) fail("MEMOIZE on empty stack"); memo[memo_next++] = stack.back(); break;                       // MEMOIZE
                 case 'h': { need(1); auto it = memo.find(*p); p += 1; if (it == memo.end()) fail("bad memo get"); stack.push_back(it->second); break; }
                 case 'j': { need(4); auto it = memo.find(rd32(p)); p += 4; if (it == memo.end()) fail("bad memo get"); stack.push_back(it->second); break; }
                 case 't': { auto v = mk(PVal::TUPLE); v->items = pop_to_mark(); stack.push_back(v); break; }       // TUPLE
@@ -276,7 +296,7 @@ struct Unpickler {
                 case 0x81: { pop(); pop(); stack.push_back(mk(PVal::OPAQUE)); break; }                             // NEWOBJ
                 case 0x92: { pop(); pop(); pop(); stack.push_back(mk(PVal::OPAQUE)); break; }                      // NEWOBJ_EX
                 case '0': pop(); break;                                               // POP
-                case '2': { PRef v = stack.empty() ? nullptr : stack.back(); stack.push_back(v); break; }          // DUP
+                case '2': { if (stack.empty()) fail("DUP on empty stack"); PRef v = stack.back(); stack.push_back(v); break; }   // DUP
                 case 0x8f: stack.push_back(mk(PVal::OPAQUE)); break;                  // EMPTY_SET
                 case 0x90: pop_to_mark(); break;                                      // ADDITEMS
                 default: {
@@ -307,6 +327,7 @@ float half_to_float(uint16_t h) {
 }
 
 void materialise(const Archive& ar, const std::string& root, const PVal& t, HostTensor& out) {
+    if (!t.storage || t.storage->kind != PVal::STORAGE || t.sizes.size() != t.strides.size()) fail("malformed tensor record");
     const PVal& st = *t.storage;
     int esize; int kind;     // kind: 0 f32, 1 f64, 2 f16, 3 bf16, 4 i64, 5 i32, 6 u8/bool
     if (st.s == "FloatStorage") { esize = 4; kind = 0; }
@@ -319,6 +340,7 @@ void materialise(const Archive& ar, const std::string& root, const PVal& t, Host
     else { fail("unsupported storage type " + st.s); return; }
     auto it = ar.entries.find(root + "data/" + st.s2);
     if (it == ar.entries.end()) fail("storage " + st.s2 + " missing from archive");
+    if (!it->second.stored) fail("compressed storage " + st.s2 + " (torch.save writes STORED entries)");
     const uint8_t* base = ar.bytes.data() + it->second.data_offset;
     const int64_t avail = (int64_t)(it->second.size / esize);
     out.shape = t.sizes;
@@ -366,12 +388,20 @@ bool read_checkpoint(const std::string& path, StateDict& out, std::string& err) 
             }
         }
         if (!found) fail("no data.pkl in archive " + path);
+        // a TorchScript archive (InferenceWrapper.trace's <name>_script.pt, python/src/inferencewrapper.py:85-87) carries
+        // the model's CODE next to data.pkl; this engine executes no TorchScript, its weights come from <name>_params.pt
+        for (auto& e : ar.entries)
+            if (e.first.compare(0, root.size() + 5, root + "code/") == 0 || e.first == root + "constants.pkl")
+                fail("'" + path + "' is a TorchScript archive: TorchScript modules are not executed by this engine; load the "
+                     "weights file written next to it by InferenceWrapper.trace (<name>_params.pt), or the training checkpoint");
         auto bo = ar.entries.find(root + "byteorder");
         if (bo != ar.entries.end()) {
-            std::string s((const char*)ar.bytes.data() + bo->second.data_offset, bo->second.size);
+            std::string s;
+            if (bo->second.stored) s.assign((const char*)ar.bytes.data() + bo->second.data_offset, bo->second.size);
             if (s.find("little") == std::string::npos) fail("big-endian checkpoints are not supported");
         }
         const ZipEntry& pk = ar.entries[root + "data.pkl"];
+        if (!pk.stored) fail("compressed data.pkl (torch.save writes STORED entries)");
         Unpickler up{ar.bytes.data() + pk.data_offset, ar.bytes.data() + pk.data_offset + pk.size, {}, {}, 0};
         PRef top = up.run();
         if (!top || top->kind != PVal::DICT) fail("checkpoint top-level object is not a dict");

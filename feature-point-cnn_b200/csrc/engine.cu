@@ -218,6 +218,9 @@ const HostConv* Engine::fold(const std::string& conv_key, const std::string& bn_
     for (const HostTensor* t : {&g, &be, &mu, &var})
         if (t->numel() != hc->cout) throw std::runtime_error(bn_key + " has the wrong number of channels");
     const HostTensor* cb = has_bias ? &need(conv_key + ".bias") : nullptr;
+    if (cb && cb->numel() != hc->cout) throw std::runtime_error(conv_key + ".bias has the wrong number of elements");
+    if (w.numel() != (int64_t)w.shape[0] * w.shape[1] * w.shape[2] * w.shape[3] || hc->cout <= 0 || hc->cin <= 0 || hc->kh <= 0 || hc->kw <= 0)
+        throw std::runtime_error(conv_key + ".weight has an invalid shape");
     hc->w.resize((size_t)hc->cout * hc->cin * hc->kh * hc->kw);
     hc->b.resize(hc->cout);
     for (int co = 0; co < hc->cout; ++co) {
@@ -878,6 +881,13 @@ void Engine::heatmap_from_logits(const float* logits_nchw, int B, int H, int W, 
     if (H % 8 || W % 8) throw std::invalid_argument("H and W must be multiples of 8");
     const int Hc = H / 8, Wc = W / 8;
     launch_heatmap(logits_nchw, (long)65 * Hc * Wc, (long)Hc * Wc, 1, B, Hc, Wc, prob, st);
+    ++launches_;
+}
+
+void Engine::restore_prob_map(const float* softmax_nchw, int B, int H, int W, float* prob, cudaStream_t st) {
+    SPB_CUDA(cudaSetDevice(device_));
+    if (H % 8 || W % 8) throw std::invalid_argument("H and W must be multiples of 8");
+    launch_depth_to_space(softmax_nchw, B, H / 8, W / 8, prob, st);
     ++launches_;
 }
 

@@ -114,6 +114,7 @@ public:
     void detect_host_u8(const uint8_t* img, int B, int H, int W, int cap, int* count, int* xy, float* conf, float* desc);
     // stage-level entry points (reference restore_prob_map / get_points / get_descriptors)
     void heatmap_from_logits(const float* logits_nchw, int B, int H, int W, float* prob, cudaStream_t st);
+    void restore_prob_map(const float* softmax_nchw, int B, int H, int W, float* prob, cudaStream_t st);
     void nms(const float* prob, int B, int H, int W, int cap, int* count, int* xy, float* conf, cudaStream_t st);
     void sample_descriptors(const float* desc_nchw, int B, int D, int H, int W, int cap, const int* count,
                             const int* xy, float* out, cudaStream_t st);

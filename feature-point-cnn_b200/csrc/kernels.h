@@ -60,6 +60,9 @@ void launch_stem_planes(StemPlanesPlan* plan, const void* planes, void* dst, int
 void launch_heatmap(const float* logits, long batch_stride, long chan_stride, long cell_stride, int B, int Hc, int Wc,
                     float* heat, cudaStream_t st);
 
+// restore_prob_map (python/src/netutils.py:64-75) on an already softmaxed B*65*Hc*Wc tensor: dustbin drop + depth-to-space
+void launch_depth_to_space(const float* softmax_nchw, int B, int Hc, int Wc, float* heat, cudaStream_t st);
+
 struct NmsWorkspace {
     unsigned long long* keys;      // [B][kcap] survivors as sortable keys (conf bits << 32 | ~pixel index)
     unsigned long long* keys_alt;  // [B][kcap] ping-pong buffer of the radix sort

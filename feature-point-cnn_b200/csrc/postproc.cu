@@ -49,6 +49,26 @@ heatmap_kernel(const float* __restrict__ logits, long batch_stride, long chan_st
     }
 }
 
+// restore_prob_map alone (python/src/netutils.py:64-75): the 65-channel tensor is already softmaxed; drop the dustbin,
+// pixel (8 i + c / 8, 8 j + c % 8) <- channel c of cell (i, j).  One thread per output pixel: a warp writes 128 contiguous
+// bytes and reads four 32-byte runs of eight cells from each of eight channel planes.
+__global__ void __launch_bounds__(256)
+depth_to_space_kernel(const float* __restrict__ src, int Hc, int Wc, float* __restrict__ heat, long total) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int W = Wc * 8, H = Hc * 8;
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const long b = i / ((long)W * H);
+    const int c = (y & 7) * 8 + (x & 7);
+    heat[i] = __ldg(src + ((b * 65 + c) * Hc + (y >> 3)) * Wc + (x >> 3));
+}
+
+void launch_depth_to_space(const float* softmax_nchw, int B, int Hc, int Wc, float* heat, cudaStream_t st) {
+    const long total = (long)B * Hc * Wc * 64;
+    depth_to_space_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(softmax_nchw, Hc, Wc, heat, total);
+    SPB_CHECK_LAUNCH();
+}
+
 void launch_heatmap(const float* logits, long batch_stride, long chan_stride, long cell_stride, int B, int Hc, int Wc,
                     float* heat, cudaStream_t st) {
     dim3 grid((Wc + kHeatCells - 1) / kHeatCells, Hc, B);

@@ -8,4 +8,5 @@ from .settings import SuperPointSettings          # noqa: F401
 from .engine import Engine, Spb200Error           # noqa: F401
 from .superpoint import SuperPoint                # noqa: F401
 from .inferencewrapper import InferenceWrapper    # noqa: F401
-from .netutils import get_points, get_descriptors, restore_prob_map   # noqa: F401
+from .netutils import get_points, get_descriptors, restore_prob_map, heatmap_from_logits   # noqa: F401
+from . import ops                                  # noqa: F401  (registers torch.ops.spb200.*)

@@ -30,6 +30,7 @@ SYMBOLS = {
     'spb200_homography_adaptation': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     'spb200_match': (_c.c_int, [_P, _P, _P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),
     'spb200_heatmap_from_logits': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
+    'spb200_restore_prob_map': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     'spb200_nms': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'spb200_sample_descriptors': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'spb200_descriptor_dim': (_c.c_int, [_P]),

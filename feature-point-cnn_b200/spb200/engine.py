@@ -201,6 +201,15 @@ class Engine:
                     'spb200_heatmap_from_logits')
         return prob
 
+    def restore_prob_map(self, softmax, h, w):
+        """Reference restore_prob_map on an already softmaxed B*65*Hc*Wc CUDA tensor -> B*H*W."""
+        softmax = softmax.contiguous()
+        b = softmax.shape[0]
+        prob = torch.empty((b, h, w), dtype=torch.float32, device=softmax.device)
+        self._check(self._lib.spb200_restore_prob_map(self._h, _ptr(softmax), b, h, w, _ptr(prob), self._stream()),
+                    'spb200_restore_prob_map')
+        return prob
+
     def nms(self, prob, capacity):
         prob = prob.contiguous()
         b, h, w = prob.shape

@@ -4,9 +4,12 @@
 float32)`` exactly as the reference documents, computed by one fused device pipeline
 (spb200_detect): only the keypoints and their descriptors leave the GPU.
 """
+import ctypes
+
 import numpy as np
 import torch
 
+from . import ops
 from .engine import Engine
 
 
@@ -23,6 +26,43 @@ class InferenceWrapper(object):
             print('Failed to load checkpoint: %s (%s)' % (weights_path, e))
             raise SystemExit(1)
         self.descriptor_enabled = True
+        self.weights_path = weights_path
+        self._net = None
+
+    @property
+    def net(self):
+        """The drop-in ``SuperPoint`` module (python/src/inferencewrapper.py:18) holding this checkpoint's 163 tensors.
+        Built on first use from the same native checkpoint reader the engine used (no torch.load); it shares the wrapper's
+        engine, so ``wrapper.net(image)`` and ``wrapper.run(image)`` run the same kernels on the same weights."""
+        if self._net is None:
+            from .superpoint import SuperPoint
+            net = SuperPoint(self.settings)
+            lib = self.engine._lib
+            sd = net.state_dict()
+            for key, dst in sd.items():
+                shape = (ctypes.c_int64 * 8)()
+                rank = ctypes.c_int()
+                buf = np.empty((max(dst.numel(), 1),), np.float32)
+                rc = lib.spb200_checkpoint_tensor(str(self.weights_path).encode(), key.encode(), ctypes.c_void_p(buf.ctypes.data),
+                                                  buf.size, shape, ctypes.byref(rank))
+                if rc != 0:
+                    raise RuntimeError('checkpoint %s has no tensor %s' % (self.weights_path, key))
+                dst.copy_(torch.from_numpy(buf[:dst.numel()]).reshape(dst.shape).to(dst.dtype))
+            net.eval()
+            net.adopt_engine(self.engine)
+            self._net = net
+        return self._net
+
+    def trace(self, img, out_file_name):
+        """python/src/inferencewrapper.py:83-91.  The weights-only file ``<out>_params.pt`` is written exactly as the
+        reference writes it (state_dict keys without their first module prefix, new zipfile serialisation) - it is what
+        the C++ side loads (cpp/src/superpoint.cc:27-53, and spb200_load_checkpoint).  ``<out>_script.pt`` is a TorchScript
+        of the reference's PyTorch modules; this implementation has no PyTorch graph to trace (the network runs in
+        libspb200.so), so no script file is written and the C++ facade rejects script files with a clear error."""
+        self.prepare_input(img)                               # same input validation as the reference
+        state_dict = {('.'.join(k.split('.')[1:])): v for k, v in self.net.state_dict().items()}
+        torch.save(state_dict, out_file_name + '_params.pt', _use_new_zipfile_serialization=True)
+        return out_file_name + '_params.pt'
 
     def _params(self):
         s = self.settings
@@ -55,7 +95,7 @@ class InferenceWrapper(object):
         cap = max(self.engine.max_keypoints(h, w, self.settings.nms_dist), 1)
         if k:
             cap = min(cap, k)
-        count, xy, conf, desc, _ = self.engine.detect(x, cap)
+        count, xy, conf, desc = torch.ops.spb200.detect(x.contiguous(), ops.register(self.engine), cap)
         count = count.cpu().numpy()
         pts, dsc = [], []
         for i in range(b):

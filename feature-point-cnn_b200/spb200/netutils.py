@@ -21,12 +21,22 @@ def _engine(settings):
     return e
 
 
-def restore_prob_map(softmax_or_logits, img_h, img_w, cell_size, settings=None, from_logits=True):
-    """Heatmap from the 65-channel LOGITS (softmax + dustbin drop + depth-to-space in one kernel)."""
+def restore_prob_map(prob_map, img_h, img_w, cell_size, settings=None):
+    """python/src/netutils.py:64-75, same contract: ``prob_map`` is the SOFTMAXED B*65*Hc*Wc tensor (what
+    SuperPoint.forward and make_prob_map_from_labels pass); the dustbin channel is dropped and the 64 channels of a cell
+    become its 8x8 pixels -> B*H*W on the GPU."""
     from .settings import SuperPointSettings
-    assert cell_size == 8 and from_logits
+    assert cell_size == 8, 'the engine is built for 8x8 cells (python/src/settings.py:7)'
     e = _engine(settings or SuperPointSettings())
-    return e.heatmap_from_logits(softmax_or_logits.to('cuda:%d' % e.device, torch.float32), img_h, img_w)
+    return e.restore_prob_map(torch.as_tensor(prob_map).to('cuda:%d' % e.device, torch.float32), img_h, img_w)
+
+
+def heatmap_from_logits(logits, img_h, img_w, settings=None):
+    """The fused form the engine uses itself: exp(l) / (sum exp(l) + 1e-5) (python/src/superpoint.py:111-112) followed by
+    restore_prob_map, in one kernel, from the 65-channel LOGITS."""
+    from .settings import SuperPointSettings
+    e = _engine(settings or SuperPointSettings())
+    return e.heatmap_from_logits(torch.as_tensor(logits).to('cuda:%d' % e.device, torch.float32), img_h, img_w)
 
 
 def get_points(prob_map, img_h, img_w, settings, engine=None):

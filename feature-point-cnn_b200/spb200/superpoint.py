@@ -6,9 +6,12 @@ python/src/saveutils.py:6-18, loads into it unchanged), same ``forward`` triple,
 ``forward`` hands them to the sm_100a engine (BatchNorm is folded there) and never runs a PyTorch
 convolution.  Inference only: there is no autograd through the engine.
 """
+import math
+
 import torch
 from torch import nn
 
+from . import ops
 from .engine import Engine
 
 
@@ -19,6 +22,15 @@ class _Conv(nn.Module):
         self.weight = nn.Parameter(torch.zeros(shape))
         if bias:
             self.bias = nn.Parameter(torch.zeros(cout))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        """nn.Conv2d / nn.ConvTranspose2d default initialisation (kaiming_uniform with a = sqrt(5))."""
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if getattr(self, 'bias', None) is not None:
+            fan_in = self.weight.shape[1] * self.weight.shape[2] * self.weight.shape[3]
+            bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+            nn.init.uniform_(self.bias, -bound, bound)
 
 
 class _BatchNorm(nn.Module):
@@ -29,6 +41,14 @@ class _BatchNorm(nn.Module):
         self.register_buffer('running_mean', torch.zeros(c))
         self.register_buffer('running_var', torch.ones(c))
         self.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+
+    def reset_parameters(self):
+        """nn.BatchNorm2d.reset_parameters."""
+        self.running_mean.zero_()
+        self.running_var.fill_(1)
+        self.num_batches_tracked.zero_()
+        nn.init.ones_(self.weight)
+        nn.init.zeros_(self.bias)
 
 
 class _Block(nn.Module):
@@ -90,11 +110,27 @@ class SuperPoint(nn.Module):
     def enable_descriptor(self):
         self.is_descriptor_enabled = True
 
+    def initialize_descriptor(self):
+        """python/src/superpoint.py:86-89: re-initialise the descriptor head's direct children that can be reset (the
+        transposed convolution and its BatchNorm; the two residual layers are Sequential containers and are left alone,
+        exactly as in the reference)."""
+        for layer in self.descriptor.children():
+            if hasattr(layer, 'reset_parameters'):
+                layer.reset_parameters()
+
+    def _weights_key(self):
+        return (getattr(self.settings, 'precision', 'fp16'), tuple(int(p._version) for p in self.state_dict().values()),
+                tuple(p.data_ptr() for p in self.state_dict().values()))
+
+    def adopt_engine(self, engine):
+        """Use an engine that already holds exactly these parameters (InferenceWrapper.net)."""
+        self._engine = engine
+        self._engine_key = self._weights_key()
+
     def engine(self):
         """The engine holding the current parameters (re-uploaded whenever they change)."""
         precision = getattr(self.settings, 'precision', 'fp16')
-        key = (precision, tuple(int(p._version) for p in self.state_dict().values()),
-               tuple(p.data_ptr() for p in self.state_dict().values()))
+        key = self._weights_key()
         if self._engine is None:
             self._engine = Engine(getattr(self.settings, 'device', 0))
         if key != self._engine_key:
@@ -113,4 +149,4 @@ class SuperPoint(nn.Module):
             return torch.empty((1,)), torch.empty((1,)), torch.empty((1,))
         eng = self.engine()
         image = image.to('cuda:%d' % eng.device, torch.float32)
-        return eng.forward(image)
+        return torch.ops.spb200.forward(image, ops.register(eng))

@@ -126,6 +126,10 @@ SPB200_API int spb200_detect_host_u8(spb200_engine* e, const uint8_t* img_host, 
 /* exp(l)/(sum exp(l)+1e-5), drop dustbin, depth-to-space: superpoint.py:111-114 + restore_prob_map
  * (netutils.py:64-75) / GetPoints (superpoint.cc:154-173).  logits B*65*(H/8)*(W/8) -> prob_map B*H*W. */
 SPB200_API int spb200_heatmap_from_logits(spb200_engine* e, const float* logits, int B, int H, int W, float* prob_map, void* stream);
+/* restore_prob_map (netutils.py:64-75) with the reference's contract: `softmax` B*65*(H/8)*(W/8) is ALREADY softmaxed
+ * (what make_prob_map_from_labels and SuperPoint.forward hand it); the dustbin is dropped and the 64 channels of a cell
+ * become its 8x8 pixels.  prob_map B*H*W. */
+SPB200_API int spb200_restore_prob_map(spb200_engine* e, const float* softmax, int B, int H, int W, float* prob_map, void* stream);
 /* get_points (netutils.py:78-100) incl. corners_nms (nms.py:4-53) / FeatureNMS (torchutis.cc:37-99). */
 SPB200_API int spb200_nms(spb200_engine* e, const float* prob_map, int B, int H, int W, int capacity, int* count, int* xy,
                float* conf, void* stream);

@@ -127,3 +127,86 @@ def test_dropin_module_has_reference_state_dict_keys():
         assert v.shape == sd[k].shape, k
     s = spb200.SuperPointSettings()
     assert (s.nms_dist, s.confidence_thresh, s.cell, s.border_remove, s.nn_thresh) == (4, 0.015, 8, 4, 0.7)
+
+
+def test_checkpoint_reader_survives_truncated_and_corrupted_archives(lib, tmp_path):
+    """A truncated or damaged checkpoint must come back as an error code with a message, never as an out-of-bounds read:
+    every prefix class of a small archive, single-byte corruptions of its pickle, central directory and end record, and
+    hostile 64-bit sizes (the reader trusts nothing it reads from the file)."""
+    t = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4)
+    good = tmp_path / 'small.pt'
+    torch.save({'model_state_dict': {'a.weight': t, 'b.bias': t[0, 0], 'c.half': t.half()}}, str(good))
+    raw = good.read_bytes()
+    assert lib.spb200_checkpoint_num_tensors(str(good).encode()) == 3
+    bad = tmp_path / 'bad.pt'
+    for cut in list(range(0, 64)) + list(range(64, len(raw), 37)) + [len(raw) - k for k in range(1, 60)]:
+        bad.write_bytes(raw[:cut])
+        assert lib.spb200_checkpoint_num_tensors(str(bad).encode()) < 0, cut
+        assert lib.spb200_last_error(None)
+    rs = np.random.RandomState(0)
+    eocd = raw.rfind(b'PK\x05\x06')
+    cdir = raw.find(b'PK\x01\x02')
+    pkl = raw.find(b'data.pkl') + 8
+    spots = (list(range(eocd, len(raw))) + list(range(cdir, min(cdir + 200, eocd))) + list(range(pkl, pkl + 400)) +
+             [int(v) for v in rs.randint(0, len(raw), 400)])
+    survived = 0
+    for pos in spots:
+        for val in (0x00, 0xff, raw[pos] ^ 0x5a):
+            b = bytearray(raw)
+            b[pos] = val
+            bad.write_bytes(bytes(b))
+            n = lib.spb200_checkpoint_num_tensors(str(bad).encode())
+            assert n < 0 or n <= 3
+            if n >= 0:                                          # still parses: every tensor must still be readable or refused
+                shape = (ctypes.c_int64 * 8)()
+                rank = ctypes.c_int()
+                buf = np.empty(64, np.float32)
+                lib.spb200_checkpoint_tensor(str(bad).encode(), b'a.weight', ctypes.c_void_p(buf.ctypes.data), buf.size, shape,
+                                             ctypes.byref(rank))
+                survived += 1
+    assert survived > 0
+    # hostile sizes in the central directory: 0xFFFFFFFF sizes with a bogus ZIP64 extra field
+    b = bytearray(raw)
+    b[cdir + 20:cdir + 28] = b'\xff' * 8
+    bad.write_bytes(bytes(b))
+    assert lib.spb200_checkpoint_num_tensors(str(bad).encode()) < 0
+
+
+def test_torchscript_archive_is_refused_with_a_clear_message(lib, tmp_path):
+    """InferenceWrapper.trace writes <name>_script.pt next to <name>_params.pt (python/src/inferencewrapper.py:83-91);
+    the script is a TorchScript archive, which this engine does not execute: the loader must say so."""
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(1, 2, 3)
+
+        def forward(self, x):
+            return self.conv(x)
+
+    p = str(tmp_path / 'tiny_script.pt')
+    torch.jit.trace(Tiny(), torch.zeros(1, 1, 8, 8)).save(p)
+    assert lib.spb200_checkpoint_num_tensors(p.encode()) < 0
+    msg = lib.spb200_last_error(None).decode()
+    assert 'TorchScript' in msg and '_params.pt' in msg
+
+
+def test_dropin_module_initialize_descriptor_and_custom_ops_registered():
+    """SuperPoint.initialize_descriptor (python/src/superpoint.py:86-89) resets the descriptor head's resettable direct
+    children only; torch.ops.spb200.{forward,detect,detect_u8} are registered with fake kernels (shape inference without
+    a GPU)."""
+    import spb200
+    net = spb200.SuperPoint(spb200.SuperPointSettings())
+    up, bn, blk = net.descriptor.up_sample.weight.clone(), net.descriptor.bn.weight.clone(), net.descriptor.layer_in[0].conv1.weight.clone()
+    with torch.no_grad():
+        net.descriptor.bn.weight.fill_(3.0)
+    net.initialize_descriptor()
+    assert not torch.equal(up, net.descriptor.up_sample.weight)
+    assert torch.equal(net.descriptor.bn.weight, torch.ones_like(bn))
+    assert torch.equal(blk, net.descriptor.layer_in[0].conv1.weight)
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        img = torch.empty((2, 1, 240, 320), device='cuda')
+        prob, desc, logits = torch.ops.spb200.forward(img, 1)
+        assert prob.shape == (2, 240, 320) and desc.shape == (2, 128, 30, 40) and logits.shape == (2, 65, 30, 40)
+        count, xy, conf, dsc = torch.ops.spb200.detect(img, 1, 500)
+        assert count.shape == (2,) and xy.shape == (2, 500, 2) and dsc.shape == (2, 500, 128) and count.dtype == torch.int32
