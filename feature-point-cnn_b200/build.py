@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libspb200.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
-SOURCES = ['ckpt_reader.cpp', 'conv_simt.cu', 'conv_tc.cu', 'block_tc.cu', 'halo_tc.cu', 'stem_tc.cu', 'stem_planes.cu', 'nms.cu', 'match.cu', 'match_tc.cu', 'homography.cu', 'postproc.cu', 'engine.cu', 'capi.cu']
+SOURCES = ['ckpt_reader.cpp', 'conv_simt.cu', 'conv_tc.cu', 'block_tc.cu', 'halo_tc.cu', 'stem_tc.cu', 'stem_planes.cu', 'nms.cu', 'match.cu', 'match_tc.cu', 'homography.cu', 'postproc.cu', 'preproc.cu', 'engine.cu', 'capi.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
          '-Xcompiler', '-fvisibility=hidden', '-I', INCLUDE, '-I', CSRC]

@@ -166,6 +166,20 @@ int spb200_restore_prob_map(spb200_engine* e, const float* softmax, int B, int H
     });
 }
 
+int spb200_preprocess_u8(spb200_engine* e, const uint8_t* frames, int B, int h, int w, int C, uint8_t* gray, int H, int W, void* stream) {
+    return guarded(e, [&](spb200::Engine& g) {
+        if (!frames || !gray) throw std::invalid_argument("preprocess_u8: null argument");
+        g.preprocess_u8(frames, B, h, w, C, gray, H, W, (cudaStream_t)stream);
+    });
+}
+
+int spb200_preprocess_f32(spb200_engine* e, const float* frames, int B, int h, int w, float* rgb, int H, int W, void* stream) {
+    return guarded(e, [&](spb200::Engine& g) {
+        if (!frames || !rgb) throw std::invalid_argument("preprocess_f32: null argument");
+        g.preprocess_f32(frames, B, h, w, rgb, H, W, (cudaStream_t)stream);
+    });
+}
+
 int spb200_nms(spb200_engine* e, const float* prob_map, int B, int H, int W, int capacity, int* count, int* xy, float* conf,
                void* stream) {
     return guarded(e, [&](spb200::Engine& g) {
@@ -178,6 +192,9 @@ int spb200_sample_descriptors(spb200_engine* e, const float* desc_map, int B, in
                               const int* count, const int* xy, float* desc, void* stream) {
     return guarded(e, [&](spb200::Engine& g) {
         if (!desc_map || !count || !xy || !desc || B <= 0 || H < 8 || W < 8) throw std::invalid_argument("bad descriptor arguments");
+        if (H % 8 || W % 8) throw std::invalid_argument("H and W must be multiples of the 8-pixel cell");
+        if (D <= 0 || D % 4) throw std::invalid_argument("descriptor dimension must be a positive multiple of 4");
+        if (capacity <= 0) throw std::invalid_argument("capacity must be positive");
         g.sample_descriptors(desc_map, B, D, H, W, capacity, count, xy, desc, (cudaStream_t)stream);
     });
 }

@@ -102,6 +102,7 @@ Engine::Engine(int device) : device_(device) {
         SPB_CUDA(cudaEventCreateWithFlags(&side_join_[i], cudaEventDisableTiming));
     }
     SPB_CUDA(cudaEventCreateWithFlags(&side_fork_, cudaEventDisableTiming));
+    SPB_CUDA(cudaEventCreateWithFlags(&ws_done_, cudaEventDisableTiming));
     const char* np = std::getenv("SPB200_NO_PHASES");
     use_phases_ = !(np && np[0] == '1');
     const char* os = std::getenv("SPB200_OLD_STEM");
@@ -109,8 +110,23 @@ Engine::Engine(int device) : device_(device) {
     buf_.fill(nullptr);
 }
 
+Engine::StreamScope::StreamScope(Engine* eng, cudaStream_t s) : e(eng), st(s) {
+    SPB_CUDA(cudaSetDevice(e->device_));
+    if (e->ws_used_ && e->ws_stream_ != st) SPB_CUDA(cudaStreamWaitEvent(st, e->ws_done_, 0));
+}
+
+Engine::StreamScope::~StreamScope() {
+    if (cudaEventRecord(e->ws_done_, st) == cudaSuccess) {
+        e->ws_stream_ = st;
+        e->ws_used_ = true;
+    } else {
+        cudaGetLastError();
+    }
+}
+
 Engine::~Engine() {
     cudaSetDevice(device_);
+    if (ws_done_) cudaEventDestroy(ws_done_);
     release_workspace();
     release_weights();
     cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und); cudaFree(nms_.ukey);
@@ -121,6 +137,7 @@ Engine::~Engine() {
     if (side_fork_) cudaEventDestroy(side_fork_);
     cudaFree(d_gtab_);
     cudaFree(d_match_ws_);
+    cudaFree(d_pre_tab_);
     cudaFree(d_match_tc_ws_);
     cudaFree(d_ha_img_); cudaFree(d_ha_prob_); cudaFree(d_ha_coeffs_); cudaFree(d_ha_maps_);
 }
@@ -807,7 +824,7 @@ void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
 
 void Engine::forward(const float* img, int B, int C, int H, int W, float* prob, float* desc_nchw, float* logits_nchw,
                      cudaStream_t st) {
-    SPB_CUDA(cudaSetDevice(device_));
+    StreamScope scope(this, st);
     run_network(img, false, B, C, H, W, st);
     const int Hc = H / 8, Wc = W / 8;
     float* heat = prob ? prob : d_prob_;
@@ -840,7 +857,7 @@ void Engine::detect_u8(const uint8_t* img, int B, int H, int W, int cap, int* co
 
 void Engine::detect_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                         float* desc, float* prob, cudaStream_t st) {
-    SPB_CUDA(cudaSetDevice(device_));
+    StreamScope scope(this, st);
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
     run_network(img, img_u8, B, C, H, W, st);
     const int Hc = H / 8, Wc = W / 8;
@@ -877,7 +894,7 @@ void Engine::detect_any(const void* img, bool img_u8, int B, int C, int H, int W
 }
 
 void Engine::heatmap_from_logits(const float* logits_nchw, int B, int H, int W, float* prob, cudaStream_t st) {
-    SPB_CUDA(cudaSetDevice(device_));
+    StreamScope scope(this, st);
     if (H % 8 || W % 8) throw std::invalid_argument("H and W must be multiples of 8");
     const int Hc = H / 8, Wc = W / 8;
     launch_heatmap(logits_nchw, (long)65 * Hc * Wc, (long)Hc * Wc, 1, B, Hc, Wc, prob, st);
@@ -885,14 +902,44 @@ void Engine::heatmap_from_logits(const float* logits_nchw, int B, int H, int W, 
 }
 
 void Engine::restore_prob_map(const float* softmax_nchw, int B, int H, int W, float* prob, cudaStream_t st) {
-    SPB_CUDA(cudaSetDevice(device_));
+    StreamScope scope(this, st);
     if (H % 8 || W % 8) throw std::invalid_argument("H and W must be multiples of 8");
     launch_depth_to_space(softmax_nchw, B, H / 8, W / 8, prob, st);
     ++launches_;
 }
 
+// one table set at a time, rebuilt when the geometry changes (a stream of frames keeps its geometry)
+const int* Engine::preprocess_table(int kind, int h, int w, int H, int W, cudaStream_t st) {
+    const int key[5] = {kind, h, w, H, W};
+    if (d_pre_tab_ && std::equal(key, key + 5, pre_key_)) return d_pre_tab_;
+    std::vector<int> tab((size_t)4 * (H + W), 0);
+    if (kind == 0) build_preprocess_u8_table(h, w, H, W, tab.data());
+    else build_preprocess_f32_table(h, w, H, W, tab.data(), reinterpret_cast<float*>(tab.data() + 2 * (W + H)));
+    SPB_CUDA(cudaDeviceSynchronize());                       // an earlier launch may still read the old table
+    cudaFree(d_pre_tab_);
+    d_pre_tab_ = dev_upload(tab);
+    (void)st;
+    std::copy(key, key + 5, pre_key_);
+    return d_pre_tab_;
+}
+
+void Engine::preprocess_u8(const uint8_t* frames, int B, int h, int w, int C, uint8_t* out, int H, int W, cudaStream_t st) {
+    StreamScope scope(this, st);
+    if (B <= 0 || h < 2 || w < 2 || H < 1 || W < 1 || (C != 1 && C != 3)) throw std::invalid_argument("preprocess_u8: bad geometry (C must be 1 or 3)");
+    launch_preprocess_u8(frames, B, h, w, C, preprocess_table(0, h, w, H, W, st), out, H, W, st);
+    ++launches_;
+}
+
+void Engine::preprocess_f32(const float* frames, int B, int h, int w, float* out, int H, int W, cudaStream_t st) {
+    StreamScope scope(this, st);
+    if (B <= 0 || h < 2 || w < 2 || H < 1 || W < 1) throw std::invalid_argument("preprocess_f32: bad geometry");
+    const int* tab = preprocess_table(1, h, w, H, W, st);
+    launch_preprocess_f32(frames, B, h, w, tab, reinterpret_cast<const float*>(tab + 2 * (W + H)), out, H, W, st);
+    ++launches_;
+}
+
 void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, int* xy, float* conf, cudaStream_t st) {
-    SPB_CUDA(cudaSetDevice(device_));
+    StreamScope scope(this, st);
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
     ensure_nms(B, H, W);
     launch_nms_round0(prob, nullptr, 0, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
@@ -902,7 +949,7 @@ void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, in
 
 void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int W, int cap, const int* count,
                                 const int* xy, float* out, cudaStream_t st) {
-    SPB_CUDA(cudaSetDevice(device_));
+    StreamScope scope(this, st);
     const int Hc = H / 8, Wc = W / 8;
     launch_sample_descriptors(desc_nchw, PREC_FP32, (long)D * Hc * Wc, (long)Hc * Wc, 1, B, D, Hc, Wc, W, grid_table(H, W), cap,
                               count, xy, out, st);
@@ -911,7 +958,7 @@ void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int
 
 void Engine::homography_adaptation(const float* img, int B, int C, int H, int W, const float* homographies, int num, int margin,
                                    int aggregation, float* prob_out, cudaStream_t st) {
-    SPB_CUDA(cudaSetDevice(device_));
+    StreamScope scope(this, st);
     if (!img || !homographies || !prob_out) throw std::invalid_argument("homography_adaptation: null argument");
     if (num < 0 || num > 4096) throw std::invalid_argument("homography_adaptation: num must be in [0, 4096]");
     if (aggregation != 0 && aggregation != 1) throw std::invalid_argument("homography_adaptation: aggregation must be 0 (mean) or 1 (max)");
@@ -988,7 +1035,7 @@ void Engine::homography_adaptation(const float* img, int B, int C, int H, int W,
 
 void Engine::match(const float* desc_a, const int* count_a, const float* desc_b, const int* count_b, int B, int cap, int D,
                    float max_dist, int* match_ab, float* dist, cudaStream_t st) {
-    SPB_CUDA(cudaSetDevice(device_));
+    StreamScope scope(this, st);
     if (B <= 0 || cap <= 0) throw std::invalid_argument("match: batch and capacity must be positive");
     const size_t need = (size_t)2 * B * cap;
     if (need > match_ws_elems_) {
@@ -1025,6 +1072,7 @@ void Engine::buffer_dims(int id, int* C, int* H, int* W) const {
 
 void Engine::export_buffer(int id, float* dst_nchw, int channels, cudaStream_t st) {
     if (id < 0 || id >= BUF_COUNT || !buf_[id]) throw std::invalid_argument("bad buffer id or no workspace");
+    StreamScope scope(this, st);
     const BufSpec& bs = bufspec_[id];
     if (bs.split)
         launch_split_to_nchw(buf_[id], precision_, wsB_, (wsH_ / bs.div) * (wsW_ / bs.div), bs.stored(), channels, dst_nchw, st);

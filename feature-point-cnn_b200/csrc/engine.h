@@ -115,6 +115,9 @@ public:
     // stage-level entry points (reference restore_prob_map / get_points / get_descriptors)
     void heatmap_from_logits(const float* logits_nchw, int B, int H, int W, float* prob, cudaStream_t st);
     void restore_prob_map(const float* softmax_nchw, int B, int H, int W, float* prob, cudaStream_t st);
+    // the demos' frame loaders (preproc.cu): frames B*h*w*C bytes -> gray B*H*W bytes; frames B*h*w*3 fp32 BGR -> B*3*H*W fp32 RGB
+    void preprocess_u8(const uint8_t* frames, int B, int h, int w, int C, uint8_t* out, int H, int W, cudaStream_t st);
+    void preprocess_f32(const float* frames, int B, int h, int w, float* out, int H, int W, cudaStream_t st);
     void nms(const float* prob, int B, int H, int W, int cap, int* count, int* xy, float* conf, cudaStream_t st);
     void sample_descriptors(const float* desc_nchw, int B, int D, int H, int W, int cap, const int* count,
                             const int* xy, float* out, cudaStream_t st);
@@ -200,6 +203,9 @@ private:
     float* d_gtab_ = nullptr;
     int gtabH_ = 0, gtabW_ = 0;
     const float* grid_table(int H, int W);
+    int* d_pre_tab_ = nullptr;                     // interpolation tables of the frame loaders, per (kind, h, w, H, W)
+    int pre_key_[5] = {0, 0, 0, 0, 0};
+    const int* preprocess_table(int kind, int h, int w, int H, int W, cudaStream_t st);
     unsigned long long* d_match_ws_ = nullptr;     // [2][B][cap] best keys of the matcher
     size_t match_ws_elems_ = 0;
     void* d_match_tc_ws_ = nullptr;                // operands + norms of the tensor-core matcher
@@ -216,6 +222,16 @@ private:
     cudaEvent_t side_fork_ = nullptr, side_join_[3] = {nullptr, nullptr, nullptr};
     bool use_phases_ = true;      // SPB200_NO_PHASES=1 keeps stride-2 blocks on the per-tap kernel
     bool use_side_ = true;        // SPB200_NO_SIDE=1 runs the phases one after the other on all SMs
+    // The workspace (activations, NMS lists, tables, side streams) is shared by every call: a call enqueued on a stream
+    // other than the previous call's first waits for the event the previous call recorded when it finished enqueueing.
+    struct StreamScope {
+        Engine* e; cudaStream_t st;
+        StreamScope(Engine* eng, cudaStream_t s);
+        ~StreamScope();
+    };
+    cudaEvent_t ws_done_ = nullptr;
+    cudaStream_t ws_stream_ = nullptr;
+    bool ws_used_ = false;
     long launches_ = 0;
     bool profiling_ = false;
     std::vector<ProfEntry> prof_;

@@ -53,6 +53,16 @@ void stem_planes_plan_destroy(StemPlanesPlan* plan);
 void launch_planes(const void* img, int img_is_u8, void* planes, int operand_type, int B, int H, int W, cudaStream_t st);
 void launch_stem_planes(StemPlanesPlan* plan, const void* planes, void* dst, int B, int H, int W, cudaStream_t st);
 
+// ---- preproc.cu ----------------------------------------------------------------------------------
+// The frame loaders of the two demos on the device (reference cpp/src/camera.cc:12-23, python/src/inference.py:72-85).
+// Tables: host-built with OpenCV's arithmetic (build_*), uploaded by the caller, read by the kernels.
+size_t preprocess_u8_table_ints(int H, int W);                                        // 4 (H + W)
+void build_preprocess_u8_table(int h, int w, int H, int W, int* tab);
+void launch_preprocess_u8(const uint8_t* src, int B, int h, int w, int C, const int* tab_dev, uint8_t* dst, int H, int W, cudaStream_t st);
+void build_preprocess_f32_table(int h, int w, int H, int W, int* itab /* 2 (W + H) */, float* ftab /* W + H */);
+void launch_preprocess_f32(const float* src, int B, int h, int w, const int* itab_dev, const float* ftab_dev, float* dst, int H, int W,
+                           cudaStream_t st);
+
 // ---- postproc.cu ---------------------------------------------------------------------------------
 // Softmax-with-epsilon over 65 channels, drop the dustbin, depth-to-space (reference
 // python/src/superpoint.py:111-114, python/src/netutils.py:64-75).  logits element (b, c, i, j) is at

@@ -131,7 +131,8 @@ sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_strid
     const int i = blockIdx.x * 8 + warp;
     if (i >= min(__ldg(count + b), cap)) return;
     const int2 pt = __ldg(reinterpret_cast<const int2*>(xy) + (size_t)b * cap + i);
-    const float ix = __ldg(gtab + pt.x), iy = __ldg(gtab + W + pt.y);
+    // caller-supplied coordinates (spb200_sample_descriptors) are clamped into the image: never an out-of-bounds read
+    const float ix = __ldg(gtab + min(max(pt.x, 0), W - 1)), iy = __ldg(gtab + W + min(max(pt.y, 0), Hc * 8 - 1));
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
     const int x0 = (int)fx0, y0 = (int)fy0;
@@ -209,7 +210,8 @@ sample_desc128_kernel(const T* __restrict__ map, long batch_stride, int Hc, int 
             for (int k = 0; k < 4; ++k) { v[u][k] = make_uint4(0u, 0u, 0u, 0u); wgt[u][k] = 0.f; }
             if (live[u]) {
                 const int2 pt = __ldg(pts + i);
-                const float ix = __ldg(gtab + pt.x), iy = __ldg(gtab + W + pt.y);
+                // caller-supplied coordinates (spb200_sample_descriptors) are clamped into the image: never an out-of-bounds read
+    const float ix = __ldg(gtab + min(max(pt.x, 0), W - 1)), iy = __ldg(gtab + W + min(max(pt.y, 0), Hc * 8 - 1));
                 const float fx0 = floorf(ix), fy0 = floorf(iy);
                 const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
                 const int x0 = (int)fx0, y0 = (int)fy0;

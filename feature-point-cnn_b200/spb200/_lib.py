@@ -31,6 +31,8 @@ SYMBOLS = {
     'spb200_match': (_c.c_int, [_P, _P, _P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),
     'spb200_heatmap_from_logits': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     'spb200_restore_prob_map': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
+    'spb200_preprocess_u8': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int, _P]),
+    'spb200_preprocess_f32': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int, _P]),
     'spb200_nms': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'spb200_sample_descriptors': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'spb200_descriptor_dim': (_c.c_int, [_P]),

@@ -210,6 +210,29 @@ class Engine:
                     'spb200_restore_prob_map')
         return prob
 
+    def preprocess_u8(self, frames, h_out, w_out):
+        """The C++ demo's loader on the device: uint8 CUDA frames B*h*w*3 (BGR) or B*h*w (gray) -> uint8 gray B*H*W
+        (cv::resize INTER_LINEAR + BGR2GRAY, bit-exact); feed the result to detect_u8."""
+        frames = frames.contiguous()
+        assert frames.dtype == torch.uint8 and frames.is_cuda and frames.dim() in (3, 4)
+        b, h, w = frames.shape[:3]
+        c = frames.shape[3] if frames.dim() == 4 else 1
+        out = torch.empty((b, h_out, w_out), dtype=torch.uint8, device=frames.device)
+        self._check(self._lib.spb200_preprocess_u8(self._h, _ptr(frames), b, h, w, c, _ptr(out), h_out, w_out, self._stream()),
+                    'spb200_preprocess_u8')
+        return out
+
+    def preprocess_f32(self, frames, h_out, w_out):
+        """The Python demo's loader on the device: float32 CUDA frames B*h*w*3 (BGR, [0,1]) -> B*3*H*W RGB
+        (make_query_image: ratio-preserving INTER_LINEAR resize + centre crop, then HWC -> CHW)."""
+        frames = frames.contiguous()
+        assert frames.dtype == torch.float32 and frames.is_cuda and frames.dim() == 4 and frames.shape[3] == 3
+        b, h, w = frames.shape[:3]
+        out = torch.empty((b, 3, h_out, w_out), dtype=torch.float32, device=frames.device)
+        self._check(self._lib.spb200_preprocess_f32(self._h, _ptr(frames), b, h, w, _ptr(out), h_out, w_out, self._stream()),
+                    'spb200_preprocess_f32')
+        return out
+
     def nms(self, prob, capacity):
         prob = prob.contiguous()
         b, h, w = prob.shape

@@ -17,8 +17,12 @@
  * ends in _host, every data pointer is DEVICE memory on the engine's GPU, owned by the caller, and the
  * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the default stream) without a
  * host synchronisation.  An engine is bound to one GPU, owns its weights and workspace, and is not
- * thread-safe; engines are independent of each other (one per GPU / per thread).  There is no CPU
- * fallback: creating an engine without a Blackwell GPU fails.
+ * thread-safe; engines are independent of each other (one per GPU / per thread).  Calls on ONE engine
+ * share its workspace and are therefore ordered by the engine even across streams: a call enqueued on
+ * a stream other than the previous call's waits (on the device, cudaStreamWaitEvent) until the previous
+ * call's work has finished; the *_host calls run on streams of their own and obey the same rule.  The
+ * caller's own buffers are the caller's to order.  There is no CPU fallback: creating an engine without
+ * a Blackwell GPU fails.
  */
 #ifndef SPB200_H
 #define SPB200_H
@@ -121,6 +125,17 @@ SPB200_API int spb200_detect_u8(spb200_engine* e, const uint8_t* img, int B, int
                      float* conf, float* desc, float* prob_map, void* stream);
 SPB200_API int spb200_detect_host_u8(spb200_engine* e, const uint8_t* img_host, int B, int H, int W, int capacity,
                           int* count_host, int* xy_host, float* conf_host, float* desc_host);
+
+/* The frame loaders in front of the path, on the device (all pointers device memory).
+ * spb200_preprocess_u8: the C++ demo's loader (cpp/src/camera.cc:12-23): cv::resize(frame, Size(W, H)) - INTER_LINEAR on
+ *   8-bit pixels - then cvtColor(BGR2GRAY); the convertTo(CV_32FC1, 1/255) that follows is what spb200_detect_u8 applies.
+ *   frames: B*h*w*C bytes, C = 3 (BGR, interleaved) or 1 (gray); gray: B*H*W bytes, bit-exact with OpenCV 4.
+ * spb200_preprocess_f32: the Python demo's loader (python/src/inference.py:72-85 make_query_image + the HWC -> CHW of
+ *   inferencewrapper.py:70-81): frames B*h*w*3 fp32 BGR in [0,1] -> BGR2RGB, INTER_LINEAR resize by max(H/h, W/w) (ratio
+ *   preserving), centre crop -> rgb: B*3*H*W fp32, the input of spb200_forward / spb200_detect with C = 3. */
+SPB200_API int spb200_preprocess_u8(spb200_engine* e, const uint8_t* frames, int B, int h, int w, int C, uint8_t* gray, int H, int W,
+                         void* stream);
+SPB200_API int spb200_preprocess_f32(spb200_engine* e, const float* frames, int B, int h, int w, float* rgb, int H, int W, void* stream);
 
 /* Stage-level entry points with the reference's tensor layouts (NCHW fp32). */
 /* exp(l)/(sum exp(l)+1e-5), drop dustbin, depth-to-space: superpoint.py:111-114 + restore_prob_map

@@ -224,3 +224,84 @@ def test_engine_loads_params_file_of_the_reference_export(tmp_path):
         e.close()
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def test_frame_loaders_match_opencv_and_the_reference(engines):
+    """N3: the demos' loaders on the device against tests/golden/preproc_kat.npz - cv::resize + BGR2GRAY on 8-bit frames
+    (cpp/src/camera.cc:12-23) bit for bit; the reference's make_query_image (python/src/inference.py:72-85) + HWC -> CHW to
+    float rounding (OpenCV's float upscale differs from the two-pass form in the last bits)."""
+    import os
+    import numpy as np
+    kat = np.load(os.path.join(GOLDEN, 'preproc_kat.npz'))
+    e = engines['fp16']
+    n8 = len([k for k in kat.files if k.startswith('u8_') and k.endswith('_in')])
+    nf = len([k for k in kat.files if k.startswith('f32_') and k.endswith('_in')])
+    assert n8 >= 5 and nf >= 5
+    for k in range(n8):
+        f, want = kat['u8_%d_in' % k], kat['u8_%d_out' % k]
+        got = e.preprocess_u8(torch.from_numpy(np.stack([f, f[::-1].copy()])).cuda(), want.shape[0], want.shape[1]).cpu().numpy()
+        np.testing.assert_array_equal(got[0], want, err_msg='u8 case %d' % k)
+        assert got[1].shape == want.shape
+    for k in range(nf):
+        f, want = kat['f32_%d_in' % k], kat['f32_%d_out' % k]
+        got = e.preprocess_f32(torch.from_numpy(f[None]).cuda(), want.shape[1], want.shape[2]).cpu().numpy()[0]
+        assert float(np.abs(got - want).max()) <= 1e-5, ('f32 case %d' % k, float(np.abs(got - want).max()))
+    # the loaded frames feed the path: 8-bit gray frames -> detect_u8
+    f = kat['u8_1_in']
+    gray = e.preprocess_u8(torch.from_numpy(f[None]).cuda(), 112, 160)
+    count, xy, conf, desc, _ = e.detect_u8(gray, e.max_keypoints(112, 160))
+    assert int(count[0]) >= 0
+
+
+def test_headless_cli_and_pseudo_label_files(tmp_path):
+    """N3: `python -m spb200.main inference` over a folder of frames (python/main.py:9-99, python/src/inference.py:10-69
+    without camera and window) writes per frame what InferenceWrapper.run returns plus the mutual-nearest-neighbour matches
+    to the previous frame; the pseudo-labelling writer produces the reference's .npz entries (preprocess_coco.py:74:
+    image (3, H, W) float32, points (3, N)) that dataset_utils.read_dataset_item consumes."""
+    import cv2
+    import spb200
+    from spb200 import main as cli, preprocess_coco as pc, homographies as hg
+    from _gpu_common import CKPT
+    imgs = np.load(os.path.join(GOLDEN, 'images.npz'))
+    frames = tmp_path / 'frames'
+    frames.mkdir()
+    for i, key in enumerate(['s240_0', 's240_1', 's240_0']):
+        cv2.imwrite(str(frames / ('f%d.png' % i)), cv2.cvtColor(imgs[key], cv2.COLOR_GRAY2BGR))
+    out = tmp_path / 'features'
+    assert cli.main(['--H', '240', '--W', '320', 'inference', '--weights-path', CKPT, '--images', str(frames), '--out', str(out),
+                     '--out-file-name', str(tmp_path / 'exported')]) == 0
+    files = sorted(os.listdir(out))
+    assert files == ['f0.npz', 'f1.npz', 'f2.npz']
+    s = spb200.SuperPointSettings()
+    w = spb200.InferenceWrapper(CKPT, s)
+    f0 = np.load(out / 'f0.npz')
+    rgb = np.repeat(imgs['s240_0'].astype(np.float32)[:, :, None] / 255., 3, axis=2)          # same size: the loader is the identity
+    pts, dsc = w.run(rgb)
+    assert f0['points'].shape == pts.shape and pts.shape[1] > 500
+    np.testing.assert_array_equal(f0['points'], pts)
+    np.testing.assert_allclose(f0['descriptors'], dsc, atol=1e-6)
+    f2 = np.load(out / 'f2.npz')
+    m = f2['matches']
+    assert m.shape[1] == 2 and len(m) > 50 and m[:, 0].max() < f2['points'].shape[1]
+    # frames 0 and 2 are the same image: matching frame 2 against frame 1 equals matching frame 0 against frame 1
+    f1 = np.load(out / 'f1.npz')
+    qi, ti, _ = matching.mutual_nearest(f2['descriptors'].T, f1['descriptors'].T, 0.7)        # settings.nn_thresh
+    np.testing.assert_array_equal(m[:, 0], qi)
+    np.testing.assert_array_equal(m[:, 1], ti)
+    # the exported weights file loads back (InferenceWrapper.trace, python/src/inferencewrapper.py:89-91)
+    w2 = spb200.InferenceWrapper(str(tmp_path / 'exported_params.pt'), s)
+    p2, _ = w2.run(rgb)
+    np.testing.assert_array_equal(p2, pts)
+    # pseudo labels
+    cfg = hg.HomographyConfig()
+    cfg.init_for_preprocess()
+    cfg.num = 5
+    w.descriptor_enabled = False
+    written = pc.preprocess_coco_folder(sorted(str(p) for p in frames.glob('*.png'))[:2], w, cfg, tmp_path / 'labels', (240, 320),
+                                        rng=np.random.default_rng(1))
+    assert len(written) == 2
+    item = np.load(written[0])
+    assert sorted(item.files) == ['image', 'points']
+    assert item['image'].shape == (3, 240, 320) and item['image'].dtype == np.float32 and 0 <= item['image'].min() and item['image'].max() <= 1
+    assert item['points'].shape[0] == 3 and item['points'].shape[1] > 50
+    assert np.all(np.diff(item['points'][2]) <= 0)                 # descending confidence, as get_points returns

@@ -314,3 +314,31 @@ def test_plane_fed_stem_is_bit_identical_to_im2col_stem(prec, shape, monkeypatch
         print('[stem planes %s %s] %d of %d differ, first (b,c,y,x): %s, max diff %.4g' %
               (prec, shape, bad, outs[0].numel(), idx[:6].tolist(), float((outs[0] - outs[1]).abs().max())))
     assert bad == 0
+
+
+def test_calls_on_two_streams_are_ordered_by_the_engine(engines):
+    """The engine's workspace is shared by every call: a call on another stream must wait for the previous one
+    (include/spb200.h, conventions).  Two different batches back to back on two streams, no host synchronisation in
+    between, against the same calls made one at a time."""
+    e = engines['fp16']
+    a = torch.stack([golden_image('shapes240_0'), golden_image('rand240_1')] * 4)[:, None].contiguous().cuda()
+    b = torch.stack([golden_image('rand240_0'), golden_image('shapes240_2')] * 4)[:, None].contiguous().cuda()
+    cap = e.max_keypoints(240, 320)
+    ra = [t.clone() for t in e.detect(a, cap)[:4]]
+    rb = [t.clone() for t in e.detect(b, cap)[:4]]
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(5):
+        oa, ob = e.alloc_outputs(8, cap, a.device), e.alloc_outputs(8, cap, a.device)
+        with torch.cuda.stream(s1):
+            e.detect(a, cap, out=oa)
+        with torch.cuda.stream(s2):
+            e.detect(b, cap, out=ob)
+        with torch.cuda.stream(s1):
+            e.detect(a, cap, out=oa)
+        torch.cuda.synchronize()
+        for got, want in ((oa, ra), (ob, rb)):
+            assert torch.equal(got[0], want[0])
+            for i in range(8):
+                n = int(want[0][i])
+                assert torch.equal(got[1][i, :n], want[1][i, :n]) and torch.equal(got[3][i, :n], want[3][i, :n])
