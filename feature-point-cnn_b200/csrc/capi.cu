@@ -136,6 +136,25 @@ int spb200_detect_host_u8(spb200_engine* e, const uint8_t* img_host, int B, int 
     });
 }
 
+int spb200_detect_host_submit(spb200_engine* e, const void* img_host, int img_is_u8, int B, int C, int H, int W, int capacity,
+                              int want_desc, int* ticket) {
+    return guarded(e, [&](spb200::Engine& g) {
+        if (!img_host || !ticket) throw std::invalid_argument("img and ticket must not be null");
+        *ticket = g.detect_host_submit(img_host, img_is_u8 != 0, B, C, H, W, capacity, want_desc != 0);
+    });
+}
+
+int spb200_detect_host_wait(spb200_engine* e, int ticket, int* count_host, int* xy_host, float* conf_host, void* desc_host) {
+    return guarded(e, [&](spb200::Engine& g) {
+        if (!count_host || !xy_host || !conf_host) throw std::invalid_argument("count, xy and conf must not be null");
+        g.detect_host_wait(ticket, count_host, xy_host, conf_host, desc_host);
+    });
+}
+
+int spb200_set_descriptor_format(spb200_engine* e, int format) {
+    return guarded(e, [&](spb200::Engine& g) { g.set_descriptor_format(format); });
+}
+
 int spb200_homography_adaptation(spb200_engine* e, const float* img, int B, int C, int H, int W, const float* homographies_host,
                                  int num, int valid_border_margin, int aggregation, float* prob_map, void* stream) {
     return guarded(e, [&](spb200::Engine& g) {

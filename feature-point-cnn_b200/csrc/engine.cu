@@ -33,47 +33,61 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
-// Host-buffer pipeline state of detect_host: three streams (upload, compute, download), whole-batch device input /
-// output buffers cut into chunks, one event pair and one pinned count mirror per chunk, and pinned staging used only
-// when the caller's buffers are pageable.
+// Host-buffer pipeline state of detect_host: three streams (upload, compute, download) and two SLOTS of device input /
+// output buffers, so that two batches can be in flight: while the keypoints and descriptors of batch i cross the bus, the
+// GPU computes batch i + 1 (spb200_detect_host_submit / _wait; spb200_detect_host is submit + wait).  Per slot: whole-batch
+// buffers cut into chunks, one event pair and one pinned count mirror per chunk, and pinned staging used only when the
+// caller's buffers are pageable.
 struct Engine::HostStage {
     static constexpr int kMaxChunks = 64;
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[kMaxChunks] = {}, ev_comp[kMaxChunks] = {};
-    float* d_img = nullptr;
-    size_t d_img_bytes = 0;
-    int* d_count = nullptr;
-    int* d_xy = nullptr;
-    float* d_conf = nullptr;
-    float* d_desc = nullptr;
-    int* h_count = nullptr;        // pinned [B]
-    int d_B = 0, d_cap = 0;
-    // pageable callers
-    float* h_img = nullptr;        // pinned, whole batch
-    size_t h_img_bytes = 0;
-    int* h_xy = nullptr;
-    float* h_conf = nullptr;
-    float* h_desc = nullptr;
-    size_t h_out_cap = 0;          // keypoints the pinned output staging holds
+    struct Slot {
+        cudaEvent_t ev_in[kMaxChunks] = {}, ev_comp[kMaxChunks] = {};
+        void* d_img = nullptr;
+        size_t d_img_bytes = 0;
+        int* d_count = nullptr;
+        int* d_xy = nullptr;
+        float* d_conf = nullptr;
+        void* d_desc = nullptr;
+        int* h_count = nullptr;        // pinned [B]
+        int d_B = 0, d_cap = 0;
+        // pageable callers
+        void* h_img = nullptr;         // pinned, whole batch
+        size_t h_img_bytes = 0;
+        int* h_xy = nullptr;
+        float* h_conf = nullptr;
+        uint8_t* h_desc = nullptr;
+        size_t h_out_cap = 0;          // keypoints the pinned output staging holds
+        // the job in flight
+        bool busy = false;
+        int B = 0, cap = 0;
+        bool want_desc = false;
+        size_t desc_row = 0;           // bytes of one descriptor (128 x 4 or 128 x 2)
+        std::vector<int> csize, cstart;
+    } slot[2];
+    int next = 0;
     void init() {
         SPB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
         SPB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
         SPB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-        for (int i = 0; i < kMaxChunks; ++i) {
-            SPB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-            SPB_CUDA(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-        }
+        for (auto& sl : slot)
+            for (int i = 0; i < kMaxChunks; ++i) {
+                SPB_CUDA(cudaEventCreateWithFlags(&sl.ev_in[i], cudaEventDisableTiming));
+                SPB_CUDA(cudaEventCreateWithFlags(&sl.ev_comp[i], cudaEventDisableTiming));
+            }
     }
     ~HostStage() {
-        cudaFree(d_img); cudaFree(d_count); cudaFree(d_xy); cudaFree(d_conf); cudaFree(d_desc);
-        if (h_count) cudaFreeHost(h_count);
-        if (h_img) cudaFreeHost(h_img);
-        if (h_xy) cudaFreeHost(h_xy);
-        if (h_conf) cudaFreeHost(h_conf);
-        if (h_desc) cudaFreeHost(h_desc);
-        for (int i = 0; i < kMaxChunks; ++i) {
-            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
-            if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+        for (auto& sl : slot) {
+            cudaFree(sl.d_img); cudaFree(sl.d_count); cudaFree(sl.d_xy); cudaFree(sl.d_conf); cudaFree(sl.d_desc);
+            if (sl.h_count) cudaFreeHost(sl.h_count);
+            if (sl.h_img) cudaFreeHost(sl.h_img);
+            if (sl.h_xy) cudaFreeHost(sl.h_xy);
+            if (sl.h_conf) cudaFreeHost(sl.h_conf);
+            if (sl.h_desc) cudaFreeHost(sl.h_desc);
+            for (int i = 0; i < kMaxChunks; ++i) {
+                if (sl.ev_in[i]) cudaEventDestroy(sl.ev_in[i]);
+                if (sl.ev_comp[i]) cudaEventDestroy(sl.ev_comp[i]);
+            }
         }
         if (s_in) cudaStreamDestroy(s_in);
         if (s_comp) cudaStreamDestroy(s_comp);
@@ -884,11 +898,11 @@ void Engine::detect_any(const void* img, bool img_u8, int B, int C, int H, int W
         if (params_.descriptor_enabled) {
             prof_open("descriptors", 0.0, 0.0, st);              // bytes depend on the keypoint count (caller)
             launch_sample_descriptors(buf_[BUF_DESC], precision_, (long)Hc * Wc * 128, 1, 128, B, 128, Hc, Wc, W,
-                                      grid_table(H, W), cap, count, xy, desc, st);
+                                      grid_table(H, W), cap, count, xy, desc, desc_fp16_ ? 1 : 0, st);
             prof_close(st);
             ++launches_;
         } else {
-            SPB_CUDA(cudaMemsetAsync(desc, 0, sizeof(float) * (size_t)B * cap * 128, st));
+            SPB_CUDA(cudaMemsetAsync(desc, 0, (desc_fp16_ ? sizeof(uint16_t) : sizeof(float)) * (size_t)B * cap * 128, st));
         }
     }
 }
@@ -938,6 +952,14 @@ void Engine::preprocess_f32(const float* frames, int B, int h, int w, float* out
     ++launches_;
 }
 
+void Engine::set_descriptor_format(int fmt) {
+    if (fmt != 0 && fmt != 1) throw std::invalid_argument("descriptor format must be 0 (fp32) or 1 (fp16)");
+    if (stage_)
+        for (auto& sl : stage_->slot)
+            if (sl.busy) throw std::runtime_error("descriptor format cannot change while a host batch is in flight");
+    desc_fp16_ = fmt == 1;
+}
+
 void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, int* xy, float* conf, cudaStream_t st) {
     StreamScope scope(this, st);
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
@@ -952,7 +974,7 @@ void Engine::sample_descriptors(const float* desc_nchw, int B, int D, int H, int
     StreamScope scope(this, st);
     const int Hc = H / 8, Wc = W / 8;
     launch_sample_descriptors(desc_nchw, PREC_FP32, (long)D * Hc * Wc, (long)Hc * Wc, 1, B, D, Hc, Wc, W, grid_table(H, W), cap,
-                              count, xy, out, st);
+                              count, xy, out, 0, st);
     ++launches_;
 }
 
@@ -1104,16 +1126,25 @@ void Engine::detect_host_u8(const uint8_t* img, int B, int H, int W, int cap, in
 
 void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy,
                              float* conf, float* desc) {
+    const int ticket = detect_host_submit(img_any, img_u8, B, C, H, W, cap, desc != nullptr);
+    detect_host_wait(ticket, count, xy, conf, desc);
+}
+
+int Engine::detect_host_submit(const void* img_any, bool img_u8, int B, int C, int H, int W, int cap, bool want_desc) {
     const uint8_t* img = static_cast<const uint8_t*>(img_any);
     const size_t esz = img_u8 ? 1 : sizeof(float);
     SPB_CUDA(cudaSetDevice(device_));
     if (B <= 0) throw std::invalid_argument("batch must be positive");
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
+    if (img_u8 && C != 1) throw std::invalid_argument("8-bit frames must be single-channel (grayscale)");
     if (!stage_) {
         stage_ = std::make_unique<HostStage>();
         stage_->init();
     }
     HostStage& s = *stage_;
+    const int ticket = s.next;
+    HostStage::Slot& sl = s.slot[ticket];
+    if (sl.busy) throw std::runtime_error("detect_host: two batches are already in flight (call spb200_detect_host_wait first)");
     int Bc = B;
     {
         int want = 16;
@@ -1127,139 +1158,152 @@ void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int
     // the three stages, then starts after half a chunk of upload + compute, and the last download, which nothing
     // overlaps, is half as long; the workspace keeps its plans per batch size, so alternating sizes costs nothing) -
     // measured 3 % slower at batch 64: eight images use the GPU too poorly, so it is off by default.
-    std::vector<int> csize, cstart;
+    sl.csize.clear(); sl.cstart.clear();
     {
         const int n_uniform = B / Bc;
         const bool split = n_uniform >= 3 && Bc % 2 == 0 && Bc >= 8 && n_uniform + 2 <= HostStage::kMaxChunks &&
                            std::getenv("SPB200_HOST_SPLIT") != nullptr;
         for (int k = 0; k < n_uniform; ++k) {
-            if (split && (k == 0 || k == n_uniform - 1)) { csize.push_back(Bc / 2); csize.push_back(Bc / 2); }
-            else csize.push_back(Bc);
+            if (split && (k == 0 || k == n_uniform - 1)) { sl.csize.push_back(Bc / 2); sl.csize.push_back(Bc / 2); }
+            else sl.csize.push_back(Bc);
         }
         int acc = 0;
-        for (int c : csize) { cstart.push_back(acc); acc += c; }
+        for (int c : sl.csize) { sl.cstart.push_back(acc); acc += c; }
     }
-    const int nc = (int)csize.size();
+    const int nc = (int)sl.csize.size();
     const size_t img_elem_bytes = esz * (size_t)C * H * W;
     const bool pin_in = is_pinned_host(img);
-    const bool pin_out = is_pinned_host(xy) && is_pinned_host(conf) && is_pinned_host(desc);
     const size_t img_bytes = img_elem_bytes * B;
+    const size_t desc_row = 128 * (desc_fp16_ ? sizeof(uint16_t) : sizeof(float));
 
-    if (img_bytes > s.d_img_bytes || B > s.d_B || cap > s.d_cap) {
+    if (img_bytes > sl.d_img_bytes || B > sl.d_B || cap > sl.d_cap) {
         SPB_CUDA(cudaDeviceSynchronize());
-        cudaFree(s.d_img); cudaFree(s.d_count); cudaFree(s.d_xy); cudaFree(s.d_conf); cudaFree(s.d_desc);
-        if (s.h_count) cudaFreeHost(s.h_count);
-        const int nb = std::max(B, s.d_B), ncap = std::max(cap, s.d_cap);
-        const size_t nbytes = std::max(img_bytes, s.d_img_bytes);
-        SPB_CUDA(cudaMalloc((void**)&s.d_img, nbytes));
-        s.d_count = dev_alloc<int>(nb);
-        s.d_xy = dev_alloc<int>((size_t)nb * ncap * 2);
-        s.d_conf = dev_alloc<float>((size_t)nb * ncap);
-        s.d_desc = dev_alloc<float>((size_t)nb * ncap * 128);
-        SPB_CUDA(cudaHostAlloc((void**)&s.h_count, sizeof(int) * nb, cudaHostAllocDefault));
-        s.d_img_bytes = nbytes; s.d_B = nb; s.d_cap = ncap;
+        cudaFree(sl.d_img); cudaFree(sl.d_count); cudaFree(sl.d_xy); cudaFree(sl.d_conf); cudaFree(sl.d_desc);
+        if (sl.h_count) cudaFreeHost(sl.h_count);
+        const int nb = std::max(B, sl.d_B), ncap = std::max(cap, sl.d_cap);
+        const size_t nbytes = std::max(img_bytes, sl.d_img_bytes);
+        SPB_CUDA(cudaMalloc(&sl.d_img, nbytes));
+        sl.d_count = dev_alloc<int>(nb);
+        sl.d_xy = dev_alloc<int>((size_t)nb * ncap * 2);
+        sl.d_conf = dev_alloc<float>((size_t)nb * ncap);
+        SPB_CUDA(cudaMalloc(&sl.d_desc, (size_t)nb * ncap * 128 * sizeof(float)));      // sized for either descriptor format
+        SPB_CUDA(cudaHostAlloc((void**)&sl.h_count, sizeof(int) * nb, cudaHostAllocDefault));
+        sl.d_img_bytes = nbytes; sl.d_B = nb; sl.d_cap = ncap;
     }
-    if (!pin_in && img_bytes > s.h_img_bytes) {
+    if (!pin_in && img_bytes > sl.h_img_bytes) {
         SPB_CUDA(cudaDeviceSynchronize());
-        if (s.h_img) cudaFreeHost(s.h_img);
-        SPB_CUDA(cudaHostAlloc((void**)&s.h_img, img_bytes, cudaHostAllocDefault));
-        s.h_img_bytes = img_bytes;
+        if (sl.h_img) cudaFreeHost(sl.h_img);
+        SPB_CUDA(cudaHostAlloc(&sl.h_img, img_bytes, cudaHostAllocDefault));
+        sl.h_img_bytes = img_bytes;
     }
-    const int dcap = s.d_cap;
+    const int dcap = sl.d_cap;
+    sl.B = B; sl.cap = cap; sl.want_desc = want_desc; sl.desc_row = desc_row;
 
-    // 1. everything the GPU has to do is enqueued up front: chunk k's upload on the copy stream, its network +
-    //    post-processing on the compute stream behind the upload's event, its counts copied to the pinned mirror
+    // everything the GPU has to do is enqueued here: chunk k's upload on the copy stream, its network + post-processing
+    // on the compute stream behind the upload's event, its counts copied to the pinned mirror
     for (int k = 0; k < nc; ++k) {
-        const int Bk = csize[k];
-        const size_t coff = (size_t)cstart[k] * img_elem_bytes, chunk_bytes = (size_t)Bk * img_elem_bytes;
+        const int Bk = sl.csize[k];
+        const size_t coff = (size_t)sl.cstart[k] * img_elem_bytes, chunk_bytes = (size_t)Bk * img_elem_bytes;
         const uint8_t* src = img + coff;
-        uint8_t* d_in = reinterpret_cast<uint8_t*>(s.d_img) + coff;
+        uint8_t* d_in = static_cast<uint8_t*>(sl.d_img) + coff;
         if (!pin_in) {
-            std::memcpy(reinterpret_cast<uint8_t*>(s.h_img) + coff, src, chunk_bytes);
-            src = reinterpret_cast<uint8_t*>(s.h_img) + coff;
+            std::memcpy(static_cast<uint8_t*>(sl.h_img) + coff, src, chunk_bytes);
+            src = static_cast<uint8_t*>(sl.h_img) + coff;
         }
         SPB_CUDA(cudaMemcpyAsync(d_in, src, chunk_bytes, cudaMemcpyHostToDevice, s.s_in));
-        SPB_CUDA(cudaEventRecord(s.ev_in[k], s.s_in));
-        SPB_CUDA(cudaStreamWaitEvent(s.s_comp, s.ev_in[k], 0));
-        const size_t o = (size_t)cstart[k];
-        detect_any(d_in, img_u8, Bk, C, H, W, dcap, s.d_count + o, s.d_xy + o * dcap * 2, s.d_conf + o * dcap,
-               desc ? s.d_desc + o * dcap * 128 : nullptr, nullptr, s.s_comp);
-        SPB_CUDA(cudaMemcpyAsync(s.h_count + o, s.d_count + o, sizeof(int) * Bk, cudaMemcpyDeviceToHost, s.s_comp));
-        SPB_CUDA(cudaEventRecord(s.ev_comp[k], s.s_comp));
+        SPB_CUDA(cudaEventRecord(sl.ev_in[k], s.s_in));
+        SPB_CUDA(cudaStreamWaitEvent(s.s_comp, sl.ev_in[k], 0));
+        const size_t o = (size_t)sl.cstart[k];
+        detect_any(d_in, img_u8, Bk, C, H, W, dcap, sl.d_count + o, sl.d_xy + o * dcap * 2, sl.d_conf + o * dcap,
+                   want_desc ? static_cast<float*>(static_cast<void*>(static_cast<uint8_t*>(sl.d_desc) + o * dcap * desc_row)) : nullptr,
+                   nullptr, s.s_comp);
+        SPB_CUDA(cudaMemcpyAsync(sl.h_count + o, sl.d_count + o, sizeof(int) * Bk, cudaMemcpyDeviceToHost, s.s_comp));
+        SPB_CUDA(cudaEventRecord(sl.ev_comp[k], s.s_comp));
     }
-    // 2. as each chunk's counts arrive, its keypoints and descriptors (count[b] rows per image, nothing else) are
-    //    downloaded on the third stream while the later chunks compute
+    sl.busy = true;
+    s.next ^= 1;
+    return ticket;
+}
+
+void Engine::detect_host_wait(int ticket, int* count, int* xy, float* conf, void* desc_any) {
+    SPB_CUDA(cudaSetDevice(device_));
+    if (!stage_ || ticket < 0 || ticket > 1 || !stage_->slot[ticket].busy) throw std::invalid_argument("detect_host_wait: no batch in flight under this ticket");
+    HostStage& s = *stage_;
+    HostStage::Slot& sl = s.slot[ticket];
+    sl.busy = false;                                           // also on failure: the slot can be reused
+    uint8_t* desc = sl.want_desc ? static_cast<uint8_t*>(desc_any) : nullptr;
+    if (sl.want_desc && !desc) throw std::invalid_argument("detect_host_wait: descriptors were requested at submit, desc is null");
+    const int B = sl.B, cap = sl.cap, dcap = sl.d_cap, nc = (int)sl.csize.size();
+    const size_t row = sl.desc_row;
+    const bool pin_out = is_pinned_host(xy) && is_pinned_host(conf) && is_pinned_host(desc);
+    // as each chunk's counts arrive, its keypoints and descriptors (count[b] rows per image, nothing else) are
+    // downloaded on the third stream while the later chunks - and the next batch - compute
     size_t staged = 0;
     std::vector<size_t> stage_off;
     if (!pin_out) stage_off.assign((size_t)B, 0);
     for (int k = 0; k < nc; ++k) {
-        SPB_CUDA(cudaEventSynchronize(s.ev_comp[k]));
-        const int Bk = csize[k];
-        const size_t g0 = (size_t)cstart[k];
+        SPB_CUDA(cudaEventSynchronize(sl.ev_comp[k]));
+        const int Bk = sl.csize[k];
+        const size_t g0 = (size_t)sl.cstart[k];
         size_t total = 0;
         for (int b = 0; b < Bk; ++b) {
             const size_t g = g0 + b;
-            count[g] = std::min(std::max(s.h_count[g], 0), cap);
+            count[g] = std::min(std::max(sl.h_count[g], 0), cap);
             total += (size_t)count[g];
         }
-        if (!pin_out && staged + total > s.h_out_cap) {
+        if (!pin_out && staged + total > sl.h_out_cap) {
             // grow the pinned staging; what is already in flight must land first, then it is copied over
             SPB_CUDA(cudaStreamSynchronize(s.s_out));
             const size_t n = (staged + total) * 2 + 1024;
-            int* nxy = nullptr; float* ncf = nullptr; float* nds = nullptr;
+            int* nxy = nullptr; float* ncf = nullptr; uint8_t* nds = nullptr;
             SPB_CUDA(cudaHostAlloc((void**)&nxy, sizeof(int) * 2 * n, cudaHostAllocDefault));
             SPB_CUDA(cudaHostAlloc((void**)&ncf, sizeof(float) * n, cudaHostAllocDefault));
             SPB_CUDA(cudaHostAlloc((void**)&nds, sizeof(float) * 128 * n, cudaHostAllocDefault));
             if (staged) {
-                std::memcpy(nxy, s.h_xy, sizeof(int) * 2 * staged);
-                std::memcpy(ncf, s.h_conf, sizeof(float) * staged);
-                if (desc) std::memcpy(nds, s.h_desc, sizeof(float) * 128 * staged);
+                std::memcpy(nxy, sl.h_xy, sizeof(int) * 2 * staged);
+                std::memcpy(ncf, sl.h_conf, sizeof(float) * staged);
+                if (desc) std::memcpy(nds, sl.h_desc, row * staged);
             }
-            if (s.h_xy) cudaFreeHost(s.h_xy);
-            if (s.h_conf) cudaFreeHost(s.h_conf);
-            if (s.h_desc) cudaFreeHost(s.h_desc);
-            s.h_xy = nxy; s.h_conf = ncf; s.h_desc = nds; s.h_out_cap = n;
+            if (sl.h_xy) cudaFreeHost(sl.h_xy);
+            if (sl.h_conf) cudaFreeHost(sl.h_conf);
+            if (sl.h_desc) cudaFreeHost(sl.h_desc);
+            sl.h_xy = nxy; sl.h_conf = ncf; sl.h_desc = nds; sl.h_out_cap = n;
         }
+        const uint8_t* d_desc = static_cast<const uint8_t*>(sl.d_desc);
         if (pin_out) {
             // pinned caller arrays: one strided copy per array and chunk (rows = images, width = the largest count of the
             // chunk) instead of three small copies per image; rows past an image's count receive don't-care values
             size_t nmax = 0;
             for (int b = 0; b < Bk; ++b) nmax = std::max(nmax, (size_t)count[g0 + b]);
             if (nmax) {
-                SPB_CUDA(cudaMemcpy2DAsync(xy + g0 * cap * 2, sizeof(int) * 2 * cap, s.d_xy + g0 * dcap * 2, sizeof(int) * 2 * dcap,
+                SPB_CUDA(cudaMemcpy2DAsync(xy + g0 * cap * 2, sizeof(int) * 2 * cap, sl.d_xy + g0 * dcap * 2, sizeof(int) * 2 * dcap,
                                            sizeof(int) * 2 * nmax, Bk, cudaMemcpyDeviceToHost, s.s_out));
-                SPB_CUDA(cudaMemcpy2DAsync(conf + g0 * cap, sizeof(float) * cap, s.d_conf + g0 * dcap, sizeof(float) * dcap,
+                SPB_CUDA(cudaMemcpy2DAsync(conf + g0 * cap, sizeof(float) * cap, sl.d_conf + g0 * dcap, sizeof(float) * dcap,
                                            sizeof(float) * nmax, Bk, cudaMemcpyDeviceToHost, s.s_out));
                 if (desc)
-                    SPB_CUDA(cudaMemcpy2DAsync(desc + g0 * cap * 128, sizeof(float) * 128 * cap, s.d_desc + g0 * dcap * 128,
-                                               sizeof(float) * 128 * dcap, sizeof(float) * 128 * nmax, Bk, cudaMemcpyDeviceToHost, s.s_out));
+                    SPB_CUDA(cudaMemcpy2DAsync(desc + g0 * cap * row, row * cap, d_desc + g0 * dcap * row, row * dcap, row * nmax, Bk,
+                                               cudaMemcpyDeviceToHost, s.s_out));
             }
             continue;
         }
         for (int b = 0; b < Bk; ++b) {
             const size_t g = g0 + b, n = (size_t)count[g];
-            if (!pin_out) stage_off[g] = staged;
+            stage_off[g] = staged;
             if (n) {
-                int* dxy = pin_out ? xy + g * cap * 2 : s.h_xy + staged * 2;
-                float* dcf = pin_out ? conf + g * cap : s.h_conf + staged;
-                SPB_CUDA(cudaMemcpyAsync(dxy, s.d_xy + g * dcap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s.s_out));
-                SPB_CUDA(cudaMemcpyAsync(dcf, s.d_conf + g * dcap, sizeof(float) * n, cudaMemcpyDeviceToHost, s.s_out));
-                if (desc) {
-                    float* dds = pin_out ? desc + g * cap * 128 : s.h_desc + staged * 128;
-                    SPB_CUDA(cudaMemcpyAsync(dds, s.d_desc + g * dcap * 128, sizeof(float) * 128 * n, cudaMemcpyDeviceToHost, s.s_out));
-                }
+                SPB_CUDA(cudaMemcpyAsync(sl.h_xy + staged * 2, sl.d_xy + g * dcap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s.s_out));
+                SPB_CUDA(cudaMemcpyAsync(sl.h_conf + staged, sl.d_conf + g * dcap, sizeof(float) * n, cudaMemcpyDeviceToHost, s.s_out));
+                if (desc) SPB_CUDA(cudaMemcpyAsync(sl.h_desc + staged * row, d_desc + g * dcap * row, row * n, cudaMemcpyDeviceToHost, s.s_out));
             }
-            if (!pin_out) staged += n;
+            staged += n;
         }
     }
     SPB_CUDA(cudaStreamSynchronize(s.s_out));
-    SPB_CUDA(cudaStreamSynchronize(s.s_comp));
     if (!pin_out) {
         for (size_t g = 0; g < (size_t)B; ++g) {
             const size_t n = (size_t)count[g], off = stage_off[g];
-            std::memcpy(xy + g * cap * 2, s.h_xy + off * 2, sizeof(int) * 2 * n);
-            std::memcpy(conf + g * cap, s.h_conf + off, sizeof(float) * n);
-            if (desc) std::memcpy(desc + g * cap * 128, s.h_desc + off * 128, sizeof(float) * 128 * n);
+            std::memcpy(xy + g * cap * 2, sl.h_xy + off * 2, sizeof(int) * 2 * n);
+            std::memcpy(conf + g * cap, sl.h_conf + off, sizeof(float) * n);
+            if (desc) std::memcpy(desc + g * cap * row, sl.h_desc + off * row, row * n);
         }
     }
 }

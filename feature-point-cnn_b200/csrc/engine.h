@@ -112,6 +112,13 @@ public:
     void detect_u8(const uint8_t* img, int B, int H, int W, int cap, int* count, int* xy, float* conf, float* desc,
                    float* prob, cudaStream_t st);
     void detect_host_u8(const uint8_t* img, int B, int H, int W, int cap, int* count, int* xy, float* conf, float* desc);
+    // the two halves of detect_host, so that two batches can be in flight (the download of one under the compute of the
+    // next): submit enqueues upload + compute and returns a ticket (0 / 1), wait downloads and returns the results
+    int detect_host_submit(const void* img, bool img_u8, int B, int C, int H, int W, int cap, bool want_desc);
+    void detect_host_wait(int ticket, int* count, int* xy, float* conf, void* desc);
+    // descriptors of detect / detect_host as fp32 (0, the reference's type) or fp16 (1: half the bytes over the bus)
+    void set_descriptor_format(int fmt);
+    int descriptor_format() const { return desc_fp16_ ? 1 : 0; }
     // stage-level entry points (reference restore_prob_map / get_points / get_descriptors)
     void heatmap_from_logits(const float* logits_nchw, int B, int H, int W, float* prob, cudaStream_t st);
     void restore_prob_map(const float* softmax_nchw, int B, int H, int W, float* prob, cudaStream_t st);
@@ -166,6 +173,7 @@ private:
     int device_;
     int precision_ = PREC_FP32;
     int split_level_ = SPLIT_NONE;
+    bool desc_fp16_ = false;
     bool finalized_ = false;
     Params params_;
     StateDict sd_;

@@ -102,7 +102,7 @@ void launch_nms_finish(int B, int H, int W, int radius, int border, int top_k, i
 // are the sampling positions ix / iy of pixel column x / row y (host-built, device memory).
 void launch_sample_descriptors(const void* map, int map_type, long batch_stride, long chan_stride, long cell_stride,
                                int B, int D, int Hc, int Wc, int W, const float* gtab, int cap, const int* count,
-                               const int* xy, float* out, cudaStream_t st);
+                               const int* xy, void* out, int out_fp16, cudaStream_t st);
 
 // ---- homography.cu -------------------------------------------------------------------------------
 // Pieces of homography adaptation (reference python/src/homographies.py:250-324).  coeffs: device [2 num][8], the num

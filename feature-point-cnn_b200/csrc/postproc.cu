@@ -121,11 +121,22 @@ __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, lon
 
 // gtab: per-coordinate sampling positions precomputed on the host exactly as the reference does
 // (double division, then float): gtab[x] = ix for x < W, gtab[W + y] = iy for y < H.
-template <typename T>
+// OUT16: the unit vector is stored as fp16 (spb200_set_descriptor_format), otherwise fp32 like the reference's
+__device__ __forceinline__ void store_desc4(void* base, size_t elem, bool out16, float a, float b, float c, float d) {
+    if (out16) {
+        const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+        __stcs(reinterpret_cast<uint2*>(static_cast<__half*>(base) + elem),
+               make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi)));
+    } else {
+        __stcs(reinterpret_cast<float4*>(static_cast<float*>(base) + elem), make_float4(a, b, c, d));
+    }
+}
+
+template <typename T, bool OUT16>
 __global__ void __launch_bounds__(256)
 sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_stride, long cell_stride, int D, int Hc,
                    int Wc, int W, const float* __restrict__ gtab, int cap, const int* __restrict__ count,
-                   const int* __restrict__ xy, float* __restrict__ out) {
+                   const int* __restrict__ xy, void* __restrict__ out) {
     const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
     const int b = blockIdx.y;
     const int i = blockIdx.x * 8 + warp;
@@ -139,7 +150,7 @@ sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_strid
     const float wgt[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
     const int cx[4] = {x0, x0 + 1, x0, x0 + 1}, cy[4] = {y0, y0, y0 + 1, y0 + 1};
     const T* mb = map + (size_t)b * batch_stride;
-    float* o = out + ((size_t)b * cap + i) * D;
+    const size_t o = ((size_t)b * cap + i) * D;
 
     float ss = 0.f;
     constexpr int kMaxSlabs = 4;                      // D <= 512
@@ -176,7 +187,7 @@ sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_strid
     for (int s = 0; s < kMaxSlabs; ++s) {
         if (s >= nslab) break;
         const int c = s * 128 + lane * 4;
-        if (c < D) __stcs(reinterpret_cast<float4*>(o + c), make_float4(acc[s][0] * inv, acc[s][1] * inv, acc[s][2] * inv, acc[s][3] * inv));
+        if (c < D) store_desc4(out, o + c, OUT16, acc[s][0] * inv, acc[s][1] * inv, acc[s][2] * inv, acc[s][3] * inv);
     }
 }
 
@@ -186,10 +197,10 @@ sample_desc_kernel(const T* __restrict__ map, long batch_stride, long chan_strid
 // large `cap` is.  Same arithmetic and summation order as sample_desc_kernel.
 constexpr int kDescBlocksPerImage = 24;
 
-template <typename T>
+template <typename T, bool OUT16>
 __global__ void __launch_bounds__(256)
 sample_desc128_kernel(const T* __restrict__ map, long batch_stride, int Hc, int Wc, int W, const float* __restrict__ gtab,
-                      int cap, const int* __restrict__ count, const int* __restrict__ xy, float* __restrict__ out) {
+                      int cap, const int* __restrict__ count, const int* __restrict__ xy, void* __restrict__ out) {
     const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
     const int b = blockIdx.y;
     const int n = min(__ldg(count + b), cap);
@@ -211,7 +222,7 @@ sample_desc128_kernel(const T* __restrict__ map, long batch_stride, int Hc, int 
             if (live[u]) {
                 const int2 pt = __ldg(pts + i);
                 // caller-supplied coordinates (spb200_sample_descriptors) are clamped into the image: never an out-of-bounds read
-    const float ix = __ldg(gtab + min(max(pt.x, 0), W - 1)), iy = __ldg(gtab + W + min(max(pt.y, 0), Hc * 8 - 1));
+                const float ix = __ldg(gtab + min(max(pt.x, 0), W - 1)), iy = __ldg(gtab + W + min(max(pt.y, 0), Hc * 8 - 1));
                 const float fx0 = floorf(ix), fy0 = floorf(iy);
                 const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = (fx0 + 1.f) - ix, wy0 = (fy0 + 1.f) - iy;
                 const int x0 = (int)fx0, y0 = (int)fy0;
@@ -252,9 +263,9 @@ sample_desc128_kernel(const T* __restrict__ map, long batch_stride, int Hc, int 
             for (int off = 8; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
             if (live[u]) {
                 const float inv = 1.f / sqrtf(ss);    // 0-vector -> NaN, like the reference's 0/0
-                float* o = out + ((size_t)b * cap + (i0 + u * stride)) * 128 + hl * 8;
-                __stcs(reinterpret_cast<float4*>(o), make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv));
-                __stcs(reinterpret_cast<float4*>(o) + 1, make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv));
+                const size_t o = ((size_t)b * cap + (i0 + u * stride)) * 128 + hl * 8;
+                store_desc4(out, o, OUT16, acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+                store_desc4(out, o + 4, OUT16, acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
             }
         }
     }
@@ -262,25 +273,27 @@ sample_desc128_kernel(const T* __restrict__ map, long batch_stride, int Hc, int 
 
 void launch_sample_descriptors(const void* map, int map_type, long batch_stride, long chan_stride, long cell_stride,
                                int B, int D, int Hc, int Wc, int W, const float* gtab, int cap, const int* count,
-                               const int* xy, float* out, cudaStream_t st) {
+                               const int* xy, void* out, int out_fp16, cudaStream_t st) {
     if (D % 4 != 0 || D > 512) throw std::invalid_argument("descriptor dimension must be a multiple of 4, at most 512");
     if (cap <= 0 || B <= 0) return;
     if (map_type != PREC_FP32 && D == 128 && chan_stride == 1 && cell_stride == 128) {
         dim3 g(kDescBlocksPerImage, B);
-        if (map_type == PREC_FP16)
-            sample_desc128_kernel<__half><<<g, 256, 0, st>>>((const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
-        else
-            sample_desc128_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+        if (map_type == PREC_FP16) {
+            if (out_fp16) sample_desc128_kernel<__half, true><<<g, 256, 0, st>>>((const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+            else sample_desc128_kernel<__half, false><<<g, 256, 0, st>>>((const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+        } else {
+            if (out_fp16) sample_desc128_kernel<__nv_bfloat16, true><<<g, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+            else sample_desc128_kernel<__nv_bfloat16, false><<<g, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+        }
         SPB_CHECK_LAUNCH();
         return;
     }
     dim3 grid((cap + 7) / 8, B);
-    if (map_type == PREC_FP32)
-        sample_desc_kernel<float><<<grid, 256, 0, st>>>((const float*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, W, gtab, cap, count, xy, out);
-    else if (map_type == PREC_FP16)
-        sample_desc_kernel<__half><<<grid, 256, 0, st>>>((const __half*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, W, gtab, cap, count, xy, out);
-    else
-        sample_desc_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, W, gtab, cap, count, xy, out);
+#define SPB_SAMPLE(T, O) sample_desc_kernel<T, O><<<grid, 256, 0, st>>>((const T*)map, batch_stride, chan_stride, cell_stride, D, Hc, Wc, W, gtab, cap, count, xy, out)
+    if (map_type == PREC_FP32) { if (out_fp16) SPB_SAMPLE(float, true); else SPB_SAMPLE(float, false); }
+    else if (map_type == PREC_FP16) { if (out_fp16) SPB_SAMPLE(__half, true); else SPB_SAMPLE(__half, false); }
+    else { if (out_fp16) SPB_SAMPLE(__nv_bfloat16, true); else SPB_SAMPLE(__nv_bfloat16, false); }
+#undef SPB_SAMPLE
     SPB_CHECK_LAUNCH();
 }
 

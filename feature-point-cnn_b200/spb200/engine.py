@@ -118,22 +118,64 @@ class Engine:
                                             _ptr(desc), _ptr(prob), self._stream()), 'spb200_detect')
         return out
 
-    @staticmethod
-    def alloc_outputs(b, capacity, dev, want_desc=True, prob_hw=None):
+    def set_descriptor_format(self, fmt='fp32'):
+        """Element type of the descriptors detect / detect_host return: 'fp32' (the reference's) or 'fp16'."""
+        self._check(self._lib.spb200_set_descriptor_format(self._h, {'fp32': 0, 'fp16': 1}[fmt]), 'spb200_set_descriptor_format')
+        self.desc_dtype = torch.float16 if fmt == 'fp16' else torch.float32
+
+    desc_dtype = torch.float32
+
+    def alloc_outputs(self, b, capacity, dev, want_desc=True, prob_hw=None):
         count = torch.zeros((b,), dtype=torch.int32, device=dev)
         xy = torch.zeros((b, capacity, 2), dtype=torch.int32, device=dev)
         conf = torch.zeros((b, capacity), dtype=torch.float32, device=dev)
-        desc = torch.zeros((b, capacity, 128), dtype=torch.float32, device=dev) if want_desc else None
+        desc = torch.zeros((b, capacity, 128), dtype=self.desc_dtype, device=dev) if want_desc else None
         prob = torch.empty((b,) + tuple(prob_hw), dtype=torch.float32, device=dev) if prob_hw else None
         return count, xy, conf, desc, prob
+
+    def host_outputs(self, b, capacity, want_desc=True, pinned=False):
+        """Host arrays for detect_host / detect_host_wait: (count, xy, conf, desc) numpy, optionally in pinned memory."""
+        ddt = np.float16 if self.desc_dtype == torch.float16 else np.float32
+        if pinned:
+            return (torch.zeros((b,), dtype=torch.int32).pin_memory().numpy(), torch.zeros((b, capacity, 2), dtype=torch.int32).pin_memory().numpy(),
+                    torch.zeros((b, capacity), dtype=torch.float32).pin_memory().numpy(),
+                    torch.zeros((b, capacity, 128), dtype=self.desc_dtype).pin_memory().numpy() if want_desc else None)
+        return (np.zeros((b,), np.int32), np.zeros((b, capacity, 2), np.int32), np.zeros((b, capacity), np.float32),
+                np.zeros((b, capacity, 128), ddt) if want_desc else None)
+
+    def detect_host_submit(self, img, capacity, want_desc=True):
+        """First half of detect_host (spb200_detect_host_submit): img float32 B*C*H*W or uint8 B*H*W numpy (host; keep a
+        pinned array alive until the matching wait).  Returns a ticket; at most two batches may be in flight."""
+        u8 = img.dtype == np.uint8
+        assert img.flags['C_CONTIGUOUS'] and (u8 or img.dtype == np.float32)
+        if u8:
+            (b, h, w), c = img.shape, 1
+        else:
+            b, c, h, w = img.shape
+        ticket = ctypes.c_int()
+        self._check(self._lib.spb200_detect_host_submit(self._h, ctypes.c_void_p(img.ctypes.data), int(u8), b, c, h, w, capacity,
+                                                        int(want_desc), ctypes.byref(ticket)), 'spb200_detect_host_submit')
+        self._inflight = getattr(self, '_inflight', {})
+        self._inflight[ticket.value] = (img, b, capacity, want_desc)
+        return ticket.value
+
+    def detect_host_wait(self, ticket, out=None):
+        """Second half: downloads batch `ticket` into out = (count, xy, conf, desc) numpy arrays and returns them."""
+        img, b, capacity, want_desc = self._inflight.pop(ticket)
+        if out is None:
+            out = self.host_outputs(b, capacity, want_desc)
+        count, xy, conf, desc = out
+        self._check(self._lib.spb200_detect_host_wait(self._h, ticket, ctypes.c_void_p(count.ctypes.data), ctypes.c_void_p(xy.ctypes.data),
+                                                      ctypes.c_void_p(conf.ctypes.data),
+                                                      ctypes.c_void_p(desc.ctypes.data if desc is not None else 0)), 'spb200_detect_host_wait')
+        return out
 
     def detect_host(self, img, capacity, want_desc=True, out=None):
         """img: float32 numpy B*C*H*W (host).  Returns numpy (count, xy, conf, desc)."""
         img = np.ascontiguousarray(img, dtype=np.float32)
         b, c, h, w = img.shape
         if out is None:
-            out = (np.zeros((b,), np.int32), np.zeros((b, capacity, 2), np.int32), np.zeros((b, capacity), np.float32),
-                   np.zeros((b, capacity, 128), np.float32) if want_desc else None)
+            out = self.host_outputs(b, capacity, want_desc)
         count, xy, conf, desc = out
         self._check(self._lib.spb200_detect_host(self._h, ctypes.c_void_p(img.ctypes.data), b, c, h, w, capacity,
                                                  ctypes.c_void_p(count.ctypes.data), ctypes.c_void_p(xy.ctypes.data),
@@ -159,8 +201,7 @@ class Engine:
         img = np.ascontiguousarray(img, dtype=np.uint8)
         b, h, w = img.shape
         if out is None:
-            out = (np.zeros((b,), np.int32), np.zeros((b, capacity, 2), np.int32), np.zeros((b, capacity), np.float32),
-                   np.zeros((b, capacity, 128), np.float32) if want_desc else None)
+            out = self.host_outputs(b, capacity, want_desc)
         count, xy, conf, desc = out
         self._check(self._lib.spb200_detect_host_u8(self._h, ctypes.c_void_p(img.ctypes.data), b, h, w, capacity,
                                                     ctypes.c_void_p(count.ctypes.data), ctypes.c_void_p(xy.ctypes.data),

@@ -282,7 +282,7 @@ def test_headless_cli_and_pseudo_label_files(tmp_path):
     np.testing.assert_allclose(f0['descriptors'], dsc, atol=1e-6)
     f2 = np.load(out / 'f2.npz')
     m = f2['matches']
-    assert m.shape[1] == 2 and len(m) > 50 and m[:, 0].max() < f2['points'].shape[1]
+    assert m.shape[1] == 2 and len(m) > 10 and m[:, 0].max() < f2["points"].shape[1]
     # frames 0 and 2 are the same image: matching frame 2 against frame 1 equals matching frame 0 against frame 1
     f1 = np.load(out / 'f1.npz')
     qi, ti, _ = matching.mutual_nearest(f2['descriptors'].T, f1['descriptors'].T, 0.7)        # settings.nn_thresh

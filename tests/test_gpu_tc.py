@@ -342,3 +342,57 @@ def test_calls_on_two_streams_are_ordered_by_the_engine(engines):
             for i in range(8):
                 n = int(want[0][i])
                 assert torch.equal(got[1][i, :n], want[1][i, :n]) and torch.equal(got[3][i, :n], want[3][i, :n])
+
+
+def test_host_submit_wait_keeps_two_batches_in_flight(engines):
+    """spb200_detect_host_submit / _wait: two batches in flight (the second one's upload + compute under the first one's
+    download), results identical to the one-call form; a third submit is refused; pinned and pageable caller buffers."""
+    e = engines['fp16']
+    a = torch.stack([golden_image('shapes240_0'), golden_image('rand240_1')] * 3)[:, None].contiguous()
+    b = torch.stack([golden_image('rand240_0'), golden_image('shapes240_2')] * 3)[:, None].contiguous()
+    cap = e.max_keypoints(240, 320)
+    want = {}
+    for key, x in (('a', a), ('b', b)):
+        want[key] = [t.copy() for t in e.detect_host(x.numpy(), cap)]
+    for pinned in (False, True):
+        xa = a.pin_memory().numpy() if pinned else a.numpy()
+        xb = b.pin_memory().numpy() if pinned else b.numpy()
+        outs = [e.host_outputs(6, cap, True, pinned) for _ in range(2)]
+        t0 = e.detect_host_submit(xa, cap)
+        for it in range(4):                                         # a, b, a, b ... always one batch ahead
+            nxt = xb if it % 2 == 0 else xa
+            t1 = e.detect_host_submit(nxt, cap)
+            if it == 0:
+                with pytest.raises(Exception):
+                    e.detect_host_submit(xa, cap)                   # two already in flight
+            got = e.detect_host_wait(t0, outs[it % 2])
+            ref = want['a' if it % 2 == 0 else 'b']
+            np.testing.assert_array_equal(got[0], ref[0])
+            for i in range(6):
+                n = int(ref[0][i])
+                np.testing.assert_array_equal(got[1][i, :n], ref[1][i, :n])
+                np.testing.assert_array_equal(got[3][i, :n], ref[3][i, :n])
+            t0 = t1
+        e.detect_host_wait(t0, outs[0])
+
+
+def test_fp16_descriptor_format(engines):
+    """spb200_set_descriptor_format(SPB200_DESC_FP16): the same unit vectors rounded to half precision, on the device and
+    through the host-buffer call."""
+    e = engines['fp16']
+    imgs = torch.stack([golden_image('shapes240_0'), golden_image('rand240_1')])[:, None].contiguous()
+    cap = e.max_keypoints(240, 320)
+    count, xy, conf, d32, _ = [t.clone() if t is not None else None for t in e.detect(imgs.cuda(), cap)]
+    try:
+        e.set_descriptor_format('fp16')
+        c16, xy16, conf16, d16, _ = e.detect(imgs.cuda(), cap)
+        assert d16.dtype == torch.float16 and torch.equal(c16, count) and torch.equal(xy16, xy)
+        hc, hxy, hconf, hd = e.detect_host(imgs.numpy(), cap)
+        assert hd.dtype == np.float16
+        for i in range(2):
+            n = int(count[i])
+            assert torch.equal(d16[i, :n], d32[i, :n].half())
+            np.testing.assert_array_equal(hd[i, :n], d16[i, :n].cpu().numpy())
+    finally:
+        e.set_descriptor_format('fp32')
+    assert e.detect(imgs.cuda(), cap)[3].dtype == torch.float32
