@@ -238,10 +238,10 @@ def time_e2e(eng, host_np, host_outs, cap, steps, pipelined):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if pipelined:
-        ticket = eng.detect_host_submit(host_np[0], cap)
+        ticket = eng.detect_host_submit(host_np[0], cap, out=host_outs[0])
         for i in range(steps):
-            nxt = eng.detect_host_submit(host_np[(i + 1) % n_rot], cap) if i + 1 < steps else None
-            out = eng.detect_host_wait(ticket, host_outs[i % 2])
+            nxt = eng.detect_host_submit(host_np[(i + 1) % n_rot], cap, out=host_outs[(i + 1) % 2]) if i + 1 < steps else None
+            out = eng.detect_host_wait(ticket)
             kp += int(out[0].sum())
             ticket = nxt
     else:

@@ -137,18 +137,15 @@ int spb200_detect_host_u8(spb200_engine* e, const uint8_t* img_host, int B, int 
 }
 
 int spb200_detect_host_submit(spb200_engine* e, const void* img_host, int img_is_u8, int B, int C, int H, int W, int capacity,
-                              int want_desc, int* ticket) {
+                              int* count_host, int* xy_host, float* conf_host, void* desc_host, int* ticket) {
     return guarded(e, [&](spb200::Engine& g) {
-        if (!img_host || !ticket) throw std::invalid_argument("img and ticket must not be null");
-        *ticket = g.detect_host_submit(img_host, img_is_u8 != 0, B, C, H, W, capacity, want_desc != 0);
+        if (!img_host || !ticket || !count_host || !xy_host || !conf_host) throw std::invalid_argument("img, count, xy, conf and ticket must not be null");
+        *ticket = g.detect_host_submit(img_host, img_is_u8 != 0, B, C, H, W, capacity, count_host, xy_host, conf_host, desc_host);
     });
 }
 
-int spb200_detect_host_wait(spb200_engine* e, int ticket, int* count_host, int* xy_host, float* conf_host, void* desc_host) {
-    return guarded(e, [&](spb200::Engine& g) {
-        if (!count_host || !xy_host || !conf_host) throw std::invalid_argument("count, xy and conf must not be null");
-        g.detect_host_wait(ticket, count_host, xy_host, conf_host, desc_host);
-    });
+int spb200_detect_host_wait(spb200_engine* e, int ticket) {
+    return guarded(e, [&](spb200::Engine& g) { g.detect_host_wait(ticket); });
 }
 
 int spb200_set_descriptor_format(spb200_engine* e, int format) {

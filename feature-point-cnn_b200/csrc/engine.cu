@@ -3,8 +3,12 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 namespace spb200 {
 
@@ -59,13 +63,52 @@ struct Engine::HostStage {
         uint8_t* h_desc = nullptr;
         size_t h_out_cap = 0;          // keypoints the pinned output staging holds
         // the job in flight
-        bool busy = false;
+        bool busy = false;             // submitted, not yet waited for
+        bool done = false;             // its results are in the caller's arrays (or `error` says why not)
+        std::string error;
         int B = 0, cap = 0;
-        bool want_desc = false;
         size_t desc_row = 0;           // bytes of one descriptor (128 x 4 or 128 x 2)
         std::vector<int> csize, cstart;
+        int* o_count = nullptr; int* o_xy = nullptr; float* o_conf = nullptr; uint8_t* o_desc = nullptr;   // the caller's arrays
     } slot[2];
     int next = 0;
+    // The download half runs on a thread of its own: it waits for each chunk's counts, issues the (count-sized) copies
+    // on the download stream and signals the slot.  The downloads of consecutive batches then follow each other without
+    // waiting for the caller to come back from its own work (PCIe device-to-host is the longest stage of the pipeline).
+    int device = 0;
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<int> queue;
+    bool quit = false;
+    void download(Slot& sl);
+    void run() {
+        cudaSetDevice(device);
+        for (;;) {
+            int t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || !queue.empty(); });
+                if (queue.empty()) return;
+                t = queue.front();
+                queue.pop_front();
+            }
+            std::string err;
+            try {
+                download(slot[t]);
+            } catch (const std::exception& e) {
+                err = e.what();
+            } catch (...) {
+                err = "unknown error in the download thread";
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                slot[t].error = err;
+                slot[t].done = true;
+            }
+            cv.notify_all();
+        }
+    }
     void init() {
         SPB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
         SPB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
@@ -77,6 +120,14 @@ struct Engine::HostStage {
             }
     }
     ~HostStage() {
+        if (worker.joinable()) {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                quit = true;
+            }
+            cv.notify_all();
+            worker.join();
+        }
         for (auto& sl : slot) {
             cudaFree(sl.d_img); cudaFree(sl.d_count); cudaFree(sl.d_xy); cudaFree(sl.d_conf); cudaFree(sl.d_desc);
             if (sl.h_count) cudaFreeHost(sl.h_count);
@@ -119,6 +170,8 @@ Engine::Engine(int device) : device_(device) {
     SPB_CUDA(cudaEventCreateWithFlags(&ws_done_, cudaEventDisableTiming));
     const char* np = std::getenv("SPB200_NO_PHASES");
     use_phases_ = !(np && np[0] == '1');
+    const char* ng = std::getenv("SPB200_NO_GRAPH");
+    use_graphs_ = !(ng && ng[0] == '1');
     const char* os = std::getenv("SPB200_OLD_STEM");
     use_planes_ = !(os && os[0] == '1');
     buf_.fill(nullptr);
@@ -140,6 +193,7 @@ Engine::StreamScope::~StreamScope() {
 
 Engine::~Engine() {
     cudaSetDevice(device_);
+    clear_graphs();
     if (ws_done_) cudaEventDestroy(ws_done_);
     release_workspace();
     release_weights();
@@ -178,6 +232,7 @@ void Engine::stash_plans() {
 }
 
 void Engine::release_workspace() {
+    clear_graphs();
     stash_plans();
     destroy_plan_cache();
     for (auto& p : buf_) { cudaFree(p); p = nullptr; }
@@ -629,6 +684,7 @@ void Engine::ensure_nms(int B, int H, int W) {
     const int r = params_.nms_dist;
     if (B <= nmsB_ && H == nmsH_ && W == nmsW_ && r == nmsR_) return;
     SPB_CUDA(cudaDeviceSynchronize());
+    clear_graphs();
     cudaFree(nms_.keys); cudaFree(nms_.keys_alt); cudaFree(nms_.counters); cudaFree(nms_.mask); cudaFree(nms_.und); cudaFree(nms_.ukey);
     nms_.kcap = max_keypoints(H, W, r);
     nms_.mask_w = (W + 31) / 32;
@@ -646,6 +702,7 @@ void Engine::ensure_nms(int B, int H, int W) {
 const float* Engine::grid_table(int H, int W) {
     if (d_gtab_ && H == gtabH_ && W == gtabW_) return d_gtab_;
     SPB_CUDA(cudaDeviceSynchronize());
+    clear_graphs();
     cudaFree(d_gtab_);
     std::vector<float> t((size_t)W + H);
     const int Hc = H / 8, Wc = W / 8;
@@ -869,10 +926,64 @@ void Engine::detect_u8(const uint8_t* img, int B, int H, int W, int cap, int* co
     detect_any(img, true, B, 1, H, W, cap, count, xy, conf, desc, prob, st);
 }
 
+void Engine::clear_graphs() {
+    for (auto& kv : graphs_)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    graphs_.clear();
+}
+
 void Engine::detect_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                         float* desc, float* prob, cudaStream_t st) {
     StreamScope scope(this, st);
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
+    // a capture cannot start on the legacy default stream; profiling brackets every launch with events of its own
+    if (!use_graphs_ || profiling_ || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+        detect_body(img, img_u8, B, C, H, W, cap, count, xy, conf, desc, prob, st);
+        return;
+    }
+    GraphKey key;
+    std::memset(&key, 0, sizeof(key));                         // padding bytes take part in the comparison
+    key.img = img; key.u8 = img_u8; key.B = B; key.C = C; key.H = H; key.W = W; key.cap = cap;
+    key.count = count; key.xy = xy; key.conf = conf; key.desc = desc; key.prob = prob;
+    if (graphs_.size() > 64) clear_graphs();
+    GraphEntry& ge = graphs_[key];
+    if (ge.exec) {
+        SPB_CUDA(cudaGraphLaunch(ge.exec, st));
+        launches_ += ge.launches;
+        return;
+    }
+    if (ge.failed || ge.seen++ == 0) {
+        // first sight: run it (this also brings workspace, NMS lists and tables to their final size - nothing may be
+        // allocated inside a capture)
+        detect_body(img, img_u8, B, C, H, W, cap, count, xy, conf, desc, prob, st);
+        return;
+    }
+    const long before = launches_;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+        try {
+            detect_body(img, img_u8, B, C, H, W, cap, count, xy, conf, desc, prob, st);
+        } catch (...) {
+            ok = false;
+        }
+        if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+    }
+    if (ok && cudaGraphInstantiate(&ge.exec, graph, 0) != cudaSuccess) { ok = false; ge.exec = nullptr; }
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+        cudaGetLastError();
+        launches_ = before;
+        ge.failed = true;                                       // this call runs the plain way, now and later
+        detect_body(img, img_u8, B, C, H, W, cap, count, xy, conf, desc, prob, st);
+        return;
+    }
+    ge.launches = launches_ - before;
+    SPB_CUDA(cudaGraphLaunch(ge.exec, st));
+}
+
+void Engine::detect_body(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                         float* desc, float* prob, cudaStream_t st) {
     run_network(img, img_u8, B, C, H, W, st);
     const int Hc = H / 8, Wc = W / 8;
     // the heatmap is written only when the caller wants it: round 0 of the NMS computes the softmax values itself
@@ -953,10 +1064,12 @@ void Engine::preprocess_f32(const float* frames, int B, int h, int w, float* out
 }
 
 void Engine::set_descriptor_format(int fmt) {
+    clear_graphs();
     if (fmt != 0 && fmt != 1) throw std::invalid_argument("descriptor format must be 0 (fp32) or 1 (fp16)");
     if (stage_)
         for (auto& sl : stage_->slot)
             if (sl.busy) throw std::runtime_error("descriptor format cannot change while a host batch is in flight");
+
     desc_fp16_ = fmt == 1;
 }
 
@@ -1126,11 +1239,12 @@ void Engine::detect_host_u8(const uint8_t* img, int B, int H, int W, int cap, in
 
 void Engine::detect_host_any(const void* img_any, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy,
                              float* conf, float* desc) {
-    const int ticket = detect_host_submit(img_any, img_u8, B, C, H, W, cap, desc != nullptr);
-    detect_host_wait(ticket, count, xy, conf, desc);
+    const int ticket = detect_host_submit(img_any, img_u8, B, C, H, W, cap, count, xy, conf, desc, 16);
+    detect_host_wait(ticket);
 }
 
-int Engine::detect_host_submit(const void* img_any, bool img_u8, int B, int C, int H, int W, int cap, bool want_desc) {
+int Engine::detect_host_submit(const void* img_any, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                               void* desc, int chunk_pref) {
     const uint8_t* img = static_cast<const uint8_t*>(img_any);
     const size_t esz = img_u8 ? 1 : sizeof(float);
     SPB_CUDA(cudaSetDevice(device_));
@@ -1140,6 +1254,8 @@ int Engine::detect_host_submit(const void* img_any, bool img_u8, int B, int C, i
     if (!stage_) {
         stage_ = std::make_unique<HostStage>();
         stage_->init();
+        stage_->device = device_;
+        stage_->worker = std::thread([st = stage_.get()] { st->run(); });
     }
     HostStage& s = *stage_;
     const int ticket = s.next;
@@ -1147,7 +1263,9 @@ int Engine::detect_host_submit(const void* img_any, bool img_u8, int B, int C, i
     if (sl.busy) throw std::runtime_error("detect_host: two batches are already in flight (call spb200_detect_host_wait first)");
     int Bc = B;
     {
-        int want = 16;
+        // chunks: a blocking call wants them small (the download of chunk k under the compute of chunk k + 1: 16), a
+        // streaming caller large (whole batches already overlap; large chunks use the GPU better: 32)
+        int want = chunk_pref > 0 ? chunk_pref : 32;
         if (const char* e = std::getenv("SPB200_HOST_CHUNK")) want = std::max(1, std::atoi(e));
         // the largest divisor of B that is at most `want` (and at least a quarter of it, so that chunks stay efficient)
         if (B > want)
@@ -1197,10 +1315,11 @@ int Engine::detect_host_submit(const void* img_any, bool img_u8, int B, int C, i
         sl.h_img_bytes = img_bytes;
     }
     const int dcap = sl.d_cap;
-    sl.B = B; sl.cap = cap; sl.want_desc = want_desc; sl.desc_row = desc_row;
+    sl.B = B; sl.cap = cap; sl.desc_row = desc_row;
+    sl.o_count = count; sl.o_xy = xy; sl.o_conf = conf; sl.o_desc = static_cast<uint8_t*>(desc);
 
     // everything the GPU has to do is enqueued here: chunk k's upload on the copy stream, its network + post-processing
-    // on the compute stream behind the upload's event, its counts copied to the pinned mirror
+    // on the compute stream behind the upload's event, its counts written to the pinned mirror
     for (int k = 0; k < nc; ++k) {
         const int Bk = sl.csize[k];
         const size_t coff = (size_t)sl.cstart[k] * img_elem_bytes, chunk_bytes = (size_t)Bk * img_elem_bytes;
@@ -1215,29 +1334,46 @@ int Engine::detect_host_submit(const void* img_any, bool img_u8, int B, int C, i
         SPB_CUDA(cudaStreamWaitEvent(s.s_comp, sl.ev_in[k], 0));
         const size_t o = (size_t)sl.cstart[k];
         detect_any(d_in, img_u8, Bk, C, H, W, dcap, sl.d_count + o, sl.d_xy + o * dcap * 2, sl.d_conf + o * dcap,
-                   want_desc ? static_cast<float*>(static_cast<void*>(static_cast<uint8_t*>(sl.d_desc) + o * dcap * desc_row)) : nullptr,
+                   desc ? static_cast<float*>(static_cast<void*>(static_cast<uint8_t*>(sl.d_desc) + o * dcap * desc_row)) : nullptr,
                    nullptr, s.s_comp);
-        SPB_CUDA(cudaMemcpyAsync(sl.h_count + o, sl.d_count + o, sizeof(int) * Bk, cudaMemcpyDeviceToHost, s.s_comp));
+        launch_counts_to_host(sl.d_count + o, sl.h_count + o, Bk, s.s_comp);
+        ++launches_;
         SPB_CUDA(cudaEventRecord(sl.ev_comp[k], s.s_comp));
     }
-    sl.busy = true;
+    {
+        std::lock_guard<std::mutex> lk(s.mu);
+        sl.busy = true;
+        sl.done = false;
+        sl.error.clear();
+        s.queue.push_back(ticket);
+    }
+    s.cv.notify_all();
     s.next ^= 1;
     return ticket;
 }
 
-void Engine::detect_host_wait(int ticket, int* count, int* xy, float* conf, void* desc_any) {
-    SPB_CUDA(cudaSetDevice(device_));
-    if (!stage_ || ticket < 0 || ticket > 1 || !stage_->slot[ticket].busy) throw std::invalid_argument("detect_host_wait: no batch in flight under this ticket");
+void Engine::detect_host_wait(int ticket) {
+    if (!stage_ || ticket < 0 || ticket > 1) throw std::invalid_argument("detect_host_wait: no batch in flight under this ticket");
     HostStage& s = *stage_;
     HostStage::Slot& sl = s.slot[ticket];
-    sl.busy = false;                                           // also on failure: the slot can be reused
-    uint8_t* desc = sl.want_desc ? static_cast<uint8_t*>(desc_any) : nullptr;
-    if (sl.want_desc && !desc) throw std::invalid_argument("detect_host_wait: descriptors were requested at submit, desc is null");
+    std::string err;
+    {
+        std::unique_lock<std::mutex> lk(s.mu);
+        if (!sl.busy) throw std::invalid_argument("detect_host_wait: no batch in flight under this ticket");
+        s.cv.wait(lk, [&] { return sl.done; });
+        sl.busy = false;
+        err = sl.error;
+    }
+    if (!err.empty()) throw std::runtime_error(err);
+}
+
+// The download half of a batch (worker thread): as each chunk's counts arrive, its keypoints and descriptors (count[b]
+// rows per image, nothing else) are copied on the download stream while later chunks - and the next batch - compute.
+void Engine::HostStage::download(Slot& sl) {
+    int* count = sl.o_count; int* xy = sl.o_xy; float* conf = sl.o_conf; uint8_t* desc = sl.o_desc;
     const int B = sl.B, cap = sl.cap, dcap = sl.d_cap, nc = (int)sl.csize.size();
     const size_t row = sl.desc_row;
     const bool pin_out = is_pinned_host(xy) && is_pinned_host(conf) && is_pinned_host(desc);
-    // as each chunk's counts arrive, its keypoints and descriptors (count[b] rows per image, nothing else) are
-    // downloaded on the third stream while the later chunks - and the next batch - compute
     size_t staged = 0;
     std::vector<size_t> stage_off;
     if (!pin_out) stage_off.assign((size_t)B, 0);
@@ -1253,7 +1389,7 @@ void Engine::detect_host_wait(int ticket, int* count, int* xy, float* conf, void
         }
         if (!pin_out && staged + total > sl.h_out_cap) {
             // grow the pinned staging; what is already in flight must land first, then it is copied over
-            SPB_CUDA(cudaStreamSynchronize(s.s_out));
+            SPB_CUDA(cudaStreamSynchronize(s_out));
             const size_t n = (staged + total) * 2 + 1024;
             int* nxy = nullptr; float* ncf = nullptr; uint8_t* nds = nullptr;
             SPB_CUDA(cudaHostAlloc((void**)&nxy, sizeof(int) * 2 * n, cudaHostAllocDefault));
@@ -1277,12 +1413,12 @@ void Engine::detect_host_wait(int ticket, int* count, int* xy, float* conf, void
             for (int b = 0; b < Bk; ++b) nmax = std::max(nmax, (size_t)count[g0 + b]);
             if (nmax) {
                 SPB_CUDA(cudaMemcpy2DAsync(xy + g0 * cap * 2, sizeof(int) * 2 * cap, sl.d_xy + g0 * dcap * 2, sizeof(int) * 2 * dcap,
-                                           sizeof(int) * 2 * nmax, Bk, cudaMemcpyDeviceToHost, s.s_out));
+                                           sizeof(int) * 2 * nmax, Bk, cudaMemcpyDeviceToHost, s_out));
                 SPB_CUDA(cudaMemcpy2DAsync(conf + g0 * cap, sizeof(float) * cap, sl.d_conf + g0 * dcap, sizeof(float) * dcap,
-                                           sizeof(float) * nmax, Bk, cudaMemcpyDeviceToHost, s.s_out));
+                                           sizeof(float) * nmax, Bk, cudaMemcpyDeviceToHost, s_out));
                 if (desc)
                     SPB_CUDA(cudaMemcpy2DAsync(desc + g0 * cap * row, row * cap, d_desc + g0 * dcap * row, row * dcap, row * nmax, Bk,
-                                               cudaMemcpyDeviceToHost, s.s_out));
+                                               cudaMemcpyDeviceToHost, s_out));
             }
             continue;
         }
@@ -1290,14 +1426,14 @@ void Engine::detect_host_wait(int ticket, int* count, int* xy, float* conf, void
             const size_t g = g0 + b, n = (size_t)count[g];
             stage_off[g] = staged;
             if (n) {
-                SPB_CUDA(cudaMemcpyAsync(sl.h_xy + staged * 2, sl.d_xy + g * dcap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s.s_out));
-                SPB_CUDA(cudaMemcpyAsync(sl.h_conf + staged, sl.d_conf + g * dcap, sizeof(float) * n, cudaMemcpyDeviceToHost, s.s_out));
-                if (desc) SPB_CUDA(cudaMemcpyAsync(sl.h_desc + staged * row, d_desc + g * dcap * row, row * n, cudaMemcpyDeviceToHost, s.s_out));
+                SPB_CUDA(cudaMemcpyAsync(sl.h_xy + staged * 2, sl.d_xy + g * dcap * 2, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s_out));
+                SPB_CUDA(cudaMemcpyAsync(sl.h_conf + staged, sl.d_conf + g * dcap, sizeof(float) * n, cudaMemcpyDeviceToHost, s_out));
+                if (desc) SPB_CUDA(cudaMemcpyAsync(sl.h_desc + staged * row, d_desc + g * dcap * row, row * n, cudaMemcpyDeviceToHost, s_out));
             }
             staged += n;
         }
     }
-    SPB_CUDA(cudaStreamSynchronize(s.s_out));
+    SPB_CUDA(cudaStreamSynchronize(s_out));
     if (!pin_out) {
         for (size_t g = 0; g < (size_t)B; ++g) {
             const size_t n = (size_t)count[g], off = stage_off[g];

@@ -5,6 +5,7 @@
 // kernel launches on the caller's stream.  Not thread-safe per instance; instances are independent.
 #pragma once
 #include <array>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <string>
@@ -92,7 +93,7 @@ public:
     void load_tensor(const std::string& key, const float* data, const int64_t* shape, int rank);
     void finalize(int precision, int split_level = SPLIT_NONE);
     int split_level() const { return split_level_; }
-    void set_params(const Params& p) { params_ = p; }
+    void set_params(const Params& p) { params_ = p; clear_graphs(); }
     const Params& params() const { return params_; }
     int precision() const { return precision_; }
     int descriptor_dim() const { return 128; }
@@ -114,8 +115,9 @@ public:
     void detect_host_u8(const uint8_t* img, int B, int H, int W, int cap, int* count, int* xy, float* conf, float* desc);
     // the two halves of detect_host, so that two batches can be in flight (the download of one under the compute of the
     // next): submit enqueues upload + compute and returns a ticket (0 / 1), wait downloads and returns the results
-    int detect_host_submit(const void* img, bool img_u8, int B, int C, int H, int W, int cap, bool want_desc);
-    void detect_host_wait(int ticket, int* count, int* xy, float* conf, void* desc);
+    int detect_host_submit(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                           void* desc, int chunk_pref = 0);
+    void detect_host_wait(int ticket);
     // descriptors of detect / detect_host as fp32 (0, the reference's type) or fp16 (1: half the bytes over the bus)
     void set_descriptor_format(int fmt);
     int descriptor_format() const { return desc_fp16_ ? 1 : 0; }
@@ -163,6 +165,19 @@ private:
     void run_network(const void* img, bool img_u8, int B, int C, int H, int W, cudaStream_t st);
     void detect_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                     float* desc, float* prob, cudaStream_t st);
+    void detect_body(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
+                     float* desc, float* prob, cudaStream_t st);
+    // CUDA graphs of whole detect calls: the ~20 launches (and the fork / join of the side streams) of a call repeated with
+    // the same buffers - a streaming caller, the chunks of the host pipeline - are captured the second time the call is
+    // seen and replayed from then on (one cudaGraphLaunch instead of ~20 launches of host work).  SPB200_NO_GRAPH=1 disables.
+    struct GraphKey {
+        const void* img; int u8, B, C, H, W, cap; const void *count, *xy, *conf, *desc, *prob;
+        bool operator<(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) < 0; }
+    };
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; long launches = 0; bool failed = false; };
+    std::map<GraphKey, GraphEntry> graphs_;
+    bool use_graphs_ = true;
+    void clear_graphs();
     void detect_host_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                          float* desc);
     ConvDev make_conv_dev(const OpSpec& op) const;

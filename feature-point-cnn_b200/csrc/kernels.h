@@ -73,6 +73,9 @@ void launch_heatmap(const float* logits, long batch_stride, long chan_stride, lo
 // restore_prob_map (python/src/netutils.py:64-75) on an already softmaxed B*65*Hc*Wc tensor: dustbin drop + depth-to-space
 void launch_depth_to_space(const float* softmax_nchw, int B, int Hc, int Wc, float* heat, cudaStream_t st);
 
+// n ints from device memory into PINNED host memory by a kernel (no copy engine involved)
+void launch_counts_to_host(const int* src, int* dst_pinned, int n, cudaStream_t st);
+
 struct NmsWorkspace {
     unsigned long long* keys;      // [B][kcap] survivors as sortable keys (conf bits << 32 | ~pixel index)
     unsigned long long* keys_alt;  // [B][kcap] ping-pong buffer of the radix sort

@@ -69,6 +69,20 @@ void launch_depth_to_space(const float* softmax_nchw, int B, int Hc, int Wc, flo
     SPB_CHECK_LAUNCH();
 }
 
+// Keypoint counts of a chunk, written straight into pinned host memory (mapped into the device's address space under
+// unified addressing): a cudaMemcpyAsync would queue behind the large descriptor downloads of the previous batch on the
+// device-to-host copy engine and stall the compute stream that issued it.
+__global__ void counts_to_host_kernel(const int* __restrict__ src, volatile int* dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+    __threadfence_system();
+}
+
+void launch_counts_to_host(const int* src, int* dst_pinned, int n, cudaStream_t st) {
+    counts_to_host_kernel<<<(n + 127) / 128, 128, 0, st>>>(src, dst_pinned, n);
+    SPB_CHECK_LAUNCH();
+}
+
 void launch_heatmap(const float* logits, long batch_stride, long chan_stride, long cell_stride, int B, int Hc, int Wc,
                     float* heat, cudaStream_t st) {
     dim3 grid((Wc + kHeatCells - 1) / kHeatCells, Hc, B);

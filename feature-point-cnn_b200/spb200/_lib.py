@@ -27,8 +27,8 @@ SYMBOLS = {
     'spb200_detect_host': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
     'spb200_detect_u8': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P, _P, _P]),
     'spb200_detect_host_u8': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P]),
-    'spb200_detect_host_submit': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.POINTER(_c.c_int)]),
-    'spb200_detect_host_wait': (_c.c_int, [_P, _c.c_int, _P, _P, _P, _P]),
+    'spb200_detect_host_submit': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _P, _P, _P, _c.POINTER(_c.c_int)]),
+    'spb200_detect_host_wait': (_c.c_int, [_P, _c.c_int]),
     'spb200_set_descriptor_format': (_c.c_int, [_P, _c.c_int]),
     'spb200_homography_adaptation': (_c.c_int, [_P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _P, _c.c_int, _c.c_int, _c.c_int, _P, _P]),
     'spb200_match': (_c.c_int, [_P, _P, _P, _P, _P, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _P, _P, _P]),

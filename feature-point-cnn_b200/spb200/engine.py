@@ -143,31 +143,33 @@ class Engine:
         return (np.zeros((b,), np.int32), np.zeros((b, capacity, 2), np.int32), np.zeros((b, capacity), np.float32),
                 np.zeros((b, capacity, 128), ddt) if want_desc else None)
 
-    def detect_host_submit(self, img, capacity, want_desc=True):
-        """First half of detect_host (spb200_detect_host_submit): img float32 B*C*H*W or uint8 B*H*W numpy (host; keep a
-        pinned array alive until the matching wait).  Returns a ticket; at most two batches may be in flight."""
+    def detect_host_submit(self, img, capacity, want_desc=True, out=None):
+        """First half of detect_host (spb200_detect_host_submit): img float32 B*C*H*W or uint8 B*H*W numpy (host), out =
+        (count, xy, conf, desc) numpy arrays the results are downloaded into (host_outputs; allocated here when None).
+        Returns a ticket; at most two batches may be in flight.  The arrays are kept alive until detect_host_wait."""
         u8 = img.dtype == np.uint8
         assert img.flags['C_CONTIGUOUS'] and (u8 or img.dtype == np.float32)
         if u8:
             (b, h, w), c = img.shape, 1
         else:
             b, c, h, w = img.shape
-        ticket = ctypes.c_int()
-        self._check(self._lib.spb200_detect_host_submit(self._h, ctypes.c_void_p(img.ctypes.data), int(u8), b, c, h, w, capacity,
-                                                        int(want_desc), ctypes.byref(ticket)), 'spb200_detect_host_submit')
-        self._inflight = getattr(self, '_inflight', {})
-        self._inflight[ticket.value] = (img, b, capacity, want_desc)
-        return ticket.value
-
-    def detect_host_wait(self, ticket, out=None):
-        """Second half: downloads batch `ticket` into out = (count, xy, conf, desc) numpy arrays and returns them."""
-        img, b, capacity, want_desc = self._inflight.pop(ticket)
         if out is None:
             out = self.host_outputs(b, capacity, want_desc)
         count, xy, conf, desc = out
-        self._check(self._lib.spb200_detect_host_wait(self._h, ticket, ctypes.c_void_p(count.ctypes.data), ctypes.c_void_p(xy.ctypes.data),
-                                                      ctypes.c_void_p(conf.ctypes.data),
-                                                      ctypes.c_void_p(desc.ctypes.data if desc is not None else 0)), 'spb200_detect_host_wait')
+        ticket = ctypes.c_int()
+        self._check(self._lib.spb200_detect_host_submit(self._h, ctypes.c_void_p(img.ctypes.data), int(u8), b, c, h, w, capacity,
+                                                        ctypes.c_void_p(count.ctypes.data), ctypes.c_void_p(xy.ctypes.data),
+                                                        ctypes.c_void_p(conf.ctypes.data),
+                                                        ctypes.c_void_p(desc.ctypes.data if desc is not None else 0),
+                                                        ctypes.byref(ticket)), 'spb200_detect_host_submit')
+        self._inflight = getattr(self, '_inflight', {})
+        self._inflight[ticket.value] = (img, out)
+        return ticket.value
+
+    def detect_host_wait(self, ticket):
+        """Second half: returns (count, xy, conf, desc) of batch `ticket` once they are complete in the arrays given at submit."""
+        img, out = self._inflight.pop(ticket)
+        self._check(self._lib.spb200_detect_host_wait(self._h, ticket), 'spb200_detect_host_wait')
         return out
 
     def detect_host(self, img, capacity, want_desc=True, out=None):

@@ -126,15 +126,16 @@ SPB200_API int spb200_detect_u8(spb200_engine* e, const uint8_t* img, int B, int
 SPB200_API int spb200_detect_host_u8(spb200_engine* e, const uint8_t* img_host, int B, int H, int W, int capacity,
                           int* count_host, int* xy_host, float* conf_host, float* desc_host);
 
-/* The two halves of spb200_detect_host / _u8, for callers that stream batches: submit copies (pageable) or registers
- * (pinned) the frames, enqueues upload + network + post-processing and returns at once with a ticket; wait downloads the
- * keypoints and descriptors of that batch and returns when they are in the caller's arrays.  At most TWO batches may be in
- * flight: submit(i + 1) before wait(i) lets batch i's download - the longest stage over PCIe - run under batch i + 1's
- * compute.  A pinned img_host must stay valid until the matching wait returns.  img_is_u8: B*H*W bytes (C = 1) instead of
- * B*C*H*W fp32.  want_desc = 0 skips the descriptors (desc_host may then be NULL in wait). */
+/* The two halves of spb200_detect_host / _u8, for callers that stream batches.  submit copies (pageable) or registers
+ * (pinned) the frames, enqueues upload + network + post-processing and returns at once with a ticket; the download of the
+ * keypoints and descriptors into the caller's arrays is driven by a thread of the engine as the results become ready;
+ * wait returns when batch `ticket` is complete in those arrays.  At most TWO batches may be in flight: submit(i + 1)
+ * before wait(i) lets batch i's download - the longest stage over PCIe - run under batch i + 1's compute.  img_host (when
+ * pinned) and the four output arrays must stay valid until the matching wait returns.  img_is_u8: B*H*W bytes (C = 1)
+ * instead of B*C*H*W fp32.  desc_host = NULL skips the descriptors. */
 SPB200_API int spb200_detect_host_submit(spb200_engine* e, const void* img_host, int img_is_u8, int B, int C, int H, int W, int capacity,
-                              int want_desc, int* ticket);
-SPB200_API int spb200_detect_host_wait(spb200_engine* e, int ticket, int* count_host, int* xy_host, float* conf_host, void* desc_host);
+                              int* count_host, int* xy_host, float* conf_host, void* desc_host, int* ticket);
+SPB200_API int spb200_detect_host_wait(spb200_engine* e, int ticket);
 
 /* Element type of the `desc` arrays that spb200_detect*, spb200_detect_host* fill: SPB200_DESC_FP32 (default: the reference
  * returns float32, netutils.py:119-121) or SPB200_DESC_FP16 - the same unit vectors rounded to half precision, B*capacity*128

@@ -1,0 +1,37 @@
+"""End-to-end sweep of the host-buffer pipeline on the GPU box: chunk sizes, graphs on / off, formats.
+    python scripts/e2e_sweep.py
+"""
+import os, subprocess, sys, json
+REPO = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+code = r'''
+import os, sys, time, json
+sys.path.insert(0, os.path.join(%r, 'feature-point-cnn_b200')); sys.path.insert(0, %r)
+import numpy as np, torch, spb200
+import bench
+B, H, W = 64, 480, 640
+eng = spb200.Engine(0); eng.load_checkpoint(bench.CKPT); eng.finalize('fp16'); eng.set_params()
+cap = eng.max_keypoints(H, W)
+hb = bench.make_batches(3, B, H, W, 0)
+host = [b.pin_memory().numpy() for b in hb]
+outs = [eng.host_outputs(B, cap, True, pinned=True) for _ in range(2)]
+res = {}
+for pipelined in (True, False):
+    bench.time_e2e(eng, host, outs, cap, 4, pipelined)
+    dt, kp = bench.time_e2e(eng, host, outs, cap, 20, pipelined)
+    res['pipelined' if pipelined else 'blocking'] = B * 20 / dt
+# host time of submit alone
+torch.cuda.synchronize(); t0 = time.perf_counter(); t = eng.detect_host_submit(host[0], cap, out=outs[0]); t1 = time.perf_counter(); eng.detect_host_wait(t)
+res['submit_ms'] = (t1 - t0) * 1e3
+eng.set_descriptor_format('fp16')
+outs16 = [eng.host_outputs(B, cap, True, pinned=True) for _ in range(2)]
+u8 = [(b.squeeze(1) * 255).round().to(torch.uint8).pin_memory().numpy() for b in hb]
+for name, inp in (('fp16desc', host), ('u8_fp16desc', u8)):
+    bench.time_e2e(eng, inp, outs16, cap, 4, True)
+    dt, kp = bench.time_e2e(eng, inp, outs16, cap, 20, True)
+    res[name] = B * 20 / dt
+print(json.dumps(res))
+''' % (REPO, REPO)
+for env in ({}, {'SPB200_NO_GRAPH': '1'}, {'SPB200_HOST_CHUNK': '32'}, {'SPB200_HOST_CHUNK': '64'}, {'SPB200_HOST_CHUNK': '8'}):
+    e = dict(os.environ); e.update(env)
+    r = subprocess.run([sys.executable, '-c', code], env=e, capture_output=True, text=True, timeout=600)
+    print(env, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:], flush=True)

@@ -358,14 +358,14 @@ def test_host_submit_wait_keeps_two_batches_in_flight(engines):
         xa = a.pin_memory().numpy() if pinned else a.numpy()
         xb = b.pin_memory().numpy() if pinned else b.numpy()
         outs = [e.host_outputs(6, cap, True, pinned) for _ in range(2)]
-        t0 = e.detect_host_submit(xa, cap)
+        t0 = e.detect_host_submit(xa, cap, out=outs[0])
         for it in range(4):                                         # a, b, a, b ... always one batch ahead
             nxt = xb if it % 2 == 0 else xa
-            t1 = e.detect_host_submit(nxt, cap)
+            t1 = e.detect_host_submit(nxt, cap, out=outs[(it + 1) % 2])
             if it == 0:
                 with pytest.raises(Exception):
                     e.detect_host_submit(xa, cap)                   # two already in flight
-            got = e.detect_host_wait(t0, outs[it % 2])
+            got = e.detect_host_wait(t0)
             ref = want['a' if it % 2 == 0 else 'b']
             np.testing.assert_array_equal(got[0], ref[0])
             for i in range(6):
@@ -373,7 +373,7 @@ def test_host_submit_wait_keeps_two_batches_in_flight(engines):
                 np.testing.assert_array_equal(got[1][i, :n], ref[1][i, :n])
                 np.testing.assert_array_equal(got[3][i, :n], ref[3][i, :n])
             t0 = t1
-        e.detect_host_wait(t0, outs[0])
+        e.detect_host_wait(t0)
 
 
 def test_fp16_descriptor_format(engines):
