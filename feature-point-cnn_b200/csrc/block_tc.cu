@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
     const uint32_t idesc = (1u << 4) | (OperandFmt<T>::value << 7) | (OperandFmt<T>::value << 10) |
                            ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const bool fused = p.ksteps2 > 0;
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
     if (warp == 0) {
         // ============================ TMA producer ============================
         // whole warp runs the loops; only the TMA issue sits under elect.sync (see halo_tc.cu)
+        pdl_wait();                                        // the activations are the previous kernel's output
         {
             int stage = 0;
             uint32_t phase = 0;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
         __syncwarp();
     } else {
         // ============================ epilogue ============================
+        pdl_wait();                                        // shortcut loads and output stores touch the chain's buffers
         const int q = warp % 4;
         const int row = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
@@ -376,8 +379,7 @@ static void launch_block_t(const TcBlockPlan* plan, cudaStream_t st) {
     auto kern = block_tc_kernel<BLOCK_N, STAGES, T>;
     const size_t smem = (size_t)STAGES * (kBlkABytes + BLOCK_N * 128) + (size_t)(BLOCK_N / 64) * kBlkABytes + 1024;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<plan->grid, kBlkThreads, smem, st>>>(plan->params);
-    SPB_CHECK_LAUNCH();
+    launch_pdl(kern, dim3(plan->grid), dim3(kBlkThreads), smem, st, plan->params);
 }
 
 template <typename T>

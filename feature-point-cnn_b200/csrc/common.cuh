@@ -23,6 +23,31 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 #define SPB_CUDA(x) ::spb200::cuda_check((x), #x, __FILE__, __LINE__)
 #define SPB_CHECK_LAUNCH() ::spb200::cuda_check(cudaGetLastError(), "kernel launch", __FILE__, __LINE__)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// The path is a chain of ~20 kernels on one stream.  Every kernel of the chain is launched with the programmatic-
+// serialisation attribute: its CTAs may come up while the previous kernel is still draining (persistent kernels: as
+// soon as a CTA of the previous kernel has retired from an SM), run their prologue - barrier initialisation, tensor-memory
+// allocation, tensor-map prefetch, weight loads, all independent of the previous kernel's output - and then block in
+// pdl_wait() until the previous kernel has completed and its writes are visible.  Rules: pdl_trigger() first thing in the
+// kernel (every thread); every thread that reads or writes global memory other than constant weights calls pdl_wait()
+// before it does.  SPB200_NO_PDL=1 launches without the attribute (both calls are then no-ops).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cuda_check(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...), "cudaLaunchKernelEx", __FILE__, __LINE__);
+}
+
 constexpr int kMaxTaps = 9;
 constexpr int kMaxSegs = 5;
 

@@ -12,6 +12,11 @@
 
 namespace spb200 {
 
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = std::getenv("SPB200_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 namespace {
 
 constexpr float kBnEps = 1e-5f;   // nn.BatchNorm2d default (reference python/src/resnet_blocks.py:8)
@@ -695,6 +700,7 @@ void Engine::ensure_nms(int B, int H, int W) {
     nms_.und = dev_alloc<unsigned>((size_t)B * H * W);
     nms_.ukey = dev_alloc<unsigned>((size_t)B * H * W);
     nmsB_ = B; nmsH_ = H; nmsW_ = W; nmsR_ = r;
+    nms_dirty_ = true;
 }
 
 // ix = ((gx + 1) / 2) * (Wc - 1) with gx = float(x / (W / 2.) - 1.): the arithmetic of the reference's
@@ -987,7 +993,8 @@ void Engine::detect_body(const void* img, bool img_u8, int B, int C, int H, int 
     run_network(img, img_u8, B, C, H, W, st);
     const int Hc = H / 8, Wc = W / 8;
     // the heatmap is written only when the caller wants it: round 0 of the NMS computes the softmax values itself
-    const bool from_logits = nms_logits_supported(params_.nms_dist);
+    static const bool force_heat = [] { const char* e = std::getenv("SPB200_NMS_FROM_HEAT"); return e && e[0] == '1'; }();
+    const bool from_logits = nms_logits_supported(params_.nms_dist) && !force_heat;
     if (prob || !from_logits) {
         prof_open("heatmap", 0.0, (double)B * (65.0 * Hc * Wc * 4 + (double)H * W * 4), st);
         launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc, prob ? prob : d_prob_, st);
@@ -998,11 +1005,14 @@ void Engine::detect_body(const void* img, bool img_u8, int B, int C, int H, int 
     // algorithmic bytes: the logits (65 channels) or the heatmap in; per survivor 8 B key out, then 8 B in and 12 B out
     // in the finish kernel (added by the caller, who knows the keypoint count)
     prof_open("nms_round0", 0.0, from_logits ? (double)B * 65.0 * Hc * Wc * 4 : (double)B * H * W * 4, st);
+    const bool zero_first = nms_dirty_;
+    nms_dirty_ = true;
     launch_nms_round0(from_logits ? nullptr : (prob ? prob : d_prob_), (const float*)buf_[BUF_LOGITS], det_c_, B, H, W,
-                      params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
+                      params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, zero_first, st);
     prof_close(st);
     prof_open("nms_finish_sort", 0.0, 0.0, st);
     launch_nms_finish(B, H, W, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_, count, xy, conf, st);
+    nms_dirty_ = false;
     prof_close(st);
     launches_ += 2;
     if (desc) {
@@ -1077,8 +1087,11 @@ void Engine::nms(const float* prob, int B, int H, int W, int cap, int* count, in
     StreamScope scope(this, st);
     if (cap <= 0) throw std::invalid_argument("capacity must be positive");
     ensure_nms(B, H, W);
-    launch_nms_round0(prob, nullptr, 0, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, st);
+    const bool zero_first = nms_dirty_;
+    nms_dirty_ = true;
+    launch_nms_round0(prob, nullptr, 0, B, H, W, params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, zero_first, st);
     launch_nms_finish(B, H, W, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_, count, xy, conf, st);
+    nms_dirty_ = false;
     launches_ += 2;
 }
 

@@ -221,6 +221,7 @@ private:
     float* d_prob_ = nullptr;
     // nms workspace
     int nmsB_ = 0, nmsH_ = 0, nmsW_ = 0, nmsR_ = -1;
+    bool nms_dirty_ = true;       // the NMS counters are not known to be zero (fresh workspace, or a call that did not get through)
     NmsWorkspace nms_{};
     // descriptor sampling positions per pixel column / row (see launch_sample_descriptors)
     float* d_gtab_ = nullptr;

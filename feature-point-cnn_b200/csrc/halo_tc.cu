@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     const uint32_t idesc = (1u << 4) | (OperandFmt<Tp>::value << 7) | (OperandFmt<Tp>::value << 10) |
                            ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int n_local = (p.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], T); }
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     // every descriptor through R2UR and wrap each instruction in an active-lane loop.
     if (warp == 0) {
         // ============================ activation producer ============================
+        pdl_wait();                                            // the activations are the previous kernel's output
         int sa = 0;
         uint32_t pha = 0;
         for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
@@ -340,6 +342,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         __syncwarp();
     } else {
         // ============================ epilogue ============================
+        pdl_wait();                                            // shortcut loads and output stores touch the chain's buffers
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
         const int eh = (warp - (2 + T)) >> 2;                        // 0/1: tile (T = 2) or column half (T = 1)
         const int row = q * 32 + lane;                         // GEMM row = TMEM lane
@@ -636,425 +639,13 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
-// Paired version of the 128-channel fused block: tcgen05.mma.cta_group::2 over a cluster of two CTAs
-// (mechanics proven by scripts/ubench/mma_pair.cu).  OFF unless SPB200_PAIR=1: written at the
-// end of round 1 without GPU time left to run it - the next round starts by testing it.
-//
-// CTA r of a pair owns tile 2 st + r: its own haloed activation stages, rows [r * n/2, (r + 1) * n/2) of every weight
-// slab, its own accumulators D1[2] | D2[2] (512 TMEM columns) and staging boxes.  One thread of the leader issues
-// M = 256 MMAs for both tiles; an MMA reads 4 KB of A and half a slab of B per CTA, and the weight slab is written
-// to shared memory once per pair instead of once per CTA.  With the accumulators double buffered the first epilogue of
-// tile j runs under GEMM 1 of tile j + 1.
-//   a_full / w_full     leader; its producer announces the bytes of both CTAs, both CTAs' TMA loads complete on it
-//   a_empty / w_empty / d1_full / d2_full   local in both CTAs, multicast tcgen05.commit of the issuing thread
-//   y_full / d2_empty   leader, count 8: four epilogue warps per CTA, the peer's through mapa + arrive.shared::cluster
-// ------------------------------------------------------------------------------------------------
-constexpr int kPairSA = 2, kPairSW = 8;
-constexpr int kPairHalfSlab = 64 * 128;                      // up to 64 weight rows x 128 B
-constexpr int kPairThreads = 256;                            // warps: 0 activations, 1 weights, 2 MMA (leader) + TMEM, 3 idle, 4-7 epilogue
-constexpr size_t kPairSmem = (size_t)kPairSA * kHaloBufBytes + (size_t)kPairSW * kPairHalfSlab + 4 * kHaloOutBox + 1024;
-
-__device__ __forceinline__ uint32_t pair_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void pair_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t pair_leader_addr(uint32_t addr) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0));
-    return r;
-}
-__device__ __forceinline__ void pair_arrive_leader(uint32_t bar_cluster) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-__device__ __forceinline__ void pair_tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void pair_tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
-                                                 int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void pair_tmem_alloc(uint32_t* slot, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void pair_tmem_dealloc(uint32_t addr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void pair_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .b64 da, db;\n"
-        "mov.b64 da, {%1, %2};\n"
-        "mov.b64 db, {%3, %4};\n"
-        "setp.ne.b32 p, %6, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
-        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void pair_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        ".reg .b64 db;\n"
-        "mov.b64 db, {%2, %3};\n"
-        "setp.ne.b32 p, %5, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n"
-        "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on the barrier at this offset in BOTH CTAs when the MMAs issued so far by this thread are complete
-__device__ __forceinline__ void pair_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-
-template <typename Tp>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1) halo_pair_kernel(const __grid_constant__ HaloParams p) {
-    constexpr int N = 128, SA = kPairSA, SW = kPairSW;
-    extern __shared__ uint8_t dyn_smem[];
-    __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full[SW], w_empty[SW];
-    __shared__ __align__(8) uint64_t d1_full[2], y_full[2], d2_full[2], d2_empty[2], res_full[4];
-    __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float s_bias1[N], s_bias2[N];
-
-    uint8_t* a_ring = dyn_smem + ((1024u - (smem_u32(dyn_smem) & 1023u)) & 1023u);
-    uint8_t* w_ring = a_ring + SA * kHaloBufBytes;
-    uint8_t* out_stage = w_ring + SW * kPairHalfSlab;        // four boxes of 16 KB: two sets of two (16-bit output), or one set of four (fp32)
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
-    const int rank = (int)pair_rank();
-    const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
-    const int n_local = (p.n_super - pair + npairs - 1) / npairs;
-    const int half_rows = p.n_mma >> 1;
-    const uint32_t idesc = (1u << 4) | (OperandFmt<Tp>::value << 7) | (OperandFmt<Tp>::value << 10) |
-                           ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&d1_full[b], 1); mbar_init(&d2_full[b], 1);
-            mbar_init(&y_full[b], 8); mbar_init(&d2_empty[b], 8);
-        }
-        for (int w = 0; w < 4; ++w) mbar_init(&res_full[w], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < kMaxSegs; ++s) prefetch_tmap(&p.tmA[s]);
-        prefetch_tmap(&p.tmW1);
-        prefetch_tmap(&p.tmW2);
-    }
-    if (warp == 2) pair_tmem_alloc(&tmem_slot, 512);
-    for (int i = threadIdx.x; i < 4 * kHaloOutBox / 16; i += kPairThreads) reinterpret_cast<uint4*>(out_stage)[i] = make_uint4(0u, 0u, 0u, 0u);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int i = threadIdx.x; i < N; i += kPairThreads) { s_bias1[i] = p.bias1[i]; s_bias2[i] = p.bias2[i]; }
-    tc_fence_before();
-    __syncthreads();
-    pair_sync();                                             // the peer's barriers exist before anything remote touches them
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;                    // D1[b] at b * 128, D2[b] at 256 + b * 128
-
-    if (warp == 0) {
-        // ============================ activation producer (both CTAs) ============================
-        int sa = 0;
-        uint32_t pha = 0;
-        for (int jt = 0; jt < n_local; ++jt) {
-            const int tile = min((pair + jt * npairs) * 2 + rank, p.total_tiles - 1);
-            const int tt = tile % p.tiles_per_img, img = tile / p.tiles_per_img;
-            const int cs = (tt / p.tiles_g) * 16 + p.lo_s, cg = (tt % p.tiles_g) * 8 + p.lo_g;
-            for (int ci = 0; ci < p.nchunks; ++ci) {
-                mbar_wait(&a_empty[sa], pha ^ 1u);
-                if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&a_full[sa], (uint32_t)(2 * kHaloLoadBytes));
-                    pair_tma_load_4d(smem_u32(a_ring + sa * kHaloBufBytes), &p.tmA[p.chunk_seg[ci]], pair_leader_addr(smem_u32(&a_full[sa])),
-                                     p.chunk_c0[ci], cg, cs, img);
-                }
-                if (++sa == SA) { sa = 0; pha ^= 1u; }
-            }
-        }
-    } else if (warp == 1) {
-        // ============================ weight producer (both CTAs): half slabs in issue order ============================
-        uint32_t cnt = 0;
-        auto fetch = [&](int e) {
-            const HaloStep s = p.steps[e];
-            const uint32_t hi = (uint32_t)(s >> 32);
-            const uint32_t slot = cnt % SW, ph = (cnt / SW) & 1u;
-            mbar_wait(&w_empty[slot], ph ^ 1u);
-            if (elect_one()) {
-                if (rank == 0) mbar_expect_tx(&w_full[slot], (uint32_t)(2 * half_rows * 128));
-                pair_tma_load_2d(smem_u32(w_ring + slot * kPairHalfSlab), ((hi >> 4) & 3u) == 0 ? &p.tmW1 : &p.tmW2,
-                                 pair_leader_addr(smem_u32(&w_full[slot])), (int)((hi >> 16) & 0xfffu) * 64, rank * half_rows);
-            }
-            ++cnt;
-        };
-        for (int j = 0; j <= n_local; ++j) {
-            if (j < n_local) for (int e = 0; e < p.n1steps; ++e) fetch(e);
-            if (j >= 1) for (int e = p.n1steps; e < p.nsteps; ++e) fetch(e);
-        }
-    } else if (warp == 2) {
-        // ============================ MMA issuer (leader only) ============================
-        if (rank == 0) {
-            int sa = 0;
-            uint32_t pha = 0, cnt = 0;
-            const uint32_t a_lo_base = umma_desc_lo(smem_u32(a_ring)), w_lo_base = umma_desc_lo(smem_u32(w_ring));
-            constexpr uint32_t kHiA = ((uint32_t)kHaloSbo >> 4) | (1u << 14) | (2u << 29);
-            constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
-            for (int j = 0; j <= n_local; ++j) {
-                if (j < n_local) {
-                    const int b = j & 1;
-                    const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-                    bool d2_ready = !p.has_ds;
-                    for (int e = 0; e < p.n1steps; ++e) {
-                        const HaloStep s = p.steps[e];
-                        const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
-                        const uint32_t nkk = (hi >> 6) & 7u, acc0 = (hi >> 11) & 1u, gemm = (hi >> 4) & 3u;
-                        const uint32_t slot = cnt % SW, wph = (cnt / SW) & 1u;
-                        if (hi & (1u << 9)) mbar_wait(&a_full[sa], pha);
-                        mbar_wait(&w_full[slot], wph);
-                        if (!d2_ready && gemm != 0) { mbar_wait(&d2_empty[b], ph ^ 1u); d2_ready = true; }
-                        tc_fence_after();
-                        const uint32_t alo = a_lo_base + (uint32_t)(sa * (kHaloBufBytes >> 4)) + (lo & 0xffffu);
-                        const uint32_t blo = w_lo_base + slot * (uint32_t)(kPairHalfSlab >> 4);
-                        const uint32_t d = tmem_base + (gemm == 0 ? 0u : 256u) + (uint32_t)(b * N);
-                        if (elect_one()) {
-                            pair_mma(d, alo, kHiA, blo, kHiB, idesc, acc0);
-                            if (nkk > 1) pair_mma(d, alo + 2, kHiA, blo + 2, kHiB, idesc, 1u);
-                            if (nkk > 2) pair_mma(d, alo + 4, kHiA, blo + 4, kHiB, idesc, 1u);
-                            if (nkk > 3) pair_mma(d, alo + 6, kHiA, blo + 6, kHiB, idesc, 1u);
-                            pair_commit(&w_empty[slot]);
-                            if (hi & (1u << 10)) pair_commit(&a_empty[sa]);
-                        }
-                        ++cnt;
-                        if (hi & (1u << 10)) { if (++sa == SA) { sa = 0; pha ^= 1u; } }
-                    }
-                    if (elect_one()) pair_commit(&d1_full[b]);
-                }
-                if (j >= 1) {
-                    const int jj = j - 1, b = jj & 1;
-                    const uint32_t ph = (uint32_t)(jj >> 1) & 1u;
-                    mbar_wait(&y_full[b], ph);                    // Y packed by the epilogue warps of BOTH CTAs
-                    if (!p.has_ds) mbar_wait(&d2_empty[b], ph ^ 1u);
-                    tc_fence_after();
-                    for (int e = p.n1steps; e < p.nsteps; ++e) {
-                        const HaloStep s = p.steps[e];
-                        const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
-                        const uint32_t nkk = (hi >> 6) & 7u, acc0 = (hi >> 11) & 1u;
-                        const uint32_t slot = cnt % SW, wph = (cnt / SW) & 1u;
-                        mbar_wait(&w_full[slot], wph);
-                        tc_fence_after();
-                        const uint32_t ya = tmem_base + (uint32_t)(b * N) + (lo & 0xffffu);
-                        const uint32_t blo = w_lo_base + slot * (uint32_t)(kPairHalfSlab >> 4);
-                        const uint32_t d = tmem_base + 256u + (uint32_t)(b * N);
-                        if (elect_one()) {
-                            pair_mma_ts(d, ya, blo, kHiB, idesc, acc0);
-                            if (nkk > 1) pair_mma_ts(d, ya + 8, blo + 2, kHiB, idesc, 1u);
-                            if (nkk > 2) pair_mma_ts(d, ya + 16, blo + 4, kHiB, idesc, 1u);
-                            if (nkk > 3) pair_mma_ts(d, ya + 24, blo + 6, kHiB, idesc, 1u);
-                            pair_commit(&w_empty[slot]);
-                        }
-                        ++cnt;
-                    }
-                    if (elect_one()) pair_commit(&d2_full[b]);
-                }
-            }
-            __syncwarp();
-        }
-    } else if (warp >= 4) {
-        // ============================ epilogue (both CTAs, one warp per TMEM lane quarter) ============================
-        const int q = warp & 3;
-        const int row = q * 32 + lane, ti = row >> 3, tr = row & 7;
-        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const int nblk = p.n_mma / 32;
-        const uint32_t y_full_leader = pair_leader_addr(smem_u32(&y_full[0])), d2_empty_leader = pair_leader_addr(smem_u32(&d2_empty[0]));
-        uint32_t rph = 0;
-        struct TileAt { int img, s, g; bool ok; };
-        auto tile_at = [&](int jt) {
-            const int tile_raw = (pair + jt * npairs) * 2 + rank;
-            const int tile = min(tile_raw, p.total_tiles - 1);
-            const int tt = tile % p.tiles_per_img;
-            return TileAt{tile / p.tiles_per_img, (tt / p.tiles_g) * 16, (tt % p.tiles_g) * 8, tile_raw < p.total_tiles};
-        };
-        // staging boxes of tile jt: 16-bit output alternates between two sets of two boxes, fp32 output uses all four
-        auto stage_of = [&](int jt) { return smem_u32(out_stage) + (uint32_t)((p.dst_fp32 ? 0 : (jt & 1) * 2) * kHaloOutBox + q * 4096); };
-        auto epi1 = [&](int jt) {
-            const int b = jt & 1;
-            const uint32_t ph = (uint32_t)(jt >> 1) & 1u;
-            const uint32_t tmem_d1 = tmem_base + (uint32_t)(b * N) + lane_off;
-            mbar_wait(&d1_full[b], ph);
-            tc_fence_after();
-#pragma unroll 1
-            for (int blk = 0; blk < nblk; ++blk) {
-                const int c0 = blk * 32;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_d1 + (uint32_t)c0, r);
-                float bb[32];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float4 f = *reinterpret_cast<const float4*>(s_bias1 + c0 + 4 * e);
-                    bb[4 * e] = f.x; bb[4 * e + 1] = f.y; bb[4 * e + 2] = f.z; bb[4 * e + 3] = f.w;
-                }
-                tmem_ld_wait();
-                uint32_t y[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    y[e] = pack2_relu<Tp>(__uint_as_float(r[2 * e]) + bb[2 * e], __uint_as_float(r[2 * e + 1]) + bb[2 * e + 1]);
-                tmem_st_32x16(tmem_d1 + (uint32_t)(c0 >> 1), y);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) pair_arrive_leader(y_full_leader + (uint32_t)(b * 8));
-        };
-        const bool tr_res = p.tma_res && p.residual != nullptr;
-        uint4 res[4][4];
-        auto prefetch_res = [&](int jt) {
-            if (p.residual == nullptr) return;
-            const TileAt ta = tile_at(jt);
-            if (tr_res) {
-                if (lane == 0) {
-                    tma_store_wait_read<1>();                     // the set's previous tile (jt - 2) has left; jt - 1 may be in flight
-                    const int nb = (p.n_mma + 63) / 64;
-                    mbar_expect_tx(&res_full[q], (uint32_t)(nb * 4096));
-                    for (int k = 0; k < nb; ++k)
-                        tma_load_4d_a(stage_of(jt) + (uint32_t)(k * kHaloOutBox), &p.tmR, smem_u32(&res_full[q]), k * 64, ta.g, ta.s + q * 4, ta.img);
-                }
-                __syncwarp();
-                return;
-            }
-            const int oy = p.orient == 0 ? ta.s + ti : ta.g + tr, ox = p.orient == 0 ? ta.g + tr : ta.s + ti;
-            if (!(ta.ok && oy < p.OH && ox < p.OW)) return;
-            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const Tp*>(p.residual) + (((size_t)ta.img * p.OH + oy) * p.OW + ox) * p.res_C);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k < nblk) {
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) res[k][jj] = __ldg(rp + k * 4 + jj);
-                }
-        };
-        auto epi_out = [&](int jt) {
-            const int b = jt & 1;
-            const uint32_t ph = (uint32_t)(jt >> 1) & 1u;
-            const TileAt ta = tile_at(jt);
-            const int oy = p.orient == 0 ? ta.s + ti : ta.g + tr, ox = p.orient == 0 ? ta.g + tr : ta.s + ti;
-            const bool has_res = p.residual != nullptr && (tr_res || (ta.ok && oy < p.OH && ox < p.OW));
-            const uint32_t stg = stage_of(jt);
-            const uint32_t sw = (uint32_t)(lane & 7);
-            if (!tr_res) {
-                if (lane == 0) { if (p.dst_fp32) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
-                __syncwarp();
-            }
-            const uint32_t tmem_out = tmem_base + 256u + (uint32_t)(b * N) + lane_off;
-            mbar_wait(&d2_full[b], ph);
-            tc_fence_after();
-            if (tr_res) { mbar_wait(&res_full[q], rph); rph ^= 1u; }
-#pragma unroll
-            for (int blk = 0; blk < 4; ++blk) {
-                if (blk >= nblk) continue;
-                const int c0 = blk * 32;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_out + (uint32_t)c0, r);
-                float v[32];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float4 f = *reinterpret_cast<const float4*>(s_bias2 + c0 + 4 * e);
-                    v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
-                }
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
-                if (has_res) {
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const uint4 rv = tr_res ? ld_shared_v4(stg + (uint32_t)((blk >> 1) * kHaloOutBox) + (uint32_t)lane * 128u +
-                                                               ((((uint32_t)(blk & 1) * 4u + (uint32_t)jj) ^ sw) << 4))
-                                                : res[blk][jj];
-                        const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 f = unpack2<Tp>(w[e]);
-                            v[jj * 8 + e * 2] += f.x;
-                            v[jj * 8 + e * 2 + 1] += f.y;
-                        }
-                    }
-                }
-                if (p.dst_fp32) {
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                    }
-                    const uint32_t box = stg + (uint32_t)(blk * kHaloOutBox);
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj)
-                        st_shared_v4(box + (uint32_t)lane * 128u + (((uint32_t)jj ^ sw) << 4), __float_as_uint(v[jj * 4]), __float_as_uint(v[jj * 4 + 1]),
-                                     __float_as_uint(v[jj * 4 + 2]), __float_as_uint(v[jj * 4 + 3]));
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0 && ta.ok) tma_store_4d(&p.tmD, box, c0, ta.g, ta.s + q * 4, ta.img);
-                } else {
-                    const uint32_t box = stg + (uint32_t)((blk >> 1) * kHaloOutBox);
-                    const uint32_t half = (uint32_t)(blk & 1) * 4u;
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        uint32_t w0, w1, w2, w3;
-                        if (p.relu) {
-                            w0 = pack2_relu<Tp>(v[jj * 8], v[jj * 8 + 1]); w1 = pack2_relu<Tp>(v[jj * 8 + 2], v[jj * 8 + 3]);
-                            w2 = pack2_relu<Tp>(v[jj * 8 + 4], v[jj * 8 + 5]); w3 = pack2_relu<Tp>(v[jj * 8 + 6], v[jj * 8 + 7]);
-                        } else {
-                            w0 = pack2<Tp>(v[jj * 8], v[jj * 8 + 1]); w1 = pack2<Tp>(v[jj * 8 + 2], v[jj * 8 + 3]);
-                            w2 = pack2<Tp>(v[jj * 8 + 4], v[jj * 8 + 5]); w3 = pack2<Tp>(v[jj * 8 + 6], v[jj * 8 + 7]);
-                        }
-                        st_shared_v4(box + (uint32_t)lane * 128u + (((half + (uint32_t)jj) ^ sw) << 4), w0, w1, w2, w3);
-                    }
-                    if ((blk & 1) || blk == nblk - 1) {
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0 && ta.ok) tma_store_4d(&p.tmD, box, (blk >> 1) * 64, ta.g, ta.s + q * 4, ta.img);
-                    }
-                }
-            }
-            if (lane == 0) tma_store_commit();                   // one bulk group per tile
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) pair_arrive_leader(d2_empty_leader + (uint32_t)(b * 8));
-        };
-        for (int j = 0; j < n_local; ++j) {
-            if (j > 0) prefetch_res(j - 1);
-            epi1(j);
-            if (j > 0) epi_out(j - 1);
-        }
-        if (n_local > 0) { prefetch_res(n_local - 1); epi_out(n_local - 1); }
-        if (lane == 0) tma_store_wait_all();
-    }
-    tc_fence_before();
-    __syncthreads();
-    pair_sync();                                             // the peer has drained its accumulators and finished its MMAs' commits
-    if (warp == 2) {
-        tc_fence_after();
-        pair_tmem_dealloc(tmem_base, 512);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Host
 // ------------------------------------------------------------------------------------------------
 static long long* g_halo_dbg = nullptr;
 struct TcHaloPlan {
     HaloParams params;
     int variant;       // 0: N=64 fused, resident weights; 1: N=128 fused, T=2; 2: N=128 single convolution, T=2;
-                       // 3: N=128 fused on CTA pairs (SPB200_PAIR=1); 4 / 5: split precision, N = 64 / 128 fused
+                       // 4 / 5: split precision, N = 64 / 128 fused (3 was the CTA-pair kernel, measured slower and removed)
     int operand_type, grid;
 };
 
@@ -1064,8 +655,7 @@ static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
     const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + (size_t)T * halo_out_slots(N, SPLIT) * kHaloOutBox + 1024;
     // function attributes are per device: set on every launch (a process may hold engines on several GPUs)
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<plan->grid, halo_threads(T), smem, st>>>(plan->params);
-    SPB_CHECK_LAUNCH();
+    launch_pdl(kern, dim3(plan->grid), dim3(halo_threads(T)), smem, st, plan->params);
 }
 
 constexpr int kHaloResidentSlabs = 11;   // variant 0: every slab of a 64-channel block stays in shared memory
@@ -1082,13 +672,6 @@ static void launch_halo_v(const TcHaloPlan* plan, cudaStream_t st) {
         case 2: launch_halo_t<128, 2, 2, 2, kHaloRing2, false, false, false, Tp>(plan, st); break;
         case 4: launch_halo_t<64, 2, 1, 2, kHaloRing4, true, false, true, Tp>(plan, st); break;
         case 5: launch_halo_t<128, 2, 1, 2, kHaloRing5, true, false, true, Tp>(plan, st); break;
-        case 3: {
-            auto kern = halo_pair_kernel<Tp>;
-            SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmem));
-            kern<<<plan->grid, kPairThreads, kPairSmem, st>>>(plan->params);
-            SPB_CHECK_LAUNCH();
-            break;
-        }
         default: throw std::invalid_argument("tcgen05 halo block: bad variant");
     }
 }
@@ -1337,23 +920,6 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         }
     }
     if (split && !p.tma_store) return nullptr;                       // the split epilogue only stores through shared memory
-    const char* pair_env = std::getenv("SPB200_PAIR");
-    if (plan->variant == 1 && p.tma_store && p.n_mma % 32 == 0 && pair_env && pair_env[0] == '1') {
-        // CTA pairs: every CTA loads its half of the rows of a weight slab; one cluster per tile pair
-        plan->variant = 3;
-        const cuuint32_t hbox[2] = {64, (cuuint32_t)(p.n_mma / 2)};
-        {
-            cuuint64_t dims[2] = {(cuuint64_t)c1.K, (cuuint64_t)N};
-            cuuint64_t str[1] = {(cuuint64_t)c1.K * 2};
-            tc_encode_tiled(&p.tmW1, dt, 2, c1.w, dims, str, hbox);
-        }
-        {
-            cuuint64_t dims[2] = {(cuuint64_t)c2->K, (cuuint64_t)N};
-            cuuint64_t str[1] = {(cuuint64_t)c2->K * 2};
-            tc_encode_tiled(&p.tmW2, dt, 2, c2->w, dims, str, hbox);
-        }
-        plan->grid = 2 * std::max(1, std::min(p.n_super, num_sms / 2));
-    }
     {
         static int v_count[3] = {0, 0, 0};
         const char* d = std::getenv("SPB200_HALO_DBG");         // "<variant><index>", e.g. 11 = second plan of variant 1

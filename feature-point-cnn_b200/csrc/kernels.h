@@ -94,8 +94,10 @@ struct NmsWorkspace {
 // launch_nms_finish: remaining rounds, sort, outputs per image: count (clamped to cap and top_k), xy int32 [cap][2]
 // as (x, y), conf fp32 [cap].
 bool nms_logits_supported(int radius);
+// zero_counters: clear the per-image counters first (a memset node); the finish kernel leaves them at zero, so only the
+// first call on a fresh workspace - or the call after a failed one - needs it
 void launch_nms_round0(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
-                       int border, const NmsWorkspace& ws, cudaStream_t st);
+                       int border, const NmsWorkspace& ws, bool zero_counters, cudaStream_t st);
 void launch_nms_finish(int B, int H, int W, int radius, int border, int top_k, int cap, const NmsWorkspace& ws, int* count,
                        int* xy, float* conf, cudaStream_t st);
 

@@ -68,9 +68,11 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
     const int ty0 = blockIdx.y * kN0TH, tx0 = blockIdx.x * kN0TW;
+    pdl_trigger();
     if (tid == 0) { s_ncand = 0; s_nund = 0; s_nkeep = 0; }
     for (int i = tid; i < EH * KW; i += kN0Threads) s_kb[i] = 0u;
     for (int i = tid; i < kN0TH * 2; i += kN0Threads) s_ub[i] = 0u;
+    pdl_wait();                                                // logits / heatmap of the previous kernel; the lists it appends to
     if (LOGITS) __syncthreads();                               // the candidate counter is used while the keys are made
 
     // 1. keys of the loaded region
@@ -495,8 +497,13 @@ nms_finish_kernel(int H, int W, int r, int border, int kcap, unsigned long long*
     const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     const int b = blockIdx.x;
     int* cnt = counters + b * kNmsCounters;
+    pdl_trigger();
+    pdl_wait();
     const int nkeep0 = min(__ldcg(cnt), kcap);
     const int n0 = (int)min((long)__ldcg(cnt + 1), (long)H * W);
+    // the counters are left at zero for the next call's round 0 (no memset node between the detector head and round 0)
+    __syncthreads();
+    if (tid < kNmsCounters) cnt[tid] = 0;
     unsigned long long* gkeys = keys + (size_t)b * kcap;
     if (tid == 0) s_n = nkeep0;
 
@@ -830,19 +837,18 @@ static void launch_round0_t(const float* src, int cell_stride, int B, int H, int
     auto kern = nms_round0_kernel<R, LOGITS>;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((W + kN0TW - 1) / kN0TW, (H + kN0TH - 1) / kN0TH, B);
-    kern<<<grid, kN0Threads, smem, st>>>(src, cell_stride, H, W, thresh, border, ws.kcap, ws.keys, ws.counters, ws.mask, ws.mask_w,
-                                         ws.und, ws.ukey);
-    SPB_CHECK_LAUNCH();
+    launch_pdl(kern, grid, dim3(kN0Threads), smem, st, src, cell_stride, H, W, thresh, border, ws.kcap, ws.keys, ws.counters, ws.mask,
+               ws.mask_w, ws.und, ws.ukey);
 }
 
 bool nms_logits_supported(int radius) { return radius >= 0 && radius <= 4; }
 
 void launch_nms_round0(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
-                       int border, const NmsWorkspace& ws, cudaStream_t st) {
+                       int border, const NmsWorkspace& ws, bool zero_counters, cudaStream_t st) {
     if (radius < 0 || radius > kNmsMaxR) throw std::invalid_argument("nms_dist must be in [0, 8]");
     if ((long)H * W >= (1l << 31)) throw std::invalid_argument("image too large");
     if (!heat && !(logits && nms_logits_supported(radius))) throw std::invalid_argument("nms: no heatmap given");
-    SPB_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * kNmsCounters * B, st));
+    if (zero_counters) SPB_CUDA(cudaMemsetAsync(ws.counters, 0, sizeof(int) * kNmsCounters * B, st));
     if (!heat) {
         switch (radius) {
             case 0: launch_round0_t<0, true>(logits, cell_stride, B, H, W, thresh, border, ws, st); break;
@@ -870,9 +876,8 @@ void launch_nms_finish(int B, int H, int W, int radius, int border, int top_k, i
                        int* xy, float* conf, cudaStream_t st) {
     const size_t smem = sizeof(unsigned long long) * kSortSmemKeys;
     SPB_CUDA(cudaFuncSetAttribute(nms_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_finish_kernel<<<B, kFinThreads, smem, st>>>(H, W, radius, border, ws.kcap, ws.keys, ws.keys_alt, ws.counters, ws.mask,
-                                                    ws.mask_w, ws.und, ws.ukey, cap, top_k, count, xy, conf);
-    SPB_CHECK_LAUNCH();
+    launch_pdl(nms_finish_kernel, dim3(B), dim3(kFinThreads), smem, st, H, W, radius, border, ws.kcap, ws.keys, ws.keys_alt, ws.counters,
+               ws.mask, ws.mask_w, ws.und, (const unsigned*)ws.ukey, cap, top_k, count, xy, conf);
 }
 
 }  // namespace spb200

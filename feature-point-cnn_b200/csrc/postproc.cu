@@ -217,6 +217,8 @@ sample_desc128_kernel(const T* __restrict__ map, long batch_stride, int Hc, int 
                       int cap, const int* __restrict__ count, const int* __restrict__ xy, void* __restrict__ out) {
     const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
     const int b = blockIdx.y;
+    pdl_trigger();
+    pdl_wait();                                                // counts and keypoints of the NMS kernel before it
     const int n = min(__ldg(count + b), cap);
     const T* mb = map + (size_t)b * batch_stride + hl * 8;
     const int2* pts = reinterpret_cast<const int2*>(xy) + (size_t)b * cap;
@@ -293,13 +295,12 @@ void launch_sample_descriptors(const void* map, int map_type, long batch_stride,
     if (map_type != PREC_FP32 && D == 128 && chan_stride == 1 && cell_stride == 128) {
         dim3 g(kDescBlocksPerImage, B);
         if (map_type == PREC_FP16) {
-            if (out_fp16) sample_desc128_kernel<__half, true><<<g, 256, 0, st>>>((const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
-            else sample_desc128_kernel<__half, false><<<g, 256, 0, st>>>((const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+            if (out_fp16) launch_pdl(sample_desc128_kernel<__half, true>, g, dim3(256), 0, st, (const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+            else launch_pdl(sample_desc128_kernel<__half, false>, g, dim3(256), 0, st, (const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
         } else {
-            if (out_fp16) sample_desc128_kernel<__nv_bfloat16, true><<<g, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
-            else sample_desc128_kernel<__nv_bfloat16, false><<<g, 256, 0, st>>>((const __nv_bfloat16*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+            if (out_fp16) launch_pdl(sample_desc128_kernel<__nv_bfloat16, true>, g, dim3(256), 0, st, (const __nv_bfloat16*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
+            else launch_pdl(sample_desc128_kernel<__nv_bfloat16, false>, g, dim3(256), 0, st, (const __nv_bfloat16*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
         }
-        SPB_CHECK_LAUNCH();
         return;
     }
     dim3 grid((cap + 7) / 8, B);

@@ -56,6 +56,8 @@ struct StemPlanesParams {
 template <typename T, typename IN>
 __global__ void __launch_bounds__(256) planes_kernel(const IN* __restrict__ img, T* __restrict__ planes, int H, int W, long total8) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = 8 pixels of one row
+    pdl_trigger();
+    pdl_wait();                                                      // the planes may still be read by a stem kernel in flight
     if (i >= total8) return;
     const int w8 = W / 8;
     const int x8 = (int)(i % w8);
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
     const int PH = p.PH, PW = p.PW, CH = 2 * PH, CW = 2 * PW;
+    pdl_trigger();
 
     if (tid == 0) {
         mbar_init(&bar_w, 1);
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
             mbar_expect_tx(&bar_w, 16384);
             tma_load_2d(s_w, &p.tmW, &bar_w, 0, 0);
             tma_load_2d(s_w + 8192, &p.tmW, &bar_w, 64, 0);
+            pdl_wait();                                          // the image planes are the previous kernel's output
             if ((int)blockIdx.x < p.total_tiles) load_tile(blockIdx.x, 0);
             if ((int)(blockIdx.x + gridDim.x) < p.total_tiles) load_tile(blockIdx.x + gridDim.x, 1);
             mbar_wait(&bar_w, 0);
@@ -228,6 +232,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
         }
     } else {
         // ---------------- epilogue warps ----------------
+        pdl_wait();                                              // the pooled tensor is read by kernels of the previous step
         const int q = warp & 3, h = warp >> 2;
         const int u = q * 32 + lane, crow = u >> 3, mp = u & 7;
         float bias[32];
@@ -329,13 +334,12 @@ void launch_planes(const void* img, int img_is_u8, void* planes, int operand_typ
     const long total8 = (long)B * H * (W / 8);
     const int grid = (int)((total8 + 255) / 256);
     if (operand_type == PREC_FP16) {
-        if (img_is_u8) planes_kernel<__half, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)img, (__half*)planes, H, W, total8);
-        else planes_kernel<__half, float><<<grid, 256, 0, st>>>((const float*)img, (__half*)planes, H, W, total8);
+        if (img_is_u8) launch_pdl(planes_kernel<__half, uint8_t>, dim3(grid), dim3(256), 0, st, (const uint8_t*)img, (__half*)planes, H, W, total8);
+        else launch_pdl(planes_kernel<__half, float>, dim3(grid), dim3(256), 0, st, (const float*)img, (__half*)planes, H, W, total8);
     } else {
-        if (img_is_u8) planes_kernel<__nv_bfloat16, uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)img, (__nv_bfloat16*)planes, H, W, total8);
-        else planes_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const float*)img, (__nv_bfloat16*)planes, H, W, total8);
+        if (img_is_u8) launch_pdl(planes_kernel<__nv_bfloat16, uint8_t>, dim3(grid), dim3(256), 0, st, (const uint8_t*)img, (__nv_bfloat16*)planes, H, W, total8);
+        else launch_pdl(planes_kernel<__nv_bfloat16, float>, dim3(grid), dim3(256), 0, st, (const float*)img, (__nv_bfloat16*)planes, H, W, total8);
     }
-    SPB_CHECK_LAUNCH();
 }
 
 void launch_stem_planes(StemPlanesPlan* plan, const void* planes, void* dst, int B, int H, int W, cudaStream_t st) {
@@ -357,13 +361,12 @@ void launch_stem_planes(StemPlanesPlan* plan, const void* planes, void* dst, int
     if (plan->operand_type == PREC_FP16) {
         auto kern = stem_planes_kernel<__half>;
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
-        kern<<<grid, kSpThreads, kSpSmem, st>>>(p);
+        launch_pdl(kern, dim3(grid), dim3(kSpThreads), (size_t)kSpSmem, st, p);
     } else {
         auto kern = stem_planes_kernel<__nv_bfloat16>;
         SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
-        kern<<<grid, kSpThreads, kSpSmem, st>>>(p);
+        launch_pdl(kern, dim3(grid), dim3(kSpThreads), (size_t)kSpSmem, st, p);
     }
-    SPB_CHECK_LAUNCH();
 }
 
 // w16: device [64][128] 16-bit K-major, k = ky*8 + kx hi parts then lo parts (the 1-channel pack of stem_tc.cu)
