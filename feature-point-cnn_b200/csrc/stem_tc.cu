@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_wide_kernel(const __grid_c
     uint8_t* s_a = base;                                              // [2 M-tiles][hi, lo][128 rows][128 B]
     uint8_t* s_w = s_a + 4 * kATile;                                  // [hi, lo][CIN][64 rows][128 B]
     constexpr int kPatch = CIN * kStIH * kStIWp;
-    T* s_in = reinterpret_cast<T*>(s_w + 2 * CIN * 64 * 128);         // [hi, lo][CIN][27][48], image * 255
+    T* s_in = reinterpret_cast<T*>(s_w + 2 * CIN * 64 * 128);         // [2 buffers][hi, lo][CIN][27][48], image * 255
     float* s_conv = reinterpret_cast<float*>(s_a);                    // aliases A after the MMAs: [16 channel quads][231 rows][4] fp32
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
@@ -309,27 +309,52 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_wide_kernel(const __grid_c
         mbar_expect_tx(&bar_w, 2 * CIN * 64 * 128);
         for (int c = 0; c < 2 * CIN; ++c) tma_load_2d(s_w + c * 64 * 128, &p.tmW, &bar_w, c * 64, 0);
     }
+    // ---- input patch of a tile as hi + lo parts, two pixels per thread and step; every load of the thread is issued
+    // before the first conversion.  The patch of the next tile is fetched while the tensor core works on this one.
+    constexpr int kPairs = CIN * kStIH * (kStIWp / 2);
+    constexpr int kPatchIters = (kPairs + kStThreads - 1) / kStThreads;
+    auto load_patch = [&](int tile, int buf) {
+        const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
+        const int iy0 = 4 * ((tt / p.tiles_x) * kStPH) - 5, ix0 = 4 * ((tt % p.tiles_x) * kStPW) - 5;
+        const float* img_b = p.img + (size_t)b * CIN * H * W;
+        uint32_t* dst_hi = reinterpret_cast<uint32_t*>(s_in + buf * 2 * kPatch);
+        uint32_t* dst_lo = reinterpret_cast<uint32_t*>(s_in + buf * 2 * kPatch + kPatch);
+        float v0[kPatchIters], v1[kPatchIters];
+#pragma unroll
+        for (int it = 0; it < kPatchIters; ++it) {
+            const int i = tid + it * kStThreads;
+            v0[it] = v1[it] = 0.f;
+            if (i < kPairs) {
+                const int c = i / (kStIH * (kStIWp / 2)), r = i % (kStIH * (kStIWp / 2));
+                const int y = iy0 + r / (kStIWp / 2), x = ix0 + 2 * (r % (kStIWp / 2));
+                if (y >= 0 && y < H) {
+                    const float* row = img_b + ((size_t)c * H + y) * W;
+                    if (x >= 0 && x < W) v0[it] = __ldg(row + x);
+                    if (x + 1 >= 0 && x + 1 < W) v1[it] = __ldg(row + x + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < kPatchIters; ++it) {
+            const int i = tid + it * kStThreads;
+            if (i < kPairs) {
+                const float a = v0[it] * 255.f, c = v1[it] * 255.f;
+                const uint32_t hw = pack2<T>(a, c);
+                const float2 f = unpack2<T>(hw);
+                dst_hi[i] = hw;
+                dst_lo[i] = pack2<T>(a - f.x, c - f.y);
+            }
+        }
+    };
     uint32_t mma_phase = 0;
     bool first = true;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int buf = 0;
+    if ((int)blockIdx.x < p.total_tiles) load_patch(blockIdx.x, 0);
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, buf ^= 1) {
         const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
         const int py0 = (tt / p.tiles_x) * kStPH, px0 = (tt % p.tiles_x) * kStPW;
         const int cy0 = 2 * py0 - 1, cx0 = 2 * px0 - 1;
-        const int iy0 = 4 * py0 - 5, ix0 = 4 * px0 - 5;
-        // ---- input patch as hi + lo parts ----
-        const float* img_b = p.img + (size_t)b * CIN * H * W;
-        for (int i = tid; i < kPatch; i += kStThreads) {
-            const int c = i / (kStIH * kStIWp), r = i % (kStIH * kStIWp);
-            const int y = iy0 + r / kStIWp, x = ix0 + r % kStIWp;
-            float v = 0.f;
-            if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img_b + ((size_t)c * H + y) * W + x) * 255.f;
-            const uint32_t hw = pack2<T>(v, 0.f);
-            const float hi = unpack2<T>(hw).x;
-            const uint32_t lw = pack2<T>(v - hi, 0.f);
-            reinterpret_cast<uint16_t*>(s_in)[i] = (uint16_t)(hw & 0xffffu);
-            reinterpret_cast<uint16_t*>(s_in)[kPatch + i] = (uint16_t)(lw & 0xffffu);
-        }
-        __syncthreads();
         for (int ck = 0; ck < CIN; ++ck) {
             // ---- im2col rows of channel ck (hi and lo), SWIZZLE_128B K-major, as in stem_tc_kernel ----
             {
@@ -340,7 +365,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_wide_kernel(const __grid_c
                 const int sw = (rr & 7) << 4;
 #pragma unroll
                 for (int part = 0; part < 2; ++part) {
-                    const T* pin = s_in + part * kPatch + ck * kStIH * kStIWp + (2 * cyl) * kStIWp + 2 * cxl;
+                    const T* pin = s_in + (buf * 2 + part) * kPatch + ck * kStIH * kStIWp + (2 * cyl) * kStIWp + 2 * cxl;
                     uint8_t* arow = s_a + (mt * 2 + part) * kATile + rr * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -378,6 +403,7 @@ __global__ void __launch_bounds__(kStThreads, 1) stem_wide_kernel(const __grid_c
             }
             __syncwarp();
             first = false;
+            if (ck == 0 && tile + (int)gridDim.x < p.total_tiles) load_patch(tile + gridDim.x, buf ^ 1);   // the other patch buffer
             mbar_wait(&bar_mma, mma_phase);                        // the A tiles may be rebuilt (or aliased by the staging)
             mma_phase ^= 1u;
             tc_fence_after();
@@ -468,7 +494,7 @@ static void launch_stem_tc_t(const StemTcPlan* plan, const float* img, void* dst
 template <int CIN, typename T>
 static void launch_stem_wide_t(const StemTcPlan* plan, const float* img, void* dst, int B, int H, int W, cudaStream_t st) {
     auto kern = stem_wide_kernel<CIN, T>;
-    const size_t smem = (size_t)4 * 128 * 128 + (size_t)2 * CIN * 64 * 128 + (size_t)2 * CIN * kStIH * kStIWp * 2 + 1024;
+    const size_t smem = (size_t)4 * 128 * 128 + (size_t)2 * CIN * 64 * 128 + (size_t)4 * CIN * kStIH * kStIWp * 2 + 1024;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     StemParams p = plan->params;
     p.img = img; p.dst = dst; p.H = H; p.W = W;
