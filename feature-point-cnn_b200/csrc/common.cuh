@@ -48,6 +48,20 @@ inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     cuda_check(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...), "cudaLaunchKernelEx", __FILE__, __LINE__);
 }
 
+// the same for a kernel that runs as thread-block clusters of `cluster_x` CTAs along x
+template <typename... KArgs, typename... Args>
+inline void launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    cuda_check(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...), "cudaLaunchKernelEx (cluster)", __FILE__, __LINE__);
+}
+
 constexpr int kMaxTaps = 9;
 constexpr int kMaxSegs = 5;
 

@@ -100,12 +100,91 @@ struct HaloParams {
     long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
 };
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster, one issuing thread in the leader, M = 256 MMAs ---------------------
+__device__ __forceinline__ uint32_t pair_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void pair_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pair_leader_addr(uint32_t addr) {       // the same shared-memory offset in CTA 0 of the pair
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0));
+    return r;
+}
+__device__ __forceinline__ void pair_arrive_leader(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void pair_tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void pair_tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void pair_tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void pair_tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void pair_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void pair_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 db;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs when the MMAs issued so far by this thread are complete
+__device__ __forceinline__ void pair_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // SPLIT: split-precision operands (three MMAs per product, common.cuh SegDev): the activation chunks and the weight slabs
 // arrive in the split layout - which only the host-built step list knows about -, the first epilogue writes Y back as
 // [hi | lo] and the second one can store the block output the same way.
-template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, bool SPLIT, typename Tp>
+//
+// PAIR (launched as clusters of two CTAs): the resident-weight kernel on tcgen05.mma.cta_group::2.  Each CTA keeps what it had -
+// its own tile pairs, activation stages, accumulators, epilogue warps and staging boxes - but holds only HALF of the rows of
+// every weight slab, and the MMAs of both CTAs are issued by the two issuing warps of the LEADER as M = 256 instructions
+// (the leader's tile in its tensor memory, the peer's tile in the peer's).  An MMA then reads 4 KB of A + 1 KB of B per CTA
+// from shared memory instead of 4 + 2 KB: the operand fetch that caps the N = 64 blocks drops from 192 to 160 B/clk.
+//   a_full, w_full    leader's barriers; its producers announce the bytes of both CTAs, both CTAs' TMA loads complete on them
+//   a_empty, d1_full, d2_full    local in both CTAs, reached by multicast tcgen05.commit
+//   y_full, d2_empty  leader's, counted over the epilogue warps of both CTAs (the peer's arrive through mapa)
+template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, bool SPLIT, bool PAIR, typename Tp>
 __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __grid_constant__ HaloParams p) {
+    static_assert(!PAIR || (FUSED && WRES && !SPLIT && NBUF == 2), "CTA pairs: the resident-weight fused kernel");
     constexpr int kWBytes = N * 128;
+    constexpr int kWSlot = PAIR ? kWBytes / 2 : kWBytes;      // bytes of a weight slab held by this CTA
     constexpr uint32_t kAccCols = NBUF * T * N;
     constexpr uint32_t kTmemCols = (FUSED ? 2 : 1) * kAccCols;
     static_assert(kTmemCols == 64 || kTmemCols == 128 || kTmemCols == 256 || kTmemCols == 512, "TMEM columns");
@@ -132,17 +211,23 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     // uniform datapath (loop counters, ring state, descriptors in uniform registers) instead of R2UR round trips
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
     const uint32_t idesc = (1u << 4) | (OperandFmt<Tp>::value << 7) | (OperandFmt<Tp>::value << 10) |
-                           ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int n_local = (p.n_super - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                           ((uint32_t)(p.n_mma >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+    // scheduling units: CTAs, or CTA pairs (both CTAs of a pair run the same number of steps; rank r takes super-tile 2 u + r)
+    const int rank = PAIR ? (int)pair_rank() : 0;
+    const int unit = PAIR ? (int)blockIdx.x >> 1 : (int)blockIdx.x, nunits = PAIR ? (int)gridDim.x >> 1 : (int)gridDim.x;
+    const int n_work = PAIR ? (p.n_super + 1) / 2 : p.n_super;
+    const int n_local = (n_work - unit + nunits - 1) / nunits;
+    auto st_of = [&](int j) { return PAIR ? (unit + j * nunits) * 2 + rank : unit + j * nunits; };
     pdl_trigger();
 
     if (threadIdx.x == 0) {
+        constexpr int kEpi = PAIR ? 16 : 8;                  // epilogue warps that arrive on the issuer's barriers
         for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], T); }
         for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], T); }
         for (int w = 0; w < 8; ++w) mbar_init(&res_full[w], 1);
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(&d1_full[b], T); mbar_init(&d2_full[b], T);
-            mbar_init(&d1_empty[b], 8); mbar_init(&y_full[b], 8); mbar_init(&d2_empty[b], 8);
+            mbar_init(&d1_empty[b], 8); mbar_init(&y_full[b], kEpi); mbar_init(&d2_empty[b], kEpi);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -152,7 +237,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         prefetch_tmap(&p.tmW1);
         if (FUSED) prefetch_tmap(&p.tmW2);
     }
-    if (warp == 2) tmem_alloc(&tmem_slot, kTmemCols);
+    if (warp == 2) { if (PAIR) pair_tmem_alloc(&tmem_slot, kTmemCols); else tmem_alloc(&tmem_slot, kTmemCols); }
     for (int i = threadIdx.x; i < T * kOutSlots * kHaloOutBox / 16; i += halo_threads(T))
         reinterpret_cast<uint4*>(out_stage)[i] = make_uint4(0u, 0u, 0u, 0u);      // channels beyond n_mma leave as zeros
     if (kOutSlots > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -162,6 +247,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) pair_sync();                                   // the peer's barriers exist before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
@@ -175,7 +261,8 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         pdl_wait();                                            // the activations are the previous kernel's output
         int sa = 0;
         uint32_t pha = 0;
-        for (int st = blockIdx.x; st < p.n_super; st += gridDim.x) {
+        for (int j = 0; j < n_local; ++j) {
+            const int st = st_of(j);
             int cg[T], cs[T], cimg[T];
 #pragma unroll
             for (int t = 0; t < T; ++t) {
@@ -188,11 +275,14 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             for (int ci = 0; ci < p.nchunks; ++ci) {
                 mbar_wait(&a_empty[sa], pha ^ 1u);
                 if (elect_one()) {
-                    mbar_expect_tx(&a_full[sa], (uint32_t)(T * kHaloLoadBytes));
+                    if (rank == 0) mbar_expect_tx(&a_full[sa], (uint32_t)((PAIR ? 2 : 1) * T * kHaloLoadBytes));
                     const CUtensorMap* tm = &p.tmA[p.chunk_seg[ci]];
 #pragma unroll
-                    for (int t = 0; t < T; ++t)
-                        tma_load_4d(a_ring + (sa * T + t) * kHaloBufBytes, tm, &a_full[sa], p.chunk_c0[ci], cg[t], cs[t], cimg[t]);
+                    for (int t = 0; t < T; ++t) {
+                        if (PAIR) pair_tma_load_4d(smem_u32(a_ring + (sa * T + t) * kHaloBufBytes), tm, pair_leader_addr(smem_u32(&a_full[sa])),
+                                                   p.chunk_c0[ci], cg[t], cs[t], cimg[t]);
+                        else tma_load_4d(a_ring + (sa * T + t) * kHaloBufBytes, tm, &a_full[sa], p.chunk_c0[ci], cg[t], cs[t], cimg[t]);
+                    }
                 }
                 if (++sa == SA) { sa = 0; pha ^= 1u; }
             }
@@ -208,9 +298,11 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 const uint32_t hi = (uint32_t)(s >> 32), slot = hi & 15u;
                 if (!WRES) { mbar_wait_a(bar_empty + slot * 8, ((eph >> slot) & 1u) ^ 1u); eph ^= 1u << slot; }
                 if (elect_one()) {
-                    mbar_expect_tx_a(bar_full + slot * 8, (uint32_t)p.w_bytes);
-                    tma_load_2d_a(ring + slot * kWBytes, ((hi >> 4) & 3u) == 0 ? &p.tmW1 : &p.tmW2, bar_full + slot * 8,
-                                  (int)((hi >> 16) & 0xfffu) * 64, 0);
+                    if (rank == 0) mbar_expect_tx_a(bar_full + slot * 8, (uint32_t)p.w_bytes);     // both halves in a pair
+                    const CUtensorMap* tw = ((hi >> 4) & 3u) == 0 ? &p.tmW1 : &p.tmW2;
+                    if (PAIR) pair_tma_load_2d(ring + slot * kWSlot, tw, pair_leader_addr(bar_full + slot * 8), (int)((hi >> 16) & 0xfffu) * 64,
+                                               rank * (p.n_mma >> 1));
+                    else tma_load_2d_a(ring + slot * kWBytes, tw, bar_full + slot * 8, (int)((hi >> 16) & 0xfffu) * 64, 0);
                 }
             }
         }
@@ -232,7 +324,18 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         constexpr uint32_t kHiA = ((uint32_t)kHaloSbo >> 4) | (1u << 14) | (2u << 29);   // SBO = haloed row pitch
         constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);                // SBO = 1024 (dense tile)
         constexpr int LAG = (FUSED && NBUF == 2) ? 1 : 0;
-        for (int j = 0; j < n_local + LAG; ++j) {
+        // a CTA pair is served by the leader's issuing warps: M = 256 instructions, multicast commits
+        auto mma = [&](uint32_t d, uint32_t alo, uint32_t blo, uint32_t acc) {
+            if (PAIR) pair_mma(d, alo, kHiA, blo, kHiB, idesc, acc); else umma_f16_w(d, alo, kHiA, blo, kHiB, idesc, acc);
+        };
+        auto mma_ts = [&](uint32_t d, uint32_t ya, uint32_t blo, uint32_t acc) {
+            if (PAIR) pair_mma_ts(d, ya, blo, kHiB, idesc, acc); else umma_f16_ts(d, ya, blo, kHiB, idesc, acc);
+        };
+        auto commit = [&](uint32_t bar) { if (PAIR) pair_commit_a(bar); else umma_commit_a(bar); };
+        auto slab_lo = [&](uint32_t lo, uint32_t hi) {           // descriptor-low of the step's weight slab in this CTA
+            return PAIR ? w_lo_base + (hi & 15u) * (uint32_t)(kWSlot >> 4) : w_lo_base + (lo >> 16);
+        };
+        for (int j = 0; j < (PAIR && rank != 0 ? 0 : n_local + LAG); ++j) {
             const bool dbg_on = p.dbg && blockIdx.x == 0 && mt == 0 && lane == 0 && j < 16;
             if (dbg_on) p.dbg[j * 8 + 0] = clock64();
             if (j < n_local) {
@@ -259,12 +362,12 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                         for (int e = e0; e < e1; ++e) {
                             const HaloStep s = p.steps[e];
                             const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
-                            const uint32_t alo = a0 + (lo & 0xffffu), blo = w_lo_base + (lo >> 16);
+                            const uint32_t alo = a0 + (lo & 0xffffu), blo = slab_lo(lo, hi);
                             const uint32_t d = d_base + (((hi >> 4) & 3u) == 0 ? 0u : kAccCols) + (uint32_t)(b * T * N);
-                            umma_f16_w(d, alo, kHiA, blo, kHiB, idesc, (hi >> 11) & 1u);
-                            umma_f16_w(d, alo + 2, kHiA, blo + 2, kHiB, idesc, 1u);
-                            umma_f16_w(d, alo + 4, kHiA, blo + 4, kHiB, idesc, 1u);
-                            umma_f16_w(d, alo + 6, kHiA, blo + 6, kHiB, idesc, 1u);
+                            mma(d, alo, blo, (hi >> 11) & 1u);
+                            mma(d, alo + 2, blo + 2, 1u);
+                            mma(d, alo + 4, blo + 4, 1u);
+                            mma(d, alo + 6, blo + 6, 1u);
                         }
                     };
                     const int e_ds = d2_ready ? p.n1steps : p.first_ds_step;
@@ -275,8 +378,8 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                         if (elect_one()) issue(e_ds, p.n1steps);
                     }
                     if (elect_one()) {
-                        umma_commit_a(bar_aempty + sa * 8);
-                        umma_commit(&d1_full[b]);
+                        commit(bar_aempty + sa * 8);
+                        commit(smem_u32(&d1_full[b]));
                     }
                     d2_ready = true;
                     if (++sa == SA) { sa = 0; pha ^= 1u; }
@@ -292,20 +395,20 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     if (!d2_ready && ((hi >> 4) & 3u) != 0) { mbar_wait(&d2_empty[b], ph ^ 1u); d2_ready = true; }
                     tc_fence_after();
                     const uint32_t alo = a_lo_base + (uint32_t)(sa * T * (kHaloBufBytes >> 4)) + (lo & 0xffffu);
-                    const uint32_t blo = w_lo_base + (lo >> 16);
+                    const uint32_t blo = slab_lo(lo, hi);
                     const uint32_t d = d_base + (((hi >> 4) & 3u) == 0 ? 0u : kAccCols) + (uint32_t)(b * T * N);
                     if (elect_one()) {
-                        umma_f16_w(d, alo, kHiA, blo, kHiB, idesc, acc0);
-                        if (nkk > 1) umma_f16_w(d, alo + 2, kHiA, blo + 2, kHiB, idesc, 1u);
-                        if (nkk > 2) umma_f16_w(d, alo + 4, kHiA, blo + 4, kHiB, idesc, 1u);
-                        if (nkk > 3) umma_f16_w(d, alo + 6, kHiA, blo + 6, kHiB, idesc, 1u);
-                        if (!WRES) umma_commit_a(bar_wempty + slot * 8);
-                        if (hi & (1u << 10)) umma_commit_a(bar_aempty + sa * 8);
+                        mma(d, alo, blo, acc0);
+                        if (nkk > 1) mma(d, alo + 2, blo + 2, 1u);
+                        if (nkk > 2) mma(d, alo + 4, blo + 4, 1u);
+                        if (nkk > 3) mma(d, alo + 6, blo + 6, 1u);
+                        if (!WRES) commit(bar_wempty + slot * 8);
+                        if (hi & (1u << 10)) commit(bar_aempty + sa * 8);
                     }
                     if (!WRES) wph ^= 1u << slot;
                     if (hi & (1u << 10)) { if (++sa == SA) { sa = 0; pha ^= 1u; } }
                 }
-                if (!(WRES && j > 0) && elect_one()) umma_commit(&d1_full[b]);
+                if (!(WRES && j > 0) && elect_one()) commit(smem_u32(&d1_full[b]));
                 if (dbg_on) p.dbg[j * 8 + 1] = clock64();
             }
             if (FUSED && j >= LAG) {
@@ -324,18 +427,18 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     tc_fence_after();
                     // A = Y, 16-bit, packed in place over the first N/2 columns of D1[b] by the epilogue warps
                     const uint32_t ya = d_base + (uint32_t)(b * T * N) + (lo & 0xffffu);
-                    const uint32_t blo = w_lo_base + (lo >> 16);
+                    const uint32_t blo = slab_lo(lo, hi);
                     const uint32_t d = d_base + kAccCols + (uint32_t)(b * T * N);
                     if (elect_one()) {
-                        umma_f16_ts(d, ya, blo, kHiB, idesc, acc0);
-                        if (nkk > 1) umma_f16_ts(d, ya + 8, blo + 2, kHiB, idesc, 1u);
-                        if (nkk > 2) umma_f16_ts(d, ya + 16, blo + 4, kHiB, idesc, 1u);
-                        if (nkk > 3) umma_f16_ts(d, ya + 24, blo + 6, kHiB, idesc, 1u);
-                        if (!WRES) umma_commit_a(bar_wempty + slot * 8);
+                        mma_ts(d, ya, blo, acc0);
+                        if (nkk > 1) mma_ts(d, ya + 8, blo + 2, 1u);
+                        if (nkk > 2) mma_ts(d, ya + 16, blo + 4, 1u);
+                        if (nkk > 3) mma_ts(d, ya + 24, blo + 6, 1u);
+                        if (!WRES) commit(bar_wempty + slot * 8);
                     }
                     if (!WRES) wph ^= 1u << slot;
                 }
-                if (elect_one()) umma_commit(&d2_full[b]);
+                if (elect_one()) commit(smem_u32(&d2_full[b]));
                 if (dbg_on) p.dbg[j * 8 + 3] = clock64();
             }
         }
@@ -356,7 +459,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         // per-tile coordinates of this thread's output pixel
         struct Pix { bool valid; size_t gpix, dpix; };
         auto pixel_of = [&](int jt) {
-            const int st = blockIdx.x + jt * gridDim.x;
+            const int st = st_of(jt);
             const int tile_raw = st * T + t;
             const int tile = min(tile_raw, p.total_tiles - 1);
             const int img = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
@@ -415,7 +518,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&y_full[b]);
+            if (lane == 0) { if (PAIR) pair_arrive_leader(pair_leader_addr(smem_u32(&y_full[b]))); else mbar_arrive(&y_full[b]); }
             if (dbg_on) p.dbg[jt * 8 + 5] = clock64();
         };
         // the identity-shortcut operand of a tile, fetched long before it is needed (the call sites put a whole first
@@ -425,7 +528,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         uint32_t rph = 0;
         struct TileAt { int img, s, g; bool ok; };
         auto tile_at = [&](int jt) {                           // origin of this warp's 32 pixels (warp-uniform)
-            const int tile_raw = (blockIdx.x + jt * gridDim.x) * T + t;
+            const int tile_raw = st_of(jt) * T + t;
             const int tile = min(tile_raw, p.total_tiles - 1);
             const int tt = tile % p.tiles_per_img;
             return TileAt{tile / p.tiles_per_img, (tt / p.tiles_g) * 16 + q * 4, (tt % p.tiles_g) * 8, tile_raw < p.total_tiles};
@@ -608,7 +711,10 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(FUSED ? &d2_empty[b] : &d1_empty[b]);
+            if (lane == 0) {
+                if (PAIR) pair_arrive_leader(pair_leader_addr(smem_u32(&d2_empty[b])));
+                else mbar_arrive(FUSED ? &d2_empty[b] : &d1_empty[b]);
+            }
             if (dbg_on) p.dbg[jt * 8 + 7] = clock64();
         };
         if (!FUSED) {
@@ -631,10 +737,12 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         }
         if (kOutSlots > 0 && lane == 0) tma_store_wait_all();
     }
+    tc_fence_before();
     __syncthreads();
+    if (PAIR) pair_sync();                                   // the peer has drained its accumulators; every multicast commit has landed
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_slot, kTmemCols);
+        if (PAIR) pair_tmem_dealloc(tmem_slot, kTmemCols); else tmem_dealloc(tmem_slot, kTmemCols);
     }
 }
 
@@ -645,33 +753,36 @@ static long long* g_halo_dbg = nullptr;
 struct TcHaloPlan {
     HaloParams params;
     int variant;       // 0: N=64 fused, resident weights; 1: N=128 fused, T=2; 2: N=128 single convolution, T=2;
-                       // 4 / 5: split precision, N = 64 / 128 fused (3 was the CTA-pair kernel, measured slower and removed)
+                       // 3: variant 0 on CTA pairs (tcgen05.mma.cta_group::2); 4 / 5: split precision, N = 64 / 128 fused
     int operand_type, grid;
 };
 
-template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, bool SPLIT, typename Tp>
+template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, bool SPLIT, bool PAIR, typename Tp>
 static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
-    auto kern = halo_tc_kernel<N, T, NBUF, SA, SW, FUSED, WRES, SPLIT, Tp>;
+    auto kern = halo_tc_kernel<N, T, NBUF, SA, SW, FUSED, WRES, SPLIT, PAIR, Tp>;
     const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + (size_t)T * halo_out_slots(N, SPLIT) * kHaloOutBox + 1024;
     // function attributes are per device: set on every launch (a process may hold engines on several GPUs)
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(kern, dim3(plan->grid), dim3(halo_threads(T)), smem, st, plan->params);
+    if (PAIR) launch_pdl_cluster(kern, dim3(plan->grid), dim3(halo_threads(T)), smem, st, 2, plan->params);
+    else launch_pdl(kern, dim3(plan->grid), dim3(halo_threads(T)), smem, st, plan->params);
 }
 
 constexpr int kHaloResidentSlabs = 11;   // variant 0: every slab of a 64-channel block stays in shared memory
 constexpr int kHaloRing1 = 4;            // variant 1: weight ring slots (16 KB each; 8 slots measured no faster)
 constexpr int kHaloRing2 = 4;            // variant 2
+constexpr bool kHaloPairDefault = false;  // variant 0 on CTA pairs unless SPB200_PAIR64 says otherwise
 constexpr int kHaloRing4 = 8;            // variant 4: split precision, N = 64 (8 KB slabs)
 constexpr int kHaloRing5 = 4;            // variant 5: split precision, N = 128
 
 template <typename Tp>
 static void launch_halo_v(const TcHaloPlan* plan, cudaStream_t st) {
     switch (plan->variant) {
-        case 0: launch_halo_t<64, 2, 2, 2, kHaloResidentSlabs, true, true, false, Tp>(plan, st); break;
-        case 1: launch_halo_t<128, 2, 1, 2, kHaloRing1, true, false, false, Tp>(plan, st); break;
-        case 2: launch_halo_t<128, 2, 2, 2, kHaloRing2, false, false, false, Tp>(plan, st); break;
-        case 4: launch_halo_t<64, 2, 1, 2, kHaloRing4, true, false, true, Tp>(plan, st); break;
-        case 5: launch_halo_t<128, 2, 1, 2, kHaloRing5, true, false, true, Tp>(plan, st); break;
+        case 0: launch_halo_t<64, 2, 2, 2, kHaloResidentSlabs, true, true, false, false, Tp>(plan, st); break;
+        case 1: launch_halo_t<128, 2, 1, 2, kHaloRing1, true, false, false, false, Tp>(plan, st); break;
+        case 2: launch_halo_t<128, 2, 2, 2, kHaloRing2, false, false, false, false, Tp>(plan, st); break;
+        case 3: launch_halo_t<64, 2, 2, 2, kHaloResidentSlabs, true, true, false, true, Tp>(plan, st); break;
+        case 4: launch_halo_t<64, 2, 1, 2, kHaloRing4, true, false, true, false, Tp>(plan, st); break;
+        case 5: launch_halo_t<128, 2, 1, 2, kHaloRing5, true, false, true, false, Tp>(plan, st); break;
         default: throw std::invalid_argument("tcgen05 halo block: bad variant");
     }
 }
@@ -920,10 +1031,27 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         }
     }
     if (split && !p.tma_store) return nullptr;                       // the split epilogue only stores through shared memory
+    // the resident-weight blocks on CTA pairs (tcgen05.mma.cta_group::2): every CTA loads its half of the rows of a weight slab
+    static const bool pair_on = [] { const char* e = std::getenv("SPB200_PAIR64"); return e ? e[0] == '1' : kHaloPairDefault; }();
+    if (plan->variant == 0 && pair_on && p.n_mma == 64 && num_sms >= 2) {
+        plan->variant = 3;
+        const cuuint32_t hbox[2] = {64, (cuuint32_t)(p.n_mma / 2)};
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)c1.K, (cuuint64_t)N};
+            cuuint64_t str[1] = {(cuuint64_t)c1.K * 2};
+            tc_encode_tiled(&p.tmW1, dt, 2, c1.w, dims, str, hbox);
+        }
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)c2->K, (cuuint64_t)N};
+            cuuint64_t str[1] = {(cuuint64_t)c2->K * 2};
+            tc_encode_tiled(&p.tmW2, dt, 2, c2->w, dims, str, hbox);
+        }
+        plan->grid = 2 * std::max(1, std::min((p.n_super + 1) / 2, num_sms / 2));
+    }
     {
-        static int v_count[3] = {0, 0, 0};
+        static int v_count[6] = {0, 0, 0, 0, 0, 0};
         const char* d = std::getenv("SPB200_HALO_DBG");         // "<variant><index>", e.g. 11 = second plan of variant 1
-        if (d && plan->variant < 3 && d[0] - '0' == plan->variant && v_count[plan->variant]++ == atoi(d + 1)) {
+        if (d && plan->variant < 6 && d[0] - '0' == plan->variant && v_count[plan->variant]++ == atoi(d + 1)) {
             cudaMalloc(&g_halo_dbg, 16 * 8 * sizeof(long long));
             cudaMemset(g_halo_dbg, 0, 16 * 8 * sizeof(long long));
             p.dbg = g_halo_dbg;

@@ -396,3 +396,33 @@ def test_fp16_descriptor_format(engines):
     finally:
         e.set_descriptor_format('fp32')
     assert e.detect(imgs.cuda(), cap)[3].dtype == torch.float32
+
+
+def test_cta_pair_variant_is_bit_identical(tmp_path):
+    """SPB200_PAIR64=1 runs the resident-weight N = 64 blocks (encoder.layer1.*) on CTA pairs (tcgen05.mma.cta_group::2, M = 256
+    instructions issued by the leader): the same products in the same order, so every output must be bit-identical to the default
+    kernel.  The switch is read once per process, hence the subprocesses.  (The pair form is slower - profiles/r02a_pair64_timeline.txt -
+    and off by default.)"""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import spb200\n"
+        "from oracle import weights\n"
+        "img = torch.stack([weights.rand_image(3, 208, 272), weights.shapes_image(5, 208, 272), weights.shapes_image(6, 208, 272)])[:, None].contiguous().cuda()\n"
+        "e = spb200.Engine(0); e.load_checkpoint(%r); e.finalize('fp16'); e.set_params()\n"
+        "prob, desc, logits = e.forward(img)\n"
+        "torch.save({'prob': prob.cpu(), 'desc': desc.cpu(), 'l1a': e.export_activation('l1a', 3).cpu(), 'l1b': e.export_activation('l1b', 3).cpu()}, sys.argv[1])\n"
+    ) % (os.path.join(os.path.dirname(GOLDEN), '..', 'feature-point-cnn_b200'), os.path.join(os.path.dirname(GOLDEN), '..'), CKPT)
+    outs = []
+    for pair in ('0', '1'):
+        env = dict(os.environ)
+        env['SPB200_PAIR64'] = pair
+        f = str(tmp_path / ('out%s.pt' % pair))
+        r = subprocess.run([sys.executable, '-c', code, f], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(torch.load(f))
+    for k in outs[0]:
+        assert outs[0][k].abs().max() > 0
+        assert torch.equal(outs[0][k], outs[1][k]), k
