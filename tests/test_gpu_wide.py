@@ -1,16 +1,19 @@
 """GPU parity on the wide set (run on the B200 box with ``pytest -m gpu``): the CUDA path, called through the C ABI,
 against outputs of THE REFERENCE (tests/golden/forward_wide.npz: keypoints, per-cell heatmap maxima, descriptors) and
-against the oracle's full heatmap.  North-star bars, asserted per image: heatmap max-abs <= 1e-2, keypoints >= 99 %
-identical integer positions where ties and threshold-edge scores are the only allowed differences (every difference is
-traced to such a root cause, _gpu_common.unexplained_differences), descriptor cosine >= 0.999.
+against the oracle's full heatmap.  North-star bars: heatmap max-abs <= 1e-2, keypoints >= 99 % identical integer positions
+where ties and threshold-edge scores are the only allowed differences, descriptor cosine >= 0.999.
 
   * default path (fp16 operands, one MMA per product): moderate checkpoint, 16 + 16 images at 240x320 and 480x640,
-    2 + 2 frames at 1088x1920 (BASELINE config 5).  Eleven mantissa bits put the heatmap's max-abs error at 5e-3 .. 1e-2
-    (the maximum over 10^5 .. 10^6 pixels of an error with sigma ~ 1.5e-3): 67 of the 68 images are under the bar, one
-    sits at 1.03e-2.  The test asserts exactly that (at most one image per family and size over 1e-2, none over 1.25e-2);
-    the first split level (SPB200_SPLIT_LAYER1) brings every image under the bar with margin and is asserted on the same set;
-  * harsh checkpoint (g = 4, d = 8): the split-precision levels (SPB200_SPLIT_LAYER2 and SPB200_SPLIT_DETECTOR) meet the
-    bars; the single-MMA path does not (1.4e-2 .. 2.4e-2) and is reported.
+    2 + 2 frames at 1088x1920 (BASELINE config 5).  Eleven mantissa bits put this path AT the bars, not inside them:
+    heatmap 5e-3 .. 9.7e-3 on 67 of the 68 images and 1.03e-2 on one; keypoints >= 99.67 % on every `shapes` image and every
+    1088x1920 frame, 98.6 .. 99.7 % on the uniform-noise `rand` images (four of the sixteen 240x320 ones below 99 %).  What
+    the tests assert for it: every keypoint difference on every image is traced to a tie or a threshold-edge score
+    (_gpu_common.unexplained_differences) and no image is below 98.5 %; the mean per family and size is >= 99 %; at most one
+    image per family and size exceeds 1e-2 on the heatmap and none 1.25e-2; descriptor cosine >= 0.999 on every image;
+  * first split level (SPB200_SPLIT_LAYER1) on the same images: INSIDE all three bars on every image (heatmap <= 8.5e-3
+    asserted, 7.5e-3 measured; keypoints >= 99 % asserted per image, 99.37 % measured);
+  * harsh checkpoint (g = 4, d = 8): SPB200_SPLIT_LAYER2 and SPB200_SPLIT_DETECTOR meet the bars on every image; the
+    single-MMA path does not (1.4e-2 .. 2.2e-2) and is reported.
 """
 import os
 
@@ -126,7 +129,8 @@ def test_first_split_level_has_margin_on_the_wide_set(size, fam, engines, sds):
     for i, name in enumerate(wide_cases('m', size, fam)):
         if size == 480 and i % 2:
             continue
-        d_cell, d_full, _ = check_case(engines[('m', 'fp16+layer1')], 'm', name, sds['m'], heat_tol=8.5e-3, full_heat=(size == 240))
+        d_cell, d_full, frac = check_case(engines[('m', 'fp16+layer1')], 'm', name, sds['m'], heat_tol=8.5e-3, full_heat=(size == 240))
+        assert frac >= 0.99, (name, frac)
         worst = max(worst, d_cell, d_full or 0.0)
     print('[wide m %s%d fp16+layer1] heatmap max-abs worst %.3e' % (fam, size, worst))
 
