@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         const int ti = row >> 3, tr = row & 7;                 // slow row, pixel within the group
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const int t = T == 2 ? eh : 0;
-        const int nblk = p.n_mma / 32;
+        const int nblk = (p.n_mma + 31) / 32;                  // the last block may be partial (n_mma is a multiple of 16)
         const int blk_lo = T == 2 ? 0 : (eh == 0 ? 0 : (nblk + 1) / 2);
         const int blk_hi = T == 2 ? nblk : (eh == 0 ? (nblk + 1) / 2 : nblk);
         constexpr int kResBlk = N / 32;
@@ -494,6 +494,11 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     bb[4 * e] = f.x; bb[4 * e + 1] = f.y; bb[4 * e + 2] = f.z; bb[4 * e + 3] = f.w;
                 }
                 tmem_ld_wait();
+                if (c0 + 32 > p.n_mma) {                       // columns beyond n_mma were never written by the MMAs: stale tensor memory
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i >= p.n_mma) { r[i] = 0u; bb[i] = 0.f; }
+                }
                 uint32_t y[16];
                 if (SPLIT) {
                     // the 32 fp32 columns of the block become 16 columns of hi pairs + 16 columns of lo pairs, in place
@@ -606,6 +611,11 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
                 }
                 tmem_ld_wait();
+                if (c0 + 32 > p.n_mma) {                       // stale columns beyond n_mma leave as zeros (padding channels stay zero)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c0 + i >= p.n_mma) { r[i] = 0u; v[i] = 0.f; }
+                }
                 if (px.valid || ts) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
@@ -847,7 +857,12 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         return (uint16_t)((vs * kHaloG + vg) * 128 / 16);
     };
 
-    p.n_mma = std::min(N, (real_cout + 31) / 32 * 32);
+    // MMA N: the real output channels rounded up to 32, the epilogues' block width (65 -> 96 for the detector).  Rounding to 16
+    // (80 columns, SPB200_N_MMA16=1; the epilogues mask the unwritten tail of the last block) was measured neutral - detector.0
+    // 87.9 -> 85.8 us, detector.1 67.3 -> 69.1 us: at N <= 128 an M = 128 MMA is bound by its shared-memory operand fetch
+    // ((4 KB of A + 32 N bytes of B) / 128 B per clock: 56 -> 52 clocks), not by the N / 2 clocks of the tensor pipe.
+    static const bool n16 = [] { const char* e = std::getenv("SPB200_N_MMA16"); return e && e[0] == '1'; }();
+    p.n_mma = std::min(N, n16 ? (real_cout + 15) / 16 * 16 : (real_cout + 31) / 32 * 32);
     auto kk_of = [](int real_c, int nchunks) {
         const int in_last = real_c - (nchunks - 1) * 64;
         return std::max(1, std::min(4, (in_last + 15) / 16));

@@ -7,6 +7,8 @@
 //                         (python/src/netutils.py:92-93) + top-k truncation, fused with the last NMS rounds
 //  K6 sample_desc_kernel  bilinear sampling (align_corners=True) + L2 normalisation
 //                         (python/src/netutils.py:103-121), one warp per keypoint, 128-bit loads
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.h"
@@ -293,7 +295,8 @@ void launch_sample_descriptors(const void* map, int map_type, long batch_stride,
     if (D % 4 != 0 || D > 512) throw std::invalid_argument("descriptor dimension must be a multiple of 4, at most 512");
     if (cap <= 0 || B <= 0) return;
     if (map_type != PREC_FP32 && D == 128 && chan_stride == 1 && cell_stride == 128) {
-        dim3 g(kDescBlocksPerImage, B);
+        static const int blocks = [] { const char* e = std::getenv("SPB200_DESC_BLOCKS"); return e ? std::max(1, atoi(e)) : kDescBlocksPerImage; }();
+        dim3 g(blocks, B);
         if (map_type == PREC_FP16) {
             if (out_fp16) launch_pdl(sample_desc128_kernel<__half, true>, g, dim3(256), 0, st, (const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
             else launch_pdl(sample_desc128_kernel<__half, false>, g, dim3(256), 0, st, (const __half*)map, batch_stride, Hc, Wc, W, gtab, cap, count, xy, out);
