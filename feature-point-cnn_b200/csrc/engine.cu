@@ -1044,7 +1044,7 @@ void Engine::restore_prob_map(const float* softmax_nchw, int B, int H, int W, fl
 }
 
 // one table set at a time, rebuilt when the geometry changes (a stream of frames keeps its geometry)
-const int* Engine::preprocess_table(int kind, int h, int w, int H, int W, cudaStream_t st) {
+const int* Engine::preprocess_table(int kind, int h, int w, int H, int W) {
     const int key[5] = {kind, h, w, H, W};
     if (d_pre_tab_ && std::equal(key, key + 5, pre_key_)) return d_pre_tab_;
     std::vector<int> tab((size_t)4 * (H + W), 0);
@@ -1053,7 +1053,6 @@ const int* Engine::preprocess_table(int kind, int h, int w, int H, int W, cudaSt
     SPB_CUDA(cudaDeviceSynchronize());                       // an earlier launch may still read the old table
     cudaFree(d_pre_tab_);
     d_pre_tab_ = dev_upload(tab);
-    (void)st;
     std::copy(key, key + 5, pre_key_);
     return d_pre_tab_;
 }
@@ -1061,14 +1060,14 @@ const int* Engine::preprocess_table(int kind, int h, int w, int H, int W, cudaSt
 void Engine::preprocess_u8(const uint8_t* frames, int B, int h, int w, int C, uint8_t* out, int H, int W, cudaStream_t st) {
     StreamScope scope(this, st);
     if (B <= 0 || h < 2 || w < 2 || H < 1 || W < 1 || (C != 1 && C != 3)) throw std::invalid_argument("preprocess_u8: bad geometry (C must be 1 or 3)");
-    launch_preprocess_u8(frames, B, h, w, C, preprocess_table(0, h, w, H, W, st), out, H, W, st);
+    launch_preprocess_u8(frames, B, h, w, C, preprocess_table(0, h, w, H, W), out, H, W, st);
     ++launches_;
 }
 
 void Engine::preprocess_f32(const float* frames, int B, int h, int w, float* out, int H, int W, cudaStream_t st) {
     StreamScope scope(this, st);
     if (B <= 0 || h < 2 || w < 2 || H < 1 || W < 1) throw std::invalid_argument("preprocess_f32: bad geometry");
-    const int* tab = preprocess_table(1, h, w, H, W, st);
+    const int* tab = preprocess_table(1, h, w, H, W);
     launch_preprocess_f32(frames, B, h, w, tab, reinterpret_cast<const float*>(tab + 2 * (W + H)), out, H, W, st);
     ++launches_;
 }

@@ -229,7 +229,7 @@ private:
     const float* grid_table(int H, int W);
     int* d_pre_tab_ = nullptr;                     // interpolation tables of the frame loaders, per (kind, h, w, H, W)
     int pre_key_[5] = {0, 0, 0, 0, 0};
-    const int* preprocess_table(int kind, int h, int w, int H, int W, cudaStream_t st);
+    const int* preprocess_table(int kind, int h, int w, int H, int W);
     unsigned long long* d_match_ws_ = nullptr;     // [2][B][cap] best keys of the matcher
     size_t match_ws_elems_ = 0;
     void* d_match_tc_ws_ = nullptr;                // operands + norms of the tensor-core matcher
