@@ -177,6 +177,7 @@ private:
     struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; long launches = 0; bool failed = false; };
     std::map<GraphKey, GraphEntry> graphs_;
     bool use_graphs_ = true;
+    bool zero_sum_rounding_ = true;   // SPB200_ROUND_NEAREST=1: plain round-to-nearest of the 16-bit weights
     void clear_graphs();
     void detect_host_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                          float* desc);
