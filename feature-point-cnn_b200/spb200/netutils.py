@@ -59,7 +59,10 @@ def get_points(prob_map, img_h, img_w, settings, engine=None):
 
 
 def get_descriptors(points, descriptors_map, img_h, img_w, settings, engine=None):
-    """python/src/netutils.py:103-121."""
+    """python/src/netutils.py:103-121.  ``points`` are the (3, N) rows x, y, confidence that get_points returns: INTEGER pixel
+    coordinates (the only kind the reference's pipeline produces).  The device kernel samples at integer keypoints through
+    per-column / per-row position tables; fractional coordinates are truncated here and coordinates outside the image are
+    clamped into it by the kernel."""
     c = descriptors_map.shape[1]
     n = points.shape[1]
     if n == 0:
