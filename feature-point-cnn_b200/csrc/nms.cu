@@ -40,40 +40,53 @@ constexpr int kFinMaskWords = 16384;         // undecided-bit mask words per ima
 // ------------------------------------------------------------------------------------------------
 // Round 0
 // ------------------------------------------------------------------------------------------------
-// Candidate-centric: only a few percent of the pixels pass the threshold, so after one dense pass that turns the
-// tile (+ 2R halo) into sortable keys and compacts the candidates of the evaluation region (interior + R), the
-// window scans run per CANDIDATE with early exit on the first stronger neighbour, keepers become bits, and a
-// candidate is suppressed when a keeper bit lies in its window (nine shifted word tests).
+// Dense and separable: a candidate is kept in round 0 when no key of its window is larger and no EQUAL key comes earlier
+// in raster order.  With F = the row maximum over dx in [-R, R], Lf / Rt = the maxima left / right of the centre:
+//     kept  <=>  Lf < key  and  Rt <= key  and  F(rows above) < key  and  F(rows below) <= key.
+// One regular pass (a thread = four neighbouring pixels of a row: three 16-byte loads, ~30 max operations) leaves F of
+// every loaded row in shared memory, a bit per pixel that passes the row test and a bit per candidate; the vertical test
+// then runs only where a row bit is set (2R loads of F).  Keepers are bits; "suppressed" is the keeper mask dilated by R
+// (shifted-word ORs); undecided = candidate and not kept and not suppressed, per 32-pixel word.  No candidate lists, no
+// per-candidate window scans, no divergence on the candidate density.
 // LOGITS: src = detector logits, channels last, `cell_stride` floats per cell (65 real), needs R <= 4 (one halo cell).
+template <int R>
+struct N0Geom {
+    static constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R;      // loaded region (halo 2R)
+    static constexpr int EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;      // region where keepers are evaluated (halo R)
+    static constexpr int KP = 4 * ((LW / 4 + 1) | 1);                 // key row pitch: 16-byte aligned rows, an odd number of 16-byte groups
+    static constexpr int FP = (EW + 3) / 4 * 4;                       // row pitch of F
+    static constexpr int BW = (EW + 31) / 32 + 1;                     // bit words per E row (+1 zero word: funnel reads of word j + 1)
+    static constexpr int kMaxKeep = ((kN0TW + R) / (R + 1) + 1) * ((kN0TH + R) / (R + 1) + 1);   // keepers are > R apart
+    static constexpr int kListWords = kN0TH * kN0TW + 2 * kMaxKeep + 2;   // undecided list + survivor keys: they reuse F
+    static constexpr int kFWords = LH * FP > kListWords ? LH * FP : kListWords;
+    static constexpr size_t kSmem = sizeof(unsigned) * ((size_t)LH * KP + kFWords + 4 * EH * BW) + 16;
+};
+
 template <int R, bool LOGITS>
 __global__ void __launch_bounds__(kN0Threads)
 nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, float thresh, int border, int kcap,
                   unsigned long long* __restrict__ keys, int* __restrict__ counters, unsigned* __restrict__ mask,
                   int mask_w, unsigned* __restrict__ und, unsigned* __restrict__ ukey) {
-    constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R;      // loaded region (halo 2R)
-    constexpr int KP = LW | 1;                                 // odd row pitch of s_key: the eight rows a cell's lanes write fall in different banks
-    constexpr int EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;      // region where keepers are evaluated (halo R)
-    constexpr int KW = (EW + 31) / 32 + 1;                     // keeper bit words per E row (+1 so a 64-bit window read stays inside)
-    constexpr int kMaxKeep = ((kN0TW + R) / (R + 1) + 1) * ((kN0TH + R) / (R + 1) + 1);   // keepers are > R apart
+    using G = N0Geom<R>;
+    constexpr int LW = G::LW, LH = G::LH, EW = G::EW, EH = G::EH, KP = G::KP, FP = G::FP, BW = G::BW, kMaxKeep = G::kMaxKeep;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned* s_key = reinterpret_cast<unsigned*>(smem_raw);   // [LH][KP]   sortable key, 0 = not a candidate
-    unsigned* s_kb = s_key + LH * KP;                          // [EH][KW]   keeper bits, bit ex of row ey
-    unsigned* s_ub = s_kb + EH * KW;                           // [TH][2]    undecided bits of the interior
-    unsigned* s_und = s_ub + kN0TH * 2;                        // [TH*TW]    undecided pixel indices
-    unsigned long long* s_keep = reinterpret_cast<unsigned long long*>(
-        (reinterpret_cast<uintptr_t>(s_und + kN0TH * kN0TW) + 7) & ~(uintptr_t)7);                 // [kMaxKeep] survivor keys
-    unsigned short* s_cand = reinterpret_cast<unsigned short*>(s_keep + kMaxKeep);               // [EH*EW] ey << 8 | ex
-    __shared__ int s_ncand, s_nund, s_nkeep, s_base_und, s_base_keep;
+    unsigned* s_F = s_key + LH * KP;                           // [LH][FP]   row maximum over dx in [-R, R], E columns
+    unsigned* s_cb = s_F + G::kFWords;                         // [EH][BW]   candidate bits, bit ex of row ey
+    unsigned* s_ok = s_cb + EH * BW;                           // [EH][BW]   passes the row test
+    unsigned* s_kb = s_ok + EH * BW;                           // [EH][BW]   keeper bits
+    unsigned* s_hd = s_kb + EH * BW;                           // [EH][BW]   keeper bits dilated along x
+    unsigned* s_und = s_F;                                     // [TH*TW]    undecided pixel indices (after the vertical test F is dead)
+    unsigned long long* s_keep = reinterpret_cast<unsigned long long*>(s_F + kN0TH * kN0TW + (kN0TH * kN0TW & 1));   // [kMaxKeep] survivor keys
+    __shared__ int s_nund, s_nkeep, s_base_und, s_base_keep;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int b = blockIdx.z;
     const int ty0 = blockIdx.y * kN0TH, tx0 = blockIdx.x * kN0TW;
     pdl_trigger();
-    if (tid == 0) { s_ncand = 0; s_nund = 0; s_nkeep = 0; }
-    for (int i = tid; i < EH * KW; i += kN0Threads) s_kb[i] = 0u;
-    for (int i = tid; i < kN0TH * 2; i += kN0Threads) s_ub[i] = 0u;
+    if (tid == 0) { s_nund = 0; s_nkeep = 0; }
+    for (int i = tid; i < 4 * EH * BW; i += kN0Threads) s_cb[i] = 0u;
     pdl_wait();                                                // logits / heatmap of the previous kernel; the lists it appends to
-    if (LOGITS) __syncthreads();                               // the candidate counter is used while the keys are made
 
     // 1. keys of the loaded region
     if (LOGITS) {
@@ -108,42 +121,26 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
             const float l[8] = {la[it].x, la[it].y, la[it].z, la[it].w, lc[it].x, lc[it].y, lc[it].z, lc[it].w};
             float h[8];
             softmax_cell_octet(l, ld[it], j, h);
-            // keys of the lane's pixel row; the candidates of the evaluation region go straight to the list (one
-            // warp prefix sum and one shared atomic per step)
             const int ly = (c / 10) * 8 + j - kOff, lx0 = (c % 10) * 8 - kOff;
-            unsigned flags = 0u;
             if (t < kTasks && ly >= 0 && ly < LH) {
+                unsigned kk[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int lx = lx0 + k;
-                    if (lx >= 0 && lx < LW) {
-                        const bool cand = in[it] && h[k] >= thresh;
-                        s_key[ly * KP + lx] = cand ? sortable_bits(h[k]) : 0u;
-                        if (cand && ly >= R && ly < R + EH && lx >= R && lx < R + EW) flags |= 1u << k;
-                    }
+                for (int k = 0; k < 8; ++k) kk[k] = (in[it] && h[k] >= thresh) ? sortable_bits(h[k]) : 0u;
+                if (kOff == 0) {                                        // R = 4: the ten cells of a row are the loaded row
+                    uint4* d = reinterpret_cast<uint4*>(s_key + ly * KP + lx0);
+                    d[0] = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+                    d[1] = make_uint4(kk[4], kk[5], kk[6], kk[7]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (lx0 + k >= 0 && lx0 + k < LW) s_key[ly * KP + lx0 + k] = kk[k];
                 }
-            }
-            const int mine = __popc(flags);
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total) {
-                int base = 0;
-                if (lane == 31) base = atomicAdd(&s_ncand, total);
-                base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (flags & (1u << k)) s_cand[base++] = (unsigned short)(((ly - R) << 8) | (lx0 + k - R));
             }
         }
     } else {
         // four pixels (one 16-byte load) per thread and step, every load of the thread issued before the first use
         const float* hmap = src + (size_t)b * H * W;
-        constexpr int LQ = (LW + 3) / 4;                       // float4 groups per loaded row
+        constexpr int LQ = LW / 4;                             // float4 groups per loaded row
         constexpr int kIters = (LH * LQ + kN0Threads - 1) / kN0Threads;
         // groups are then 16-byte aligned and never straddle the image edge
         const bool vec_ok = ((2 * R) % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(hmap) & 15) == 0);
@@ -173,95 +170,123 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
             const int i = it * kN0Threads + tid;
             if (i < LH * LQ) {
                 const int ly = i / LQ, lx = (i % LQ) * 4;
-                const float h[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (lx + e < LW) s_key[ly * KP + lx + e] = h[e] >= thresh ? sortable_bits(h[e]) : 0u;
+                *reinterpret_cast<uint4*>(s_key + ly * KP + lx) =
+                    make_uint4(v[it].x >= thresh ? sortable_bits(v[it].x) : 0u, v[it].y >= thresh ? sortable_bits(v[it].y) : 0u,
+                               v[it].z >= thresh ? sortable_bits(v[it].z) : 0u, v[it].w >= thresh ? sortable_bits(v[it].w) : 0u);
             }
         }
     }
     __syncthreads();
 
-    // 1b. (heatmap input) candidates of the evaluation region, compacted with one ballot and one shared atomic per warp
-    // and step
-    for (int i0 = 0; i0 < (LOGITS ? 0 : EH * EW); i0 += kN0Threads) {
-        const int i = i0 + tid;
-        const int ey = i / EW, ex = i - ey * EW;
-        const bool c = i < EH * EW && s_key[(ey + R) * KP + ex + R] != 0u;
-        const unsigned bal = __ballot_sync(0xffffffffu, c);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_ncand, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (c) s_cand[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)((ey << 8) | ex);
-        }
-    }
-    __syncthreads();
-    const int ncand = s_ncand;
-
-    // 2. keeper test per candidate: no stronger key in the window, no equal key earlier in raster order
-    for (int c = tid; c < ncand; c += kN0Threads) {
-        const int ey = s_cand[c] >> 8, ex = s_cand[c] & 255;
-        const unsigned* centre = s_key + (ey + R) * KP + ex + R;
-        const unsigned me = *centre;
-        bool keep = true;
-        for (int dy = -R; dy <= R && keep; ++dy) {
-            const unsigned* row = centre + dy * KP;
+    // 2. row pass: F of every loaded row, candidate bits and row-test bits of the E rows
+    {
+        constexpr int TPR = FP / 4, NV = (4 + 2 * R + 3) / 4;
+        for (int t = tid; t < LH * TPR; t += kN0Threads) {
+            const int ly = t / TPR, ex0 = (t - ly * TPR) * 4;
+            unsigned k[NV * 4];
+            const uint4* kp = reinterpret_cast<const uint4*>(s_key + ly * KP + ex0);
 #pragma unroll
-            for (int dx = -R; dx <= R; ++dx) {
-                const unsigned v = row[dx];
-                if (v > me || (v == me && (dy < 0 || (dy == 0 && dx < 0)))) keep = false;
+            for (int v = 0; v < NV; ++v) {
+                const uint4 q = kp[v];
+                k[4 * v] = q.x; k[4 * v + 1] = q.y; k[4 * v + 2] = q.z; k[4 * v + 3] = q.w;
+            }
+            unsigned f[4], cbits = 0u, okbits = 0u;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                unsigned lf = 0u, rt = 0u;
+#pragma unroll
+                for (int d = 0; d < R; ++d) { lf = max(lf, k[o + d]); rt = max(rt, k[o + R + 1 + d]); }
+                const unsigned c = k[o + R];
+                f[o] = max(max(lf, rt), c);
+                if (c != 0u && ex0 + o < EW) {
+                    cbits |= 1u << o;
+                    if (lf < c && rt <= c) okbits |= 1u << o;
+                }
+            }
+            *reinterpret_cast<uint4*>(s_F + ly * FP + ex0) = make_uint4(f[0], f[1], f[2], f[3]);
+            const int ey = ly - R;
+            if (cbits && ey >= 0 && ey < EH) {
+                atomicOr(&s_cb[ey * BW + (ex0 >> 5)], cbits << (ex0 & 31));
+                if (okbits) atomicOr(&s_ok[ey * BW + (ex0 >> 5)], okbits << (ex0 & 31));
             }
         }
-        if (keep) atomicOr(&s_kb[ey * KW + (ex >> 5)], 1u << (ex & 31));
     }
     __syncthreads();
 
-    // 3. interior candidates: kept / suppressed by a keeper in the window / still undecided
+    // 3. vertical test where the row test passed: nothing as large above, nothing larger below
+    {
+        constexpr int CH = (EW + 15) / 16;                     // 16-pixel chunks per E row
+        for (int t = tid; t < EH * CH; t += kN0Threads) {
+            const int ey = t / CH, ch = t - ey * CH;
+            unsigned bits = (s_ok[ey * BW + (ch >> 1)] >> ((ch & 1) * 16)) & 0xffffu;
+            unsigned keep = 0u;
+            while (bits) {
+                const int bp = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const int ex = ch * 16 + bp;
+                const unsigned c = s_key[(ey + R) * KP + ex + R];
+                bool ok = true;
+#pragma unroll
+                for (int d = 1; d <= R; ++d) {
+                    if (s_F[(ey + R - d) * FP + ex] >= c) ok = false;
+                    if (s_F[(ey + R + d) * FP + ex] > c) ok = false;
+                }
+                if (ok) keep |= 1u << bp;
+            }
+            if (keep) atomicOr(&s_kb[ey * BW + (ch >> 1)], keep << ((ch & 1) * 16));
+        }
+    }
+    __syncthreads();
+
+    // 4. keeper bits dilated along x
+    for (int t = tid; t < EH * (BW - 1); t += kN0Threads) {
+        const int ey = t / (BW - 1), w = t - ey * (BW - 1);
+        const unsigned cur = s_kb[ey * BW + w], prev = w ? s_kb[ey * BW + w - 1] : 0u, next = s_kb[ey * BW + w + 1];
+        unsigned o = cur;
+#pragma unroll
+        for (int d = 1; d <= R; ++d) o |= (cur << d) | (prev >> (32 - d)) | (cur >> d) | (next << (32 - d));
+        s_hd[ey * BW + w] = o;
+    }
+    __syncthreads();
+
+    // 5. interior words: suppressed = dilated along y; undecided = candidate, not kept, not suppressed; lists
     int* cnt = counters + b * kNmsCounters;
     unsigned* uk = ukey + (size_t)b * H * W;
-    for (int c = tid; c < ncand; c += kN0Threads) {
-        const int ey = s_cand[c] >> 8, ex = s_cand[c] & 255;
-        const int iy = ey - R, ix = ex - R;
-        if (iy < 0 || iy >= kN0TH || ix < 0 || ix >= kN0TW) continue;
-        const int gy = ty0 + iy, gx = tx0 + ix;
-        const bool keep = (s_kb[ey * KW + (ex >> 5)] >> (ex & 31)) & 1u;
-        const unsigned pix = (unsigned)(gy * W + gx);
-        const unsigned me = s_key[(ey + R) * KP + ex + R];
-        if (keep) {
+    unsigned* mrow = mask + (size_t)b * H * mask_w;
+    for (int t = tid; t < kN0TH * 2; t += kN0Threads) {
+        const int iy = t >> 1, j = t & 1, ey = iy + R;
+        // the interior starts at bit R of the E row: 32 bits from bit R + 32 j
+        auto ext = [&](const unsigned* a, int row) { return __funnelshift_r(a[row * BW + j], a[row * BW + j + 1], R); };
+        unsigned sup = 0u;
+#pragma unroll
+        for (int dy = -R; dy <= R; ++dy) sup |= ext(s_hd, ey + dy);
+        const unsigned keep = ext(s_kb, ey);
+        const unsigned undw = ext(s_cb, ey) & ~keep & ~sup;
+        const int gy = ty0 + iy, wcol = (tx0 >> 5) + j;
+        if (gy < H && wcol < mask_w) mrow[(size_t)gy * mask_w + wcol] = undw;
+        const unsigned* krow = s_key + (ey + R) * KP + 2 * R + 32 * j;
+        unsigned kb = keep;
+        while (kb) {
+            const int bp = __ffs(kb) - 1;
+            kb &= kb - 1u;
+            const int gx = tx0 + 32 * j + bp;
             if (!(gx < border || gx >= W - border || gy < border || gy >= H - border)) {
                 const int pos = atomicAdd(&s_nkeep, 1);
-                if (pos < kMaxKeep) s_keep[pos] = survivor_key(me, pix);
+                if (pos < kMaxKeep) s_keep[pos] = survivor_key(krow[bp], (unsigned)(gy * W + gx));
             }
-            continue;
         }
-        // window columns ex-R .. ex+R of rows ey-R .. ey+R in E coordinates (keepers are evaluated on the whole E
-        // region because one within R outside the interior can cover an interior pixel)
-        unsigned any = 0u;
-        const int x0 = ex - R;
-#pragma unroll
-        for (int dy = -R; dy <= R; ++dy) {
-            const int yy = ey + dy;
-            if (yy < 0 || yy >= EH) continue;
-            const unsigned* kr = s_kb + yy * KW;
-            const int w0 = x0 >> 5, sh = x0 & 31;
-            const unsigned long long two = (unsigned long long)kr[w0] | ((unsigned long long)kr[w0 + 1] << 32);
-            any |= (unsigned)(two >> sh) & ((1u << (2 * R + 1)) - 1u);
-        }
-        if (!any) {
-            atomicOr(&s_ub[iy * 2 + (ix >> 5)], 1u << (ix & 31));
+        unsigned ub = undw;
+        while (ub) {
+            const int bp = __ffs(ub) - 1;
+            ub &= ub - 1u;
+            const unsigned pix = (unsigned)(gy * W + tx0 + 32 * j + bp);
             s_und[atomicAdd(&s_nund, 1)] = pix;
-            uk[pix] = me;
+            uk[pix] = krow[bp];
         }
     }
     __syncthreads();
 
-    // 4. write out: undecided mask words of every interior row, the two compact lists behind one atomicAdd each
-    unsigned* mrow = mask + (size_t)b * H * mask_w;
-    for (int i = tid; i < kN0TH * 2; i += kN0Threads) {
-        const int gy = ty0 + (i >> 1), wcol = (tx0 >> 5) + (i & 1);
-        if (gy < H && wcol < mask_w) mrow[(size_t)gy * mask_w + wcol] = s_ub[i];
-    }
+    // 6. the two compact lists behind one atomicAdd each
     const int nund = s_nund, nkeep = min(s_nkeep, kMaxKeep);
     if (tid == 0) {
         s_base_und = nund ? atomicAdd(cnt + 1, nund) : 0;
@@ -829,11 +854,7 @@ nms_finish_kernel(int H, int W, int r, int border, int kcap, unsigned long long*
 template <int R, bool LOGITS>
 static void launch_round0_t(const float* src, int cell_stride, int B, int H, int W, float thresh, int border,
                             const NmsWorkspace& ws, cudaStream_t st) {
-    constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R, EW = kN0TW + 2 * R, EH = kN0TH + 2 * R;
-    constexpr int KW = (EW + 31) / 32 + 1;
-    constexpr int kMaxKeep = ((kN0TW + R) / (R + 1) + 1) * ((kN0TH + R) / (R + 1) + 1);
-    const size_t smem = sizeof(unsigned) * ((size_t)LH * (LW | 1) + EH * KW + kN0TH * 2 + kN0TH * kN0TW) + sizeof(unsigned long long) * kMaxKeep +
-                        sizeof(unsigned short) * ((size_t)EH * EW) + 16;
+    const size_t smem = N0Geom<R>::kSmem;
     auto kern = nms_round0_kernel<R, LOGITS>;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((W + kN0TW - 1) / kN0TW, (H + kN0TH - 1) / kN0TH, B);

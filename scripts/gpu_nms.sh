@@ -1,0 +1,13 @@
+#!/bin/bash
+# NMS check: bit-exact tests + detect-path tests + bench profile.  Usage: scripts/gpu_nms.sh tag
+TAG=${1:-nms}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > "$OUT/t_parity.log" 2>&1; echo "parity exit $?"; tail -5 "$OUT/t_parity.log"
+timeout 900 python -m pytest tests/test_gpu_tc.py -m gpu -q -x -k "meets_bars or detect or other_checkpoints" > "$OUT/t_tc.log" 2>&1; echo "tc exit $?"; tail -3 "$OUT/t_tc.log"
+timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-extras --profile-out "$OUT/prof_fp16.json" > "$OUT/bench_fp16.log" 2>&1; echo "bench exit $?"; tail -1 "$OUT/bench_fp16.log" | cut -c1-200
+python - <<PY
+import json
+d=json.load(open('$OUT/prof_fp16.json'))
+print('step ms', d['step_ms_profiled'], 'kp/img', d['keypoints_per_image'])
+for r in d['per_kernel']:
+    print('%-36s %7.3f ms %5.1f%%  %s %s' % (r['kernel'], r['ms'], 100*r['share'], ('%.0f TF/s (%.1f%%)' % (r['tflops'], 100*r['frac_tc_sustained'])) if 'tflops' in r else '', ('%.0f GB/s (%.1f%%)' % (r['gbs'], 100*r['frac_hbm'])) if 'gbs' in r else ''))
+PY
