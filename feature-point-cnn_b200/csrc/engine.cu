@@ -167,6 +167,8 @@ Engine::Engine(int device) : device_(device) {
     use_halo_ = !(nh && nh[0] == '1');
     const char* ns = std::getenv("SPB200_NO_SIDE");
     use_side_ = !(ns && ns[0] == '1');
+    const char* nfh = std::getenv("SPB200_NO_FUSED_HEAT");
+    fused_heat_ = !(nfh && nfh[0] == '1');
     for (int i = 0; i < 3; ++i) {
         SPB_CUDA(cudaStreamCreateWithFlags(&side_stream_[i], cudaStreamNonBlocking));
         SPB_CUDA(cudaEventCreateWithFlags(&side_join_[i], cudaEventDisableTiming));
@@ -244,6 +246,7 @@ void Engine::release_workspace() {
     destroy_plan_cache();
     for (auto& p : buf_) { cudaFree(p); p = nullptr; }
     cudaFree(d_prob_); d_prob_ = nullptr;
+    cudaFree(d_inv_); d_inv_ = nullptr;
     cudaFree(d_planes_); d_planes_ = nullptr;
     cudaFree(d_imgf_); d_imgf_ = nullptr;
     wsB_ = wsH_ = wsW_ = capB_ = 0;
@@ -696,6 +699,7 @@ void Engine::ensure_workspace(int B, int C, int H, int W, cudaStream_t st) {
         SPB_CUDA(cudaMemset(buf_[i], 0, bytes));     // padded channels stay zero forever
     }
     d_prob_ = dev_alloc<float>((size_t)cap * H * W);
+    d_inv_ = dev_alloc<float>((size_t)cap * (H / 8) * (W / 8));
     if (precision_ != PREC_FP32) SPB_CUDA(cudaMalloc(&d_planes_, (size_t)cap * H * W * 2));
     wsB_ = B; wsH_ = H; wsW_ = W; capB_ = cap;
     build_plans();
@@ -854,7 +858,8 @@ double Engine::op_flops(const OpSpec& op) const {
     return 2.0 * rows * k * op.cout_real;
 }
 
-void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, int W, cudaStream_t st) {
+bool Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, int W, cudaStream_t st, float* heat_out) {
+    bool heat_written = false;
     ensure_workspace(B, C, H, W, st);
     if (img_u8 && C != 1) throw std::invalid_argument("8-bit frames must be single-channel (grayscale)");
     const float* img = static_cast<const float*>(img_any);
@@ -926,8 +931,14 @@ void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
                 prof_open(block ? op.name.substr(0, op.name.size() - 6) : op.name,
                           op_flops(op) + (block ? op_flops(ops_[i + 1]) : 0.0), 0.0, st);
             }
-            if (op.halo) launch_halo_tc(op.halo, ls);
-            else launch_block_tc(op.fused, ls);
+            if (op.halo && heat_out && fused_heat_ && op.name == "detector.layer.1.conv1" && tc_halo_heat_capable(op.halo)) {
+                launch_halo_tc_heat(op.halo, heat_out, d_inv_, B, ls);
+                heat_written = true;
+            } else if (op.halo) {
+                launch_halo_tc(op.halo, ls);
+            } else {
+                launch_block_tc(op.fused, ls);
+            }
             if (ls != st) {
                 SPB_CUDA(cudaEventRecord(side_join_[op.side - 1], ls));
                 SPB_CUDA(cudaStreamWaitEvent(st, side_join_[op.side - 1], 0));
@@ -945,6 +956,7 @@ void Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
         prof_close(st);
         ++launches_;
     }
+    return heat_written;
 }
 
 void Engine::forward(const float* img, int B, int C, int H, int W, float* prob, float* desc_nchw, float* logits_nchw,
@@ -1038,14 +1050,25 @@ void Engine::detect_any(const void* img, bool img_u8, int B, int C, int H, int W
 
 void Engine::detect_body(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                          float* desc, float* prob, cudaStream_t st) {
-    run_network(img, img_u8, B, C, H, W, st);
+    // The detector's last block leaves the softmax itself (fused into its epilogue, halo_tc.cu): exp(logit) of the 64 pixel channels
+    // in depth-to-space order and one normaliser per cell - no logits buffer, no heatmap pass, and round 0 of the NMS reads four
+    // bytes per pixel (+ 4 per cell) and multiplies.  A caller who wants the heatmap gets it by one in-place scaling pass.  Where
+    // that block does not run on the haloed-tile kernel (fp32 and split-precision modes, A/B switches) round 0 computes the
+    // softmax values from the logits and the heatmap is written only when the caller wants it.
+    ensure_workspace(B, C, H, W, st);                           // d_prob_ exists before it is handed to the network
+    float* heat = prob ? prob : d_prob_;
+    const bool heat_done = run_network(img, img_u8, B, C, H, W, st, heat);
     const int Hc = H / 8, Wc = W / 8;
-    // the heatmap is written only when the caller wants it: round 0 of the NMS computes the softmax values itself
     static const bool force_heat = [] { const char* e = std::getenv("SPB200_NMS_FROM_HEAT"); return e && e[0] == '1'; }();
-    const bool from_logits = nms_logits_supported(params_.nms_dist) && !force_heat;
-    if (prob || !from_logits) {
+    const bool from_logits = !heat_done && nms_logits_supported(params_.nms_dist) && !force_heat;
+    if (heat_done && prob) {
+        prof_open("heatmap_scale", 0.0, (double)B * H * W * 8, st);
+        launch_heat_scale(prob, d_inv_, B, H, W, st);
+        prof_close(st);
+        ++launches_;
+    } else if (!heat_done && (prob || !from_logits)) {
         prof_open("heatmap", 0.0, (double)B * (65.0 * Hc * Wc * 4 + (double)H * W * 4), st);
-        launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc, prob ? prob : d_prob_, st);
+        launch_heatmap((const float*)buf_[BUF_LOGITS], (long)Hc * Wc * det_c_, 1, det_c_, B, Hc, Wc, heat, st);
         prof_close(st);
         ++launches_;
     }
@@ -1055,8 +1078,9 @@ void Engine::detect_body(const void* img, bool img_u8, int B, int C, int H, int 
     prof_open("nms_round0", 0.0, from_logits ? (double)B * 65.0 * Hc * Wc * 4 : (double)B * H * W * 4, st);
     const bool zero_first = nms_dirty_;
     nms_dirty_ = true;
-    launch_nms_round0(from_logits ? nullptr : (prob ? prob : d_prob_), (const float*)buf_[BUF_LOGITS], det_c_, B, H, W,
-                      params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, zero_first, st);
+    launch_nms_round0(from_logits ? nullptr : heat, (const float*)buf_[BUF_LOGITS], det_c_, B, H, W,
+                      params_.conf_thresh, params_.nms_dist, params_.border_remove, nms_, zero_first, st,
+                      heat_done && !prob ? d_inv_ : nullptr);
     prof_close(st);
     prof_open("nms_finish_sort", 0.0, 0.0, st);
     launch_nms_finish(B, H, W, params_.nms_dist, params_.border_remove, params_.top_k, cap, nms_, count, xy, conf, st);

@@ -162,7 +162,9 @@ private:
     void ensure_nms(int B, int H, int W);
     void release_workspace();
     void release_weights();
-    void run_network(const void* img, bool img_u8, int B, int C, int H, int W, cudaStream_t st);
+    // heat_out: when the detector's last block can (tc_halo_heat_capable) it writes exp(logit) there, depth-to-space, and the
+    // per-cell normaliser to d_inv_ instead of the logits; returns whether it did
+    bool run_network(const void* img, bool img_u8, int B, int C, int H, int W, cudaStream_t st, float* heat_out = nullptr);
     void detect_any(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
                     float* desc, float* prob, cudaStream_t st);
     void detect_body(const void* img, bool img_u8, int B, int C, int H, int W, int cap, int* count, int* xy, float* conf,
@@ -220,6 +222,7 @@ private:
     void destroy_plan_cache();
     std::array<void*, BUF_COUNT> buf_{};
     float* d_prob_ = nullptr;
+    float* d_inv_ = nullptr;      // [capB][H/8][W/8] per-cell softmax normaliser of the fused detector tail
     // nms workspace
     int nmsB_ = 0, nmsH_ = 0, nmsW_ = 0, nmsR_ = -1;
     bool nms_dirty_ = true;       // the NMS counters are not known to be zero (fresh workspace, or a call that did not get through)
@@ -246,6 +249,7 @@ private:
     cudaStream_t side_stream_[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t side_fork_ = nullptr, side_join_[3] = {nullptr, nullptr, nullptr};
     bool use_phases_ = true;      // SPB200_NO_PHASES=1 keeps stride-2 blocks on the per-tap kernel
+    bool fused_heat_ = true;      // SPB200_NO_FUSED_HEAT=1: the detector tail writes logits, the NMS computes the softmax values
     bool use_side_ = true;        // SPB200_NO_SIDE=1 runs the phases one after the other on all SMs
     // The workspace (activations, NMS lists, tables, side streams) is shared by every call: a call enqueued on a stream
     // other than the previous call's first waits for the event the previous call recorded when it finished enqueueing.

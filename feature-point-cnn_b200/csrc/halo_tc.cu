@@ -96,6 +96,9 @@ struct HaloParams {
     int w_bytes;                   // bytes of one weight slab as loaded: n_mma rows x 128 B
     int tma_res;                   // the identity shortcut arrives by TMA (needs tma_store)
     int tma_store;                 // fused variants: the output leaves through shared memory and TMA stores
+    float* heat_inv;               // [B][OH][OW]: 1 / (sum_c exp(l_c) + 1e-5) per cell
+    int heat;                      // detector tail (variant 1): the epilogue stores exp(l_c), c < 64, depth-to-space into the full-resolution
+                                   // map (tmD is then a map of it) and the cell's normaliser into heat_inv: heat = exp * inv
     int split_out;                 // SPLIT kernels: the output is stored as [hi 32 | lo 32] per 32 channels (common.cuh, SegDev)
     long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
 };
@@ -598,6 +601,24 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             if (tr) { mbar_wait(&res_full[ew], rph); rph ^= 1u; }
             const bool dbg_on = p.dbg && blockIdx.x == 0 && warp == 2 + T && lane == 0 && jt < 16;
             if (dbg_on) p.dbg[jt * 8 + 6] = clock64();
+            // detector tail: exp(logit) staged per block, the sums of eight channels kept in the order of softmax_cell.cuh
+            constexpr bool kHeat = N == 128 && FUSED && !WRES && !SPLIT && !PAIR;
+            const bool heat = kHeat && p.heat != 0;
+            float hs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dust = 0.f;
+            // Staging address of half `half` (four pixels) of heat row r of this lane's cell, in the layout of the boxes that leave:
+            // orient 0 (the warp's cells: 8 along x, 4 along y): two boxes {32 px, 8 rows, 4 cell rows} = the x halves;
+            // orient 1 (4 along x, 8 along y): two boxes {32 px, 4 rows, 8 cell rows} = the row halves.  128-byte swizzle.
+            const int cg = lane & 7, cs = lane >> 3;
+            const uint32_t h_box = p.orient == 0 ? (uint32_t)(cg >> 2) * kHaloOutBox : 0u;
+            const uint32_t h_row = p.orient == 0 ? (uint32_t)cs * 8u : (uint32_t)cg * 4u;
+            const uint32_t h_chunk = p.orient == 0 ? 2u * (uint32_t)(cg & 3) : 2u * (uint32_t)cs;
+            // lanes whose chunks would meet in a bank store the two halves of a row in the other order
+            const bool h_swap = p.orient == 0 ? (cg >> 2) != 0 : ((cg >> 1) & 1) != 0;
+            auto heat_addr = [&](int r, uint32_t half) {
+                const uint32_t row = h_row + (uint32_t)(p.orient == 0 ? r : (r & 3));
+                const uint32_t box = p.orient == 0 ? h_box : (uint32_t)(r >> 2) * kHaloOutBox;
+                return stg + box + row * 128u + (((h_chunk + half) ^ (row & 7u)) << 4);
+            };
 #pragma unroll
             for (int blk = 0; blk < kResBlk; ++blk) {
                 if (blk < blk_lo || blk >= blk_hi) continue;
@@ -666,7 +687,27 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                         ++nbox;
                     } else if (ts) {
                         const uint32_t sw = (uint32_t)(lane & 7);
-                        if (p.dst_fp32) {
+                        if (kHeat && heat) {
+                            if (blk < 2) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = expf(v[i]);
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {      // eight channels = one row of the cell, summed in the order of softmax_cell.cuh
+                                    float sg = v[8 * g];
+#pragma unroll
+                                    for (int k = 1; k < 8; ++k) sg += v[8 * g + k];
+                                    hs[(blk & 1) * 4 + g] = sg;
+                                    const int r = 4 * (blk & 1) + g;
+                                    const float4 lo4 = make_float4(v[8 * g], v[8 * g + 1], v[8 * g + 2], v[8 * g + 3]);
+                                    const float4 hi4 = make_float4(v[8 * g + 4], v[8 * g + 5], v[8 * g + 6], v[8 * g + 7]);
+                                    const float4 f0 = h_swap ? hi4 : lo4, f1 = h_swap ? lo4 : hi4;
+                                    st_shared_v4(heat_addr(r, h_swap ? 1u : 0u), __float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f0.z), __float_as_uint(f0.w));
+                                    st_shared_v4(heat_addr(r, h_swap ? 0u : 1u), __float_as_uint(f1.x), __float_as_uint(f1.y), __float_as_uint(f1.z), __float_as_uint(f1.w));
+                                }
+                            } else if (blk == 2) {
+                                dust = expf(v[0]);                     // channel 64: the dustbin only enters the sum
+                            }
+                        } else if (p.dst_fp32) {
                             // one box per block of 32 fp32 channels; the two slots alternate
                             const uint32_t box = stg + (uint32_t)((nbox & 1) * kHaloOutBox);
                             if (nbox >= 2) { if (lane == 0) tma_store_wait_read<1>(); __syncwarp(); }
@@ -725,6 +766,27 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 if (PAIR) pair_arrive_leader(pair_leader_addr(smem_u32(&d2_empty[b])));
                 else mbar_arrive(FUSED ? &d2_empty[b] : &d1_empty[b]);
             }
+            if (kHeat && heat) {
+                // heat = exp(l) / (sum + 1e-5) (python/src/superpoint.py:111-112) = exp(l) * inv: the exponentials leave as they are
+                // and the cell's inv goes to its own small map (the butterfly of softmax_cell.cuh over the eight row sums)
+                hs[0] += dust;
+                const float inv = 1.f / ((((hs[0] + hs[1]) + (hs[2] + hs[3])) + ((hs[4] + hs[5]) + (hs[6] + hs[7]))) + 0.00001f);
+                const int oy = p.orient == 0 ? tc_s + cs : tc_g + cg;
+                const int ox = p.orient == 0 ? tc_g + cg : tc_s + cs;
+                if (tile_ok && oy < p.OH && ox < p.OW) p.heat_inv[((size_t)tc_img * p.OH + oy) * p.OW + ox] = inv;
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0 && tile_ok) {
+                    if (p.orient == 0) {
+                        tma_store_4d(&p.tmD, stg, 8 * tc_g, 0, tc_s, tc_img);
+                        tma_store_4d(&p.tmD, stg + (uint32_t)kHaloOutBox, 8 * tc_g + 32, 0, tc_s, tc_img);
+                    } else {
+                        tma_store_4d(&p.tmD, stg, 8 * tc_s, 0, tc_g, tc_img);
+                        tma_store_4d(&p.tmD, stg + (uint32_t)kHaloOutBox, 8 * tc_s, 4, tc_g, tc_img);
+                    }
+                    tma_store_commit();
+                }
+            }
             if (dbg_on) p.dbg[jt * 8 + 7] = clock64();
         };
         if (!FUSED) {
@@ -765,16 +827,18 @@ struct TcHaloPlan {
     int variant;       // 0: N=64 fused, resident weights; 1: N=128 fused, T=2; 2: N=128 single convolution, T=2;
                        // 3: variant 0 on CTA pairs (tcgen05.mma.cta_group::2); 4 / 5: split precision, N = 64 / 128 fused
     int operand_type, grid;
+    int real_cout;
 };
 
 template <int N, int T, int NBUF, int SA, int SW, bool FUSED, bool WRES, bool SPLIT, bool PAIR, typename Tp>
-static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st) {
+static void launch_halo_t(const TcHaloPlan* plan, cudaStream_t st, const HaloParams* override = nullptr) {
     auto kern = halo_tc_kernel<N, T, NBUF, SA, SW, FUSED, WRES, SPLIT, PAIR, Tp>;
     const size_t smem = (size_t)SA * T * kHaloBufBytes + (size_t)SW * N * 128 + (size_t)T * halo_out_slots(N, SPLIT) * kHaloOutBox + 1024;
     // function attributes are per device: set on every launch (a process may hold engines on several GPUs)
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (PAIR) launch_pdl_cluster(kern, dim3(plan->grid), dim3(halo_threads(T)), smem, st, 2, plan->params);
-    else launch_pdl(kern, dim3(plan->grid), dim3(halo_threads(T)), smem, st, plan->params);
+    const HaloParams& prm = override ? *override : plan->params;
+    if (PAIR) launch_pdl_cluster(kern, dim3(plan->grid), dim3(halo_threads(T)), smem, st, 2, prm);
+    else launch_pdl(kern, dim3(plan->grid), dim3(halo_threads(T)), smem, st, prm);
 }
 
 constexpr int kHaloResidentSlabs = 11;   // variant 0: every slab of a 64-channel block stays in shared memory
@@ -801,6 +865,30 @@ void launch_halo_tc(const TcHaloPlan* plan, cudaStream_t st) {
     if (!plan) throw std::runtime_error("tcgen05 halo block: no plan");
     if (plan->operand_type == PREC_FP16) launch_halo_v<__half>(plan, st);
     else launch_halo_v<__nv_bfloat16>(plan, st);
+}
+
+// The detector's last block (variant 1, 65 real channels, fp32 output through shared memory) can leave the softmax in
+// depth-to-space order instead of the logits - exp(l_c) per pixel and 1 / (sum + 1e-5) per cell, heat = exp * inv -: same kernel,
+// the destination map is the full-resolution map as {x, row within the cell, cell row, image}, and an epilogue warp's 32 cells
+// leave as two boxes of 32 pixels x 32 rows.
+bool tc_halo_heat_capable(const TcHaloPlan* plan) {
+    return plan && plan->variant == 1 && plan->real_cout == 65 && plan->params.dst_fp32 && plan->params.tma_store &&
+           !plan->params.tma_res && plan->params.n_mma >= 80 && plan->params.n_mma <= 96 && plan->params.relu;
+}
+
+void launch_halo_tc_heat(const TcHaloPlan* plan, float* heat_exp, float* heat_inv, int B, cudaStream_t st) {
+    if (!tc_halo_heat_capable(plan)) throw std::runtime_error("tcgen05 halo block: not a detector tail");
+    HaloParams p = plan->params;
+    const cuuint64_t Hc = p.OH, W = 8 * (cuuint64_t)p.OW, H = 8 * Hc;
+    // heatmap as {x, row within the cell, cell row, image}
+    cuuint64_t dims[4] = {W, 8, Hc, (cuuint64_t)B};
+    cuuint64_t str[3] = {W * 4, 8 * W * 4, H * W * 4};
+    cuuint32_t box0[4] = {32, 8, 4, 1}, box1[4] = {32, 4, 8, 1};
+    tc_encode_tiled(&p.tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, heat_exp, dims, str, p.orient == 0 ? box0 : box1);
+    p.heat = 1;
+    p.heat_inv = heat_inv;
+    if (plan->operand_type == PREC_FP16) launch_halo_t<128, 2, 1, 2, kHaloRing1, true, false, false, false, __half>(plan, st, &p);
+    else launch_halo_t<128, 2, 1, 2, kHaloRing1, true, false, false, false, __nv_bfloat16>(plan, st, &p);
 }
 
 void tc_halo_plan_destroy(TcHaloPlan* plan) { delete plan; }
@@ -837,6 +925,7 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     std::memset(&p, 0, sizeof(p));
     const CUtensorMapDataType dt = operand_type == PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     plan->operand_type = operand_type;
+    plan->real_cout = real_cout;
     plan->variant = split ? (N == 64 ? 4 : 5) : (N == 64 ? 0 : (c2 ? 1 : 2));
     const int T = 2;
 

@@ -35,6 +35,10 @@ struct TcHaloPlan;   // stride-1 blocks with 64/128 output channels: haloed acti
 TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operand_type, int real_cout, int num_sms);
 void tc_halo_plan_destroy(TcHaloPlan* plan);
 void launch_halo_tc(const TcHaloPlan* plan, cudaStream_t st);
+// the detector's last block writing the softmax in depth-to-space order instead of the logits: heat_exp [B][8 OH][8 OW] = exp(l_c) of
+// channels 0..63, heat_inv [B][OH][OW] = 1 / (sum over the 65 channels + 1e-5); heatmap = heat_exp * heat_inv of the pixel's cell
+bool tc_halo_heat_capable(const TcHaloPlan* plan);
+void launch_halo_tc_heat(const TcHaloPlan* plan, float* heat_exp, float* heat_inv, int B, cudaStream_t st);
 
 // ---- stem_tc.cu ----------------------------------------------------------------------------------
 struct StemTcPlan;
@@ -67,6 +71,8 @@ void launch_preprocess_f32(const float* src, int B, int h, int w, const int* ita
 // Softmax-with-epsilon over 65 channels, drop the dustbin, depth-to-space (reference
 // python/src/superpoint.py:111-114, python/src/netutils.py:64-75).  logits element (b, c, i, j) is at
 // logits[b*batch_stride + c*chan_stride + (i*Wc + j)*cell_stride].
+// heat[b][y][x] *= inv[b][y / 8][x / 8] in place: the full heatmap from the detector tail's exp / normaliser pair
+void launch_heat_scale(float* heat, const float* inv, int B, int H, int W, cudaStream_t st);
 void launch_heatmap(const float* logits, long batch_stride, long chan_stride, long cell_stride, int B, int Hc, int Wc,
                     float* heat, cudaStream_t st);
 
@@ -96,8 +102,10 @@ struct NmsWorkspace {
 bool nms_logits_supported(int radius);
 // zero_counters: clear the per-image counters first (a memset node); the finish kernel leaves them at zero, so only the
 // first call on a fresh workspace - or the call after a failed one - needs it
+// heat_inv (with heat only, may be null): [B][H/8][W/8], a pixel's value is heat * heat_inv of its cell (the detector tail's fused
+// softmax, launch_halo_tc_heat)
 void launch_nms_round0(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
-                       int border, const NmsWorkspace& ws, bool zero_counters, cudaStream_t st);
+                       int border, const NmsWorkspace& ws, bool zero_counters, cudaStream_t st, const float* heat_inv = nullptr);
 void launch_nms_finish(int B, int H, int W, int radius, int border, int top_k, int cap, const NmsWorkspace& ws, int* count,
                        int* xy, float* conf, cudaStream_t st);
 

@@ -49,6 +49,8 @@ constexpr int kFinMaskWords = 16384;         // undecided-bit mask words per ima
 // (shifted-word ORs); undecided = candidate and not kept and not suppressed, per 32-pixel word.  No candidate lists, no
 // per-candidate window scans, no divergence on the candidate density.
 // LOGITS: src = detector logits, channels last, `cell_stride` floats per cell (65 real), needs R <= 4 (one halo cell).
+// inv (heatmap input only, may be null): [B][H/8][W/8], the value of a pixel is src * inv of its cell - the detector tail's
+// fused softmax leaves exp(l) and the per-cell normaliser separately (halo_tc.cu).
 template <int R>
 struct N0Geom {
     static constexpr int LW = kN0TW + 4 * R, LH = kN0TH + 4 * R;      // loaded region (halo 2R)
@@ -66,7 +68,7 @@ template <int R, bool LOGITS>
 __global__ void __launch_bounds__(kN0Threads)
 nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, float thresh, int border, int kcap,
                   unsigned long long* __restrict__ keys, int* __restrict__ counters, unsigned* __restrict__ mask,
-                  int mask_w, unsigned* __restrict__ und, unsigned* __restrict__ ukey) {
+                  int mask_w, unsigned* __restrict__ und, unsigned* __restrict__ ukey, const float* __restrict__ inv) {
     using G = N0Geom<R>;
     constexpr int LW = G::LW, LH = G::LH, EW = G::EW, EH = G::EH, KP = G::KP, FP = G::FP, BW = G::BW, kMaxKeep = G::kMaxKeep;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -140,40 +142,51 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
     } else {
         // four pixels (one 16-byte load) per thread and step, every load of the thread issued before the first use
         const float* hmap = src + (size_t)b * H * W;
+        const int Wc = W >> 3;
+        const float* ivb = inv ? inv + (size_t)b * (H >> 3) * Wc : nullptr;
         constexpr int LQ = LW / 4;                             // float4 groups per loaded row
         constexpr int kIters = (LH * LQ + kN0Threads - 1) / kN0Threads;
         // groups are then 16-byte aligned and never straddle the image edge
         const bool vec_ok = ((2 * R) % 4 == 0) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(hmap) & 15) == 0);
         float4 v[kIters];
+        int koff[kIters];                                      // s_key offset of the group, -1 past the end
+        // (row, group) of the thread's it-th group without a division per step: i = it * kN0Threads + tid
+        constexpr int kDq = kN0Threads / LQ, kDr = kN0Threads % LQ;
+        const int q0 = tid / LQ, r0 = tid - q0 * LQ;
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
-            const int i = it * kN0Threads + tid;
+            int ly = q0 + it * kDq, lq = r0 + it * kDr;
+#pragma unroll
+            for (int c = 0; c < (it * kDr + LQ - 1) / LQ; ++c)
+                if (lq >= LQ) { lq -= LQ; ++ly; }
+            const int lx = lq * 4;
+            koff[it] = ly < LH ? ly * KP + lx : -1;
             v[it] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);      // outside the image: never a candidate
-            if (i < LH * LQ) {
-                const int ly = i / LQ, lx = (i % LQ) * 4;
+            if (ly < LH) {
                 const int gy = ty0 - 2 * R + ly, gx = tx0 - 2 * R + lx;
                 if (gy >= 0 && gy < H) {
-                    const float* p = hmap + (size_t)gy * W + gx;
+                    const float* p = hmap + ((size_t)gy * W + gx);
+                    const float* ir = ivb ? ivb + (size_t)(gy >> 3) * Wc : nullptr;
                     if (vec_ok) {
-                        if (gx >= 0 && gx < W) v[it] = __ldg(reinterpret_cast<const float4*>(p));
+                        if (gx >= 0 && gx < W) {
+                            v[it] = __ldg(reinterpret_cast<const float4*>(p));
+                            if (ir) { const float s = __ldg(ir + (gx >> 3)); v[it].x *= s; v[it].y *= s; v[it].z *= s; v[it].w *= s; }
+                        }
                     } else {
-                        if (gx >= 0 && gx < W) v[it].x = __ldg(p);
-                        if (gx + 1 >= 0 && gx + 1 < W) v[it].y = __ldg(p + 1);
-                        if (gx + 2 >= 0 && gx + 2 < W) v[it].z = __ldg(p + 2);
-                        if (gx + 3 >= 0 && gx + 3 < W) v[it].w = __ldg(p + 3);
+                        if (gx >= 0 && gx < W) v[it].x = __ldg(p) * (ir ? __ldg(ir + (gx >> 3)) : 1.f);
+                        if (gx + 1 >= 0 && gx + 1 < W) v[it].y = __ldg(p + 1) * (ir ? __ldg(ir + ((gx + 1) >> 3)) : 1.f);
+                        if (gx + 2 >= 0 && gx + 2 < W) v[it].z = __ldg(p + 2) * (ir ? __ldg(ir + ((gx + 2) >> 3)) : 1.f);
+                        if (gx + 3 >= 0 && gx + 3 < W) v[it].w = __ldg(p + 3) * (ir ? __ldg(ir + ((gx + 3) >> 3)) : 1.f);
                     }
                 }
             }
         }
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
-            const int i = it * kN0Threads + tid;
-            if (i < LH * LQ) {
-                const int ly = i / LQ, lx = (i % LQ) * 4;
-                *reinterpret_cast<uint4*>(s_key + ly * KP + lx) =
+            if (koff[it] >= 0)
+                *reinterpret_cast<uint4*>(s_key + koff[it]) =
                     make_uint4(v[it].x >= thresh ? sortable_bits(v[it].x) : 0u, v[it].y >= thresh ? sortable_bits(v[it].y) : 0u,
                                v[it].z >= thresh ? sortable_bits(v[it].z) : 0u, v[it].w >= thresh ? sortable_bits(v[it].w) : 0u);
-            }
         }
     }
     __syncthreads();
@@ -191,14 +204,26 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
                 k[4 * v] = q.x; k[4 * v + 1] = q.y; k[4 * v + 2] = q.z; k[4 * v + 3] = q.w;
             }
             unsigned f[4], cbits = 0u, okbits = 0u;
+            unsigned m4[R == 4 ? 9 : 1];                       // R = 4: maxima of four neighbours by doubling, shared between the outputs
+            if (R == 4) {
+                unsigned m2[11];
+#pragma unroll
+                for (int i = 0; i < 11; ++i) m2[i] = max(k[i], k[i + 1]);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) m4[R == 4 ? i : 0] = (i == 4) ? 0u : max(m2[i], m2[i + 2]);
+            }
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
                 unsigned lf = 0u, rt = 0u;
+                if (R == 4) {
+                    lf = m4[R == 4 ? o : 0]; rt = m4[R == 4 ? o + 5 : 0];
+                } else {
 #pragma unroll
-                for (int d = 0; d < R; ++d) { lf = max(lf, k[o + d]); rt = max(rt, k[o + R + 1 + d]); }
+                    for (int d = 0; d < R; ++d) { lf = max(lf, k[o + d]); rt = max(rt, k[o + R + 1 + d]); }
+                }
                 const unsigned c = k[o + R];
                 f[o] = max(max(lf, rt), c);
-                if (c != 0u && ex0 + o < EW) {
+                if (c != 0u && (FP == EW || ex0 + o < EW)) {
                     cbits |= 1u << o;
                     if (lf < c && rt <= c) okbits |= 1u << o;
                 }
@@ -253,8 +278,9 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
     int* cnt = counters + b * kNmsCounters;
     unsigned* uk = ukey + (size_t)b * H * W;
     unsigned* mrow = mask + (size_t)b * H * mask_w;
-    for (int t = tid; t < kN0TH * 2; t += kN0Threads) {
-        const int iy = t >> 1, j = t & 1, ey = iy + R;
+    for (int t = tid; t < kN0TH * 2 * 4; t += kN0Threads) {
+        // four threads per 32-pixel word, each emits the list entries of eight pixels (the bit loops are the serial part)
+        const int iy = t >> 3, j = (t >> 2) & 1, part = t & 3, ey = iy + R;
         // the interior starts at bit R of the E row: 32 bits from bit R + 32 j
         auto ext = [&](const unsigned* a, int row) { return __funnelshift_r(a[row * BW + j], a[row * BW + j + 1], R); };
         unsigned sup = 0u;
@@ -263,9 +289,10 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
         const unsigned keep = ext(s_kb, ey);
         const unsigned undw = ext(s_cb, ey) & ~keep & ~sup;
         const int gy = ty0 + iy, wcol = (tx0 >> 5) + j;
-        if (gy < H && wcol < mask_w) mrow[(size_t)gy * mask_w + wcol] = undw;
+        if (part == 0 && gy < H && wcol < mask_w) mrow[(size_t)gy * mask_w + wcol] = undw;
         const unsigned* krow = s_key + (ey + R) * KP + 2 * R + 32 * j;
-        unsigned kb = keep;
+        const unsigned slice = 0xffu << (8 * part);
+        unsigned kb = keep & slice;
         while (kb) {
             const int bp = __ffs(kb) - 1;
             kb &= kb - 1u;
@@ -275,7 +302,7 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
                 if (pos < kMaxKeep) s_keep[pos] = survivor_key(krow[bp], (unsigned)(gy * W + gx));
             }
         }
-        unsigned ub = undw;
+        unsigned ub = undw & slice;
         while (ub) {
             const int bp = __ffs(ub) - 1;
             ub &= ub - 1u;
@@ -288,10 +315,8 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
 
     // 6. the two compact lists behind one atomicAdd each
     const int nund = s_nund, nkeep = min(s_nkeep, kMaxKeep);
-    if (tid == 0) {
-        s_base_und = nund ? atomicAdd(cnt + 1, nund) : 0;
-        s_base_keep = nkeep ? atomicAdd(cnt, nkeep) : 0;
-    }
+    if (tid == 0) s_base_und = nund ? atomicAdd(cnt + 1, nund) : 0;          // two warps: the two round trips overlap
+    if (tid == 32) s_base_keep = nkeep ? atomicAdd(cnt, nkeep) : 0;
     __syncthreads();
     unsigned* uout = und + (size_t)b * H * W + s_base_und;
     for (int i = tid; i < nund; i += kN0Threads) uout[i] = s_und[i];
@@ -853,19 +878,20 @@ nms_finish_kernel(int H, int W, int r, int border, int kcap, unsigned long long*
 
 template <int R, bool LOGITS>
 static void launch_round0_t(const float* src, int cell_stride, int B, int H, int W, float thresh, int border,
-                            const NmsWorkspace& ws, cudaStream_t st) {
+                            const NmsWorkspace& ws, cudaStream_t st, const float* inv = nullptr) {
     const size_t smem = N0Geom<R>::kSmem;
     auto kern = nms_round0_kernel<R, LOGITS>;
     SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((W + kN0TW - 1) / kN0TW, (H + kN0TH - 1) / kN0TH, B);
     launch_pdl(kern, grid, dim3(kN0Threads), smem, st, src, cell_stride, H, W, thresh, border, ws.kcap, ws.keys, ws.counters, ws.mask,
-               ws.mask_w, ws.und, ws.ukey);
+               ws.mask_w, ws.und, ws.ukey, inv);
 }
 
 bool nms_logits_supported(int radius) { return radius >= 0 && radius <= 4; }
 
 void launch_nms_round0(const float* heat, const float* logits, int cell_stride, int B, int H, int W, float thresh, int radius,
-                       int border, const NmsWorkspace& ws, bool zero_counters, cudaStream_t st) {
+                       int border, const NmsWorkspace& ws, bool zero_counters, cudaStream_t st, const float* heat_inv) {
+    if (heat_inv && (!heat || H % 8 || W % 8)) throw std::invalid_argument("nms: a normaliser map needs a heatmap of whole cells");
     if (radius < 0 || radius > kNmsMaxR) throw std::invalid_argument("nms_dist must be in [0, 8]");
     if ((long)H * W >= (1l << 31)) throw std::invalid_argument("image too large");
     if (!heat && !(logits && nms_logits_supported(radius))) throw std::invalid_argument("nms: no heatmap given");
@@ -880,15 +906,15 @@ void launch_nms_round0(const float* heat, const float* logits, int cell_stride, 
         }
     } else {
         switch (radius) {
-            case 0: launch_round0_t<0, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
-            case 1: launch_round0_t<1, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
-            case 2: launch_round0_t<2, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
-            case 3: launch_round0_t<3, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
-            case 4: launch_round0_t<4, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
-            case 5: launch_round0_t<5, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
-            case 6: launch_round0_t<6, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
-            case 7: launch_round0_t<7, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
-            default: launch_round0_t<8, false>(heat, 0, B, H, W, thresh, border, ws, st); break;
+            case 0: launch_round0_t<0, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
+            case 1: launch_round0_t<1, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
+            case 2: launch_round0_t<2, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
+            case 3: launch_round0_t<3, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
+            case 4: launch_round0_t<4, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
+            case 5: launch_round0_t<5, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
+            case 6: launch_round0_t<6, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
+            case 7: launch_round0_t<7, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
+            default: launch_round0_t<8, false>(heat, 0, B, H, W, thresh, border, ws, st, heat_inv); break;
         }
     }
 }

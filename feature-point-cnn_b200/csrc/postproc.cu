@@ -85,6 +85,28 @@ void launch_counts_to_host(const int* src, int* dst_pinned, int n, cudaStream_t 
     SPB_CHECK_LAUNCH();
 }
 
+// exp(l) * inv: the multiplication softmax_cell.cuh ends with, so the result equals heatmap_kernel's bit for bit
+__global__ void __launch_bounds__(256) heat_scale_kernel(float* __restrict__ heat, const float* __restrict__ inv, int H, int W, long total4) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;      // four pixels of one row (W is a multiple of 8: one cell)
+    pdl_trigger();
+    pdl_wait();
+    if (i >= total4) return;
+    const int w4 = W / 4;
+    const int x = (int)(i % w4) * 4;
+    const long row = i / w4;
+    const int y = (int)(row % H);
+    const long b = row / H;
+    const float s = __ldg(inv + (b * (H / 8) + (y >> 3)) * (W / 8) + (x >> 3));
+    float4 v = reinterpret_cast<float4*>(heat)[i];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(heat)[i] = v;
+}
+
+void launch_heat_scale(float* heat, const float* inv, int B, int H, int W, cudaStream_t st) {
+    const long total4 = (long)B * H * (W / 4);
+    launch_pdl(heat_scale_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, st, heat, inv, H, W, total4);
+}
+
 void launch_heatmap(const float* logits, long batch_stride, long chan_stride, long cell_stride, int B, int Hc, int Wc,
                     float* heat, cudaStream_t st) {
     dim3 grid((Wc + kHeatCells - 1) / kHeatCells, Hc, B);

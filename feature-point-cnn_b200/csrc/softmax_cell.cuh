@@ -19,9 +19,11 @@ __device__ __forceinline__ void softmax_cell_octet(const float (&l)[8], float l6
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    const float den = s + 0.00001f;
+    // one division per cell: e * (1 / den) is within an ulp of e / den, and every kernel that produces heatmap values
+    // (this helper and the detector's fused epilogue, halo_tc.cu) forms them this way, so they agree bit for bit
+    const float inv = 1.f / (s + 0.00001f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) h[k] = e[k] / den;
+    for (int k = 0; k < 8; ++k) h[k] = e[k] * inv;
 }
 
 }  // namespace spb200
