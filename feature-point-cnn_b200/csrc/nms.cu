@@ -142,8 +142,17 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
     } else {
         // four pixels (one 16-byte load) per thread and step, every load of the thread issued before the first use
         const float* hmap = src + (size_t)b * H * W;
-        const int Wc = W >> 3;
-        const float* ivb = inv ? inv + (size_t)b * (H >> 3) * Wc : nullptr;
+        // per-cell normalisers of the cells the loaded region touches: into shared memory while the pixel loads are in flight
+        constexpr int kIC = LW / 8 + 2;                        // cells per axis (the region need not start on a cell boundary)
+        __shared__ float s_inv[kIC * kIC];
+        const int cy0 = (ty0 - 2 * R) >> 3, cx0 = (tx0 - 2 * R) >> 3;         // arithmetic shifts: floor for the negative halo
+        if (inv) {
+            const int Hc = H >> 3, Wc = W >> 3;
+            for (int i = tid; i < kIC * kIC; i += kN0Threads) {
+                const int cy = cy0 + i / kIC, cx = cx0 + i % kIC;
+                s_inv[i] = (cy >= 0 && cy < Hc && cx >= 0 && cx < Wc) ? __ldg(inv + ((size_t)b * Hc + cy) * Wc + cx) : 0.f;
+            }
+        }
         constexpr int LQ = LW / 4;                             // float4 groups per loaded row
         constexpr int kIters = (LH * LQ + kN0Threads - 1) / kN0Threads;
         // groups are then 16-byte aligned and never straddle the image edge
@@ -161,30 +170,45 @@ nms_round0_kernel(const float* __restrict__ src, int cell_stride, int H, int W, 
                 if (lq >= LQ) { lq -= LQ; ++ly; }
             const int lx = lq * 4;
             koff[it] = ly < LH ? ly * KP + lx : -1;
+            if (ly < LH) {                                     // + the group's cell in s_inv (bits 16-23) and its column within the cell
+                const int gy = ty0 - 2 * R + ly, gx = tx0 - 2 * R + lx;
+                koff[it] |= ((((gy >> 3) - cy0) * kIC + ((gx >> 3) - cx0)) << 16) | ((gx & 7) << 24);
+            }
             v[it] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);      // outside the image: never a candidate
             if (ly < LH) {
                 const int gy = ty0 - 2 * R + ly, gx = tx0 - 2 * R + lx;
                 if (gy >= 0 && gy < H) {
                     const float* p = hmap + ((size_t)gy * W + gx);
-                    const float* ir = ivb ? ivb + (size_t)(gy >> 3) * Wc : nullptr;
                     if (vec_ok) {
-                        if (gx >= 0 && gx < W) {
-                            v[it] = __ldg(reinterpret_cast<const float4*>(p));
-                            if (ir) { const float s = __ldg(ir + (gx >> 3)); v[it].x *= s; v[it].y *= s; v[it].z *= s; v[it].w *= s; }
-                        }
+                        if (gx >= 0 && gx < W) v[it] = __ldg(reinterpret_cast<const float4*>(p));
                     } else {
-                        if (gx >= 0 && gx < W) v[it].x = __ldg(p) * (ir ? __ldg(ir + (gx >> 3)) : 1.f);
-                        if (gx + 1 >= 0 && gx + 1 < W) v[it].y = __ldg(p + 1) * (ir ? __ldg(ir + ((gx + 1) >> 3)) : 1.f);
-                        if (gx + 2 >= 0 && gx + 2 < W) v[it].z = __ldg(p + 2) * (ir ? __ldg(ir + ((gx + 2) >> 3)) : 1.f);
-                        if (gx + 3 >= 0 && gx + 3 < W) v[it].w = __ldg(p + 3) * (ir ? __ldg(ir + ((gx + 3) >> 3)) : 1.f);
+                        if (gx >= 0 && gx < W) v[it].x = __ldg(p);
+                        if (gx + 1 >= 0 && gx + 1 < W) v[it].y = __ldg(p + 1);
+                        if (gx + 2 >= 0 && gx + 2 < W) v[it].z = __ldg(p + 2);
+                        if (gx + 3 >= 0 && gx + 3 < W) v[it].w = __ldg(p + 3);
                     }
+                }
+            }
+        }
+        if (inv) {
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < kIters; ++it) {
+                if (koff[it] < 0) continue;
+                const float* ir = s_inv + ((koff[it] >> 16) & 255);
+                if ((2 * R) % 4 == 0) {                        // groups of four never straddle a cell
+                    const float sc = ir[0];
+                    v[it].x *= sc; v[it].y *= sc; v[it].z *= sc; v[it].w *= sc;
+                } else {
+                    const int c = (koff[it] >> 24) & 7;
+                    v[it].x *= ir[c >> 3]; v[it].y *= ir[(c + 1) >> 3]; v[it].z *= ir[(c + 2) >> 3]; v[it].w *= ir[(c + 3) >> 3];
                 }
             }
         }
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
             if (koff[it] >= 0)
-                *reinterpret_cast<uint4*>(s_key + koff[it]) =
+                *reinterpret_cast<uint4*>(s_key + (koff[it] & 0xffff)) =
                     make_uint4(v[it].x >= thresh ? sortable_bits(v[it].x) : 0u, v[it].y >= thresh ? sortable_bits(v[it].y) : 0u,
                                v[it].z >= thresh ? sortable_bits(v[it].z) : 0u, v[it].w >= thresh ? sortable_bits(v[it].w) : 0u);
         }

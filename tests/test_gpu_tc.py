@@ -426,3 +426,56 @@ def test_cta_pair_variant_is_bit_identical(tmp_path):
     for k in outs[0]:
         assert outs[0][k].abs().max() > 0
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+@pytest.mark.parametrize('shape', [(3, 240, 320), (2, 64, 256), (1, 112, 176)])
+def test_fused_detector_tail_is_bit_identical_to_the_logits_path(shape, monkeypatch):
+    """Default detect path: the detector's last block leaves exp(logit) in depth-to-space order plus one softmax normaliser per
+    cell (halo_tc.cu, fused epilogue) and NMS round 0 multiplies the two; SPB200_NO_FUSED_HEAT=1 (read when an engine is created)
+    writes logits and lets round 0 / heatmap_kernel compute the softmax.  Same arithmetic in the same order: heatmap, keypoints,
+    confidences and descriptors must be bit-identical, with and without the heatmap output, for both tile orientations
+    (64 x 256 is tiled 8 rows x 16 columns), and equal to forward()'s heatmap."""
+    from oracle import weights
+    spb = load_spb()
+    b, h, w = shape
+    img = torch.stack([weights.shapes_image(10 + i, h, w) for i in range(b)])[:, None].contiguous().cuda()
+    outs = []
+    for plain in ('0', '1'):
+        monkeypatch.setenv('SPB200_NO_FUSED_HEAT', plain)
+        e = spb.Engine(0)
+        e.load_checkpoint(CKPT)
+        e.finalize('fp16')
+        e.set_params()
+        cap = e.max_keypoints(h, w)
+        runs = []
+        for rep in range(3):                                          # eager, graph capture, graph replay
+            count, xy, conf, desc, prob = e.detect(img, cap, want_prob=True)
+            count2, xy2, conf2, desc2 = e.detect(img, cap)[:4]
+            runs.append([t.clone() for t in (count, xy, conf, desc, prob, count2, xy2, conf2, desc2)])
+        prob_f = e.forward(img)[0]
+        torch.cuda.synchronize()
+        assert torch.equal(runs[-1][4], prob_f), 'heatmap of detect() and of forward() differ'
+        # an odd NMS radius: round 0's four-pixel groups straddle cells, every pixel looks up its own cell's normaliser
+        e.set_params(nms_dist=3, border_remove=2)
+        odd = [t.clone() for t in e.detect(img, e.max_keypoints(h, w, 3))[:3]]
+        e.set_params()
+        for r in runs[1:]:
+            n = runs[0][0]
+            assert torch.equal(r[0], n) and torch.equal(r[5], n) and torch.equal(r[4], runs[0][4])
+            for i in range(b):
+                k = int(n[i])
+                for a, c in ((1, 6), (2, 7), (3, 8)):
+                    assert torch.equal(r[a][i, :k], runs[0][a][i, :k]) and torch.equal(r[c][i, :k], runs[0][a][i, :k])
+        outs.append([t.cpu() for t in runs[0]] + [t.cpu() for t in odd])
+        e.close()
+    n = outs[0][0]
+    assert int(n.min()) > 0 and torch.equal(n, outs[1][0])
+    assert torch.equal(outs[0][4], outs[1][4]), 'heatmaps differ'
+    for i in range(b):
+        k = int(n[i])
+        for a in (1, 2, 3):
+            assert torch.equal(outs[0][a][i, :k], outs[1][a][i, :k])
+    assert torch.equal(outs[0][9], outs[1][9])
+    for i in range(b):
+        k = int(outs[0][9][i])
+        assert k > 0 and torch.equal(outs[0][10][i, :k], outs[1][10][i, :k]) and torch.equal(outs[0][11][i, :k], outs[1][11][i, :k])
