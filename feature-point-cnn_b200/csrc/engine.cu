@@ -167,6 +167,8 @@ Engine::Engine(int device) : device_(device) {
     use_halo_ = !(nh && nh[0] == '1');
     const char* ns = std::getenv("SPB200_NO_SIDE");
     use_side_ = !(ns && ns[0] == '1');
+    const char* nfp = std::getenv("SPB200_NO_FUSED_PLANES");
+    fused_planes_ = !(nfp && nfp[0] == '1');
     const char* nfh = std::getenv("SPB200_NO_FUSED_HEAT");
     fused_heat_ = !(nfh && nfh[0] == '1');
     for (int i = 0; i < 3; ++i) {
@@ -875,20 +877,22 @@ bool Engine::run_network(const void* img_any, bool img_u8, int B, int C, int H, 
     }
     // gray-folded stem: 49 MACs per output (the reference's 3-channel stem does 147 on replicated input)
     const bool planes = precision_ != PREC_FP32 && C == 1 && use_planes_ && !wide_stem;
-    if (planes) {
+    // fp32 frames feed the plane-fed stem directly (its shifter warps convert on the way); 8-bit frames go through the plane pass
+    const bool direct = planes && !img_u8 && fused_planes_ && (reinterpret_cast<uintptr_t>(img_any) & 15) == 0;
+    if (planes && !direct) {
         prof_open("image_planes", 0.0, (double)B * H * W * ((img_u8 ? 1 : 4) + 2), st);
         launch_planes(img_any, img_u8 ? 1 : 0, d_planes_, precision_, B, H, W, st);
         prof_close(st);
         ++launches_;
     }
     prof_open("stem_pool", 2.0 * B * (H / 2) * (W / 2) * 64.0 * 49.0 * C,
-              (double)B * C * H * W * (planes ? 2 : 4) + (double)B * (H / 4) * (W / 4) * 64 * (precision_ == PREC_FP32 ? 4 : 2), st);
+              (double)B * C * H * W * (planes && !direct ? 2 : 4) + (double)B * (H / 4) * (W / 4) * 64 * (precision_ == PREC_FP32 ? 4 : 2), st);
     if (precision_ == PREC_FP32)
         launch_stem_pool(img, B, C, H, W, d_stem_w_[C == 1 ? 0 : 1], d_stem_b_, buf_[BUF_POOL], precision_, st);
     else if (wide_stem)
         launch_stem_wide(stem_plan_[C == 1 ? 0 : 1], img, buf_[BUF_POOL], B, H, W, st);
     else if (planes)
-        launch_stem_planes(stem_planes_, d_planes_, buf_[BUF_POOL], B, H, W, st);
+        launch_stem_planes(stem_planes_, direct ? img_any : d_planes_, direct ? 1 : 0, buf_[BUF_POOL], B, H, W, st);
     else
         launch_stem_tc(stem_plan_[C == 1 ? 0 : 1], img, buf_[BUF_POOL], B, H, W, st);
     prof_close(st);

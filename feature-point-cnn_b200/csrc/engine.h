@@ -249,6 +249,7 @@ private:
     cudaStream_t side_stream_[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t side_fork_ = nullptr, side_join_[3] = {nullptr, nullptr, nullptr};
     bool use_phases_ = true;      // SPB200_NO_PHASES=1 keeps stride-2 blocks on the per-tap kernel
+    bool fused_planes_ = true;    // SPB200_NO_FUSED_PLANES=1: fp32 frames go through the plane pass like 8-bit ones
     bool fused_heat_ = true;      // SPB200_NO_FUSED_HEAT=1: the detector tail writes logits, the NMS computes the softmax values
     bool use_side_ = true;        // SPB200_NO_SIDE=1 runs the phases one after the other on all SMs
     // The workspace (activations, NMS lists, tables, side streams) is shared by every call: a call enqueued on a stream

@@ -55,7 +55,8 @@ StemPlanesPlan* stem_planes_plan_create(const void* w16, const float* bias, int 
 void stem_planes_plan_destroy(StemPlanesPlan* plan);
 // img: [B][H][W] fp32 in [0,1] (img_is_u8 = 0) or 8-bit (1) -> planes [B][2][H/2][W] 16-bit, value x255
 void launch_planes(const void* img, int img_is_u8, void* planes, int operand_type, int B, int H, int W, cudaStream_t st);
-void launch_stem_planes(StemPlanesPlan* plan, const void* planes, void* dst, int B, int H, int W, cudaStream_t st);
+// src: the planes (src_is_f32 = 0) or the fp32 image itself (1, 16-byte aligned): the kernel then converts on the way, no plane pass
+void launch_stem_planes(StemPlanesPlan* plan, const void* src, int src_is_f32, void* dst, int B, int H, int W, cudaStream_t st);
 
 // ---- preproc.cu ----------------------------------------------------------------------------------
 // The frame loaders of the two demos on the device (reference cpp/src/camera.cc:12-23, python/src/inference.py:72-85).

@@ -39,13 +39,17 @@ constexpr int kSpStage = 8 * kSpCopy;            // 4 phases x 2 parities
 constexpr int kSpX = 32 * 16 * 128;              // x-pooled rows: [conv row][pooled px 16][64 ch] 16-bit
 constexpr int kSpRawPlane = 44 * 128;             // 35 rows x 160 B of one parity plane as loaded, padded to 128 B
 constexpr int kSpRawStage = 2 * kSpRawPlane;
+constexpr int kSpRawPlaneF = 88 * 128;            // the same patch of an fp32 image (35 rows x 320 B): no plane pass, the shifters convert
+constexpr int kSpRawStageF = 2 * kSpRawPlaneF;
 constexpr int kSpShiftWarps = 2;
 constexpr int kSpThreads = (9 + kSpShiftWarps) * 32;
 constexpr int kSpSmem = 16384 + 2 * kSpStage + 2 * kSpRawStage + kSpX + 1024;
+constexpr int kSpSmemF = 16384 + 2 * kSpStage + 2 * kSpRawStageF + kSpX + 1024;
 
 struct StemPlanesParams {
     CUtensorMap tmW;          // [64 cout][128] K-major 16-bit: hi | lo, 128B-swizzled boxes of 64
-    CUtensorMap tmI;          // planes [2B][H/2][W] 16-bit, box 80 x 35 x 1, no swizzle
+    CUtensorMap tmI;          // planes [2B][H/2][W] 16-bit, box 80 x 35 x 1, no swizzle; F32SRC: the image as {W, row parity, H/2, B} fp32,
+                              // box 80 x 1 x 35 x 1
     const float* bias;        // [64]
     void* dst;                // NHWC [B][PH][PW][64] 16-bit
     int PH, PW;
@@ -90,8 +94,12 @@ __device__ __forceinline__ void tma_load_3d_a(uint32_t dst, const CUtensorMap* m
         : "memory");
 }
 
-template <typename T>
+// F32SRC: the raw patches come from the fp32 image itself (row parity is a dimension of the tensor map) and the shifter warps
+// do the plane pass's conversion - pixel x 255 rounded to 16 bits, the same two operations - on the way: five 16-byte loads,
+// 14 multiplications and seven conversions per 16-byte chunk of the four copies instead of 3 loads and 7 funnel shifts.
+template <typename T, bool F32SRC>
 __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid_constant__ StemPlanesParams p) {
+    constexpr int kRawPlane = F32SRC ? kSpRawPlaneF : kSpRawPlane, kRawStage = 2 * kRawPlane;
     constexpr uint32_t kIdesc = (1u << 4) | (OperandFmt<T>::value << 7) | (OperandFmt<T>::value << 10) |
                                 ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     extern __shared__ uint8_t dyn_smem[];
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
     uint8_t* s_w = base;                         // hi [64][128 B], lo [64][128 B] (swizzled by TMA)
     uint8_t* s_cp = s_w + 16384;                 // [2 stages][4 phases][odd rows, even rows][35 rows][128 B]: the A operand
     uint8_t* s_raw = s_cp + 2 * kSpStage;        // [2 stages][odd rows, even rows][35 rows][160 B] as loaded by TMA
-    uint8_t* s_x = s_raw + 2 * kSpRawStage;      // [32 conv rows][16 pooled px][128 B], 16-byte chunks XORed with (px >> 1)
+    uint8_t* s_x = s_raw + 2 * kRawStage;        // [32 conv rows][16 pooled px][128 B], 16-byte chunks XORed with (px >> 1)
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid / 32, 0), lane = tid % 32;
     const int PH = p.PH, PW = p.PW, CH = 2 * PH, CW = 2 * PW;
@@ -136,13 +144,18 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
                 const int b = tile / p.tiles_per_img, tt = tile % p.tiles_per_img;
                 const int p0 = (tt / p.tiles_x) * kSpP, q0 = (tt % p.tiles_x) * kSpP;
                 const uint32_t bar = smem_u32(&bar_rfull[stage]);
-                const uint32_t dst = raw_addr + stage * kSpRawStage;
+                const uint32_t dst = raw_addr + stage * kRawStage;
                 // TMA start columns must be 16-byte aligned: the patch starts at the multiple of 8 below 4 q0 - 5
                 const int xs = 4 * q0 - 8;                       // q0 even: 4 q0 - 5 - 3; q0 odd: 4 q0 - 5 - 7 = 4 q0 - 12
-                mbar_expect_tx_a(bar, 2 * kSpRows * 160);
+                mbar_expect_tx_a(bar, 2 * kSpRows * (F32SRC ? 320 : 160));
                 // odd image rows from y2 = cy0 - 2, even rows from y2 = cy0 - 1, with cy0 = 2 p0 - 1
-                tma_load_3d_a(dst, &p.tmI, bar, xs - 4 * (q0 & 1), 2 * p0 - 3, 2 * b + 1);
-                tma_load_3d_a(dst + kSpRawPlane, &p.tmI, bar, xs - 4 * (q0 & 1), 2 * p0 - 2, 2 * b);
+                if (F32SRC) {
+                    tma_load_4d_a(dst, &p.tmI, bar, xs - 4 * (q0 & 1), 1, 2 * p0 - 3, b);
+                    tma_load_4d_a(dst + kRawPlane, &p.tmI, bar, xs - 4 * (q0 & 1), 0, 2 * p0 - 2, b);
+                } else {
+                    tma_load_3d_a(dst, &p.tmI, bar, xs - 4 * (q0 & 1), 2 * p0 - 3, 2 * b + 1);
+                    tma_load_3d_a(dst + kRawPlane, &p.tmI, bar, xs - 4 * (q0 & 1), 2 * p0 - 2, 2 * b);
+                }
             };
             mbar_expect_tx(&bar_w, 16384);
             tma_load_2d(s_w, &p.tmW, &bar_w, 0, 0);
@@ -202,21 +215,35 @@ __global__ void __launch_bounds__(kSpThreads, 1) stem_planes_kernel(const __grid
             const int c0 = ((tt % p.tiles_x) & 1) ? 3 : 1;               // (o0 - 1) / 2; q0 = 15 tx has the parity of tx
             mbar_wait(&bar_rfull[stage], par);
             if (it >= 2) mbar_wait(&bar_cempty[stage], par ^ 1u);        // the MMAs of tile it-2 have read the copies
-            const uint8_t* raw = s_raw + stage * kSpRawStage;
+            const uint8_t* raw = s_raw + stage * kRawStage;
             uint8_t* cp = s_cp + stage * kSpStage;
             for (int i = st; i < 2 * kSpRows * 8; i += 32 * kSpShiftWarps) {
                 const int m = i & 7, row = i >> 3;
                 const int pl = row >= kSpRows ? 1 : 0, r = row - pl * kSpRows;
-                const uint4* src = reinterpret_cast<const uint4*>(raw + pl * kSpRawPlane + r * 160 + m * 16);
-                const uint4 a = src[0], bq = src[1], cq = src[2];
-                const uint32_t R[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, cq.x, cq.y, cq.z, cq.w};
                 uint32_t F[7];
-                if (c0 == 1) {
+                if (F32SRC) {
+                    // pixels 8m + o0 .. 8m + o0 + 13 of the raw row: with the first load at pixel 8m (o0 = 3) or 8m + 4 (o0 = 7) they
+                    // are elements 3 .. 16 of five 16-byte loads
+                    const float4* src = reinterpret_cast<const float4*>(raw + pl * kRawPlane + r * 320) + 2 * m + (c0 == 3 ? 1 : 0);
+                    float f[20];
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) F[k] = __funnelshift_r(R[1 + k], R[2 + k], 16);
+                    for (int k = 0; k < 5; ++k) {
+                        const float4 q = src[k];
+                        f[4 * k] = q.x; f[4 * k + 1] = q.y; f[4 * k + 2] = q.z; f[4 * k + 3] = q.w;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) F[k] = pack2<T>(f[3 + 2 * k] * 255.f, f[4 + 2 * k] * 255.f);
                 } else {
+                    const uint4* src = reinterpret_cast<const uint4*>(raw + pl * kRawPlane + r * 160 + m * 16);
+                    const uint4 a = src[0], bq = src[1], cq = src[2];
+                    const uint32_t R[12] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w, cq.x, cq.y, cq.z, cq.w};
+                    if (c0 == 1) {
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) F[k] = __funnelshift_r(R[3 + k], R[4 + k], 16);
+                        for (int k = 0; k < 7; ++k) F[k] = __funnelshift_r(R[1 + k], R[2 + k], 16);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) F[k] = __funnelshift_r(R[3 + k], R[4 + k], 16);
+                    }
                 }
                 uint8_t* dst = cp + pl * kSpCopy + r * 128 + m * 16;
 #pragma unroll
@@ -322,7 +349,7 @@ struct StemPlanesPlan {
     StemPlanesParams params;
     int operand_type, num_sms;
     const void* planes = nullptr;     // what tmI was encoded for
-    int B = 0, H = 0, W = 0;
+    int B = 0, H = 0, W = 0, f32 = -1;
 };
 
 static void encode_tiled_plain(CUtensorMap* map, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
@@ -342,14 +369,23 @@ void launch_planes(const void* img, int img_is_u8, void* planes, int operand_typ
     }
 }
 
-void launch_stem_planes(StemPlanesPlan* plan, const void* planes, void* dst, int B, int H, int W, cudaStream_t st) {
+// src: the 16-bit parity planes of launch_planes (src_is_f32 = 0), or the fp32 image [B][H][W] itself (1; 16-byte aligned)
+void launch_stem_planes(StemPlanesPlan* plan, const void* src, int src_is_f32, void* dst, int B, int H, int W, cudaStream_t st) {
     const CUtensorMapDataType dt = plan->operand_type == PREC_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    if (plan->planes != planes || plan->B != B || plan->H != H || plan->W != W) {
-        cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)(H / 2), (cuuint64_t)2 * B};
-        cuuint64_t str[2] = {(cuuint64_t)W * 2, (cuuint64_t)(H / 2) * W * 2};
-        cuuint32_t box[3] = {80, (cuuint32_t)kSpRows, 1};
-        encode_tiled_plain(&plan->params.tmI, dt, 3, planes, dims, str, box);
-        plan->planes = planes; plan->B = B; plan->H = H; plan->W = W;
+    if (plan->planes != src || plan->B != B || plan->H != H || plan->W != W || plan->f32 != src_is_f32) {
+        if (src_is_f32) {
+            if (reinterpret_cast<uintptr_t>(src) & 15) throw std::invalid_argument("stem: the fp32 image must be 16-byte aligned");
+            cuuint64_t dims[4] = {(cuuint64_t)W, 2, (cuuint64_t)(H / 2), (cuuint64_t)B};
+            cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * 8, (cuuint64_t)H * W * 4};
+            cuuint32_t box[4] = {80, 1, (cuuint32_t)kSpRows, 1};
+            encode_tiled_plain(&plan->params.tmI, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, src, dims, str, box);
+        } else {
+            cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)(H / 2), (cuuint64_t)2 * B};
+            cuuint64_t str[2] = {(cuuint64_t)W * 2, (cuuint64_t)(H / 2) * W * 2};
+            cuuint32_t box[3] = {80, (cuuint32_t)kSpRows, 1};
+            encode_tiled_plain(&plan->params.tmI, dt, 3, src, dims, str, box);
+        }
+        plan->planes = src; plan->B = B; plan->H = H; plan->W = W; plan->f32 = src_is_f32;
     }
     StemPlanesParams p = plan->params;
     p.dst = dst;
@@ -358,14 +394,14 @@ void launch_stem_planes(StemPlanesPlan* plan, const void* planes, void* dst, int
     p.tiles_per_img = p.tiles_x * ((p.PH + kSpP - 1) / kSpP);
     p.total_tiles = p.tiles_per_img * B;
     const int grid = std::min(p.total_tiles, plan->num_sms);
+    auto go = [&](auto kern, int smem) {
+        SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        launch_pdl(kern, dim3(grid), dim3(kSpThreads), (size_t)smem, st, p);
+    };
     if (plan->operand_type == PREC_FP16) {
-        auto kern = stem_planes_kernel<__half>;
-        SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
-        launch_pdl(kern, dim3(grid), dim3(kSpThreads), (size_t)kSpSmem, st, p);
+        if (src_is_f32) go(stem_planes_kernel<__half, true>, kSpSmemF); else go(stem_planes_kernel<__half, false>, kSpSmem);
     } else {
-        auto kern = stem_planes_kernel<__nv_bfloat16>;
-        SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem));
-        launch_pdl(kern, dim3(grid), dim3(kSpThreads), (size_t)kSpSmem, st, p);
+        if (src_is_f32) go(stem_planes_kernel<__nv_bfloat16, true>, kSpSmemF); else go(stem_planes_kernel<__nv_bfloat16, false>, kSpSmem);
     }
 }
 
