@@ -465,7 +465,9 @@ TcBlockPlan* tc_block_plan_create(const ConvDev& c1, const ConvDev* c2, int oper
             throw std::invalid_argument("tcgen05 block: stride must be 1 or 2");
         }
     }
-    if (ksteps * 64 != c1.K) throw std::invalid_argument("tcgen05 block: K does not match the segments");
+    int ktail = 0;                                            // packed K tails follow the segments (common.cuh, SegDev): unused here
+    for (int s = 0; s < c1.nseg; ++s) ktail += c1.seg[s].koff_tail > 0 ? 3 : 0;
+    if ((ksteps + ktail) * 64 != c1.K) throw std::invalid_argument("tcgen05 block: K does not match the segments");
     {
         cuuint64_t dims[2] = {(cuuint64_t)c1.K, (cuuint64_t)N};
         cuuint64_t str[1] = {(cuuint64_t)c1.K * 2};

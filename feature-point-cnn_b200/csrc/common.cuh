@@ -85,6 +85,11 @@ struct SegDev {
     // weights are exact in 16 bits).
     int split;
     int koff_lo;
+    // Packed K tail (tensor-core path, 3x3 segments whose last 64-channel chunk holds at most 16 real channels - the detector's
+    // 65): > 0 = first K index of three extra 64-value slabs, one per filter row dy = -1, 0, 1, whose K = 16 step kk holds the
+    // weights of tap (dy, dx = kk - 1) for the chunk's first 16 channels - the same values as in the main range.  A kernel may
+    // run the tail as three slabs of three MMAs (A views one pixel apart) instead of nine slabs of one.  0: none.
+    int koff_tail;
     int8_t dy[kMaxTaps], dx[kMaxTaps];
 };
 

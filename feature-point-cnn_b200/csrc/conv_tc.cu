@@ -321,7 +321,9 @@ TcConvPlan* tc_plan_create(const ConvDev& c, int operand_type) {
             throw std::invalid_argument("tcgen05 conv: stride must be 1 or 2");
         }
     }
-    if (ksteps * 64 != c.K) throw std::invalid_argument("tcgen05 conv: K does not match the segments");
+    int ktail = 0;                                            // packed K tails follow the segments (common.cuh, SegDev): unused here
+    for (int s = 0; s < c.nseg; ++s) ktail += c.seg[s].koff_tail > 0 ? 3 : 0;
+    if ((ksteps + ktail) * 64 != c.K) throw std::invalid_argument("tcgen05 conv: K does not match the segments");
     p.ksteps = ksteps;
     {
         cuuint64_t dims[2] = {(cuuint64_t)c.K, (cuuint64_t)c.cout_pad};

@@ -508,6 +508,20 @@ void Engine::build_ops() {
             if (bufspec_[s.src_buf].split != any_split) throw std::runtime_error("internal: mixed split / plain sources in " + op.name);
         op.K_main = K;
         op.K = any_split ? 2 * K : K;        // split sources: the lo-weight ranges mirror the main ranges
+        // packed K tail (common.cuh, SegDev): a full 3x3 segment whose last chunk holds 1..16 real channels
+        for (auto& s : op.segs) {
+            const int cpad = bufspec_[s.src_buf].stored();
+            const int in_last = s.cin_real - (cpad / 64 - 1) * 64;
+            bool full3x3 = s.taps.size() == 9;
+            for (size_t t = 0; t < s.taps.size() && full3x3; ++t)
+                full3x3 = s.taps[t].dy == (int)t / 3 - 1 && s.taps[t].dx == (int)t % 3 - 1;
+            s.koff_tail = 0;
+            if (precision_ != PREC_FP32 && !any_split && full3x3 && cpad >= 128 && cpad % 64 == 0 && in_last >= 1 && in_last <= 16 &&
+                s.view == 1 && s.stride == 1) {
+                s.koff_tail = op.K;
+                op.K += 3 * 64;
+            }
+        }
         K = op.K;
         std::vector<float> w32((size_t)K * op.cout_pad, 0.f);
         int koff = 0;
@@ -577,6 +591,20 @@ void Engine::build_ops() {
                         }
                     }
                 }
+            }
+        }
+        // the packed K tails repeat the (rounded) weights of the main range
+        {
+            int k0 = 0;
+            for (auto& sg : op.segs) {
+                const int cpad = bufspec_[sg.src_buf].stored();
+                if (sg.koff_tail > 0)
+                    for (int t = 0; t < 9; ++t)
+                        for (int i = 0; i < 16; ++i)
+                            for (int co = 0; co < op.cout_pad; ++co)
+                                w32[(size_t)(sg.koff_tail + (t / 3) * 64 + (t % 3) * 16 + i) * op.cout_pad + co] =
+                                    w32[(size_t)(k0 + t * cpad + (cpad - 64) + i) * op.cout_pad + co];
+                k0 += (int)sg.taps.size() * cpad;
             }
         }
         if (precision_ == PREC_FP32) {
@@ -803,6 +831,7 @@ ConvDev Engine::make_conv_dev(const OpSpec& op) const {
         sd.ntaps = (int)s.taps.size();
         sd.stride = s.stride;
         sd.koff = koff;
+        sd.koff_tail = s.koff_tail;
         for (int t = 0; t < sd.ntaps; ++t) { sd.dy[t] = (int8_t)s.taps[t].dy; sd.dx[t] = (int8_t)s.taps[t].dx; }
         koff += sd.ntaps * bs.stored();
     }

@@ -40,6 +40,7 @@ struct SegSpec {
     int stride;
     std::vector<TapSpec> taps;
     int view = 1, vy = 0, vx = 0;   // view > 1: the segment reads the pixels (view*y + vy, view*x + vx) of its source
+    int koff_tail = 0;              // > 0: first K index of the packed K tail (common.cuh, SegDev)
 };
 
 struct OpSpec {

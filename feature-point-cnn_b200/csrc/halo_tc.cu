@@ -65,12 +65,15 @@ constexpr int kHaloOutBox = 16384;                          // one staged output
 //   bits 38-40  nkk     K = 16 MMA steps in this slab (1..4)
 //   bit  41     first slab of an activation chunk (wait for it);  bit 42  last slab using it (release it)
 //   bit  43     acc0    accumulate flag of the first MMA of the slab
+//   bits 44-45  astep   what the A view advances by per K = 16 step: 0 = 32 B (the next 16 channels of the same pixels),
+//                       1 = one pixel along the group axis, 2 = one haloed row - the packed K tail (common.cuh, SegDev): the
+//                       K steps of such a slab are the taps of one filter row over the chunk's first 16 channels
 //   bits 48-59  kcoord  K coordinate / 64 in the weight tensor (W1 for gemm 0, W2 otherwise)
 using HaloStep = unsigned long long;
 __host__ __device__ constexpr HaloStep halo_step(unsigned a_lo, unsigned w_lo, unsigned slot, unsigned gemm, unsigned nkk,
-                                                 unsigned first, unsigned last, unsigned acc0, unsigned kcoord) {
+                                                 unsigned first, unsigned last, unsigned acc0, unsigned kcoord, unsigned astep = 0) {
     return (HaloStep)a_lo | ((HaloStep)w_lo << 16) | ((HaloStep)slot << 32) | ((HaloStep)gemm << 36) | ((HaloStep)nkk << 38) |
-           ((HaloStep)first << 41) | ((HaloStep)last << 42) | ((HaloStep)acc0 << 43) | ((HaloStep)kcoord << 48);
+           ((HaloStep)first << 41) | ((HaloStep)last << 42) | ((HaloStep)acc0 << 43) | ((HaloStep)astep << 44) | ((HaloStep)kcoord << 48);
 }
 
 struct HaloParams {
@@ -400,11 +403,13 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     const uint32_t alo = a_lo_base + (uint32_t)(sa * T * (kHaloBufBytes >> 4)) + (lo & 0xffffu);
                     const uint32_t blo = slab_lo(lo, hi);
                     const uint32_t d = d_base + (((hi >> 4) & 3u) == 0 ? 0u : kAccCols) + (uint32_t)(b * T * N);
+                    const uint32_t asel = (hi >> 12) & 3u;
+                    const uint32_t as = asel == 0 ? 2u : (asel == 1 ? 8u : (uint32_t)(kHaloSbo >> 4));
                     if (elect_one()) {
                         mma(d, alo, blo, acc0);
-                        if (nkk > 1) mma(d, alo + 2, blo + 2, 1u);
-                        if (nkk > 2) mma(d, alo + 4, blo + 4, 1u);
-                        if (nkk > 3) mma(d, alo + 6, blo + 6, 1u);
+                        if (nkk > 1) mma(d, alo + as, blo + 2, 1u);
+                        if (nkk > 2) mma(d, alo + 2 * as, blo + 4, 1u);
+                        if (nkk > 3) mma(d, alo + 3 * as, blo + 6, 1u);
                         if (!WRES) commit(bar_wempty + slot * 8);
                         if (hi & (1u << 10)) commit(bar_aempty + sa * 8);
                     }
@@ -970,10 +975,11 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     const int ring = plan->variant == 0 ? kHaloResidentSlabs
                    : plan->variant == 1 ? kHaloRing1 : plan->variant == 2 ? kHaloRing2 : plan->variant == 4 ? kHaloRing4 : kHaloRing5;
     bool first_g1 = true, first_ds = true;
-    auto add_step = [&](unsigned a_lo, unsigned gemm, unsigned nkk, bool first, bool last, bool acc0, int kcoord) {
+    auto add_step = [&](unsigned a_lo, unsigned gemm, unsigned nkk, bool first, bool last, bool acc0, int kcoord, unsigned astep = 0) {
         const unsigned slot = (unsigned)(nsteps % ring);
-        p.steps[nsteps++] = halo_step(a_lo, slot * (unsigned)(N * 128 / 16), slot, gemm, nkk, first, last, acc0, (unsigned)kcoord);
+        p.steps[nsteps++] = halo_step(a_lo, slot * (unsigned)(N * 128 / 16), slot, gemm, nkk, first, last, acc0, (unsigned)kcoord, astep);
     };
+    static const bool tail_pack = [] { const char* e = std::getenv("SPB200_NO_TAIL_PACK"); return !(e && e[0] == '1'); }();
     // K = 16 steps of a split-layout chunk holding `real` (1..32) channels: the main slab spans the hi half and the
     // lo half (a.hi w.hi + a.lo w.hi), the lo-weight slab the hi half only (a.hi w.lo)
     auto kk_split_main = [](int real) { return 2 + (std::min(real, 32) + 15) / 16; };
@@ -1004,21 +1010,30 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
             p.chunk_c0[nchunks] = c * 64;
             ++nchunks;
             // the slabs that read this chunk, in issue order: (view, gemm, K steps, K coordinate)
-            struct Use { unsigned view, gemm, nkk; int kcoord; };
+            struct Use { unsigned view, gemm, nkk; int kcoord; unsigned astep; };
             std::vector<Use> uses;
             const int nkk = split ? kk_split_main(real_here) : (c == nch - 1 ? kk_last : 4);
-            for (int t = 0; t < sg.ntaps; ++t) uses.push_back({view16(sg.dy[t], sg.dx[t]), 0u, (unsigned)nkk, sg.koff / 64 + t * nch + c});
+            // packed K tail: the last chunk's nine one-MMA slabs as three slabs of three MMAs, one per filter row; the K steps
+            // of a slab are the row's taps dx = -1, 0, 1, i.e. A views one pixel apart along x (the group axis, or a haloed row)
+            const bool packed = tail_pack && !split && c == nch - 1 && nkk == 1 && sg.koff_tail > 0 && sg.koff_tail % 64 == 0 &&
+                                sg.ntaps == 9 && plan->variant != 0;
+            if (packed) {
+                for (int r = 0; r < 3; ++r)
+                    uses.push_back({view16(r - 1, -1), 0u, 3u, sg.koff_tail / 64 + r, p.orient == 0 ? 1u : 2u});
+            } else {
+                for (int t = 0; t < sg.ntaps; ++t) uses.push_back({view16(sg.dy[t], sg.dx[t]), 0u, (unsigned)nkk, sg.koff / 64 + t * nch + c, 0u});
+            }
             if (split && sg.koff_lo >= 0)
                 for (int t = 0; t < sg.ntaps; ++t)
-                    uses.push_back({view16(sg.dy[t], sg.dx[t]), 0u, (unsigned)kk_split_lo(real_here), sg.koff_lo / 64 + t * nch + c});
+                    uses.push_back({view16(sg.dy[t], sg.dx[t]), 0u, (unsigned)kk_split_lo(real_here), sg.koff_lo / 64 + t * nch + c, 0u});
             if (ds) {
-                uses.push_back({view16(0, 0), 1u, (unsigned)nkk, ds->koff / 64 + c});
-                if (split && ds->koff_lo >= 0) uses.push_back({view16(0, 0), 1u, (unsigned)kk_split_lo(real_here), ds->koff_lo / 64 + c});
+                uses.push_back({view16(0, 0), 1u, (unsigned)nkk, ds->koff / 64 + c, 0u});
+                if (split && ds->koff_lo >= 0) uses.push_back({view16(0, 0), 1u, (unsigned)kk_split_lo(real_here), ds->koff_lo / 64 + c, 0u});
             }
             for (size_t u = 0; u < uses.size(); ++u) {
                 if (nsteps >= kMaxSteps) return nullptr;
                 const bool acc = uses[u].gemm == 0 ? !first_g1 : !first_ds;
-                add_step(uses[u].view, uses[u].gemm, uses[u].nkk, u == 0, u + 1 == uses.size(), acc, uses[u].kcoord);
+                add_step(uses[u].view, uses[u].gemm, uses[u].nkk, u == 0, u + 1 == uses.size(), acc, uses[u].kcoord, uses[u].astep);
                 (uses[u].gemm == 0 ? first_g1 : first_ds) = false;
             }
         }
