@@ -979,7 +979,7 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         const unsigned slot = (unsigned)(nsteps % ring);
         p.steps[nsteps++] = halo_step(a_lo, slot * (unsigned)(N * 128 / 16), slot, gemm, nkk, first, last, acc0, (unsigned)kcoord, astep);
     };
-    static const bool tail_pack = [] { const char* e = std::getenv("SPB200_NO_TAIL_PACK"); return !(e && e[0] == '1'); }();
+    const bool tail_pack = [] { const char* e = std::getenv("SPB200_NO_TAIL_PACK"); return !(e && e[0] == '1'); }();   // per plan build
     // K = 16 steps of a split-layout chunk holding `real` (1..32) channels: the main slab spans the hi half and the
     // lo half (a.hi w.hi + a.lo w.hi), the lo-weight slab the hi half only (a.hi w.lo)
     auto kk_split_main = [](int real) { return 2 + (std::min(real, 32) + 15) / 16; };

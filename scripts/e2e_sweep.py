@@ -29,9 +29,20 @@ for name, inp in (('fp16desc', host), ('u8_fp16desc', u8)):
     bench.time_e2e(eng, inp, outs16, cap, 4, True)
     dt, kp = bench.time_e2e(eng, inp, outs16, cap, 20, True)
     res[name] = B * 20 / dt
+if os.environ.get('SWEEP_UNEVEN'):
+    # every other image black: no keypoints there, the largest count of a chunk is twice its mean
+    eng.set_descriptor_format('fp32')
+    hu = [b.clone() for b in hb]
+    for b in hu: b[1::2] = 0
+    hostu = [b.pin_memory().numpy() for b in hu]
+    bench.time_e2e(eng, hostu, outs, cap, 4, True)
+    dt, kp = bench.time_e2e(eng, hostu, outs, cap, 20, True)
+    res['uneven_counts'] = B * 20 / dt
+    res['uneven_kp_per_image'] = kp / 20 / B
 print(json.dumps(res))
 ''' % (REPO, REPO)
-for env in ({}, {'SPB200_NO_GRAPH': '1'}, {'SPB200_HOST_CHUNK': '32'}, {'SPB200_HOST_CHUNK': '64'}, {'SPB200_HOST_CHUNK': '8'}):
+ENVS = [{'SWEEP_UNEVEN': '1'}, {'SPB200_HOST_ONE_COPY': '1', 'SWEEP_UNEVEN': '1'}, {'SWEEP_UNEVEN': '1'}, {'SPB200_HOST_ONE_COPY': '1', 'SWEEP_UNEVEN': '1'}] if len(sys.argv) > 1 and sys.argv[1] == 'copies' else None
+for env in ENVS or ({}, {'SPB200_NO_GRAPH': '1'}, {'SPB200_HOST_CHUNK': '32'}, {'SPB200_HOST_CHUNK': '64'}, {'SPB200_HOST_CHUNK': '8'}):
     e = dict(os.environ); e.update(env)
     r = subprocess.run([sys.executable, '-c', code], env=e, capture_output=True, text=True, timeout=600)
     print(env, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:], flush=True)

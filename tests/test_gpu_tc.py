@@ -479,3 +479,36 @@ def test_fused_detector_tail_is_bit_identical_to_the_logits_path(shape, monkeypa
     for i in range(b):
         k = int(outs[0][9][i])
         assert k > 0 and torch.equal(outs[0][10][i, :k], outs[1][10][i, :k]) and torch.equal(outs[0][11][i, :k], outs[1][11][i, :k])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('shape', [(2, 240, 320), (2, 64, 256)])
+def test_packed_detector_k_tail_is_bit_identical(shape, monkeypatch):
+    """detector.layer.1 reads 65 channels: its 65th runs as three weight slabs of three MMAs (one per filter row, A views one
+    pixel apart: the packed K tail of common.cuh / halo_tc.cu) instead of nine one-MMA slabs; SPB200_NO_TAIL_PACK=1 (read when a
+    plan is built) restores the nine.  Same products accumulated in the same order: logits, heatmap and keypoints must be
+    bit-identical, for both tile orientations (64 x 256 is tiled 8 rows x 16 columns, where the taps of a filter row are one
+    haloed row apart)."""
+    from oracle import weights
+    spb = load_spb()
+    b, h, w = shape
+    img = torch.stack([weights.shapes_image(20 + i, h, w) for i in range(b)])[:, None].contiguous().cuda()
+    outs = []
+    for plain in ('1', '0'):
+        monkeypatch.setenv('SPB200_NO_TAIL_PACK', plain)
+        e = spb.Engine(0)
+        e.load_checkpoint(CKPT)
+        e.finalize('fp16')
+        e.set_params()
+        prob, desc, logits = e.forward(img)
+        count, xy, conf = e.detect(img, e.max_keypoints(h, w))[:3]
+        torch.cuda.synchronize()
+        outs.append([t.cpu().clone() for t in (prob, logits, count, xy, conf)])
+        e.close()
+    assert float(outs[0][1].abs().max()) > 0 and int(outs[0][2].min()) > 0
+    assert torch.equal(outs[0][1], outs[1][1]), 'logits differ'
+    assert torch.equal(outs[0][0], outs[1][0]), 'heatmaps differ'
+    assert torch.equal(outs[0][2], outs[1][2])
+    for i in range(b):
+        k = int(outs[0][2][i])
+        assert torch.equal(outs[0][3][i, :k], outs[1][3][i, :k]) and torch.equal(outs[0][4][i, :k], outs[1][4][i, :k])
