@@ -103,6 +103,7 @@ struct HaloParams {
     int heat;                      // detector tail (variant 1): the epilogue stores exp(l_c), c < 64, depth-to-space into the full-resolution
                                    // map (tmD is then a map of it) and the cell's normaliser into heat_inv: heat = exp * inv
     int split_out;                 // SPLIT kernels: the output is stored as [hi 32 | lo 32] per 32 channels (common.cuh, SegDev)
+    int alt_issue;                 // streamed-weight variants: the two issuing warps take alternate steps, each for both tiles (below)
     long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
 };
 
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full[SW], w_empty[SW];
     __shared__ __align__(8) uint64_t d1_full[NBUF], d1_empty[NBUF], y_full[NBUF], d2_full[NBUF], d2_empty[NBUF];
     __shared__ __align__(8) uint64_t res_full[8];          // one per epilogue warp: its shortcut sub-boxes have landed
+    __shared__ __align__(8) uint64_t tok[2];               // alternating issue: "the step before yours has been issued"
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_bias1[N], s_bias2[N];
 
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], T); }
         for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], T); }
         for (int w = 0; w < 8; ++w) mbar_init(&res_full[w], 1);
+        mbar_init(&tok[0], 1); mbar_init(&tok[1], 1);
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(&d1_full[b], T); mbar_init(&d2_full[b], T);
             mbar_init(&d1_empty[b], 8); mbar_init(&y_full[b], kEpi); mbar_init(&d2_empty[b], kEpi);
@@ -312,6 +315,108 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 }
             }
         }
+    } else if (warp < 2 + T && !WRES && !PAIR && T == 2 && p.alt_issue) {
+        // ============================ MMA issuers, alternating steps ============================
+        // With one issuing warp per tile both warps wait for the same slab, issue their four MMAs side by side and then
+        // walk through the same per-step overhead (commit, step decode, barrier polls: ~180 clocks) at the same time - and
+        // the tensor pipe, whose queue holds about two MMAs, runs dry once per step (step traces: 660-710 clocks per step
+        // of eight MMAs where the pipe needs 384-512).  Here the warps take ALTERNATE steps, each issuing the step's MMAs
+        // for both tiles: while one issues, the other is through its overhead and waiting for the token "the step before
+        // yours has been issued" (an mbarrier handed back and forth), so the order of the MMAs on every accumulator - and
+        // with it every result bit - is the one of the step list, as before.
+        const int w = warp - 2;
+        int sa = 0;
+        uint32_t pha = 0, wph = 0, gpar = 0, tokph = 0;
+        bool first_step = true;                                  // this warp has not issued yet (warp 0: no token before step 0)
+        const uint32_t a_lo_base = umma_desc_lo(smem_u32(a_ring));
+        const uint32_t w_lo_base = umma_desc_lo(smem_u32(w_ring));
+        const uint32_t bar_wfull = smem_u32(&w_full[0]), bar_wempty = smem_u32(&w_empty[0]);
+        const uint32_t bar_afull = smem_u32(&a_full[0]), bar_aempty = smem_u32(&a_empty[0]);
+        constexpr uint32_t kHiA = ((uint32_t)kHaloSbo >> 4) | (1u << 14) | (2u << 29);
+        constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+        constexpr uint32_t kTileA = (uint32_t)(kHaloBufBytes >> 4);
+        auto take_token = [&]() {
+            if (!(first_step && w == 0)) { mbar_wait(&tok[w], tokph); tokph ^= 1u; }
+            first_step = false;
+        };
+        for (int j = 0; j < n_local; ++j) {
+            const bool dbg_on = p.dbg && blockIdx.x == 0 && w == 0 && lane == 0 && j < 16;
+            if (dbg_on) p.dbg[j * 8 + 0] = clock64();
+            const int b = j % NBUF;
+            const uint32_t ph = (uint32_t)(j / NBUF) & 1u;
+            if (!FUSED) mbar_wait(&d1_empty[b], ph ^ 1u);              // epilogue has drained D1[b]
+            bool d2_ready = !(FUSED && p.has_ds);
+            HaloStep rec = p.steps[0];
+            for (int e = 0; e < p.n1steps; ++e) {
+                const HaloStep s = rec;
+                rec = p.steps[e + 1];
+                const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+                const uint32_t slot = hi & 15u, nkk = (hi >> 6) & 7u, acc0 = (hi >> 11) & 1u;
+                if (gpar == (uint32_t)w) {
+                    if (hi & (1u << 9)) mbar_wait_a(bar_afull + sa * 8, pha);
+                    mbar_wait_a(bar_wfull + slot * 8, (wph >> slot) & 1u);
+                    if (!d2_ready && ((hi >> 4) & 3u) != 0) mbar_wait(&d2_empty[b], ph ^ 1u);
+                    take_token();
+                    tc_fence_after();
+                    const uint32_t alo = a_lo_base + (uint32_t)(sa * T) * kTileA + (lo & 0xffffu);
+                    const uint32_t blo = w_lo_base + (lo >> 16);
+                    const uint32_t d = tmem_base + (((hi >> 4) & 3u) == 0 ? 0u : kAccCols) + (uint32_t)(b * T * N);
+                    const uint32_t asel = (hi >> 12) & 3u;
+                    const uint32_t as = asel == 0 ? 2u : (asel == 1 ? 8u : (uint32_t)(kHaloSbo >> 4));
+                    if (elect_one()) {
+                        umma_f16_w(d, alo, kHiA, blo, kHiB, idesc, acc0);
+                        umma_f16_w(d + N, alo + kTileA, kHiA, blo, kHiB, idesc, acc0);
+                        if (nkk > 1) { umma_f16_w(d, alo + as, kHiA, blo + 2, kHiB, idesc, 1u); umma_f16_w(d + N, alo + kTileA + as, kHiA, blo + 2, kHiB, idesc, 1u); }
+                        if (nkk > 2) { umma_f16_w(d, alo + 2 * as, kHiA, blo + 4, kHiB, idesc, 1u); umma_f16_w(d + N, alo + kTileA + 2 * as, kHiA, blo + 4, kHiB, idesc, 1u); }
+                        if (nkk > 3) { umma_f16_w(d, alo + 3 * as, kHiA, blo + 6, kHiB, idesc, 1u); umma_f16_w(d + N, alo + kTileA + 3 * as, kHiA, blo + 6, kHiB, idesc, 1u); }
+                        umma_commit_a(bar_wempty + slot * 8);               // the barriers count one arrival per tile
+                        umma_commit_a(bar_wempty + slot * 8);
+                        if (hi & (1u << 10)) { umma_commit_a(bar_aempty + sa * 8); umma_commit_a(bar_aempty + sa * 8); }
+                        mbar_arrive(&tok[1 - w]);
+                    }
+                }
+                if (!d2_ready && ((hi >> 4) & 3u) != 0) d2_ready = true;
+                wph ^= 1u << slot;
+                gpar ^= 1u;
+                if (hi & (1u << 10)) { if (++sa == SA) { sa = 0; pha ^= 1u; } }
+            }
+            if (elect_one()) umma_commit_a(smem_u32(&d1_full[b]));           // each warp for the MMAs it issued
+            if (dbg_on) p.dbg[j * 8 + 1] = clock64();
+            if (FUSED) {
+                mbar_wait(&y_full[b], ph);                 // Y written by the epilogue warps
+                if (!p.has_ds) mbar_wait(&d2_empty[b], ph ^ 1u);
+                tc_fence_after();
+                if (dbg_on) p.dbg[j * 8 + 2] = clock64();
+                for (int e = p.n1steps; e < p.nsteps; ++e) {
+                    const HaloStep s = p.steps[e];
+                    const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
+                    const uint32_t slot = hi & 15u, nkk = (hi >> 6) & 7u, acc0 = (hi >> 11) & 1u;
+                    if (gpar == (uint32_t)w) {
+                        mbar_wait_a(bar_wfull + slot * 8, (wph >> slot) & 1u);
+                        take_token();
+                        tc_fence_after();
+                        const uint32_t ya = tmem_base + (uint32_t)(b * T * N) + (lo & 0xffffu);
+                        const uint32_t blo = w_lo_base + (lo >> 16);
+                        const uint32_t d = tmem_base + kAccCols + (uint32_t)(b * T * N);
+                        if (elect_one()) {
+                            umma_f16_ts(d, ya, blo, kHiB, idesc, acc0);
+                            umma_f16_ts(d + N, ya + N, blo, kHiB, idesc, acc0);
+                            if (nkk > 1) { umma_f16_ts(d, ya + 8, blo + 2, kHiB, idesc, 1u); umma_f16_ts(d + N, ya + N + 8, blo + 2, kHiB, idesc, 1u); }
+                            if (nkk > 2) { umma_f16_ts(d, ya + 16, blo + 4, kHiB, idesc, 1u); umma_f16_ts(d + N, ya + N + 16, blo + 4, kHiB, idesc, 1u); }
+                            if (nkk > 3) { umma_f16_ts(d, ya + 24, blo + 6, kHiB, idesc, 1u); umma_f16_ts(d + N, ya + N + 24, blo + 6, kHiB, idesc, 1u); }
+                            umma_commit_a(bar_wempty + slot * 8);
+                            umma_commit_a(bar_wempty + slot * 8);
+                            mbar_arrive(&tok[1 - w]);
+                        }
+                    }
+                    wph ^= 1u << slot;
+                    gpar ^= 1u;
+                }
+                if (elect_one()) umma_commit_a(smem_u32(&d2_full[b]));
+                if (dbg_on) p.dbg[j * 8 + 3] = clock64();
+            }
+        }
+        __syncwarp();
     } else if (warp < 2 + T) {
         // ============================ MMA issuers: one warp per tile ============================
         // Non-MMA instructions of an issuing warp are not hidden behind the tensor pipe (measured: every branch, wait
@@ -1094,6 +1199,10 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
         p.tmW2 = p.tmW1;
     }
     p.nsteps = nsteps;
+    {
+        const char* e = std::getenv("SPB200_NO_ALT_ISSUE");        // per plan build
+        p.alt_issue = (!(e && e[0] == '1') && plan->variant != 0 && plan->variant != 3) ? 1 : 0;
+    }
     if (plan->variant == 0 && nsteps > kHaloResidentSlabs) return nullptr;
     if (plan->variant == 0) {      // the resident-weight fast path issues four K steps per slab from one activation chunk
         if (nchunks != 1) return nullptr;

@@ -512,3 +512,35 @@ def test_packed_detector_k_tail_is_bit_identical(shape, monkeypatch):
     for i in range(b):
         k = int(outs[0][2][i])
         assert torch.equal(outs[0][3][i, :k], outs[1][3][i, :k]) and torch.equal(outs[0][4][i, :k], outs[1][4][i, :k])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('prec', ['fp16', 'fp16+all'])
+def test_alternating_mma_issue_is_bit_identical(prec, monkeypatch):
+    """Streamed-weight residual-block kernels (halo_tc.cu): the two MMA-issuing warps take alternate steps of the step list, each
+    for both tiles of the pair, handing a token back and forth, instead of one warp per tile (SPB200_NO_ALT_ISSUE=1, read when a
+    plan is built).  Every accumulator still receives its MMAs in step-list order, so every output - plain and split-precision
+    blocks, transposed-convolution phases, the fused detector tail - must be bit-identical."""
+    from oracle import weights
+    spb = load_spb()
+    b, h, w = 3, 240, 320
+    img = torch.stack([weights.shapes_image(30 + i, h, w) for i in range(b)])[:, None].contiguous().cuda()
+    outs = []
+    for plain in ('1', '0'):
+        monkeypatch.setenv('SPB200_NO_ALT_ISSUE', plain)
+        e = spb.Engine(0)
+        e.load_checkpoint(CKPT)
+        e.finalize(prec)
+        e.set_params()
+        prob, desc, logits = e.forward(img)
+        count, xy, conf, d = e.detect(img, e.max_keypoints(h, w))[:4]
+        torch.cuda.synchronize()
+        outs.append([t.cpu().clone() for t in (prob, desc, logits, count, xy, conf, d)])
+        e.close()
+    assert float(outs[0][2].abs().max()) > 0 and int(outs[0][3].min()) > 0
+    for k, name in ((0, 'heatmap'), (1, 'descriptor map'), (2, 'logits'), (3, 'counts')):
+        assert torch.equal(outs[0][k], outs[1][k]), name + ' differ'
+    for i in range(b):
+        n = int(outs[0][3][i])
+        for k in (4, 5, 6):
+            assert torch.equal(outs[0][k][i, :n], outs[1][k][i, :n])
