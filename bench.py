@@ -253,6 +253,42 @@ def time_e2e(eng, host_np, host_outs, cap, steps, pipelined):
     return time.perf_counter() - t0, kp
 
 
+def measure_link(h2d_bytes, d2h_bytes, reps=5):
+    """What the host link of this box moves: one pinned upload of a step's input bytes and one pinned download of a step's
+    output bytes, each alone and both at once (two streams, CUDA events), best of `reps`.  The host-buffer path can be
+    no faster than the download of its results while the next upload runs - `e2e.link` states how close it is."""
+    h_in = torch.empty(int(h2d_bytes), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(int(d2h_bytes), dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(int(h2d_bytes), dtype=torch.uint8, device='cuda')
+    d_out = torch.empty(int(d2h_bytes), dtype=torch.uint8, device='cuda')
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up, dn):
+        best_up = best_dn = None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            if up:
+                with torch.cuda.stream(s_up):
+                    e[0].record(); d_in.copy_(h_in, non_blocking=True); e[1].record()
+            if dn:
+                with torch.cuda.stream(s_dn):
+                    e[2].record(); h_out.copy_(d_out, non_blocking=True); e[3].record()
+            torch.cuda.synchronize()
+            if up:
+                t = e[0].elapsed_time(e[1]); best_up = t if best_up is None else min(best_up, t)
+            if dn:
+                t = e[2].elapsed_time(e[3]); best_dn = t if best_dn is None else min(best_dn, t)
+        return (h2d_bytes / (best_up * 1e-3) / 1e9 if up else None, d2h_bytes / (best_dn * 1e-3) / 1e9 if dn else None)
+
+    run(True, True)
+    up_alone, _ = run(True, False)
+    _, dn_alone = run(False, True)
+    up_both, dn_both = run(True, True)
+    return {'h2d_gbs_alone': up_alone, 'd2h_gbs_alone': dn_alone, 'h2d_gbs_duplex': up_both, 'd2h_gbs_duplex': dn_both,
+            'how': 'one pinned copy of a step\'s bytes per direction, alone and both directions at once, best of %d (CUDA events)' % reps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -354,6 +390,13 @@ def main():
     e2e_value = shard.whole_job_rate(B * e2e_steps, dt, dev)
     d2h = kp * (8 + 4 + 512) // e2e_steps + 4 * B
     e2e_more = None
+    link = None
+    if not args.no_extras:
+        barrier()
+        link = measure_link(B * H * W * 4, max(int(d2h), 1))
+        # the download of a step's results is the longest stage of the pipeline: its share of the duplex download rate
+        link['d2h_gbs_e2e'] = (d2h * e2e_steps / dt) / 1e9         # this rank's own download rate inside the e2e loop
+        link['e2e_frac_of_duplex_d2h'] = link['d2h_gbs_e2e'] / link['d2h_gbs_duplex'] if link['d2h_gbs_duplex'] else None
     if not args.no_extras:
         e2e_more = {}
         barrier()
@@ -579,7 +622,7 @@ def main():
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * H * W * 4, 'd2h_bytes_per_step': int(d2h),
                     'api': 'spb200_detect_host_submit / spb200_detect_host_wait: pinned host buffers in and out, two batches in flight '
                            '(upload / compute / download pipelined in 16-image chunks), fp32 descriptors; every step ends with its results on the host',
-                    'steps': e2e_steps, 'variants': e2e_more},
+                    'steps': e2e_steps, 'link': link, 'variants': e2e_more},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': roofline,
