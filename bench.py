@@ -253,27 +253,39 @@ def time_e2e(eng, host_np, host_outs, cap, steps, pipelined):
     return time.perf_counter() - t0, kp
 
 
-def measure_link(h2d_bytes, d2h_bytes, reps=5):
-    """What the host link of this box moves: one pinned upload of a step's input bytes and one pinned download of a step's
-    output bytes, each alone and both at once (two streams, CUDA events), best of `reps`.  The host-buffer path can be
-    no faster than the download of its results while the next upload runs - `e2e.link` states how close it is."""
-    h_in = torch.empty(int(h2d_bytes), dtype=torch.uint8).pin_memory()
-    h_out = torch.empty(int(d2h_bytes), dtype=torch.uint8).pin_memory()
-    d_in = torch.empty(int(h2d_bytes), dtype=torch.uint8, device='cuda')
-    d_out = torch.empty(int(d2h_bytes), dtype=torch.uint8, device='cuda')
+def measure_link(h2d_bytes, d2h_bytes, reps=6):
+    """What the host link of this box moves: a step's input bytes up and a step's output bytes down from / to pinned memory,
+    each direction alone and both at once (two streams, CUDA events), as one copy and as four quarter copies (the
+    pipeline's chunks), best of `reps` and of the two shapes.  The host-buffer path can be no faster than the download of
+    its results while the next upload runs - `e2e.link` states how close it is."""
+    h_in = torch.zeros(int(h2d_bytes), dtype=torch.uint8).pin_memory()
+    h_out = torch.zeros(int(d2h_bytes), dtype=torch.uint8).pin_memory()
+    d_in = torch.zeros(int(h2d_bytes), dtype=torch.uint8, device='cuda')
+    d_out = torch.zeros(int(d2h_bytes), dtype=torch.uint8, device='cuda')
     s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def pieces(n, k):
+        q = (n + k - 1) // k
+        return [(i * q, min(n, (i + 1) * q)) for i in range(k) if i * q < n]
 
     def run(up, dn):
         best_up = best_dn = None
-        for _ in range(reps):
+        for r in range(reps):
+            k = 1 if r % 2 == 0 else 4
             torch.cuda.synchronize()
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             if up:
                 with torch.cuda.stream(s_up):
-                    e[0].record(); d_in.copy_(h_in, non_blocking=True); e[1].record()
+                    e[0].record()
+                    for lo, hi in pieces(int(h2d_bytes), k):
+                        d_in[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
+                    e[1].record()
             if dn:
                 with torch.cuda.stream(s_dn):
-                    e[2].record(); h_out.copy_(d_out, non_blocking=True); e[3].record()
+                    e[2].record()
+                    for lo, hi in pieces(int(d2h_bytes), k):
+                        h_out[lo:hi].copy_(d_out[lo:hi], non_blocking=True)
+                    e[3].record()
             torch.cuda.synchronize()
             if up:
                 t = e[0].elapsed_time(e[1]); best_up = t if best_up is None else min(best_up, t)
@@ -286,7 +298,8 @@ def measure_link(h2d_bytes, d2h_bytes, reps=5):
     _, dn_alone = run(False, True)
     up_both, dn_both = run(True, True)
     return {'h2d_gbs_alone': up_alone, 'd2h_gbs_alone': dn_alone, 'h2d_gbs_duplex': up_both, 'd2h_gbs_duplex': dn_both,
-            'how': 'one pinned copy of a step\'s bytes per direction, alone and both directions at once, best of %d (CUDA events)' % reps}
+            'how': 'a step\'s bytes per direction between pinned host memory and the device, alone and both directions at once, '
+                   'as one copy and as four, best of %d (CUDA events); the duplex upload is half as long as the download, as in the pipeline' % reps}
 
 
 def main():
@@ -396,7 +409,8 @@ def main():
         link = measure_link(B * H * W * 4, max(int(d2h), 1))
         # the download of a step's results is the longest stage of the pipeline: its share of the duplex download rate
         link['d2h_gbs_e2e'] = (d2h * e2e_steps / dt) / 1e9         # this rank's own download rate inside the e2e loop
-        link['e2e_frac_of_duplex_d2h'] = link['d2h_gbs_e2e'] / link['d2h_gbs_duplex'] if link['d2h_gbs_duplex'] else None
+        link['e2e_frac_of_duplex_d2h'] = link['d2h_gbs_e2e'] / link['d2h_gbs_duplex']
+        link['e2e_frac_of_d2h_alone'] = link['d2h_gbs_e2e'] / link['d2h_gbs_alone']
     if not args.no_extras:
         e2e_more = {}
         barrier()
