@@ -253,11 +253,13 @@ def time_e2e(eng, host_np, host_outs, cap, steps, pipelined):
     return time.perf_counter() - t0, kp
 
 
-def measure_link(h2d_bytes, d2h_bytes, reps=6):
+def measure_link(h2d_bytes, d2h_bytes, reps=6, sync=None, median=False):
     """What the host link of this box moves: a step's input bytes up and a step's output bytes down from / to pinned memory,
     each direction alone and both at once (two streams, CUDA events), as one copy and as four quarter copies (the
     pipeline's chunks), best of `reps` and of the two shapes.  The host-buffer path can be no faster than the download of
-    its results while the next upload runs - `e2e.link` states how close it is."""
+    its results while the next upload runs - `e2e.link` states how close it is.  With several ranks every repetition starts
+    behind a barrier (`sync`) and the MEDIAN is reported: the ranks share the host's PCIe / memory fabric, and the best
+    repetition of a rank is the one in which its neighbours happened to be idle."""
     h_in = torch.zeros(int(h2d_bytes), dtype=torch.uint8).pin_memory()
     h_out = torch.zeros(int(d2h_bytes), dtype=torch.uint8).pin_memory()
     d_in = torch.zeros(int(h2d_bytes), dtype=torch.uint8, device='cuda')
@@ -269,10 +271,12 @@ def measure_link(h2d_bytes, d2h_bytes, reps=6):
         return [(i * q, min(n, (i + 1) * q)) for i in range(k) if i * q < n]
 
     def run(up, dn):
-        best_up = best_dn = None
+        ups, dns = [], []
         for r in range(reps):
             k = 1 if r % 2 == 0 else 4
             torch.cuda.synchronize()
+            if sync is not None:
+                sync()
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             if up:
                 with torch.cuda.stream(s_up):
@@ -288,10 +292,11 @@ def measure_link(h2d_bytes, d2h_bytes, reps=6):
                     e[3].record()
             torch.cuda.synchronize()
             if up:
-                t = e[0].elapsed_time(e[1]); best_up = t if best_up is None else min(best_up, t)
+                ups.append(e[0].elapsed_time(e[1]))
             if dn:
-                t = e[2].elapsed_time(e[3]); best_dn = t if best_dn is None else min(best_dn, t)
-        return (h2d_bytes / (best_up * 1e-3) / 1e9 if up else None, d2h_bytes / (best_dn * 1e-3) / 1e9 if dn else None)
+                dns.append(e[2].elapsed_time(e[3]))
+        pick = (lambda v: float(np.median(v))) if median else min
+        return (h2d_bytes / (pick(ups) * 1e-3) / 1e9 if up else None, d2h_bytes / (pick(dns) * 1e-3) / 1e9 if dn else None)
 
     run(True, True)
     up_alone, _ = run(True, False)
@@ -299,7 +304,8 @@ def measure_link(h2d_bytes, d2h_bytes, reps=6):
     up_both, dn_both = run(True, True)
     return {'h2d_gbs_alone': up_alone, 'd2h_gbs_alone': dn_alone, 'h2d_gbs_duplex': up_both, 'd2h_gbs_duplex': dn_both,
             'how': 'a step\'s bytes per direction between pinned host memory and the device, alone and both directions at once, '
-                   'as one copy and as four, best of %d (CUDA events); the duplex upload is half as long as the download, as in the pipeline' % reps}
+                   'as one copy and as four, %s of %d (CUDA events); the duplex upload is half as long as the download, as in the pipeline'
+                   % ('median' if median else 'best', reps)}
 
 
 def main():
@@ -406,7 +412,7 @@ def main():
     link = None
     if not args.no_extras:
         barrier()
-        link = measure_link(B * H * W * 4, max(int(d2h), 1))
+        link = measure_link(B * H * W * 4, max(int(d2h), 1), sync=barrier if world > 1 else None, median=world > 1)
         # the download of a step's results is the longest stage of the pipeline: its share of the duplex download rate
         link['d2h_gbs_e2e'] = (d2h * e2e_steps / dt) / 1e9         # this rank's own download rate inside the e2e loop
         link['e2e_frac_of_duplex_d2h'] = link['d2h_gbs_e2e'] / link['d2h_gbs_duplex']
