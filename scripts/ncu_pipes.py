@@ -1,7 +1,7 @@
 """Pipe utilisation per launch from an ncu --set full report: tensor pipe, the shared-memory data pipe split into the
 tensor core's operand fetches (l1tex__data_pipe_tc_wavefronts_mem_shared) and the LSU's loads / stores
-(l1tex__data_pipe_lsu_wavefronts_mem_shared), L1 / L2 / DRAM throughput, issue slots.  The shared-memory pipe is the
-bound the residual-block kernels sit on: its two parts add up.  Usage: python scripts/ncu_pipes.py prof.ncu-rep"""
+(l1tex__data_pipe_lsu_wavefronts_mem_shared), L1 / L2 / DRAM throughput, issue slots.  The two are separate data pipes (they do not add up:
+l1tex% is the larger of them); the operand fetch is the bound the residual-block kernels sit on (4.0).  Usage: python scripts/ncu_pipes.py prof.ncu-rep"""
 import csv, io, subprocess, sys
 
 COLS = [('gpu__time_duration.sum', 'us', 1), ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed', 'tensor%', 1),
