@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
 
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
-    __shared__ __align__(8) uint64_t d1_full, d1_empty, y_full, y_empty, d2_full, d2_empty;
+    __shared__ __align__(8) uint64_t d1_full, d1_empty, y_full[kYChunks], y_empty, d2_full, d2_empty;   // y_full: one per 64-channel chunk of Y
     __shared__ __align__(8) uint64_t res_full[4];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_bias1[BLOCK_N], s_bias2[BLOCK_N];
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&d1_full, 1); mbar_init(&y_empty, 1); mbar_init(&d2_full, 1);
-        mbar_init(&d1_empty, 4); mbar_init(&y_full, 4); mbar_init(&d2_empty, 4);
+        mbar_init(&d1_empty, 4); mbar_init(&d2_empty, 4);
+        for (int c = 0; c < kYChunks; ++c) mbar_init(&y_full[c], 4);
         for (int w = 0; w < 4; ++w) mbar_init(&res_full[w], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -193,11 +194,12 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                 }
                 if (elect_one()) umma_commit(&d1_full);
                 if (fused) {
-                    mbar_wait(&y_full, tph);               // Y tile written by the epilogue warps
+                    // GEMM 2 follows the first epilogue chunk by chunk: the MMAs over the first 64 channels of Y run while the
+                    // epilogue warps convert the next ones (Y chunk c is complete when y_full[c] flips)
                     mbar_wait(&d2_empty, tph ^ 1u);        // epilogue 2 of the previous tile has drained D2
-                    tc_fence_after();
                     acc = 0;
                     for (int c = 0; c < p.y_chunks; ++c) {
+                        mbar_wait(&y_full[c], tph);        // this chunk of the Y tile has been written by the epilogue warps
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint32_t b_addr = smem_u32(ring + stage * kStageBytes) + kBlkABytes;
@@ -279,11 +281,17 @@ __global__ void __launch_bounds__(kBlkThreads) block_tc_kernel(const __grid_cons
                         *reinterpret_cast<uint4*>(ychunk + ((cj ^ (row & 7)) << 4)) =
                             make_uint4(pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]), pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
                     }
+                    if ((c0 & 32) || c0 + 32 >= p.n_mma) {            // a 64-channel chunk of Y is complete: GEMM 2 may read it
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&y_full[c0 >> 6]);
+                    }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // chunks of Y beyond n_mma (never written: all-zero weights there) still have to flip for the issuer
+                for (int c = (p.n_mma + 63) >> 6; c < p.y_chunks; ++c) { __syncwarp(); if (lane == 0) mbar_arrive(&y_full[c]); }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&d1_empty); mbar_arrive(&y_full); }
+                if (lane == 0) mbar_arrive(&d1_empty);
                 mbar_wait(&d2_full, tph);
                 tc_fence_after();
                 if (tr) {

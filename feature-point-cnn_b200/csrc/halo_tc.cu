@@ -104,6 +104,7 @@ struct HaloParams {
                                    // map (tmD is then a map of it) and the cell's normaliser into heat_inv: heat = exp * inv
     int split_out;                 // SPLIT kernels: the output is stored as [hi 32 | lo 32] per 32 channels (common.cuh, SegDev)
     int alt_issue;                 // streamed-weight variants: the two issuing warps take alternate steps, each for both tiles (below)
+    int y_early;                   // with alt_issue: GEMM 2 starts on the first 64 channels of Y while the first epilogue converts the rest
     long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
 };
 
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
     extern __shared__ uint8_t dyn_smem[];
     __shared__ __align__(8) uint64_t a_full[SA], a_empty[SA], w_full[SW], w_empty[SW];
     __shared__ __align__(8) uint64_t d1_full[NBUF], d1_empty[NBUF], y_full[NBUF], d2_full[NBUF], d2_empty[NBUF];
+    __shared__ __align__(8) uint64_t y_half[NBUF];         // y_early: the first 64 channels of Y (both tiles) are in tensor memory
     __shared__ __align__(8) uint64_t res_full[8];          // one per epilogue warp: its shortcut sub-boxes have landed
     __shared__ __align__(8) uint64_t tok[2];               // alternating issue: "the step before yours has been issued"
     __shared__ uint32_t tmem_slot;
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
         for (int b = 0; b < NBUF; ++b) {
             mbar_init(&d1_full[b], T); mbar_init(&d2_full[b], T);
             mbar_init(&d1_empty[b], 8); mbar_init(&y_full[b], kEpi); mbar_init(&d2_empty[b], kEpi);
+            mbar_init(&y_half[b], kEpi);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -383,11 +386,14 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
             if (elect_one()) umma_commit_a(smem_u32(&d1_full[b]));           // each warp for the MMAs it issued
             if (dbg_on) p.dbg[j * 8 + 1] = clock64();
             if (FUSED) {
-                mbar_wait(&y_full[b], ph);                 // Y written by the epilogue warps
+                // y_early: the first slab of GEMM 2 reads the first 64 channels of Y only (packed columns 0-31, complete after the
+                // first epilogue's second block); its eight MMAs run while the epilogue converts the remaining blocks
+                mbar_wait(p.y_early ? &y_half[b] : &y_full[b], ph);                 // Y written by the epilogue warps
                 if (!p.has_ds) mbar_wait(&d2_empty[b], ph ^ 1u);
                 tc_fence_after();
                 if (dbg_on) p.dbg[j * 8 + 2] = clock64();
                 for (int e = p.n1steps; e < p.nsteps; ++e) {
+                    if (p.y_early && e == p.n1steps + 1) { mbar_wait(&y_full[b], ph); tc_fence_after(); }
                     const HaloStep s = p.steps[e];
                     const uint32_t lo = (uint32_t)s, hi = (uint32_t)(s >> 32);
                     const uint32_t slot = hi & 15u, nkk = (hi >> 6) & 7u, acc0 = (hi >> 11) & 1u;
@@ -631,6 +637,12 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                     for (int e = 0; e < 16; ++e)
                         y[e] = pack2_relu<Tp>(__uint_as_float(r[2 * e]) + bb[2 * e], __uint_as_float(r[2 * e + 1]) + bb[2 * e + 1]);
                     tmem_st_32x16(tmem_d1 + (uint32_t)(c0 >> 1), y);
+                    if (T == 2 && !SPLIT && !PAIR && p.y_early && blk == blk_lo + 1) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&y_half[b]);
+                    }
                 }
             }
             tmem_st_wait();
@@ -1202,6 +1214,10 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     {
         const char* e = std::getenv("SPB200_NO_ALT_ISSUE");        // per plan build
         p.alt_issue = (!(e && e[0] == '1') && plan->variant != 0 && plan->variant != 3) ? 1 : 0;
+    }
+    {
+        const char* e = std::getenv("SPB200_NO_Y_EARLY");
+        p.y_early = (!(e && e[0] == '1') && p.alt_issue && plan->variant == 1 && c2 && p.nsteps - p.n1steps == 2 && p.n_mma > 64) ? 1 : 0;
     }
     if (plan->variant == 0 && nsteps > kHaloResidentSlabs) return nullptr;
     if (plan->variant == 0) {      // the resident-weight fast path issues four K steps per slab from one activation chunk
