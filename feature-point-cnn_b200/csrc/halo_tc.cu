@@ -69,6 +69,8 @@ constexpr int kHaloOutBox = 16384;                          // one staged output
 //                       1 = one pixel along the group axis, 2 = one haloed row - the packed K tail (common.cuh, SegDev): the
 //                       K steps of such a slab are the taps of one filter row over the chunk's first 16 channels
 //   bits 48-59  kcoord  K coordinate / 64 in the weight tensor (W1 for gemm 0, W2 otherwise)
+//   bit  60     d1done  alternating issue: the warp that issues this slab has issued its last GEMM-1 MMA of the tile pair with it and
+//                       commits D1 right after it - the shortcut slab that follows runs while the first epilogue already reads D1
 using HaloStep = unsigned long long;
 __host__ __device__ constexpr HaloStep halo_step(unsigned a_lo, unsigned w_lo, unsigned slot, unsigned gemm, unsigned nkk,
                                                  unsigned first, unsigned last, unsigned acc0, unsigned kcoord, unsigned astep = 0) {
@@ -105,6 +107,7 @@ struct HaloParams {
     int split_out;                 // SPLIT kernels: the output is stored as [hi 32 | lo 32] per 32 channels (common.cuh, SegDev)
     int alt_issue;                 // streamed-weight variants: the two issuing warps take alternate steps, each for both tiles (below)
     int y_early;                   // with alt_issue: GEMM 2 starts on the first 64 channels of Y while the first epilogue converts the rest
+    int early_d1;                  // with alt_issue: D1 is committed per warp at its d1done slab instead of after the last slab of GEMM 1 + shortcut
     long long* dbg;                // SPB200_HALO_DBG: clock stamps of CTA 0 (scripts/halo_dbg.py)
 };
 
@@ -375,6 +378,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                         umma_commit_a(bar_wempty + slot * 8);               // the barriers count one arrival per tile
                         umma_commit_a(bar_wempty + slot * 8);
                         if (hi & (1u << 10)) { umma_commit_a(bar_aempty + sa * 8); umma_commit_a(bar_aempty + sa * 8); }
+                        if (hi & (1u << 28)) umma_commit_a(smem_u32(&d1_full[b]));   // d1done: this warp's share of D1 is on its way
                         mbar_arrive(&tok[1 - w]);
                     }
                 }
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(halo_threads(T), 1) halo_tc_kernel(const __gri
                 gpar ^= 1u;
                 if (hi & (1u << 10)) { if (++sa == SA) { sa = 0; pha ^= 1u; } }
             }
-            if (elect_one()) umma_commit_a(smem_u32(&d1_full[b]));           // each warp for the MMAs it issued
+            if (!p.early_d1 && elect_one()) umma_commit_a(smem_u32(&d1_full[b]));           // each warp for the MMAs it issued
             if (dbg_on) p.dbg[j * 8 + 1] = clock64();
             if (FUSED) {
                 // y_early: the first slab of GEMM 2 reads the first 64 channels of Y only (packed columns 0-31, complete after the
@@ -1214,6 +1218,20 @@ TcHaloPlan* tc_halo_plan_create(const ConvDev& c1, const ConvDev* c2, int operan
     {
         const char* e = std::getenv("SPB200_NO_ALT_ISSUE");        // per plan build
         p.alt_issue = (!(e && e[0] == '1') && plan->variant != 0 && plan->variant != 3) ? 1 : 0;
+    }
+    {
+        // d1done (step record bit 60): the last two slabs of GEMM 1, one per issuing warp, when a shortcut slab follows them
+        const char* e = std::getenv("SPB200_NO_EARLY_D1");
+        int last_g1 = -1;
+        for (int k = 0; k < p.n1steps; ++k)
+            if (((p.steps[k] >> 36) & 3u) == 0u) last_g1 = k;
+        p.early_d1 = 0;
+        if (!(e && e[0] == '1') && p.alt_issue && plan->variant == 1 && c2 && last_g1 >= 1 && last_g1 < p.n1steps - 1 &&
+            ((p.steps[last_g1 - 1] >> 36) & 3u) == 0u) {
+            p.steps[last_g1] |= (HaloStep)1 << 60;
+            p.steps[last_g1 - 1] |= (HaloStep)1 << 60;
+            p.early_d1 = 1;
+        }
     }
     {
         const char* e = std::getenv("SPB200_NO_Y_EARLY");
