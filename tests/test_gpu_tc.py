@@ -544,3 +544,36 @@ def test_alternating_mma_issue_is_bit_identical(prec, monkeypatch):
         n = int(outs[0][3][i])
         for k in (4, 5, 6):
             assert torch.equal(outs[0][k][i, :n], outs[1][k][i, :n])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('switch', ['SPB200_NO_Y_EARLY', 'SPB200_NO_EARLY_D1'])
+def test_early_hand_overs_are_bit_identical(switch, monkeypatch):
+    """The hand-overs between the two GEMMs of a streamed-weight block (halo_tc.cu, alternating issue): GEMM 2 starts on the first
+    64 channels of Y while the first epilogue still converts the rest (SPB200_NO_Y_EARLY=1: one hand-over for the whole Y), and
+    each issuing warp commits D1 at its last GEMM-1 slab so that the trailing shortcut slab runs beside the first epilogue
+    (SPB200_NO_EARLY_D1=1: commit after the last slab).  Neither changes the order of the MMAs on an accumulator: every output
+    must be bit-identical with and without them."""
+    from oracle import weights
+    spb = load_spb()
+    b, h, w = 3, 240, 320
+    img = torch.stack([weights.shapes_image(40 + i, h, w) for i in range(b)])[:, None].contiguous().cuda()
+    outs = []
+    for off in ('1', '0'):
+        monkeypatch.setenv(switch, off)
+        e = spb.Engine(0)
+        e.load_checkpoint(CKPT)
+        e.finalize('fp16')
+        e.set_params()
+        prob, desc, logits = e.forward(img)
+        count, xy, conf, d = e.detect(img, e.max_keypoints(h, w))[:4]
+        torch.cuda.synchronize()
+        outs.append([t.cpu().clone() for t in (prob, desc, logits, count, xy, conf, d)])
+        e.close()
+    assert float(outs[0][2].abs().max()) > 0 and int(outs[0][3].min()) > 0
+    for k, name in ((0, 'heatmap'), (1, 'descriptor map'), (2, 'logits'), (3, 'counts')):
+        assert torch.equal(outs[0][k], outs[1][k]), name + ' differ'
+    for i in range(b):
+        n = int(outs[0][3][i])
+        for k in (4, 5, 6):
+            assert torch.equal(outs[0][k][i, :n], outs[1][k][i, :n])
