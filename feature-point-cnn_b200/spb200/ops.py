@@ -42,6 +42,12 @@ def _engine(eid):
         raise RuntimeError('spb200 op: no engine registered under id %d (spb200.ops.register)' % int(eid))
 
 
+def _desc_dtype(eid):
+    """fp32 unless the engine was switched to 16-bit descriptors (spb200_set_descriptor_format); fp32 for an unknown id (tracing)."""
+    e = _engines.get(int(eid))
+    return getattr(e, 'desc_dtype', torch.float32) if e is not None else torch.float32
+
+
 @torch.library.custom_op('spb200::forward', mutates_args=(), device_types='cuda')
 def forward(image: torch.Tensor, engine: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     return _engine(engine).forward(image)
@@ -63,7 +69,7 @@ def detect(image: torch.Tensor, engine: int, capacity: int) -> tuple[torch.Tenso
 def _(image, engine, capacity):
     b = image.shape[0]
     return (image.new_empty((b,), dtype=torch.int32), image.new_empty((b, capacity, 2), dtype=torch.int32),
-            image.new_empty((b, capacity)), image.new_empty((b, capacity, 128)))
+            image.new_empty((b, capacity), dtype=torch.float32), image.new_empty((b, capacity, 128), dtype=_desc_dtype(engine)))
 
 
 @torch.library.custom_op('spb200::detect_u8', mutates_args=(), device_types='cuda')
@@ -76,4 +82,4 @@ def detect_u8(frames: torch.Tensor, engine: int, capacity: int) -> tuple[torch.T
 def _(frames, engine, capacity):
     b = frames.shape[0]
     return (frames.new_empty((b,), dtype=torch.int32), frames.new_empty((b, capacity, 2), dtype=torch.int32),
-            frames.new_empty((b, capacity), dtype=torch.float32), frames.new_empty((b, capacity, 128), dtype=torch.float32))
+            frames.new_empty((b, capacity), dtype=torch.float32), frames.new_empty((b, capacity, 128), dtype=_desc_dtype(engine)))
